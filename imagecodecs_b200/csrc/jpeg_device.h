@@ -1,0 +1,73 @@
+// jpeg_device.h -- the handful of device primitives the encode kernel is written against.
+//
+// Under nvcc these are the real sm_100a intrinsics.  When JG_EMULATE is defined (tests only,
+// see tests/emu/) the same names are provided by a tiny thread-per-CUDA-thread emulator so
+// that the control logic of the kernel (tile bookkeeping, scans, bit packing, stuffing,
+// look-back) can be exercised on a machine without a GPU.  The emulation is test
+// infrastructure; nothing in the product links against it.
+#pragma once
+#include <stdint.h>
+
+#if defined(JG_EMULATE)
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+
+#define JG_DEV __device__ __forceinline__
+#define JG_DEV_NOINLINE __device__ __noinline__
+#define JG_TID ((int)threadIdx.x)
+#define JG_KERNEL(threads, min_ctas) __global__ __launch_bounds__(threads, min_ctas)
+#define JG_GRID_CONSTANT __grid_constant__
+#define JG_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+
+namespace jg {
+
+// ---- exactly-rounded binary32 arithmetic: never contracted into FMA ----------------------
+JG_DEV float f_add(float a, float b) { return __fadd_rn(a, b); }
+JG_DEV float f_sub(float a, float b) { return __fsub_rn(a, b); }
+JG_DEV float f_mul(float a, float b) { return __fmul_rn(a, b); }
+JG_DEV int f_floor_i(float a) { return __float2int_rd(a); }   // (int)floorf(a)
+JG_DEV float u8_to_f(unsigned v) { return (float)v; }          // exact
+
+// ---- integer helpers ---------------------------------------------------------------------
+JG_DEV int i_clz(unsigned v) { return __clz((int)v); }
+JG_DEV int i_ffs(unsigned v) { return __ffs((int)v); }
+JG_DEV int i_popc(unsigned v) { return __popc(v); }
+JG_DEV unsigned funnel_l(unsigned lo, unsigned hi, unsigned s) { return __funnelshift_l(lo, hi, s); }
+// per-byte compare: 0xff in every byte lane where a == b
+JG_DEV unsigned v_cmpeq4(unsigned a, unsigned b) { return __vcmpeq4(a, b); }
+
+// ---- CTA / warp collectives --------------------------------------------------------------
+JG_DEV void cta_sync() { __syncthreads(); }
+JG_DEV unsigned warp_ballot(int pred) { return __ballot_sync(0xffffffffu, pred); }
+JG_DEV unsigned warp_shfl_u32(unsigned v, int lane) { return __shfl_sync(0xffffffffu, v, lane); }
+JG_DEV unsigned warp_shfl_up_u32(unsigned v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+JG_DEV unsigned long long warp_shfl_u64(unsigned long long v, int lane) { return __shfl_sync(0xffffffffu, v, lane); }
+JG_DEV unsigned long long warp_shfl_xor_u64(unsigned long long v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// ---- memory ------------------------------------------------------------------------------
+JG_DEV uint32_t ldg_u32(const void* p) { return __ldg(reinterpret_cast<const unsigned*>(p)); }
+JG_DEV uint32_t ldg_u8(const void* p) { return __ldg(reinterpret_cast<const unsigned char*>(p)); }
+JG_DEV void smem_atomic_or(unsigned* p, unsigned v) { atomicOr(p, v); }
+JG_DEV unsigned gmem_atomic_add(unsigned* p, unsigned v) { return atomicAdd(p, v); }
+JG_DEV void gmem_atomic_or(unsigned* p, unsigned v) { atomicOr(p, v); }
+JG_DEV unsigned long long ld_flag64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+JG_DEV void st_flag64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+JG_DEV unsigned ld_flag32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+JG_DEV void backoff() { __nanosleep(64); }
+
+}  // namespace jg
+#endif

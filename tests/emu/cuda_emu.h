@@ -1,0 +1,102 @@
+// tests/emu/cuda_emu.h -- TEST INFRASTRUCTURE.  A minimal "one OS thread per CUDA thread"
+// emulation of the device primitives in imagecodecs_b200/csrc/jpeg_device.h, so that the
+// real kernel source (jpeg_kernel.cuh) can be compiled with g++ and its control logic
+// (tile bookkeeping, scans, bit packing, byte stuffing, decoupled look-back between
+// concurrently running CTAs) checked against the oracle on a machine without a GPU.
+// It is never linked into the product library.
+#pragma once
+#include <pthread.h>
+#include <sched.h>
+#include <stdint.h>
+#include <string.h>
+
+#define JG_DEV inline
+#define JG_DEV_NOINLINE static
+#define JG_KERNEL(threads, min_ctas)
+#define JG_GRID_CONSTANT
+#define JG_TID (::jg::emu::tls.tid)
+#define JG_DYNAMIC_SMEM(name) unsigned char* name = ::jg::emu::tls.cta->smem
+
+struct uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+
+namespace jg {
+namespace emu {
+
+struct Cta {
+    pthread_barrier_t bar;            // all threads of the CTA
+    pthread_barrier_t wbar[32];       // one per warp
+    unsigned long long xch[32][32];   // warp exchange slots
+    unsigned char* smem;
+    int nthreads;
+};
+struct Tls { int tid; Cta* cta; };
+extern thread_local Tls tls;
+
+inline void warp_barrier() { pthread_barrier_wait(&tls.cta->wbar[tls.tid >> 5]); }
+
+}  // namespace emu
+
+JG_DEV float f_add(float a, float b) { return a + b; }   // TU is built with -ffp-contract=off
+JG_DEV float f_sub(float a, float b) { return a - b; }
+JG_DEV float f_mul(float a, float b) { return a * b; }
+JG_DEV int f_floor_i(float a) { return (int)__builtin_floorf(a); }
+JG_DEV float u8_to_f(unsigned v) { return (float)v; }
+
+JG_DEV int i_clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+JG_DEV int i_ffs(unsigned v) { return __builtin_ffs((int)v); }
+JG_DEV int i_popc(unsigned v) { return __builtin_popcount(v); }
+JG_DEV unsigned v_cmpeq4(unsigned a, unsigned b)
+{
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i)
+        if (((a >> (8 * i)) & 0xffu) == ((b >> (8 * i)) & 0xffu)) r |= 0xffu << (8 * i);
+    return r;
+}
+
+JG_DEV void cta_sync() { pthread_barrier_wait(&emu::tls.cta->bar); }
+
+JG_DEV unsigned long long warp_exchange(unsigned long long v, int src_lane)
+{
+    emu::Cta* c = emu::tls.cta;
+    const int w = emu::tls.tid >> 5, lane = emu::tls.tid & 31;
+    c->xch[w][lane] = v;
+    emu::warp_barrier();
+    const unsigned long long r = (src_lane >= 0 && src_lane < 32) ? c->xch[w][src_lane] : v;
+    emu::warp_barrier();
+    return r;
+}
+JG_DEV unsigned warp_ballot(int pred)
+{
+    emu::Cta* c = emu::tls.cta;
+    const int w = emu::tls.tid >> 5, lane = emu::tls.tid & 31;
+    c->xch[w][lane] = pred ? 1 : 0;
+    emu::warp_barrier();
+    unsigned m = 0;
+    for (int i = 0; i < 32; ++i) m |= (unsigned)(c->xch[w][i] & 1) << i;
+    emu::warp_barrier();
+    return m;
+}
+JG_DEV unsigned warp_shfl_u32(unsigned v, int lane) { return (unsigned)warp_exchange(v, lane); }
+JG_DEV unsigned warp_shfl_up_u32(unsigned v, int d)
+{
+    const int lane = emu::tls.tid & 31;
+    return (unsigned)warp_exchange(v, lane - d >= 0 ? lane - d : lane);
+}
+JG_DEV unsigned long long warp_shfl_u64(unsigned long long v, int lane) { return warp_exchange(v, lane); }
+JG_DEV unsigned long long warp_shfl_xor_u64(unsigned long long v, int m)
+{
+    return warp_exchange(v, (emu::tls.tid & 31) ^ m);
+}
+
+JG_DEV uint32_t ldg_u32(const void* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+JG_DEV uint32_t ldg_u8(const void* p) { return *(const unsigned char*)p; }
+JG_DEV void smem_atomic_or(unsigned* p, unsigned v) { __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+JG_DEV unsigned gmem_atomic_add(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+JG_DEV void gmem_atomic_or(unsigned* p, unsigned v) { __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+JG_DEV unsigned long long ld_flag64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+JG_DEV void st_flag64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+JG_DEV unsigned ld_flag32(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+JG_DEV void backoff() { sched_yield(); }
+
+}  // namespace jg

@@ -1,0 +1,63 @@
+"""ctypes front-end for the CPU emulation of the kernel source (TEST INFRASTRUCTURE)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_SO = os.path.join(_HERE, "libjpeg_emu.so")
+_SRC = [os.path.join(_HERE, "emu_driver.cpp"), os.path.join(_HERE, "cuda_emu.h"),
+        os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_kernel.cuh"),
+        os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_device.h"),
+        os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_tables.h"),
+        os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_host.cpp")]
+_lib = None
+
+
+def build():
+    if os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in _SRC):
+        return
+    csrc = os.path.join(_ROOT, "imagecodecs_b200", "csrc")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+                    "-I" + _HERE, "-I" + csrc, "-o", _SO, _SRC[0], _SRC[-1]], check=True)
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.emu_encode.restype = C.c_int
+        L.emu_encode.argtypes = [C.c_void_p] + [C.c_int] * 10 + [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                                                C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def emu_encode(batch, qmode=0, quality=3, sub=0, win_words=0, n_ctas=2, stages=False, cap=None):
+    """batch: uint8 [n,h,w,c].  Returns list of scan bytes (entropy-coded segment + EOI) [, coefs, bits]."""
+    batch = np.ascontiguousarray(batch, dtype=np.uint8)
+    if batch.ndim == 3:
+        batch = batch[None]
+    n, h, w, c = batch.shape
+    mcu = 16 if (sub and c != 1) else 8
+    bpm = 1 if c == 1 else (6 if sub else 3)
+    nblk = ((w + mcu - 1) // mcu) * ((h + mcu - 1) // mcu) * bpm
+    if cap is None:
+        cap = nblk * 416 + 64
+    out = np.zeros((n, cap), dtype=np.uint8)
+    sizes = np.zeros(n, dtype=np.uint64)
+    status = np.zeros(n, dtype=np.uint32)
+    coefs = np.zeros((n * nblk, 64), dtype=np.int16) if stages else None
+    bits = np.zeros(n * nblk, dtype=np.uint32) if stages else None
+    rc = _load().emu_encode(batch.ctypes.data, n, w, h, c, 0, sub, qmode, quality, win_words, n_ctas,
+                            out.ctypes.data, cap, sizes.ctypes.data, status.ctypes.data,
+                            coefs.ctypes.data if stages else None, bits.ctypes.data if stages else None)
+    if rc != 0:
+        raise RuntimeError("emulated kernel reported error %d" % rc)
+    scans = [out[i, :min(int(sizes[i]), cap)].tobytes() for i in range(n)]
+    if stages:
+        return scans, sizes, status, coefs.reshape(n, nblk, 64), bits.reshape(n, nblk)
+    return scans, sizes, status

@@ -1,0 +1,125 @@
+// tests/emu/emu_driver.cpp -- TEST INFRASTRUCTURE.  Runs the product's kernel source
+// (imagecodecs_b200/csrc/jpeg_kernel.cuh) on CPU threads through cuda_emu.h and exposes
+// one C function the CPU test-suite calls.  See cuda_emu.h for why this exists.
+#define JG_EMULATE 1
+#include "jpeg_kernel.cuh"
+
+#include <stdlib.h>
+#include <vector>
+
+namespace jg {
+namespace emu {
+thread_local Tls tls;
+}
+}  // namespace jg
+
+namespace {
+
+using namespace jg;
+
+struct ThreadArg {
+    emu::Cta* cta;
+    int tid;
+    int layout, nc;
+    const LaunchParams* P;
+    const QuantSet* Q;
+};
+
+void* thread_main(void* p)
+{
+    ThreadArg* a = (ThreadArg*)p;
+    emu::tls.tid = a->tid;
+    emu::tls.cta = a->cta;
+    if (a->layout == LAYOUT_444 && a->nc == 3) encode_tiles_kernel<LAYOUT_444, 3>(*a->P, *a->Q);
+    else if (a->layout == LAYOUT_444 && a->nc == 4) encode_tiles_kernel<LAYOUT_444, 4>(*a->P, *a->Q);
+    else if (a->layout == LAYOUT_420 && a->nc == 3) encode_tiles_kernel<LAYOUT_420, 3>(*a->P, *a->Q);
+    else if (a->layout == LAYOUT_420 && a->nc == 4) encode_tiles_kernel<LAYOUT_420, 4>(*a->P, *a->Q);
+    else encode_tiles_kernel<LAYOUT_GRAY, 1>(*a->P, *a->Q);
+    return nullptr;
+}
+
+size_t smem_bytes(int layout, int nc)
+{
+    if (layout == LAYOUT_444) return nc == 3 ? sizeof(Smem<LAYOUT_444, 3>) : sizeof(Smem<LAYOUT_444, 4>);
+    if (layout == LAYOUT_420) return nc == 3 ? sizeof(Smem<LAYOUT_420, 3>) : sizeof(Smem<LAYOUT_420, 4>);
+    return sizeof(Smem<LAYOUT_GRAY, 1>);
+}
+
+}  // namespace
+
+extern "C" {
+
+// Encode `n_images` images of identical geometry/quality with `n_ctas` emulated CTAs
+// running concurrently.  scan_out: [n_images][scan_cap]; scan_bytes: [n_images].
+// Returns 0 on success, otherwise the kernel's error flag / a negative setup error.
+int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int stride, int subsampling,
+               int quality_mode, int quality, int win_words, int n_ctas,
+               uint8_t* scan_out, size_t scan_cap, unsigned long long* scan_bytes, unsigned* img_status,
+               int16_t* dbg_coefs, uint32_t* dbg_bits)
+{
+    const int layout = ncomp == 1 ? LAYOUT_GRAY : (subsampling ? LAYOUT_420 : LAYOUT_444);
+    uint8_t ql[64], qc[64];
+    if (!build_qt(quality_mode, quality, ql, qc)) return -1;
+    QuantSet Q;
+    build_pqt(ql, Q.luma);
+    build_pqt(qc, Q.chroma);
+    HuffLut lut;
+    build_huff_lut(&lut);
+
+    const int mcu = layout == LAYOUT_420 ? 16 : 8;
+    const int bpm = layout == LAYOUT_444 ? 3 : (layout == LAYOUT_420 ? 6 : 1);
+    const int mcus_x = (w + mcu - 1) / mcu, mcus_y = (h + mcu - 1) / mcu;
+    const int n_mcus = mcus_x * mcus_y;
+    const int M = kBlocksPerTile / bpm;
+    const int tiles = (n_mcus + M - 1) / M;
+    if (stride == 0) stride = w * ncomp;
+
+    std::vector<ImageDesc> imgs(n_images);
+    for (int i = 0; i < n_images; ++i) {
+        ImageDesc& d = imgs[i];
+        d.px = pixels + (size_t)i * stride * h;
+        d.out = scan_out + (size_t)i * scan_cap;
+        d.out_cap = scan_cap;
+        d.first_block = (unsigned long long)i * n_mcus * bpm;
+        d.w = w; d.h = h; d.stride = stride; d.mcus_x = mcus_x; d.n_mcus = n_mcus;
+        d.first_tile = i * tiles; d.n_tiles = tiles;
+        d.aligned4 = ((size_t)d.px % 4 == 0) && (stride % 4 == 0);
+    }
+    const int n_tiles = tiles * n_images;
+    std::vector<unsigned long long> desc_bits(n_tiles, 0), desc_ff(n_tiles, 0);
+    unsigned ticket = 0, error = 0;
+    for (int i = 0; i < n_images; ++i) { scan_bytes[i] = 0; img_status[i] = 0; }
+
+    LaunchParams P;
+    P.images = imgs.data(); P.n_images = n_images; P.n_tiles = n_tiles;
+    P.tiles_per_image = (n_images % 2) ? tiles : 0;   // exercise both tile->image paths
+    P.win_words = win_words ? win_words : kWinWordsMax;
+    P.ticket = &ticket; P.desc_bits = desc_bits.data(); P.desc_ff = desc_ff.data();
+    P.scan_bytes = scan_bytes; P.img_status = img_status; P.error = &error; P.huff = &lut;
+    P.dbg_coefs = dbg_coefs; P.dbg_bits = dbg_bits;
+
+    if (n_ctas > n_tiles) n_ctas = n_tiles;
+    std::vector<emu::Cta> ctas(n_ctas);
+    std::vector<ThreadArg> args((size_t)n_ctas * kThreads);
+    std::vector<pthread_t> th((size_t)n_ctas * kThreads);
+    const size_t sb = smem_bytes(layout, ncomp);
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 256 * 1024);
+    for (int c = 0; c < n_ctas; ++c) {
+        emu::Cta& cta = ctas[c];
+        cta.nthreads = kThreads;
+        cta.smem = (unsigned char*)aligned_alloc(64, (sb + 63) / 64 * 64);
+        pthread_barrier_init(&cta.bar, nullptr, kThreads);
+        for (int wv = 0; wv < kThreads / 32; ++wv) pthread_barrier_init(&cta.wbar[wv], nullptr, 32);
+        for (int t = 0; t < kThreads; ++t) {
+            ThreadArg& a = args[(size_t)c * kThreads + t];
+            a.cta = &cta; a.tid = t; a.layout = layout; a.nc = ncomp; a.P = &P; a.Q = &Q;
+            pthread_create(&th[(size_t)c * kThreads + t], &attr, thread_main, &a);
+        }
+    }
+    for (auto& x : th) pthread_join(x, nullptr);
+    for (auto& cta : ctas) free(cta.smem);
+    return (int)error;
+}
+}
