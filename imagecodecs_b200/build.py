@@ -1,0 +1,81 @@
+"""Build libjpeg_gpu.so (the C-ABI library) in-tree with nvcc for sm_100a.
+
+    python -m imagecodecs_b200.build [--force]
+
+Five kernel specialisations are compiled as separate translation units in parallel, then
+linked with the host API into imagecodecs_b200/libjpeg_gpu.so (static cudart, no torch).
+nvcc cross-compiles without a GPU, so this also runs in the CPU-only dev container.
+"""
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libjpeg_gpu.so")
+
+SPECS = [(0, 3), (0, 4), (1, 3), (1, 4), (2, 1)]   # (layout, channels): 444/420/gray
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+# --fmad=false: the reference's float math must not be contracted
+NVCC_FLAGS = ["-std=c++17", "-O3", "--fmad=false", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
+              "-I" + CSRC, "-I" + os.path.join(ROOT, "include")] + ARCH
+
+
+def _nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "jpeg_gpu.h"), __file__]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+    return r.stdout + r.stderr
+
+
+def build(force=False, verbose=False):
+    deps = _deps()
+    if not force and not _stale(LIB, deps):
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    jobs = []
+    for layout, nc in SPECS:
+        obj = os.path.join(OBJ, "kernel_%d_%d.o" % (layout, nc))
+        jobs.append((obj, [_nvcc()] + NVCC_FLAGS + ["-Xptxas", "-v", "-DJG_LAYOUT=%d" % layout, "-DJG_NC=%d" % nc,
+                                                   "-c", os.path.join(CSRC, "jpeg_kernel_inst.cu"), "-o", obj]))
+    for src in ("jpeg_gpu_api.cpp", "jpeg_host.cpp", "codecs_jpeg.cpp"):
+        if not os.path.exists(os.path.join(CSRC, src)):
+            continue
+        obj = os.path.join(OBJ, src.replace(".cpp", ".o"))
+        jobs.append((obj, [_nvcc()] + NVCC_FLAGS + ["-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]))
+    logs = []
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        futs = {ex.submit(_run, cmd): obj for obj, cmd in jobs if force or _stale(obj, deps)}
+        for f in cf.as_completed(futs):
+            logs.append((futs[f], f.result()))
+    _run([_nvcc(), "-shared", "-cudart", "static"] + ARCH + ["-o", LIB] + [obj for obj, _ in jobs])
+    with open(os.path.join(OBJ, "ptxas.log"), "w") as fh:
+        for obj, log in sorted(logs):
+            fh.write("== %s\n%s\n" % (os.path.basename(obj), log))
+    if verbose:
+        for obj, log in sorted(logs):
+            print("==", os.path.basename(obj)); print(log)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

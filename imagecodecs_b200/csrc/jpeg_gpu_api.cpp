@@ -1,0 +1,692 @@
+// jpeg_gpu_api.cpp -- host side of the C ABI declared in include/jpeg_gpu.h.
+//
+// What stays on the host (as in the reference): argument validation (jpeg_enc.h:954-960,
+// :1223-1226), quantiser / Huffman table construction (:1230-1266, :962-987) and marker
+// emission (:989-1077).  What goes to the GPU: the block loop (:1094-1172), as ONE kernel
+// launch per (layout, channels, quantiser) group of the batch -- see jpeg_kernel.cuh.
+//
+// There is no CPU encode path in this library: if CUDA is unusable every entry point fails.
+#include "jpeg_gpu.h"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <tuple>
+#include <vector>
+
+#include "jpeg_launch.h"
+#include "jpeg_tables.h"
+
+namespace {
+
+using namespace jg;
+
+thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+#define JG_CUDA(call)                                                                       \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return false;                                                                   \
+        }                                                                                   \
+    } while (0)
+
+// ---- kernel specialisations -------------------------------------------------------------
+struct Spec {
+    int layout, nc;
+    cudaError_t (*prepare)(int*);
+    cudaError_t (*launch)(int, cudaStream_t, const LaunchParams&, const QuantSet&);
+};
+const Spec kSpecs[5] = {
+    {LAYOUT_444, 3, prepare_0_3, launch_0_3}, {LAYOUT_444, 4, prepare_0_4, launch_0_4},
+    {LAYOUT_420, 3, prepare_1_3, launch_1_3}, {LAYOUT_420, 4, prepare_1_4, launch_1_4},
+    {LAYOUT_GRAY, 1, prepare_2_1, launch_2_1}};
+
+int spec_index(int layout, int nc)
+{
+    for (int i = 0; i < 5; ++i)
+        if (kSpecs[i].layout == layout && kSpecs[i].nc == nc) return i;
+    return -1;
+}
+
+// ---- devices ----------------------------------------------------------------------------
+struct Device {
+    int id = -1;
+    int sm_count = 0;
+    int ctas_per_sm[5] = {0, 0, 0, 0, 0};
+    HuffLut* d_huff = nullptr;
+    cudaStream_t stream = nullptr;   // used when the caller gives none
+};
+
+std::mutex g_mutex;
+std::vector<Device> g_devices;
+
+bool init_device(Device& d, int id)
+{
+    d.id = id;
+    JG_CUDA(cudaSetDevice(id));
+    cudaDeviceProp prop;
+    JG_CUDA(cudaGetDeviceProperties(&prop, id));
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; this library carries sm_100a code only", id, prop.major, prop.minor);
+        return false;
+    }
+    d.sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < 5; ++i) {
+        JG_CUDA(kSpecs[i].prepare(&d.ctas_per_sm[i]));
+        if (d.ctas_per_sm[i] < 1) { set_error("kernel spec %d does not fit an SM", i); return false; }
+    }
+    HuffLut lut;
+    build_huff_lut(&lut);
+    JG_CUDA(cudaMalloc(&d.d_huff, sizeof(HuffLut)));
+    JG_CUDA(cudaMemcpy(d.d_huff, &lut, sizeof(HuffLut), cudaMemcpyHostToDevice));
+    JG_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    return true;
+}
+
+bool ensure_init()
+{
+    {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        if (!g_devices.empty()) return true;
+    }
+    return jpeg_gpu_init(nullptr, 0) > 0;
+}
+
+// ---- geometry ---------------------------------------------------------------------------
+struct Geometry {
+    int layout, nc_in, ncomp_out, mcu, bpm, mcus_x, mcus_y, n_mcus, n_tiles;
+    size_t n_blocks;
+};
+
+bool geometry_of(const jpeg_gpu_image& im, Geometry* g)
+{
+    // jpeg_enc.h:954-960 (+ the extended 1-channel input)
+    if (im.ncomp != 1 && im.ncomp != 3 && im.ncomp != 4) return false;
+    if (im.width <= 0 || im.height <= 0 || im.width > 0xffff || im.height > 0xffff) return false;
+    if (im.subsampling != JPEG_GPU_SUB_444 && im.subsampling != JPEG_GPU_SUB_420) return false;
+    if (im.ncomp == 1 && im.subsampling != JPEG_GPU_SUB_444) return false;
+    if (im.stride != 0 && im.stride < im.width * im.ncomp) return false;
+    g->layout = im.ncomp == 1 ? LAYOUT_GRAY : (im.subsampling == JPEG_GPU_SUB_420 ? LAYOUT_420 : LAYOUT_444);
+    g->nc_in = im.ncomp;
+    g->ncomp_out = im.ncomp == 1 ? 1 : 3;
+    g->mcu = g->layout == LAYOUT_420 ? 16 : 8;
+    g->bpm = g->layout == LAYOUT_444 ? 3 : (g->layout == LAYOUT_420 ? 6 : 1);
+    g->mcus_x = (im.width + g->mcu - 1) / g->mcu;
+    g->mcus_y = (im.height + g->mcu - 1) / g->mcu;
+    g->n_mcus = g->mcus_x * g->mcus_y;
+    const int M = kBlocksPerTile / g->bpm;
+    g->n_tiles = (g->n_mcus + M - 1) / M;
+    g->n_blocks = (size_t)g->n_mcus * g->bpm;
+    return true;
+}
+
+// worst case of one block: DC 11+11 bits, 63 x (16+10) AC bits = 1660 bits -> 208 bytes,
+// doubled if every byte were 0xFF; + EOI
+size_t worst_scan_bytes(size_t n_blocks) { return n_blocks * 416 + 16; }
+
+// what the arena reserves per image: generous for real content (uniform noise at all-ones
+// quantisers needs ~4.1 B/px colour, ~1.4 B/px gray); anything beyond that is re-encoded
+// with the worst-case bound by jpeg_gpu_encode_batch.
+size_t default_scan_bytes(const jpeg_gpu_image& im, const Geometry& g)
+{
+    const size_t px = (size_t)im.width * im.height;
+    const size_t guess = (g.ncomp_out == 3 ? 6 * px : 5 * px / 2) + 4096;
+    return std::min(guess, worst_scan_bytes(g.n_blocks));
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// =========================================================================================
+// plan
+// =========================================================================================
+struct jpeg_gpu_plan {
+    struct Item {
+        jpeg_gpu_image img;
+        Geometry geo;
+        bool valid = false;
+        int group = -1, index_in_group = -1;
+        std::vector<uint8_t> header;
+        size_t scan_cap = 0, arena_off = 0;
+        size_t pixel_off = 0, pixel_bytes = 0;   // in the plan-owned upload buffer
+        const uint8_t* d_pixels = nullptr;
+        size_t first_block = 0;
+    };
+    struct Group {
+        int spec = -1;
+        QuantSet quant;
+        std::vector<int> items;
+        int n_tiles = 0, tiles_per_image = 0;
+        size_t state_off = 0;     // offset of {ticket, error, pad, desc_bits[], desc_ff[]} in d_state
+        ImageDesc* d_images = nullptr;
+        unsigned long long* d_scan_bytes = nullptr;   // into d_results
+        unsigned* d_status = nullptr;
+        size_t result_off = 0;    // index of first image of the group in the results arrays
+    };
+    int dev_index = 0;
+    int win_words = kWinWordsMax;
+    bool worst_case = false;
+    std::vector<Item> items;
+    std::vector<Group> groups;
+    uint8_t* d_arena = nullptr;      size_t arena_bytes = 0;
+    uint8_t* d_pixels = nullptr;     size_t pixels_bytes = 0;
+    uint8_t* d_state = nullptr;      size_t state_bytes = 0;    // zeroed before every run
+    uint8_t* d_results = nullptr;    size_t results_bytes = 0;  // scan_bytes[n] u64, status[n] u32
+    uint8_t* h_results = nullptr;                               // pinned mirror
+    ImageDesc* d_images = nullptr;
+    std::vector<ImageDesc> h_images;
+    bool images_dirty = true;
+    int16_t* dbg_coefs = nullptr;
+    uint32_t* dbg_bits = nullptr;
+    size_t n_blocks = 0;
+    int n_valid = 0;
+    bool fetched_results = false;
+};
+
+namespace {
+
+bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool worst_case)
+{
+    Device& dev = g_devices[p->dev_index];
+    JG_CUDA(cudaSetDevice(dev.id));
+    p->worst_case = worst_case;
+    p->items.resize(n);
+    std::map<std::tuple<int, int, int>, int> group_of;   // (spec, qmode, quality) -> group
+    size_t arena = 0, pixels = 0, blocks = 0;
+    for (int i = 0; i < n; ++i) {
+        jpeg_gpu_plan::Item& it = p->items[i];
+        it.img = images[i];
+        uint8_t ql[64], qc[64];
+        if (!geometry_of(it.img, &it.geo) || !build_qt(it.img.quality_mode, it.img.quality, ql, qc)) continue;
+        it.valid = true;
+        ++p->n_valid;
+        if (it.img.stride == 0) it.img.stride = it.img.width * it.img.ncomp;
+        it.header.resize(1024);
+        it.header.resize(emit_headers(it.img.width, it.img.height, it.geo.ncomp_out, it.img.subsampling, ql, qc,
+                                      it.header.data(), it.header.size()));
+        const int spec = spec_index(it.geo.layout, it.geo.nc_in);
+        auto key = std::make_tuple(spec, it.img.quality_mode, it.img.quality);
+        auto f = group_of.find(key);
+        if (f == group_of.end()) {
+            jpeg_gpu_plan::Group g;
+            g.spec = spec;
+            build_pqt(ql, g.quant.luma);
+            build_pqt(qc, g.quant.chroma);
+            f = group_of.emplace(key, (int)p->groups.size()).first;
+            p->groups.push_back(g);
+        }
+        jpeg_gpu_plan::Group& g = p->groups[f->second];
+        it.group = f->second;
+        it.index_in_group = (int)g.items.size();
+        g.items.push_back(i);
+        it.scan_cap = align_up(worst_case ? worst_scan_bytes(it.geo.n_blocks) : default_scan_bytes(it.img, it.geo), 256);
+        it.arena_off = arena;
+        arena += it.scan_cap;
+        it.pixel_bytes = (size_t)it.img.stride * it.img.height;
+        if (!it.img.pixels_on_device) {
+            it.pixel_off = pixels;
+            pixels += align_up(it.pixel_bytes, 256);
+        }
+        it.first_block = blocks;
+        blocks += it.geo.n_blocks;
+    }
+    p->n_blocks = blocks;
+    p->arena_bytes = arena;
+    p->pixels_bytes = pixels;
+
+    // device state: per group {ticket u32, error u32, pad} + desc_bits + desc_ff
+    size_t state = 0, res_index = 0;
+    for (auto& g : p->groups) {
+        int tiles = 0;
+        bool uniform = true;
+        const int t0 = p->items[g.items[0]].geo.n_tiles;
+        for (int idx : g.items) {
+            tiles += p->items[idx].geo.n_tiles;
+            uniform = uniform && p->items[idx].geo.n_tiles == t0;
+        }
+        g.n_tiles = tiles;
+        g.tiles_per_image = uniform ? t0 : 0;
+        g.state_off = state;
+        state += 16 + (size_t)tiles * 16;
+        g.result_off = res_index;
+        res_index += g.items.size();
+    }
+    p->state_bytes = state;
+    const size_t nres = res_index;
+    p->results_bytes = nres * 8 + nres * 4;
+    if (nres == 0) return true;
+
+    JG_CUDA(cudaMalloc(&p->d_arena, std::max<size_t>(arena, 256)));
+    if (pixels) JG_CUDA(cudaMalloc(&p->d_pixels, pixels));
+    JG_CUDA(cudaMalloc(&p->d_state, state));
+    JG_CUDA(cudaMalloc(&p->d_results, p->results_bytes));
+    JG_CUDA(cudaMemset(p->d_results, 0, p->results_bytes));
+    JG_CUDA(cudaMallocHost(&p->h_results, p->results_bytes));
+    JG_CUDA(cudaMalloc(&p->d_images, nres * sizeof(ImageDesc)));
+    p->h_images.resize(nres);
+    for (auto& g : p->groups) {
+        g.d_images = p->d_images + g.result_off;
+        g.d_scan_bytes = reinterpret_cast<unsigned long long*>(p->d_results) + g.result_off;
+        g.d_status = reinterpret_cast<unsigned*>(p->d_results + nres * 8) + g.result_off;
+        int tile = 0;
+        for (size_t k = 0; k < g.items.size(); ++k) {
+            jpeg_gpu_plan::Item& it = p->items[g.items[k]];
+            if (!it.img.pixels_on_device) it.d_pixels = p->d_pixels + it.pixel_off;
+            else it.d_pixels = it.img.pixels;
+            ImageDesc& d = p->h_images[g.result_off + k];
+            d.px = it.d_pixels;
+            d.out = p->d_arena + it.arena_off;
+            d.out_cap = it.scan_cap;
+            d.first_block = it.first_block;
+            d.w = it.img.width; d.h = it.img.height; d.stride = it.img.stride;
+            d.mcus_x = it.geo.mcus_x; d.n_mcus = it.geo.n_mcus;
+            d.first_tile = tile; d.n_tiles = it.geo.n_tiles;
+            d.aligned4 = ((size_t)d.px % 4 == 0) && (d.stride % 4 == 0);
+            tile += it.geo.n_tiles;
+        }
+    }
+    p->images_dirty = true;
+    return true;
+}
+
+bool plan_sync_images(jpeg_gpu_plan* p, cudaStream_t s)
+{
+    if (!p->images_dirty || p->h_images.empty()) return true;
+    // h_images is pageable: the copy is staged by the runtime before the call returns
+    JG_CUDA(cudaMemcpyAsync(p->d_images, p->h_images.data(), p->h_images.size() * sizeof(ImageDesc),
+                            cudaMemcpyHostToDevice, s));
+    p->images_dirty = false;
+    return true;
+}
+
+bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
+{
+    Device& dev = g_devices[p->dev_index];
+    JG_CUDA(cudaSetDevice(dev.id));
+    if (p->groups.empty()) return true;
+    if (!plan_sync_images(p, s)) return false;
+    JG_CUDA(cudaMemsetAsync(p->d_state, 0, p->state_bytes, s));
+    for (auto& g : p->groups) {
+        LaunchParams P;
+        P.images = g.d_images;
+        P.n_images = (int)g.items.size();
+        P.n_tiles = g.n_tiles;
+        P.tiles_per_image = g.tiles_per_image;
+        P.win_words = p->win_words;
+        uint8_t* st = p->d_state + g.state_off;
+        P.ticket = reinterpret_cast<unsigned*>(st);
+        P.error = reinterpret_cast<unsigned*>(st + 4);
+        P.desc_bits = reinterpret_cast<unsigned long long*>(st + 16);
+        P.desc_ff = P.desc_bits + g.n_tiles;
+        P.scan_bytes = g.d_scan_bytes;
+        P.img_status = g.d_status;
+        P.huff = dev.d_huff;
+        P.dbg_coefs = p->dbg_coefs;
+        P.dbg_bits = p->dbg_bits;
+        const int grid = std::min(g.n_tiles, dev.sm_count * dev.ctas_per_sm[g.spec]);
+        JG_CUDA(kSpecs[g.spec].launch(grid, s, P, g.quant));
+    }
+    p->fetched_results = false;
+    return true;
+}
+
+// bring scan sizes / status / error flags to the host (synchronises `s`)
+bool plan_results(jpeg_gpu_plan* p, cudaStream_t s)
+{
+    if (p->fetched_results || p->groups.empty()) return true;
+    JG_CUDA(cudaMemcpyAsync(p->h_results, p->d_results, p->results_bytes, cudaMemcpyDeviceToHost, s));
+    std::vector<unsigned> errs(p->groups.size());
+    for (size_t k = 0; k < p->groups.size(); ++k)
+        JG_CUDA(cudaMemcpyAsync(&errs[k], p->d_state + p->groups[k].state_off + 4, 4, cudaMemcpyDeviceToHost, s));
+    JG_CUDA(cudaStreamSynchronize(s));
+    for (unsigned e : errs)
+        if (e) { set_error("encode kernel aborted (look-back timeout, flag %u)", e); return false; }
+    p->fetched_results = true;
+    return true;
+}
+
+void plan_free(jpeg_gpu_plan* p)
+{
+    if (!p) return;
+    if (p->dev_index < (int)g_devices.size()) cudaSetDevice(g_devices[p->dev_index].id);
+    cudaFree(p->d_arena); cudaFree(p->d_pixels); cudaFree(p->d_state); cudaFree(p->d_results);
+    cudaFree(p->d_images);
+    if (p->h_results) cudaFreeHost(p->h_results);
+    delete p;
+}
+
+jpeg_gpu_plan* plan_create(const jpeg_gpu_image* images, int n, int device, int win_words, bool worst_case)
+{
+    if (!ensure_init()) return nullptr;
+    if (n < 0 || (n > 0 && !images)) { set_error("bad image list"); return nullptr; }
+    if (device < 0 || device >= (int)g_devices.size()) { set_error("device index %d out of range", device); return nullptr; }
+    jpeg_gpu_plan* p = new jpeg_gpu_plan();
+    p->dev_index = device;
+    if (win_words) p->win_words = std::max(kWinWordsMin, std::min(kWinWordsMax, win_words));
+    if (!plan_build(p, images, n, worst_case)) { plan_free(p); return nullptr; }
+    return p;
+}
+
+// per-image result after plan_results()
+void item_result(jpeg_gpu_plan* p, int i, size_t* file_size, int* status)
+{
+    const jpeg_gpu_plan::Item& it = p->items[i];
+    if (!it.valid) { *file_size = 0; *status = JPEG_GPU_ERR_ARG; return; }
+    const jpeg_gpu_plan::Group& g = p->groups[it.group];
+    const size_t nres = p->h_images.size();
+    const unsigned long long scan = reinterpret_cast<unsigned long long*>(p->h_results)[g.result_off + it.index_in_group];
+    const unsigned st = reinterpret_cast<unsigned*>(p->h_results + nres * 8)[g.result_off + it.index_in_group];
+    *file_size = it.header.size() + (size_t)scan;
+    *status = (st & 1u) ? JPEG_GPU_ERR_CAPACITY : JPEG_GPU_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+int jpeg_gpu_init(const int* device_ids, int n_devices)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (!g_devices.empty()) return (int)g_devices.size();
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    if (e != cudaSuccess || visible == 0) {
+        set_error("no usable CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return 0;
+    }
+    std::vector<int> ids;
+    if (device_ids && n_devices > 0) ids.assign(device_ids, device_ids + n_devices);
+    else for (int i = 0; i < visible; ++i) ids.push_back(i);
+    std::vector<Device> devs(ids.size());
+    for (size_t i = 0; i < ids.size(); ++i) {
+        if (ids[i] < 0 || ids[i] >= visible) { set_error("device id %d not visible", ids[i]); return 0; }
+        if (!init_device(devs[i], ids[i])) return 0;
+    }
+    g_devices = devs;
+    return (int)g_devices.size();
+}
+
+void jpeg_gpu_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    for (auto& d : g_devices) {
+        cudaSetDevice(d.id);
+        cudaFree(d.d_huff);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    g_devices.clear();
+}
+
+int jpeg_gpu_device_count(void)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return (int)g_devices.size();
+}
+
+const char* jpeg_gpu_last_error(void) { return g_last_error.c_str(); }
+
+size_t jpeg_gpu_max_encoded_size(int width, int height, int ncomp, int subsampling)
+{
+    jpeg_gpu_image im;
+    memset(&im, 0, sizeof im);
+    im.width = width; im.height = height; im.ncomp = ncomp; im.subsampling = subsampling;
+    Geometry g;
+    if (!geometry_of(im, &g)) return 0;
+    return 1024 + worst_scan_bytes(g.n_blocks);
+}
+
+size_t jpeg_gpu_emit_headers(int width, int height, int ncomp, int quality_mode, int quality, int subsampling,
+                             uint8_t* out, size_t capacity)
+{
+    jpeg_gpu_image im;
+    memset(&im, 0, sizeof im);
+    im.width = width; im.height = height; im.ncomp = ncomp; im.subsampling = subsampling;
+    Geometry g;
+    uint8_t ql[64], qc[64];
+    if (!geometry_of(im, &g) || !build_qt(quality_mode, quality, ql, qc)) return 0;
+    return emit_headers(width, height, g.ncomp_out, subsampling, ql, qc, out, capacity);
+}
+
+jpeg_gpu_plan* jpeg_gpu_plan_create(const jpeg_gpu_image* images, int n, int device, int debug_window_words)
+{
+    return plan_create(images, n, device, debug_window_words, false);
+}
+
+int jpeg_gpu_plan_set_pixels(jpeg_gpu_plan* p, int i, const uint8_t* device_pixels)
+{
+    if (!p || i < 0 || i >= (int)p->items.size() || !p->items[i].valid) return 0;
+    jpeg_gpu_plan::Item& it = p->items[i];
+    it.d_pixels = device_pixels;
+    ImageDesc& d = p->h_images[p->groups[it.group].result_off + it.index_in_group];
+    d.px = device_pixels;
+    d.aligned4 = ((size_t)d.px % 4 == 0) && (d.stride % 4 == 0);
+    p->images_dirty = true;
+    return 1;
+}
+
+int jpeg_gpu_plan_upload(jpeg_gpu_plan* p, int i, const uint8_t* host_pixels, void* stream)
+{
+    if (!p || i < 0 || i >= (int)p->items.size() || !p->items[i].valid) return 0;
+    jpeg_gpu_plan::Item& it = p->items[i];
+    if (it.img.pixels_on_device) { set_error("image %d was declared device-resident", i); return 0; }
+    cudaStream_t s = stream ? (cudaStream_t)stream : g_devices[p->dev_index].stream;
+    if (cudaSetDevice(g_devices[p->dev_index].id) != cudaSuccess) return 0;
+    cudaError_t e = cudaMemcpyAsync(p->d_pixels + it.pixel_off, host_pixels, it.pixel_bytes, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { set_error("pixel upload failed: %s", cudaGetErrorString(e)); return 0; }
+    return 1;
+}
+
+int jpeg_gpu_plan_run(jpeg_gpu_plan* p, void* stream)
+{
+    if (!p) return 0;
+    cudaStream_t s = stream ? (cudaStream_t)stream : g_devices[p->dev_index].stream;
+    return plan_run(p, s) ? 1 : 0;
+}
+
+int jpeg_gpu_plan_launches(const jpeg_gpu_plan* p) { return p ? (int)p->groups.size() : 0; }
+
+size_t jpeg_gpu_plan_num_blocks(const jpeg_gpu_plan* p) { return p ? p->n_blocks : 0; }
+
+int jpeg_gpu_plan_attach_debug(jpeg_gpu_plan* p, int16_t* dev_coefs, uint32_t* dev_block_bits)
+{
+    if (!p) return 0;
+    p->dbg_coefs = dev_coefs;
+    p->dbg_bits = dev_block_bits;
+    return 1;
+}
+
+size_t jpeg_gpu_plan_encoded_size(jpeg_gpu_plan* p, int i)
+{
+    if (!p || i < 0 || i >= (int)p->items.size()) return 0;
+    if (!plan_results(p, g_devices[p->dev_index].stream)) return 0;
+    size_t sz; int st;
+    item_result(p, i, &sz, &st);
+    return sz;
+}
+
+int jpeg_gpu_plan_fetch(jpeg_gpu_plan* p, jpeg_gpu_output* outs, int outputs_on_device, void* stream)
+{
+    if (!p || !outs) return 0;
+    cudaStream_t s = stream ? (cudaStream_t)stream : g_devices[p->dev_index].stream;
+    if (cudaSetDevice(g_devices[p->dev_index].id) != cudaSuccess) return 0;
+    if (!plan_results(p, s)) {
+        for (size_t i = 0; i < p->items.size(); ++i) { outs[i].size = 0; outs[i].status = JPEG_GPU_ERR_CUDA; }
+        return 0;
+    }
+    int ok = 0;
+    bool copies = false;
+    for (size_t i = 0; i < p->items.size(); ++i) {
+        size_t sz; int st;
+        item_result(p, (int)i, &sz, &st);
+        outs[i].size = sz;
+        outs[i].status = st;
+        if (st != JPEG_GPU_OK) continue;
+        if (!outs[i].data || outs[i].capacity < sz) { outs[i].status = JPEG_GPU_ERR_CAPACITY; continue; }
+        const jpeg_gpu_plan::Item& it = p->items[i];
+        const size_t hdr = it.header.size();
+        cudaError_t e;
+        if (outputs_on_device) {
+            e = cudaMemcpyAsync(outs[i].data, it.header.data(), hdr, cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(outs[i].data + hdr, p->d_arena + it.arena_off, sz - hdr, cudaMemcpyDeviceToDevice, s);
+        } else {
+            memcpy(outs[i].data, it.header.data(), hdr);
+            e = cudaMemcpyAsync(outs[i].data + hdr, p->d_arena + it.arena_off, sz - hdr, cudaMemcpyDeviceToHost, s);
+        }
+        if (e != cudaSuccess) {
+            set_error("output copy failed: %s", cudaGetErrorString(e));
+            outs[i].status = JPEG_GPU_ERR_CUDA;
+            continue;
+        }
+        copies = true;
+        ++ok;
+    }
+    if (copies && cudaStreamSynchronize(s) != cudaSuccess) { set_error("stream sync failed"); return 0; }
+    return ok;
+}
+
+void jpeg_gpu_plan_destroy(jpeg_gpu_plan* p) { plan_free(p); }
+
+// -----------------------------------------------------------------------------------------
+static int encode_on_device(const jpeg_gpu_image* images, int n, jpeg_gpu_output* outs, int device,
+                            int outputs_on_device, cudaStream_t stream, int win_words)
+{
+    jpeg_gpu_plan* p = plan_create(images, n, device, win_words, false);
+    if (!p) {
+        for (int i = 0; i < n; ++i) { outs[i].size = 0; outs[i].status = JPEG_GPU_ERR_CUDA; }
+        return 0;
+    }
+    cudaStream_t s = stream ? stream : g_devices[device].stream;
+    bool good = true;
+    for (int i = 0; i < n && good; ++i)
+        if (p->items[i].valid && !images[i].pixels_on_device) good = jpeg_gpu_plan_upload(p, i, images[i].pixels, s) != 0;
+    int ok = 0;
+    if (good && plan_run(p, s)) ok = jpeg_gpu_plan_fetch(p, outs, outputs_on_device, s);
+    else for (int i = 0; i < n; ++i) { outs[i].size = 0; outs[i].status = JPEG_GPU_ERR_CUDA; }
+
+    // content that outgrew the default reservation: once more, alone, with the worst-case bound
+    for (int i = 0; i < n; ++i) {
+        if (!p->items[i].valid || outs[i].status != JPEG_GPU_ERR_CAPACITY) continue;
+        size_t sz; int st;
+        item_result(p, i, &sz, &st);
+        if (st != JPEG_GPU_ERR_CAPACITY) continue;   // the caller's buffer is what is too small
+        jpeg_gpu_plan* q = plan_create(&images[i], 1, device, win_words, true);
+        if (!q) continue;
+        if ((images[i].pixels_on_device || jpeg_gpu_plan_upload(q, 0, images[i].pixels, s)) && plan_run(q, s))
+            ok += jpeg_gpu_plan_fetch(q, &outs[i], outputs_on_device, s);
+        plan_free(q);
+    }
+    plan_free(p);
+    return ok;
+}
+
+int jpeg_gpu_encode_batch(const jpeg_gpu_image* images, int n, jpeg_gpu_output* outs, const jpeg_gpu_batch_opts* opts)
+{
+    if (n <= 0 || !images || !outs) { set_error("empty batch"); return 0; }
+    if (!ensure_init()) {
+        for (int i = 0; i < n; ++i) { outs[i].size = 0; outs[i].status = JPEG_GPU_ERR_CUDA; }
+        return 0;
+    }
+    const int device = opts ? opts->device : -1;
+    const int on_dev = opts ? opts->outputs_on_device : 0;
+    const int win = opts ? opts->debug_window_words : 0;
+    if (device >= 0)
+        return encode_on_device(images, n, outs, device, on_dev, opts ? (cudaStream_t)opts->stream : nullptr, win);
+
+    // shard by image index: GPU g takes [g*n/G, (g+1)*n/G); no inter-GPU traffic
+    const int G = std::min((int)g_devices.size(), n);
+    if (G == 1) return encode_on_device(images, n, outs, 0, on_dev, nullptr, win);
+    std::vector<int> oks(G, 0);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < G; ++g) {
+        workers.emplace_back([&, g] {
+            const int lo = (int)((long long)g * n / G), hi = (int)((long long)(g + 1) * n / G);
+            oks[g] = encode_on_device(images + lo, hi - lo, outs + lo, g, on_dev, nullptr, win);
+            errs[g] = g_last_error;
+        });
+    }
+    int ok = 0;
+    for (int g = 0; g < G; ++g) {
+        workers[g].join();
+        ok += oks[g];
+        if (!errs[g].empty()) g_last_error = errs[g];
+    }
+    return ok;
+}
+
+// ---- drop-in twins -------------------------------------------------------------------------
+int jpeg_gpu_encode_with_func(jpeg_gpu_write_func* func, void* context, const int quality, const int width,
+                              const int height, const int num_components, const unsigned char* src_data)
+{
+    if (quality < 1 || quality > 3) { set_error("valid quality values are 1, 2, 3"); return 0; }   // jpeg_enc.h:1223
+    if (num_components != 3 && num_components != 4) { set_error("3 or 4 components only"); return 0; }  // :954
+    if (!func || !src_data) { set_error("null argument"); return 0; }
+    jpeg_gpu_image im;
+    memset(&im, 0, sizeof im);
+    im.pixels = src_data; im.width = width; im.height = height; im.ncomp = num_components;
+    im.quality_mode = JPEG_GPU_QMODE_TJE; im.quality = quality; im.subsampling = JPEG_GPU_SUB_444;
+    Geometry g;
+    if (!geometry_of(im, &g)) { set_error("unsupported geometry"); return 0; }   // :958-960
+    std::vector<uint8_t> buf(1024 + default_scan_bytes(im, g));
+    jpeg_gpu_output out;
+    out.data = buf.data(); out.capacity = buf.size(); out.size = 0; out.status = 0;
+    jpeg_gpu_batch_opts opts;
+    memset(&opts, 0, sizeof opts);
+    opts.device = 0;
+    if (jpeg_gpu_encode_batch(&im, 1, &out, &opts) != 1) {
+        if (out.status != JPEG_GPU_ERR_CAPACITY) return 0;
+        buf.resize(out.size);                     // pathological content: retry with the exact size
+        out.data = buf.data(); out.capacity = buf.size();
+        if (jpeg_gpu_encode_batch(&im, 1, &out, &opts) != 1) return 0;
+    }
+    // hand the bytes over the way tjei_write does: 1023-byte chunks, then the rest (jpeg_enc.h:487-490, :1169-1172)
+    const size_t chunk = 1023;
+    for (size_t off = 0; off < out.size; off += chunk)
+        func(context, buf.data() + off, (int)std::min(chunk, out.size - off));
+    return 1;
+}
+
+static void file_sink(void* ctx, void* data, int size) { fwrite(data, (size_t)size, 1, (FILE*)ctx); }   // jpeg_enc.h:1187-1191
+
+int jpeg_gpu_encode_to_file_at_quality(const char* dest_path, const int quality, const int width, const int height,
+                                       const int num_components, const unsigned char* src_data)
+{
+    FILE* fd = fopen(dest_path, "wb");   // like jpeg_enc.h:1201: the file is created before anything is checked
+    if (!fd) { set_error("could not open %s for writing", dest_path); return 0; }
+    int result = jpeg_gpu_encode_with_func(file_sink, fd, quality, width, height, num_components, src_data);
+    if (fclose(fd) != 0) result = 0;
+    return result;
+}
+
+int jpeg_gpu_encode_to_file(const char* dest_path, const int width, const int height, const int num_components,
+                            const unsigned char* src_data)
+{
+    return jpeg_gpu_encode_to_file_at_quality(dest_path, 3, width, height, num_components, src_data);   // jpeg_enc.h:1183
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// jpeg_launch.h -- what the host side (jpeg_gpu_api.cu) and the kernel agree on: tile
+// constants, the per-image record, the launch parameter block, and the per-specialisation
+// launchers defined by jpeg_kernel_inst.cu.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#if !defined(JG_EMULATE)
+#include <cuda_runtime.h>
+#endif
+
+#include "jpeg_tables.h"
+
+namespace jg {
+
+constexpr int kThreads = 192;
+constexpr int kBlocksPerTile = 192;
+constexpr int kWarps = kThreads / 32;
+constexpr int kWinWordsMax = 4096;   // 16 KB of unstuffed scan per group
+constexpr int kWinWordsMin = 64;     // must hold one worst-case block (1658 bits) + slack
+constexpr unsigned kSpinLimit = 1u << 24;
+
+constexpr unsigned long long kStatusAgg = 1ull << 62;
+constexpr unsigned long long kStatusPrefix = 2ull << 62;
+constexpr unsigned long long kBitsMask = (1ull << 55) - 1;   // desc_bits: [54:0] bits, [61:55] tail7
+constexpr unsigned long long kCountMask = (1ull << 62) - 1;  // desc_ff:   [61:0] count
+
+struct ImageDesc {
+    const uint8_t* px;               // device pixels
+    uint8_t* out;                    // device destination of the entropy-coded segment (+EOI)
+    unsigned long long out_cap;      // bytes available at `out`
+    unsigned long long first_block;  // index of the image's first block in the debug dumps
+    int w, h;
+    int stride;      // bytes per pixel row
+    int mcus_x;      // MCUs per MCU row
+    int n_mcus;
+    int first_tile;  // launch-local index of the image's first tile
+    int n_tiles;
+    int aligned4;    // px and stride are multiples of 4 (word loads allowed)
+};
+
+struct LaunchParams {
+    const ImageDesc* images;
+    int n_images;
+    int n_tiles;
+    int tiles_per_image;             // > 0 when every image of the launch has this many tiles
+    int win_words;                   // window size actually used (<= kWinWordsMax)
+    unsigned* ticket;                // zeroed before the launch
+    unsigned long long* desc_bits;   // [n_tiles], zeroed before the launch
+    unsigned long long* desc_ff;     // [n_tiles], zeroed before the launch
+    unsigned long long* scan_bytes;  // [n_images] OUT: bytes of scan + EOI
+    unsigned* img_status;            // [n_images] OUT: bit0 = capacity exceeded
+    unsigned* error;                 // OUT: non-zero if a look-back timed out
+    const HuffLut* huff;
+    int16_t* dbg_coefs;              // optional [blocks*64], zigzag order
+    uint32_t* dbg_bits;              // optional [blocks]
+};
+
+
+#if !defined(JG_EMULATE)
+// one set per (layout, channels) specialisation; see jpeg_kernel_inst.cu
+#define JG_DECLARE_SPEC(L, N)                                                                   \
+    size_t smem_bytes_##L##_##N();                                                              \
+    cudaError_t prepare_##L##_##N(int* ctas_per_sm);                                            \
+    cudaError_t launch_##L##_##N(int grid, cudaStream_t stream, const LaunchParams& P, const QuantSet& Q);
+JG_DECLARE_SPEC(0, 3)
+JG_DECLARE_SPEC(0, 4)
+JG_DECLARE_SPEC(1, 3)
+JG_DECLARE_SPEC(1, 4)
+JG_DECLARE_SPEC(2, 1)
+#undef JG_DECLARE_SPEC
+#endif
+
+}  // namespace jg
