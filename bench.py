@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- JPEG encode throughput of the B200 path (and of the CPU reference arm).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
+    synthetic 1920x1080 RGB, batch of 256 per GPU, IJG quality 75, 4:2:0.
+A step = one pass of the encode path over the whole batch.  `value` is device-timed MP/s
+with pixels resident in HBM and the encoded scans left in HBM; `e2e` is the same batch
+through the C ABI's plan calls with pinned HOST pixels in and HOST JPEG files out.
+
+Under torchrun (N > 1) every rank encodes its own 256-image shard (weak scaling, no data
+path collective); the time is the max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NC = 1920, 1080, 3
+BATCH = 256
+QMODE, QUALITY, SUB = 1, 75, 1          # IJG 75, 4:2:0
+TWIN_QMODE, TWIN_QUALITY, TWIN_SUB = 0, 2, 0   # byte-pinned native twin: tje quality 2, 4:4:4
+METRIC = "jpeg_encode_mp_per_s"
+UNIT = "MP/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arms
+# ------------------------------------------------------------------------------------------
+def cpu_encode_rate(images, qmode, quality, sub, threads, min_seconds=2.0, max_seconds=25.0):
+    """MP/s of the CPU checker on `images` (list of HxWxC uint8), `threads` host threads.
+    Uses oracle/_ref (the compiled, unmodified reference) when the mode is one the reference
+    has, else the oracle port.  Returns (mp_per_s, kind, n_encoded, seconds)."""
+    import oracle
+    native = (qmode == 0 and sub == 0 and images[0].shape[2] in (3, 4))
+    use_ref = native and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libtje_ref.so"))
+    if use_ref:
+        enc = lambda im: oracle.ref_encode(im, quality)[1]
+    else:
+        oracle.build()
+        enc = lambda im: oracle.oracle_encode(im, qmode, quality, sub)
+    enc(images[0])   # warm (page-in, table setup)
+    mp = images[0].shape[0] * images[0].shape[1] / 1e6
+    done = [0]
+    lock = threading.Lock()
+    t_end = [0.0]
+    start = time.perf_counter()
+
+    def worker(k):
+        i = k
+        while True:
+            now = time.perf_counter() - start
+            if now > max_seconds or (now > min_seconds and i >= len(images)):
+                break
+            enc(images[i % len(images)])
+            i += threads
+            with lock:
+                done[0] += 1
+                t_end[0] = time.perf_counter() - start
+
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(threads)]
+    for t in ths: t.start()
+    for t in ths: t.join()
+    secs = t_end[0]
+    return done[0] * mp / secs, ("reference" if use_ref else "port"), done[0], secs
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import synth_batch
+    cores = os.cpu_count() or 1
+    sample = synth_batch(min(cores, 16), W, H, NC)
+    imgs = [sample[i] for i in range(sample.shape[0])]
+    rates = []
+    for _ in range(args.warmup):
+        cpu_encode_rate(imgs, QMODE, QUALITY, SUB, cores, min_seconds=0.5, max_seconds=3.0)
+    t0 = time.perf_counter()
+    n_total = 0
+    for _ in range(args.steps):
+        r, kind, n, secs = cpu_encode_rate(imgs, QMODE, QUALITY, SUB, cores, min_seconds=1.0, max_seconds=6.0)
+        rates.append(r); n_total += n
+    wall = time.perf_counter() - t0
+    v = float(np.median(rates))
+    sample_txt = "%d x %dx%d RGB synthetic photo images per step on %d threads (the reference has no 4:2:0/q75 mode: jpeg_enc.h:1223,1038 -> oracle port of its algorithm)" % (
+        len(imgs), W, H, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * wall / max(args.steps, 1), 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "1920x1080 RGB, IJG q=75, 4:2:0 (BASELINE configs[1]), CPU sample", "images_per_step": n_total // max(args.steps, 1)},
+        "cpu_baseline": {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_txt},
+        "e2e": {"value": round(v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU every 50 ms while `running`."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import imagecodecs_b200 as jg
+    from imagecodecs_b200.synth import synth_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    jg.init([local])
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.Stream(device=dev)      # explicit stream: events and kernels share it
+    torch.cuda.set_stream(stream)
+    sptr = C.c_void_p(stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # rank r encodes images [r*BATCH, (r+1)*BATCH) of the synthetic sequence
+    pixels = synth_batch(BATCH, W, H, NC, "photo", seed=1, first=rank * BATCH, device=dev)
+    imgs = [pixels[i] for i in range(BATCH)]
+    mp_per_step = BATCH * W * H / 1e6
+
+    def timed(plan, steps, warmup):
+        for _ in range(warmup):
+            plan.run(sptr)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            plan.run(sptr)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        return max_over_ranks(ms) / steps
+
+    # ---- device-timed headline ------------------------------------------------------------
+    plan = jg.Plan.for_arrays(imgs, QMODE, QUALITY, SUB, device=0)
+    with ClockSampler(local) as clk:
+        ms_step = timed(plan, args.steps, args.warmup)
+    clocks = clk.summary()
+    sizes = [plan.encoded_size(i) for i in range(BATCH)]
+    hdr_len = len(jg.emit_headers(W, H, NC, QMODE, QUALITY, SUB))
+    scan_bytes = sum(sizes) - BATCH * hdr_len
+    value = world * mp_per_step / (ms_step * 1e-3)
+
+    # roofline of the one kernel a step launches: algorithmic bytes = RGB in + scan out
+    peak, peak_src = measured_peak()
+    algo_bytes = BATCH * W * H * NC + scan_bytes
+    achieved = algo_bytes / (ms_step * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get("encode_420_3_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "kernel": "jg::encode_tiles_kernel<LAYOUT_420,3>",
+                "algorithmic_bytes_per_launch": int(algo_bytes),
+                "note": "a step = 1 state memset (<1% of the step) + 1 kernel launch; duration = CUDA-event step time"}
+
+    # ---- parity spot check against the oracle (not timed) ------------------------------------
+    parity = None
+    if rank == 0:
+        import oracle
+        files = None
+        try:
+            chk = jg.Plan.for_arrays(imgs[:2], QMODE, QUALITY, SUB, device=0)
+            chk.run(sptr); torch.cuda.synchronize()
+            files = chk.fetch(sptr); chk.close()
+            parity = all(files[i] == oracle.oracle_encode(pixels[i].cpu().numpy(), QMODE, QUALITY, SUB) for i in range(2))
+        except Exception as e:   # the bench still reports, but says so
+            parity = "check failed: %r" % (e,)
+
+    # ---- end to end: pinned host pixels -> C ABI -> host JPEG files -----------------------------
+    host_px = pixels.cpu().pin_memory()
+    img_bytes = W * H * NC
+    cap = max(sizes) + 4096
+    host_out = torch.empty((BATCH, cap), dtype=torch.uint8).pin_memory()
+    descs = [jg.Image(0, W, H, NC, 0, QMODE, QUALITY, SUB, 0) for _ in range(BATCH)]
+    eplan = jg.Plan(descs, device=0)
+    outs = (jg.Output * BATCH)()
+    for i in range(BATCH):
+        outs[i] = jg.Output(host_out[i].data_ptr(), cap, 0, 0)
+    base = host_px.data_ptr()
+
+    def e2e_step():
+        for i in range(BATCH):
+            eplan.upload(i, base + i * img_bytes, sptr)
+        eplan.run(sptr)
+        ok = eplan.fetch_into(outs, 0, sptr)   # synchronises: headers + scans are in host memory after this
+        if ok != BATCH:
+            raise RuntimeError("e2e step encoded %d of %d" % (ok, BATCH))
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    e2e_steps = max(2, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    barrier()
+    e2e_ms = max_over_ranks(e2e_ms)
+    d2h = int(sum(outs[i].size for i in range(BATCH)) - BATCH * hdr_len)
+    e2e = {"value": round(world * mp_per_step / (e2e_ms * 1e-3), 2), "unit": UNIT,
+           "h2d_bytes_per_step": BATCH * img_bytes, "d2h_bytes_per_step": d2h,
+           "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
+           "api": "jpeg_gpu_plan_upload x256 + jpeg_gpu_plan_run + jpeg_gpu_plan_fetch (pinned host in/out)"}
+    if rank == 0 and parity is True:
+        parity = bytes(host_out[0][:outs[0].size].numpy().tobytes()) == files[0]
+    eplan.close()
+
+    # ---- byte-pinned native twin of the same shape (tje quality 2, 4:4:4), device-timed ----------
+    twin = None
+    if rank == 0 and not args.no_twin:
+        tplan = jg.Plan.for_arrays(imgs, TWIN_QMODE, TWIN_QUALITY, TWIN_SUB, device=0)
+        tms = None
+        for _ in range(3): tplan.run(sptr)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tsteps = max(3, min(args.steps, 10))
+        e0.record(stream)
+        for _ in range(tsteps): tplan.run(sptr)
+        e1.record(stream); torch.cuda.synchronize()
+        tms = e0.elapsed_time(e1) / tsteps
+        tsz = sum(tplan.encoded_size(i) for i in range(BATCH)) - BATCH * len(jg.emit_headers(W, H, NC, 0, 2, 0))
+        tach = (BATCH * img_bytes + tsz) / (tms * 1e-3) / 1e9
+        twin = {"workload": "same pixels, tje quality 2, 4:4:4 (byte-identical to jpeg_enc.h)", "value": round(mp_per_step / (tms * 1e-3), 1),
+                "unit": UNIT, "ms_per_step": round(tms, 3), "roofline_frac": round(tach / peak, 4),
+                "out_bytes_per_px": round(tsz / (BATCH * W * H), 3)}
+        tplan.close()
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample) ------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = [pixels[i].cpu().numpy() for i in range(8)]
+        v1, kind, n1, s1 = cpu_encode_rate(sample, QMODE, QUALITY, SUB, 1, min_seconds=2.0, max_seconds=10.0)
+        cpu = {"value": round(v1, 3), "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": "%d encodes of 1920x1080 RGB q75 4:2:0 images (first 8 of the batch, cycled) in %.1f s, 1 thread; "
+                         "the reference has no 4:2:0/q75 mode, so this is the oracle port of its algorithm" % (n1, s1)}
+        if twin is not None:
+            v2, kind2, n2, s2 = cpu_encode_rate(sample, TWIN_QMODE, TWIN_QUALITY, TWIN_SUB, 1, min_seconds=2.0, max_seconds=10.0)
+            twin["cpu_baseline"] = {"value": round(v2, 3), "unit": UNIT, "cores": 1, "kind": kind2,
+                                    "sample": "%d encodes in %.1f s, 1 thread, jpeg_enc.h compiled -O2 -ffp-contract=off" % (n2, s2)}
+
+    plan.close()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "1920x1080 RGB x %d per GPU, IJG q=75, 4:2:0 (BASELINE configs[1])" % BATCH,
+                       "images_per_gpu": BATCH, "l2_policy": "inputs (1.59 GB) + outputs larger than the 126 MB L2; no flush needed",
+                       "out_bytes_per_px": round(scan_bytes / (BATCH * W * H), 4),
+                       "sharding": "image index, no collective", "parity_spot_check": parity},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": args.steps * plan_launches_per_step(),
+            "native_twin": twin,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def plan_launches_per_step():
+    return 1   # one (layout, channels, quantiser) group -> one kernel launch per step
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-twin", action="store_true", help="skip the native-twin leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
