@@ -255,7 +255,7 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
     p->arena_bytes = arena;
     p->pixels_bytes = pixels;
 
-    // device state: per group {ticket u32, error u32, pad} + desc_bits + desc_ff
+    // device state: per group {ticket u32, error u32, pad} + desc_bits + desc_tail + desc_ff
     size_t state = 0, res_index = 0;
     for (auto& g : p->groups) {
         int tiles = 0;
@@ -268,7 +268,7 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
         g.n_tiles = tiles;
         g.tiles_per_image = uniform ? t0 : 0;
         g.state_off = state;
-        state += 16 + (size_t)tiles * 16;
+        state += 16 + (size_t)tiles * 24;
         g.result_off = res_index;
         res_index += g.items.size();
     }
@@ -338,7 +338,8 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
         P.ticket = reinterpret_cast<unsigned*>(st);
         P.error = reinterpret_cast<unsigned*>(st + 4);
         P.desc_bits = reinterpret_cast<unsigned long long*>(st + 16);
-        P.desc_ff = P.desc_bits + g.n_tiles;
+        P.desc_tail = P.desc_bits + g.n_tiles;
+        P.desc_ff = P.desc_tail + g.n_tiles;
         P.scan_bytes = g.d_scan_bytes;
         P.img_status = g.d_status;
         P.huff = dev.d_huff;

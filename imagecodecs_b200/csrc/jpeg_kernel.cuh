@@ -89,16 +89,28 @@ JG_DEV constexpr int zz_of(int i)
 // ------------------------------------------------------------------------------------------
 JG_DEV unsigned byte_of(const uint32_t* w, int idx) { return (w[idx >> 2] >> ((idx & 3) * 8)) & 0xffu; }
 
-template <int COMP>
-JG_DEV float ycc(float r, float g, float b)
+// Chroma weights of one component.  Cb and Cr share ONE code path (keeps the kernel small);
+// x - y == x + (-y) and (-c)*g == -(c*g) exactly in IEEE arithmetic, so
+//   Cb = (-0.1687f*r - 0.3313f*g) + 0.5f*b   and   Cr = (0.5f*r - 0.4187f*g) - 0.0813f*b
+// are both ((k0*r + k1*g) + k2*b) with the signs folded into the constants.
+struct ChromaK { float k0, k1, k2; };
+JG_DEV ChromaK chroma_k(int comp)
 {
-    if (COMP == 0) return f_sub(f_add(f_add(f_mul(0.299f, r), f_mul(0.587f, g)), f_mul(0.114f, b)), 128.0f);
-    if (COMP == 1) return f_add(f_sub(f_mul(-0.1687f, r), f_mul(0.3313f, g)), f_mul(0.5f, b));
-    return f_sub(f_sub(f_mul(0.5f, r), f_mul(0.4187f, g)), f_mul(0.0813f, b));
+    ChromaK k;
+    if (comp == 1) { k.k0 = -0.1687f; k.k1 = -0.3313f; k.k2 = 0.5f; }
+    else { k.k0 = 0.5f; k.k1 = -0.4187f; k.k2 = -0.0813f; }
+    return k;
 }
 
-template <int NC, int COMP>
-JG_DEV float sample_of(const uint32_t* w, int i)
+template <int CLS>   // 0 = luma, 1 = chroma
+JG_DEV float ycc(float r, float g, float b, const ChromaK& k)
+{
+    if (CLS == 0) return f_sub(f_add(f_add(f_mul(0.299f, r), f_mul(0.587f, g)), f_mul(0.114f, b)), 128.0f);
+    return f_add(f_add(f_mul(k.k0, r), f_mul(k.k1, g)), f_mul(k.k2, b));
+}
+
+template <int NC, int CLS>
+JG_DEV float sample_of(const uint32_t* w, int i, const ChromaK& k)
 {
     float r, g, b;
     if (NC == 4) {
@@ -107,7 +119,7 @@ JG_DEV float sample_of(const uint32_t* w, int i)
     } else {
         r = u8_to_f(byte_of(w, 3 * i)); g = u8_to_f(byte_of(w, 3 * i + 1)); b = u8_to_f(byte_of(w, 3 * i + 2));
     }
-    return ycc<COMP>(r, g, b);
+    return ycc<CLS>(r, g, b, k);
 }
 
 template <int N>
@@ -123,8 +135,8 @@ JG_DEV void lds_words(const uint32_t* p, uint32_t (&w)[N])
 
 // Row r (0..7) of the thread's 8x8 block, as 8 level-shifted / colour-converted samples.
 // q: quadrant of the Y block inside a 4:2:0 MCU (ignored otherwise).
-template <int LAYOUT, int NC, int COMP>
-JG_DEV void fetch_row(const uint32_t* stage, int slot, int q, int r, float (&s)[8])
+template <int LAYOUT, int NC, int CLS>
+JG_DEV void fetch_row(const uint32_t* stage, int slot, int q, int r, const ChromaK& ck, float (&s)[8])
 {
     using G = Geo<LAYOUT, NC>;
     if (LAYOUT == LAYOUT_GRAY) {
@@ -132,14 +144,14 @@ JG_DEV void fetch_row(const uint32_t* stage, int slot, int q, int r, float (&s)[
         lds_words<2>(stage + (r * G::SLOTS + slot) * G::WPR, w);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s[i] = f_sub(u8_to_f(byte_of(w, i)), 128.0f);
-    } else if (LAYOUT == LAYOUT_444 || COMP == 0) {
+    } else if (LAYOUT == LAYOUT_444 || CLS == 0) {
         constexpr int W8 = 8 * NC / 4;  // words of 8 pixels
         const int row = LAYOUT == LAYOUT_420 ? r + 8 * (q >> 1) : r;
         const int xoff = LAYOUT == LAYOUT_420 ? (q & 1) * W8 : 0;
         uint32_t w[W8];
         lds_words<W8>(stage + (row * G::SLOTS + slot) * G::WPR + xoff, w);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s[i] = sample_of<NC, COMP>(w, i);
+        for (int i = 0; i < 8; ++i) s[i] = sample_of<NC, CLS>(w, i, ck);
     } else {
         // 4:2:0 chroma: ((a+b)+(c+d))*0.25f over the 2x2 float Cb/Cr values (extended mode)
         constexpr int W16 = 16 * NC / 4;
@@ -148,8 +160,8 @@ JG_DEV void fetch_row(const uint32_t* stage, int slot, int q, int r, float (&s)[
         lds_words<W16>(stage + ((2 * r + 1) * G::SLOTS + slot) * G::WPR, w1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float a = sample_of<NC, COMP>(w0, 2 * i), b = sample_of<NC, COMP>(w0, 2 * i + 1);
-            const float c = sample_of<NC, COMP>(w1, 2 * i), d = sample_of<NC, COMP>(w1, 2 * i + 1);
+            const float a = sample_of<NC, CLS>(w0, 2 * i, ck), b = sample_of<NC, CLS>(w0, 2 * i + 1, ck);
+            const float c = sample_of<NC, CLS>(w1, 2 * i, ck), d = sample_of<NC, CLS>(w1, 2 * i + 1, ck);
             s[i] = f_mul(f_add(f_add(a, b), f_add(c, d)), 0.25f);
         }
     }
@@ -202,14 +214,14 @@ JG_DEV int quantise(float v, float pq)
 }
 
 // samples -> 64 quantised coefficients in ZIGZAG order, all in registers
-template <int LAYOUT, int NC, int COMP>
-JG_DEV void transform_block(const uint32_t* stage, int slot, int q, const QuantSet& Q, int (&c)[64])
+template <int LAYOUT, int NC, int CLS>
+JG_DEV void transform_block(const uint32_t* stage, int slot, int q, const ChromaK& ck, const QuantSet& Q, int (&c)[64])
 {
     float d[64];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         float s[8];
-        fetch_row<LAYOUT, NC, COMP>(stage, slot, q, r, s);
+        fetch_row<LAYOUT, NC, CLS>(stage, slot, q, r, ck, s);
         aan8(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[8 * r + i] = s[i];
@@ -218,21 +230,21 @@ JG_DEV void transform_block(const uint32_t* stage, int slot, int q, const QuantS
     for (int x = 0; x < 8; ++x)
         aan8(d[x], d[8 + x], d[16 + x], d[24 + x], d[32 + x], d[40 + x], d[48 + x], d[56 + x]);
 #pragma unroll
-    for (int i = 0; i < 64; ++i) c[zz_of(i)] = quantise(d[i], COMP == 0 ? Q.luma[i] : Q.chroma[i]);
+    for (int i = 0; i < 64; ++i) c[zz_of(i)] = quantise(d[i], CLS == 0 ? Q.luma[i] : Q.chroma[i]);
 }
 
 // quantised DC of a block without the other 63 outputs (same roundings as transform_block)
-template <int LAYOUT, int NC, int COMP>
-JG_DEV int transform_dc_only(const uint32_t* stage, int slot, int q, const QuantSet& Q)
+template <int LAYOUT, int NC, int CLS>
+JG_DEV int transform_dc_only(const uint32_t* stage, int slot, int q, const ChromaK& ck, const QuantSet& Q)
 {
     float col[8];
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < 8; ++r) {
         float s[8];
-        fetch_row<LAYOUT, NC, COMP>(stage, slot, q, r, s);
+        fetch_row<LAYOUT, NC, CLS>(stage, slot, q, r, ck, s);
         col[r] = aan8_dc(s);
     }
-    return quantise(aan8_dc(col), COMP == 0 ? Q.luma[0] : Q.chroma[0]);
+    return quantise(aan8_dc(col), CLS == 0 ? Q.luma[0] : Q.chroma[0]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -249,12 +261,11 @@ JG_DEV unsigned amplitude(int v, unsigned cat)  // jpeg_enc.h:601-609: (v<0 ? v-
 }
 
 // walk 1: size only
-template <int CLS>
-JG_DEV unsigned block_bits(const int (&c)[64], int diff, const uint32_t (&ac)[2][256], const uint32_t (&dc)[2][16])
+JG_DEV unsigned block_bits(const int (&c)[64], int diff, const uint32_t* ac, const uint32_t* dc)
 {
-    const unsigned zrl_len = ac[CLS][0xF0] & 0xffu;
+    const unsigned zrl_len = ac[0xF0] & 0xffu;
     const unsigned dcat = diff ? category(diff) : 0u;
-    unsigned n = (dc[CLS][dcat] & 0xffu) + dcat;
+    unsigned n = (dc[dcat] & 0xffu) + dcat;
     int last = 0;
 #pragma unroll
     for (int k = 1; k < 64; ++k) {
@@ -265,10 +276,10 @@ JG_DEV unsigned block_bits(const int (&c)[64], int diff, const uint32_t (&ac)[2]
             n += (run >> 4) * zrl_len;   // one ZRL per 16 zeros (jpeg_enc.h:863-867)
             run &= 15u;
             const unsigned cat = category(v);
-            n += (ac[CLS][(run << 4) | cat] & 0xffu) + cat;
+            n += (ac[(run << 4) | cat] & 0xffu) + cat;
         }
     }
-    if (last != 63) n += ac[CLS][0] & 0xffu;  // EOB (jpeg_enc.h:884-887)
+    if (last != 63) n += ac[0] & 0xffu;  // EOB (jpeg_enc.h:884-887)
     return n;
 }
 
@@ -306,16 +317,14 @@ struct BitPacker {
 };
 
 // walk 2: emit the block's bits at `bitpos` of `buf`
-template <int CLS>
-JG_DEV void block_pack(const int (&c)[64], int diff, const uint32_t (&ac)[2][256], const uint32_t (&dc)[2][16],
-                       uint32_t* buf, unsigned bitpos)
+JG_DEV void block_pack(const int (&c)[64], int diff, const uint32_t* ac, const uint32_t* dc, uint32_t* buf, unsigned bitpos)
 {
     BitPacker bp;
     bp.init(buf, bitpos);
-    const unsigned zrl = ac[CLS][0xF0];
+    const unsigned zrl = ac[0xF0];
     {
         const unsigned cat = diff ? category(diff) : 0u;
-        const unsigned e = dc[CLS][cat];
+        const unsigned e = dc[cat];
         const unsigned amp = diff ? amplitude(diff, cat) : 0u;
         bp.put(((e >> 8) << cat) | amp, (e & 0xffu) + cat);
     }
@@ -328,11 +337,11 @@ JG_DEV void block_pack(const int (&c)[64], int diff, const uint32_t (&ac)[2][256
             last = k;
             while (run >= 16u) { bp.put(zrl >> 8, zrl & 0xffu); run -= 16u; }
             const unsigned cat = category(v);
-            const unsigned e = ac[CLS][(run << 4) | cat];
+            const unsigned e = ac[(run << 4) | cat];
             bp.put(((e >> 8) << cat) | amplitude(v, cat), (e & 0xffu) + cat);
         }
     }
-    if (last != 63) { const unsigned e = ac[CLS][0]; bp.put(e >> 8, e & 0xffu); }
+    if (last != 63) { const unsigned e = ac[0]; bp.put(e >> 8, e & 0xffu); }
     bp.finish();
 }
 
@@ -463,18 +472,26 @@ JG_DEV void stage_tile(uint32_t* stage, const ImageDesc& im, int m0, int nM)
 }
 
 // ------------------------------------------------------------------------------------------
-// per-thread compute for one component class; leaves the coefficients in `c`
+// per-thread compute for one table class (0 = luma, 1 = chroma); leaves the coefficients in `c`
 // ------------------------------------------------------------------------------------------
-template <int LAYOUT, int NC, int COMP>
-JG_DEV void thread_transform(Smem<LAYOUT, NC>& S, const QuantSet& Q, bool active, int slot, int q, int s,
+template <int LAYOUT, int NC, int CLS>
+JG_DEV void thread_transform(Smem<LAYOUT, NC>& S, const QuantSet& Q, int comp, bool active, int slot, int q, int s,
                              bool pred_outside, bool have_prev_mcu, int pred_q, int (&c)[64], int& outside_dc)
 {
     outside_dc = 0;
     if (active) {
-        transform_block<LAYOUT, NC, COMP>(S.a, slot, q, Q, c);
+        const ChromaK ck = chroma_k(comp);
+        transform_block<LAYOUT, NC, CLS>(S.a, slot, q, ck, Q, c);
         S.dc_s[s] = c[0];
-        if (pred_outside && have_prev_mcu) outside_dc = transform_dc_only<LAYOUT, NC, COMP>(S.a, 0, pred_q, Q);
+        if (pred_outside && have_prev_mcu) outside_dc = transform_dc_only<LAYOUT, NC, CLS>(S.a, 0, pred_q, ck, Q);
     }
+}
+
+// byte offset `o` of a little-endian byte array held as aligned words
+JG_DEV unsigned word_at_byte(const uint32_t* w, unsigned o)
+{
+    const unsigned i = o >> 2, sh = (o & 3u) * 8u;
+    return sh ? (w[i] >> sh) | (w[i + 1] << (32u - sh)) : w[i];
 }
 
 template <int LAYOUT, int NC>
@@ -524,20 +541,21 @@ JG_DEV void encode_tile(const LaunchParams& P, const QuantSet& Q, Smem<LAYOUT, N
         comp = 0; ml = t; s = t; pred_s = s - 1; pred_outside = ml == 0;
     }
     const bool active = ml < nM;
+    const int cls = comp ? 1 : 0;
     int c[64];
     int outside_dc;
-    if (comp == 0) thread_transform<LAYOUT, NC, 0>(S, Q, active, ml + 1, q, s, pred_outside, m0 > 0, pred_q, c, outside_dc);
-    else if (comp == 1) thread_transform<LAYOUT, NC, 1>(S, Q, active, ml + 1, q, s, pred_outside, m0 > 0, pred_q, c, outside_dc);
-    else thread_transform<LAYOUT, NC, 2>(S, Q, active, ml + 1, q, s, pred_outside, m0 > 0, pred_q, c, outside_dc);
+    if (cls == 0) thread_transform<LAYOUT, NC, 0>(S, Q, comp, active, ml + 1, q, s, pred_outside, m0 > 0, pred_q, c, outside_dc);
+    else thread_transform<LAYOUT, NC, 1>(S, Q, comp, active, ml + 1, q, s, pred_outside, m0 > 0, pred_q, c, outside_dc);
     cta_sync();   // dc_s complete; staging area dead from here on
 
     // ---- 3. size ------------------------------------------------------------------------
+    const uint32_t* hac = S.huff_ac[cls];
+    const uint32_t* hdc = S.huff_dc[cls];
     int diff = 0;
-    unsigned my_bits = 0;
     if (active) {
         const int pred = pred_outside ? outside_dc : S.dc_s[pred_s];   // jpeg_enc.h:834-835
         diff = c[0] - pred;
-        my_bits = comp == 0 ? block_bits<0>(c, diff, S.huff_ac, S.huff_dc) : block_bits<1>(c, diff, S.huff_ac, S.huff_dc);
+        const unsigned my_bits = block_bits(c, diff, hac, hdc);
         S.bits_s[s] = my_bits;
         if (P.dbg_bits) P.dbg_bits[im.first_block + (unsigned long long)(m0 * G::BPM + s)] = my_bits;
         if (P.dbg_coefs) {
@@ -554,188 +572,185 @@ JG_DEV void encode_tile(const LaunchParams& P, const QuantSet& Q, Smem<LAYOUT, N
         S.off_s[t] = ex;
         if (t == 0) S.off_s[kBlocksPerTile] = T;
     }
-    // group partition (one group unless the tile overflows the window)
+    // Publish the tile's bit count NOW, before packing: successors can then resolve their
+    // look-back while we are still busy (the look-back needs every predecessor's count).
     const unsigned cap_bits = (unsigned)P.win_words * 32u - 64u;
-    cta_sync();   // off_s visible
     if (t == 0) {
-        int ng = 0;
-        S.gstart[0] = 0;
-        if (T > cap_bits) {
+        st_flag64(P.desc_bits + g, (first_tile ? kStatusPrefix : kStatusAgg) | (unsigned long long)T);
+        S.n_groups = 1;
+    }
+    cta_sync();   // off_s visible
+    if (T > cap_bits) {   // pathological tile: split into groups that fit the window
+        if (t == 0) {
+            int ng = 0;
             unsigned gbase = 0;
+            S.gstart[0] = 0;
             for (int b = 0; b < nblk; ++b) {
                 const unsigned end = S.off_s[b] + S.bits_s[b];
                 if (end - gbase > cap_bits) { ++ng; S.gstart[ng] = (uint16_t)b; gbase = S.off_s[b]; }
             }
+            ++ng;
+            S.gstart[ng] = (uint16_t)nblk;
+            S.n_groups = ng;
         }
-        ++ng;
-        S.gstart[ng] = (uint16_t)nblk;
-        S.n_groups = ng;
+        cta_sync();
     }
-    cta_sync();
     const int n_groups = S.n_groups;
 
-    // pack the blocks [b0,b1) at their offsets relative to block b0 into the (zeroed) window
-    auto pack_range = [&](int b0, int b1) {
+    // ---- 4..7 as a list of jobs with ONE pack call site ------------------------------------
+    //   one group   : [ALL]
+    //   many groups : [TAIL, COUNT_0..COUNT_{n-1}, EMIT_0..EMIT_{n-1}]   (walk 2 is repeated)
+    const int n_jobs = n_groups == 1 ? 1 : 1 + 2 * n_groups;
+    unsigned long long bit_base = 0, pos = 0;
+    unsigned k0 = 0, hb0 = 0, k = 0, hb = 0;
+    unsigned ff_tile = 0;
+    bool overflow = false, have_pos = false;
+
+    for (int job = 0; job < n_jobs; ++job) {
+        const bool is_all = n_groups == 1;
+        const bool is_tail = !is_all && job == 0;
+        const bool is_count = !is_all && job >= 1 && job <= n_groups;
+        const bool is_emit = !is_all && job > n_groups;
+        const int j = is_all ? 0 : (is_count ? job - 1 : (is_emit ? job - 1 - n_groups : 0));
+        int b0, b1;
+        if (is_all) { b0 = 0; b1 = nblk; }
+        else if (is_tail) { b0 = nblk >= 2 ? nblk - 2 : 0; b1 = nblk; }   // only to learn the last 7 bits
+        else { b0 = S.gstart[j]; b1 = S.gstart[j + 1]; }
+
+        // ---- 4. pack blocks [b0,b1) at their offsets relative to block b0 ----------------------
         const unsigned base = S.off_s[b0];
-        const unsigned end = S.off_s[b1];
-        const int words = (int)((end - base) >> 5) + 3;
-        for (int i = t; i < words; i += kThreads) S.a[i] = 0u;
+        const unsigned tg = S.off_s[b1] - base;
+        for (int i = t; i < (int)(tg >> 5) + 3; i += kThreads) S.a[i] = 0u;
         cta_sync();
-        if (active && s >= b0 && s < b1) {
-            const unsigned pos = S.off_s[s] - base;
-            if (comp == 0) block_pack<0>(c, diff, S.huff_ac, S.huff_dc, S.a, pos);
-            else block_pack<1>(c, diff, S.huff_ac, S.huff_dc, S.a, pos);
-        }
+        if (active && s >= b0 && s < b1) block_pack(c, diff, hac, hdc, S.a, S.off_s[s] - base);
         cta_sync();
-        return end - base;   // bits in the window
-    };
 
-    // ---- 4. pack (+ the tile's last 7 bits for the successor) ----------------------------
-    unsigned Tg;
-    if (n_groups == 1) Tg = pack_range(0, nblk);
-    else Tg = pack_range(nblk >= 2 ? nblk - 2 : 0, nblk);   // only to learn the tail bits
+        // ---- 5. chain #1: publish our last 7 bits, learn our bit offset --------------------------
+        if (is_all || is_tail) {
+            if (t < 32) {
+                const unsigned tail = tg >= 7u ? peek_bits(S.a, tg - 7u, 7u) : peek_bits(S.a, 0u, tg);
+                if (t == 0) st_flag64(P.desc_tail + g, kStatusAgg | (unsigned long long)tail);
+                unsigned long long excl = 0, nearest = 0, ptail = 0;
+                int timed_out = 0;
+                if (!first_tile) {
+                    excl = lookback(P.desc_bits, g, im.first_tile, kCountMask, &nearest, P.error, &timed_out);
+                    if (t == 0 && !timed_out) st_flag64(P.desc_bits + g, kStatusPrefix | (excl + T));
+                    // the byte we share with the predecessor needs its last bits
+                    unsigned spins = 0;
+                    while (!timed_out && ((ptail = ld_flag64(P.desc_tail + g - 1)) >> 62) == 0) {
+                        if (++spins > kSpinLimit || ld_flag32(P.error) != 0u) timed_out = 1;
+                        backoff();
+                    }
+                    timed_out = warp_ballot(timed_out) != 0u;
+                }
+                if (t == 0) {
+                    S.bit_base = excl;
+                    S.pred_tail = (unsigned)ptail & 0x7fu;
+                    S.abort = timed_out;
+                    if (timed_out) gmem_atomic_or(P.error, 1u);
+                }
+            }
+            cta_sync();
+            if (S.abort) return;
+            bit_base = S.bit_base;
+            k0 = (unsigned)(bit_base & 7ull);            // bits of our first byte owned by the predecessor
+            hb0 = S.pred_tail & ((1u << k0) - 1u);
+            k = k0; hb = hb0;
+            if (is_tail) continue;
+        }
 
-    // ---- 5. chain #1: bit offset of the tile ----------------------------------------------
-    if (t < 32) {
-        const unsigned tail = Tg >= 7u ? peek_bits(S.a, Tg - 7u, 7u) : peek_bits(S.a, 0u, Tg);
-        const unsigned long long payload = ((unsigned long long)tail << 55) | (unsigned long long)T;
-        unsigned long long excl = 0, nearest = 0;
-        int timed_out = 0;
-        if (first_tile) {
-            if (t == 0) st_flag64(P.desc_bits + g, kStatusPrefix | payload);
-        } else {
-            if (t == 0) st_flag64(P.desc_bits + g, kStatusAgg | payload);
-            excl = lookback(P.desc_bits, g, im.first_tile, kBitsMask, &nearest, P.error, &timed_out);
-            if (t == 0 && !timed_out)
-                st_flag64(P.desc_bits + g, kStatusPrefix | ((unsigned long long)tail << 55) | (excl + T));
+        // ---- 6. geometry of the byte-aligned stream X = (k head bits) ++ (group bits) ---------------
+        const bool final_group = last_tile && j == n_groups - 1;
+        unsigned n_bytes = (k + tg) >> 3, k_out = (k + tg) & 7u, hb_out = 0;
+        if (k_out) {
+            if (final_group) { n_bytes += 1; k_out = 0; }             // zero padding, jpeg_enc.h:1161-1164
+            else if (tg >= k_out) hb_out = peek_bits(S.a, tg - k_out, k_out);
+            else hb_out = ((hb << tg) | peek_bits(S.a, 0u, tg)) & ((1u << k_out) - 1u);
         }
-        if (t == 0) {
-            S.bit_base = excl;
-            S.pred_tail = (unsigned)(nearest >> 55) & 0x7fu;
-            S.abort = timed_out;
-            if (timed_out) gmem_atomic_or(P.error, 1u);
-        }
-    }
-    cta_sync();
-    if (S.abort) return;
-    const unsigned long long bit_base = S.bit_base;
-    const unsigned k0 = (unsigned)(bit_base & 7ull);                 // bits of our first byte owned by the predecessor
-    const unsigned hb0 = S.pred_tail & ((1u << k0) - 1u);
-
-    // per-group geometry of the byte-aligned stream X = head bits ++ group bits
-    struct GroupGeom { unsigned n_bytes, k_out, hb_out; };
-    auto group_geom = [&](unsigned k, unsigned hb, unsigned tg, bool final_group) {
-        GroupGeom gg;
-        const unsigned total = k + tg;
-        gg.n_bytes = total >> 3;
-        gg.k_out = total & 7u;
-        gg.hb_out = 0;
-        if (gg.k_out) {
-            if (final_group) { gg.n_bytes += 1; gg.k_out = 0; }       // zero padding, jpeg_enc.h:1161-1164
-            else if (tg >= gg.k_out) gg.hb_out = peek_bits(S.a, tg - gg.k_out, gg.k_out);
-            else gg.hb_out = ((hb << tg) | peek_bits(S.a, 0u, tg)) & ((1u << gg.k_out) - 1u);
-        }
-        return gg;
-    };
-    // per-thread chunk of X words: odd stride keeps the shared-memory banks apart
-    auto chunk_words = [&](unsigned n_bytes) { return (((n_bytes + 3u) / 4u + kThreads - 1u) / kThreads) | 1u; };
-    // number of 0xFF bytes among this thread's bytes of X
-    auto count_ff = [&](unsigned k, unsigned hb, unsigned n_bytes) {
-        const unsigned cw = chunk_words(n_bytes);
+        // per-thread chunk of X words; the odd stride keeps the shared-memory banks apart
+        const unsigned cw = (((n_bytes + 3u) / 4u + kThreads - 1u) / kThreads) | 1u;
+        const unsigned w_lo = (unsigned)t * cw;
         unsigned cnt = 0;
-        for (unsigned i = (unsigned)t * cw; i < ((unsigned)t + 1u) * cw && i * 4u < n_bytes; ++i) {
+        for (unsigned i = w_lo; i < w_lo + cw && i * 4u < n_bytes; ++i) {
             unsigned m = v_cmpeq4(xword(S.a, (int)i, k, hb), 0xffffffffu);
             const unsigned valid = n_bytes - i * 4u;
             if (valid < 4u) m &= 0xffffffffu << (8u * (4u - valid));
             cnt += (unsigned)i_popc(m) >> 3;
         }
-        return cnt;
-    };
+        unsigned ff_group;
+        const unsigned ff_ex = cta_scan_excl(cnt, S.warp_tmp, ff_group);
+        if (!is_emit) ff_tile += ff_group;
 
-    // ---- 6a. count the 0xFF bytes this tile owns ---------------------------------------------
-    unsigned ff_tile = 0, my_ff_ex = 0, my_ff_total = 0;
-    {
-        unsigned k = k0, hb = hb0;
-        for (int j = 0; j < n_groups; ++j) {
-            unsigned tg = Tg;
-            if (n_groups > 1) tg = pack_range(S.gstart[j], S.gstart[j + 1]);
-            const GroupGeom gg = group_geom(k, hb, tg, last_tile && j == n_groups - 1);
-            unsigned tot;
-            my_ff_ex = cta_scan_excl(count_ff(k, hb, gg.n_bytes), S.warp_tmp, tot);
-            my_ff_total = tot;
-            ff_tile += tot;
-            k = gg.k_out; hb = gg.hb_out;
-        }
-    }
+        // publish the stuffed-byte count as soon as it is complete
+        if ((is_all || (is_count && j == n_groups - 1)) && t == 0)
+            st_flag64(P.desc_ff + g, (first_tile ? kStatusPrefix : kStatusAgg) | (unsigned long long)ff_tile);
 
-    // ---- 6b. chain #2: stuffed-byte offset of the tile ------------------------------------------
-    if (t < 32) {
-        unsigned long long excl = 0, nearest = 0;
-        int timed_out = 0;
-        if (first_tile) {
-            if (t == 0) st_flag64(P.desc_ff + g, kStatusPrefix | (unsigned long long)ff_tile);
-        } else {
-            if (t == 0) st_flag64(P.desc_ff + g, kStatusAgg | (unsigned long long)ff_tile);
-            excl = lookback(P.desc_ff, g, im.first_tile, kCountMask, &nearest, P.error, &timed_out);
-            if (t == 0 && !timed_out) st_flag64(P.desc_ff + g, kStatusPrefix | (excl + ff_tile));
+        if (is_count) {
+            if (j == n_groups - 1) { k = k0; hb = hb0; } else { k = k_out; hb = hb_out; }
+            continue;
         }
-        if (t == 0) {
-            S.ff_base = excl;
-            S.abort = timed_out;
-            if (timed_out) gmem_atomic_or(P.error, 1u);
-        }
-    }
-    cta_sync();
-    if (S.abort) return;
 
-    // ---- 7. stuff + write ----------------------------------------------------------------------------
-    unsigned long long pos = (bit_base >> 3) + S.ff_base;   // byte position of the tile's first owned byte
-    bool overflow = false;
-    {
-        unsigned k = k0, hb = hb0;
-        for (int j = 0; j < n_groups; ++j) {
-            unsigned tg = Tg;
-            if (n_groups > 1) tg = pack_range(S.gstart[j], S.gstart[j + 1]);
-            const GroupGeom gg = group_geom(k, hb, tg, last_tile && j == n_groups - 1);
-            if (n_groups > 1) {
-                unsigned tot;
-                my_ff_ex = cta_scan_excl(count_ff(k, hb, gg.n_bytes), S.warp_tmp, tot);
-                my_ff_total = tot;
-            }
-            const unsigned out_bytes = gg.n_bytes + my_ff_total;
-            uint8_t* dst = im.out + pos;
-            const unsigned pad = (unsigned)((size_t)dst & 15u);   // keep smem and gmem 16B phases equal
-            {
-                const unsigned cw = chunk_words(gg.n_bytes);
-                unsigned o = pad + (unsigned)t * cw * 4u + my_ff_ex;
-                for (unsigned i = (unsigned)t * cw; i < ((unsigned)t + 1u) * cw && i * 4u < gg.n_bytes; ++i) {
-                    const unsigned x = xword(S.a, (int)i, k, hb);
-                    const unsigned valid = gg.n_bytes - i * 4u < 4u ? gg.n_bytes - i * 4u : 4u;
-                    for (unsigned b = 0; b < valid; ++b) {
-                        const unsigned byte = (x >> (24u - 8u * b)) & 0xffu;
-                        S.sbuf[o++] = (uint8_t)byte;
-                        if (byte == 0xffu) S.sbuf[o++] = 0;               // jpeg_enc.h:634-638
-                    }
+        // ---- 7a. emit stuffed bytes into sbuf (position independent) ----------------------------------
+        {
+            unsigned o = w_lo * 4u + ff_ex;
+            for (unsigned i = w_lo; i < w_lo + cw && i * 4u < n_bytes; ++i) {
+                const unsigned x = xword(S.a, (int)i, k, hb);
+                const unsigned valid = n_bytes - i * 4u < 4u ? n_bytes - i * 4u : 4u;
+                for (unsigned b = 0; b < valid; ++b) {
+                    const unsigned byte = (x >> (24u - 8u * b)) & 0xffu;
+                    S.sbuf[o++] = (uint8_t)byte;
+                    if (byte == 0xffu) S.sbuf[o++] = 0;               // jpeg_enc.h:634-638
                 }
             }
-            cta_sync();
-            if (pos + out_bytes + (last_tile ? 2u : 0u) > im.out_cap) {
-                overflow = true;
-            } else {
-                unsigned head = (16u - pad) & 15u;
-                if (head > out_bytes) head = out_bytes;
-                const unsigned nvec = (out_bytes - head) >> 4;
-                const unsigned tail0 = head + (nvec << 4);
-                if ((unsigned)t < head) dst[t] = S.sbuf[pad + t];
-                const uint4* src4 = reinterpret_cast<const uint4*>(S.sbuf + pad + head);
-                uint4* dst4 = reinterpret_cast<uint4*>(dst + head);
-                for (unsigned i = (unsigned)t; i < nvec; i += kThreads) dst4[i] = src4[i];
-                if (tail0 + (unsigned)t < out_bytes) dst[tail0 + t] = S.sbuf[pad + tail0 + t];
-            }
-            pos += out_bytes;
-            k = gg.k_out; hb = gg.hb_out;
-            cta_sync();   // sbuf / window are reused by the next group
         }
+        // ---- 6b. chain #2 (after the emit, so predecessors had time to publish) ---------------------------
+        if (!have_pos) {
+            if (t < 32) {
+                unsigned long long excl = 0, nearest = 0;
+                int timed_out = 0;
+                if (!first_tile) {
+                    excl = lookback(P.desc_ff, g, im.first_tile, kCountMask, &nearest, P.error, &timed_out);
+                    if (t == 0 && !timed_out) st_flag64(P.desc_ff + g, kStatusPrefix | (excl + ff_tile));
+                }
+                if (t == 0) {
+                    S.ff_base = excl;
+                    S.abort = timed_out;
+                    if (timed_out) gmem_atomic_or(P.error, 1u);
+                }
+            }
+            cta_sync();   // also orders the sbuf writes above
+            if (S.abort) return;
+            pos = (bit_base >> 3) + S.ff_base;   // byte position of the tile's first owned byte
+            have_pos = true;
+        } else {
+            cta_sync();
+        }
+
+        // ---- 7b. copy out: bytes to the first 16B boundary, aligned 16B stores, tail bytes ------------------
+        const unsigned out_bytes = n_bytes + ff_group;
+        if (pos + out_bytes + (last_tile ? 2u : 0u) > im.out_cap) {
+            overflow = true;
+        } else {
+            uint8_t* dst = im.out + pos;
+            unsigned head = (16u - (unsigned)((size_t)dst & 15u)) & 15u;
+            if (head > out_bytes) head = out_bytes;
+            const unsigned nvec = (out_bytes - head) >> 4;
+            const unsigned tail0 = head + (nvec << 4);
+            const uint32_t* sw = reinterpret_cast<const uint32_t*>(S.sbuf);
+            if ((unsigned)t < head) dst[t] = S.sbuf[t];
+            uint4* dst4 = reinterpret_cast<uint4*>(dst + head);
+            for (unsigned i = (unsigned)t; i < nvec; i += kThreads) {
+                const unsigned o = head + (i << 4);
+                uint4 v;
+                v.x = word_at_byte(sw, o); v.y = word_at_byte(sw, o + 4u);
+                v.z = word_at_byte(sw, o + 8u); v.w = word_at_byte(sw, o + 12u);
+                dst4[i] = v;
+            }
+            if (tail0 + (unsigned)t < out_bytes) dst[tail0 + t] = S.sbuf[tail0 + t];
+        }
+        pos += out_bytes;
+        k = k_out; hb = hb_out;
+        if (job + 1 < n_jobs) cta_sync();   // sbuf / window are reused by the next group
     }
     if (t == 0) {
         if (last_tile) {

@@ -22,8 +22,7 @@ constexpr unsigned kSpinLimit = 1u << 24;
 
 constexpr unsigned long long kStatusAgg = 1ull << 62;
 constexpr unsigned long long kStatusPrefix = 2ull << 62;
-constexpr unsigned long long kBitsMask = (1ull << 55) - 1;   // desc_bits: [54:0] bits, [61:55] tail7
-constexpr unsigned long long kCountMask = (1ull << 62) - 1;  // desc_ff:   [61:0] count
+constexpr unsigned long long kCountMask = (1ull << 62) - 1;  // descriptors: status[63:62] | value[61:0]
 
 struct ImageDesc {
     const uint8_t* px;               // device pixels
@@ -46,7 +45,8 @@ struct LaunchParams {
     int tiles_per_image;             // > 0 when every image of the launch has this many tiles
     int win_words;                   // window size actually used (<= kWinWordsMax)
     unsigned* ticket;                // zeroed before the launch
-    unsigned long long* desc_bits;   // [n_tiles], zeroed before the launch
+    unsigned long long* desc_bits;   // [n_tiles], zeroed before the launch: bits of the tile / inclusive prefix
+    unsigned long long* desc_tail;   // [n_tiles], zeroed before the launch: the tile's last 7 bits
     unsigned long long* desc_ff;     // [n_tiles], zeroed before the launch
     unsigned long long* scan_bytes;  // [n_images] OUT: bytes of scan + EOI
     unsigned* img_status;            // [n_images] OUT: bit0 = capacity exceeded

@@ -86,7 +86,7 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
         d.aligned4 = ((size_t)d.px % 4 == 0) && (stride % 4 == 0);
     }
     const int n_tiles = tiles * n_images;
-    std::vector<unsigned long long> desc_bits(n_tiles, 0), desc_ff(n_tiles, 0);
+    std::vector<unsigned long long> desc_bits(n_tiles, 0), desc_tail(n_tiles, 0), desc_ff(n_tiles, 0);
     unsigned ticket = 0, error = 0;
     for (int i = 0; i < n_images; ++i) { scan_bytes[i] = 0; img_status[i] = 0; }
 
@@ -94,7 +94,7 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
     P.images = imgs.data(); P.n_images = n_images; P.n_tiles = n_tiles;
     P.tiles_per_image = (n_images % 2) ? tiles : 0;   // exercise both tile->image paths
     P.win_words = win_words ? win_words : kWinWordsMax;
-    P.ticket = &ticket; P.desc_bits = desc_bits.data(); P.desc_ff = desc_ff.data();
+    P.ticket = &ticket; P.desc_bits = desc_bits.data(); P.desc_tail = desc_tail.data(); P.desc_ff = desc_ff.data();
     P.scan_bytes = scan_bytes; P.img_status = img_status; P.error = &error; P.huff = &lut;
     P.dbg_coefs = dbg_coefs; P.dbg_bits = dbg_bits;
 
