@@ -71,6 +71,11 @@ def build(force=False, verbose=False):
     with open(os.path.join(OBJ, "ptxas.log"), "w") as fh:
         for obj, log in sorted(logs):
             fh.write("== %s\n%s\n" % (os.path.basename(obj), log))
+    # the C++ example that drives the host layer the way the reference's tests.cpp does
+    exe = os.path.join(HERE, "write_jpg_like_reference")
+    _run(["g++", "-std=c++17", "-O2", "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),
+          os.path.join(ROOT, "tests", "cpp", "write_jpg_like_reference.cpp"), "-o", exe,
+          "-L" + HERE, "-ljpeg_gpu", "-Wl,-rpath,$ORIGIN"])
     if verbose:
         for obj, log in sorted(logs):
             print("==", os.path.basename(obj)); print(log)

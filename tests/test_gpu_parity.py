@@ -1,0 +1,298 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle, the compiled
+reference (oracle/_ref, travels as a built artefact) and the committed known answers.
+
+Bit-exactness is the bar: every comparison below is == on bytes.
+"""
+import ctypes as C
+import io
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from tests.helpers import kat_image, psnr, sha
+
+pytestmark = pytest.mark.gpu
+
+REF_SO = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libtje_ref.so")
+HAVE_REF = os.path.exists(REF_SO)
+
+
+def encode_one(jg, img, qm=0, q=3, sub=0, **kw):
+    files, st = jg.encode_batch([img], qm, q, sub, device=0, **kw)
+    assert st == [0]
+    return files[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# native (byte-pinned) modes
+# ---------------------------------------------------------------------------------------------
+def test_known_answers_native_modes(gpu, kat, fixture_pixels):
+    """Every SURVEY 8(c) known answer, incl. BASELINE config 1 (cat.bmp via the codecs.h path)."""
+    for e in kat:
+        got = encode_one(gpu, kat_image(e, fixture_pixels), 0, e["tje_quality"])
+        assert len(got) == e["bytes"] and sha(got) == e["sha256"], e["name"]
+
+
+def test_reference_output_files(gpu, kat, fixture_pixels, golden_dir):
+    for e in kat:
+        if "file" in e:
+            want = open(os.path.join(golden_dir, e["file"]), "rb").read()
+            assert encode_one(gpu, kat_image(e, fixture_pixels), 0, e["tje_quality"]) == want
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+def test_against_compiled_reference_random(gpu):
+    rng = np.random.default_rng(11)
+    imgs, qs = [], []
+    for k in range(40):
+        w, h = int(rng.integers(1, 300)), int(rng.integers(1, 200))
+        img = rng.integers(0, 256, size=(h, w, int(rng.choice([3, 4]))), dtype=np.uint8)
+        if k % 4 == 0:
+            img[:] = rng.integers(0, 256, size=(1, 1, img.shape[2]))     # flat: EOB-only blocks
+        if k % 4 == 1:
+            img = (img // 64 * 64).astype(np.uint8)                        # posterised: long runs, ZRL
+        imgs.append(img); qs.append(int(rng.integers(1, 4)))
+    files, st = gpu.encode_batch(imgs, 0, qs, 0, device=0)                 # one mixed batch
+    assert st == [0] * len(imgs)
+    for img, q, f in zip(imgs, qs, files):
+        rc, ref = oracle.ref_encode(img, q)
+        assert rc == 1 and f == ref, (img.shape, q)
+
+
+@pytest.mark.parametrize("w,h", [(8, 8), (1, 1), (7, 9), (17, 13), (64, 64), (395, 348), (512, 512), (1921, 1083)])
+@pytest.mark.parametrize("q", [1, 2, 3])
+def test_sizes_and_edge_clamp(gpu, w, h, q):
+    for nc in (3, 4):
+        img = oracle.synth_image(w, h, nc, n=3, kind="photo")
+        assert encode_one(gpu, img, 0, q) == oracle.oracle_encode(img, 0, q)
+
+
+def test_checkerboards_reach_coefficient_bounds(gpu):
+    """F(0,4)/F(4,4)-style patterns hit the largest AC magnitudes."""
+    yy, xx = np.mgrid[0:64, 0:64]
+    for pat in [((xx // 1 + yy // 1) % 2), (xx % 2), (yy % 2), ((xx // 4 + yy // 4) % 2), np.zeros_like(xx), np.ones_like(xx)]:
+        img = np.repeat((pat * 255).astype(np.uint8)[..., None], 3, axis=2)
+        for q in (1, 3):
+            assert encode_one(gpu, img, 0, q) == oracle.oracle_encode(img, 0, q)
+
+
+def test_stage_parity(gpu):
+    """Quantised coefficients, per-block bit lengths and the file, stage by stage."""
+    import torch
+    for (qm, q, sub, nc) in [(0, 3, 0, 3), (0, 2, 0, 4), (1, 75, 1, 3), (1, 85, 0, 1)]:
+        batch = oracle.synth_batch(2, 203, 117, nc, "noise" if q == 3 else "photo")
+        dev = torch.from_numpy(batch).cuda()
+        plan = gpu.Plan.for_arrays([dev[0], dev[1]], qm, q, sub, device=0)
+        nb = plan.num_blocks
+        coefs = torch.zeros(nb * 64, dtype=torch.int16, device="cuda")
+        bits = torch.zeros(nb, dtype=torch.int32, device="cuda")
+        plan.attach_debug(coefs.data_ptr(), bits.data_ptr())
+        plan.run(); files = plan.fetch(); plan.close()
+        coefs = coefs.cpu().numpy().reshape(2, -1, 64); bits = bits.cpu().numpy().reshape(2, -1)
+        for i in range(2):
+            st = oracle.oracle_stages(batch[i], qm, q, sub)
+            assert np.array_equal(coefs[i], st["coefs"])
+            assert np.array_equal(bits[i].astype(np.uint32), st["block_bits"])
+            assert files[i] == st["jpeg"]
+
+
+def test_window_overflow_path(gpu):
+    """Tiles whose bits exceed the shared-memory window are processed in groups: same bytes."""
+    img = oracle.synth_image(256, 256, 3, kind="noise")
+    want = oracle.oracle_encode(img, 0, 3)
+    for win in (64, 100, 128, 1000):
+        assert encode_one(gpu, img, 0, 3, win_words=win) == want
+    img2 = oracle.synth_image(640, 480, 3)
+    assert encode_one(gpu, img2, 1, 50, 1, win_words=100) == oracle.oracle_encode(img2, 1, 50, 1)
+    # natural overflow (no forced window): 1080p noise at all-ones quantisers
+    big = oracle.synth_image(1920, 1080, 3, kind="noise")
+    assert sha(encode_one(gpu, big, 0, 3, capacity=12 << 20)) == "e4393984ae95a4980fed6e23e98e56d9f3877a0c48a7ef364e8afaabf35c5412"
+
+
+# ---------------------------------------------------------------------------------------------
+# extended modes
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,h", [(16, 16), (33, 47), (200, 120), (1920, 1080)])
+def test_extended_modes_match_oracle(gpu, w, h):
+    for (qm, q, sub, nc) in [(1, 75, 1, 3), (1, 90, 0, 3), (1, 50, 1, 4), (1, 95, 1, 3), (1, 85, 0, 1), (0, 3, 1, 3), (1, 1, 0, 3)]:
+        img = oracle.synth_image(w, h, nc, n=2)
+        assert encode_one(gpu, img, qm, q, sub) == oracle.oracle_encode(img, qm, q, sub), (qm, q, sub, nc)
+
+
+def test_extended_modes_collapse_to_native(gpu):
+    img = oracle.synth_image(395, 348, 3, n=9)
+    assert encode_one(gpu, img, 1, 50) == encode_one(gpu, img, 0, 1)
+    assert encode_one(gpu, img, 1, 100) == encode_one(gpu, img, 0, 3)
+
+
+def test_extended_output_decodes(gpu):
+    from PIL import Image
+    yy, xx = np.mgrid[0:240, 0:320]
+    img = np.stack([xx * 255 // 319, yy * 255 // 239, (xx + yy) * 255 // 558], -1).astype(np.uint8)
+    for (qm, q, sub, floor) in [(1, 75, 1, 34.0), (1, 90, 0, 40.0)]:
+        dec = np.array(Image.open(io.BytesIO(encode_one(gpu, img, qm, q, sub))).convert("RGB"))
+        assert psnr(dec, img) > floor
+    g = img[..., :1].copy()
+    dec = np.array(Image.open(io.BytesIO(encode_one(gpu, g, 1, 85, 0))))
+    assert dec.shape == (240, 320) and psnr(dec, g[..., 0]) > 40.0
+
+
+# ---------------------------------------------------------------------------------------------
+# batches, sharding, BASELINE-size properties
+# ---------------------------------------------------------------------------------------------
+def test_mixed_batch_and_shard_invariance(gpu):
+    """Config 5 in miniature: mixed quality by n%3, and image i's bytes do not depend on the batch."""
+    n = 24
+    batch = oracle.synth_batch(n, 512, 512, 3)
+    q = [[50, 75, 95][i % 3] for i in range(n)]
+    whole, st = gpu.encode_batch([batch[i] for i in range(n)], 1, q, 1, device=0)
+    assert st == [0] * n
+    for i in range(0, n, 5):
+        assert whole[i] == oracle.oracle_encode(batch[i], 1, q[i], 1)
+    halves = gpu.encode_batch([batch[i] for i in range(n // 2)], 1, q[:n // 2], 1, device=0)[0] + \
+        gpu.encode_batch([batch[i] for i in range(n // 2, n)], 1, q[n // 2:], 1, device=0)[0]
+    assert halves == whole
+    assert encode_one(gpu, batch[7], 1, q[7], 1) == whole[7]
+    # device = -1 shards by image index over every initialised GPU: still the same bytes
+    assert gpu.encode_batch([batch[i] for i in range(n)], 1, q, 1, device=-1)[0] == whole
+    # native twin of config 5: tje {1,2,3} by n%3, 4:4:4
+    tq = [1 + i % 3 for i in range(n)]
+    twin = gpu.encode_batch([batch[i] for i in range(n)], 0, tq, 0, device=0)[0]
+    for i in (0, 1, 2, 23):
+        assert twin[i] == oracle.oracle_encode(batch[i], 0, tq[i], 0)
+
+
+def test_mixed_layouts_in_one_call(gpu):
+    imgs = [oracle.synth_image(100, 60, 3), oracle.synth_image(64, 64, 1), oracle.synth_image(33, 20, 4),
+            oracle.synth_image(100, 60, 3, n=1)]
+    qm, q, sub = [0, 1, 1, 1], [3, 85, 75, 75], [0, 0, 1, 1]
+    files, st = gpu.encode_batch(imgs, qm, q, sub, device=0)
+    assert st == [0, 0, 0, 0]
+    for i in range(4):
+        assert files[i] == oracle.oracle_encode(imgs[i], qm[i], q[i], sub[i])
+
+
+def test_device_resident_pixels_and_plan_reuse(gpu):
+    import torch
+    from imagecodecs_b200.synth import synth_batch
+    dev = synth_batch(6, 1920, 1080, 3, device="cuda")
+    plan = gpu.Plan.for_arrays([dev[i] for i in range(6)], 1, 75, 1, device=0)
+    plan.run(); a = plan.fetch()
+    plan.run(); b = plan.fetch()            # same plan, second launch: state is reset correctly
+    assert a == b and plan.launches == 1
+    host = dev.cpu().numpy()
+    for i in (0, 5):
+        assert a[i] == oracle.oracle_encode(host[i], 1, 75, 1)
+    # re-point image 0 at other pixels of the same geometry
+    other = synth_batch(1, 1920, 1080, 3, first=100, device="cuda")
+    plan.set_pixels(0, other.data_ptr()); plan.run(); c = plan.fetch(); plan.close()
+    assert c[0] == oracle.oracle_encode(other[0].cpu().numpy(), 1, 75, 1) and c[1:] == a[1:]
+
+
+def test_full_size_4k_444_q90(gpu):
+    """BASELINE config 3 shape (3840x2160, q=90, 4:4:4): bytes vs oracle, plus the pinned twin."""
+    img = oracle.synth_image(3840, 2160, 3, n=1)
+    assert encode_one(gpu, img, 1, 90, 0) == oracle.oracle_encode(img, 1, 90, 0)
+
+
+def test_full_size_16k_gray_roundtrip(gpu):
+    """BASELINE config 4: one 16384x16384 grayscale image, q=85: a single 4.2 M-block scan chain.
+    Full-size property (the oracle would need ~10 s; we use decode + a checksum of band checksums):
+    the GPU file must equal the oracle's on a horizontal band whose scan we can isolate? No --
+    scans are not separable, so compare the complete file hash with the oracle's once, and decode."""
+    import torch
+    from imagecodecs_b200.synth import synth_batch
+    dev = synth_batch(1, 16384, 16384, 1, device="cuda")
+    plan = gpu.Plan.for_arrays([dev[0]], 1, 85, 0, device=0)
+    plan.run(); f = plan.fetch()[0]; plan.close()
+    host = dev[0].cpu().numpy()
+    del dev; torch.cuda.empty_cache()
+    assert f == oracle.oracle_encode(host, 1, 85, 0)
+    import cv2
+    dec = cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_UNCHANGED)
+    assert dec.shape == (16384, 16384) and psnr(dec[::8, ::8], host[::8, ::8, 0]) > 30.0
+
+
+def test_16k_rgb_native_twin(gpu):
+    """Native twin of config 4: 16384x16384 RGB, tje quality 2 -- byte-pinned by the reference."""
+    import torch
+    from imagecodecs_b200.synth import synth_batch
+    dev = synth_batch(1, 16384, 16384, 3, device="cuda", chunk=1)
+    plan = gpu.Plan.for_arrays([dev[0]], 0, 2, 0, device=0)
+    plan.run(); f = plan.fetch()[0]; plan.close()
+    host = dev[0].cpu().numpy()
+    del dev; torch.cuda.empty_cache()
+    if HAVE_REF:
+        rc, ref = oracle.ref_encode(host, 2)
+        assert rc == 1 and f == ref
+    else:
+        assert f == oracle.oracle_encode(host, 0, 2, 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# error behaviour and the drop-in twins
+# ---------------------------------------------------------------------------------------------
+def test_invalid_images_are_rejected_individually(gpu):
+    good = oracle.synth_image(32, 32, 3)
+    files, st = gpu.encode_batch([good, good, good], [0, 0, 1], [3, 7, 101], 0, device=0)
+    assert st == [gpu.OK, gpu.ERR_ARG, gpu.ERR_ARG] and files[1] is None
+    assert files[0] == oracle.oracle_encode(good, 0, 3)
+
+
+def test_capacity_error_reports_needed_size(gpu):
+    img = oracle.synth_image(128, 128, 3, kind="noise")
+    want = oracle.oracle_encode(img, 0, 3)
+    files, st = gpu.encode_batch([img], 0, 3, 0, device=0, capacity=1000)
+    assert st == [gpu.ERR_CAPACITY] and files[0] is None
+    files, st = gpu.encode_batch([img], 0, 3, 0, device=0, capacity=len(want))
+    assert st == [gpu.OK] and files[0] == want
+
+
+def test_tje_twins(gpu, tmp_path):
+    L = gpu.lib()
+    img = oracle.synth_image(395, 348, 4, n=4)
+    chunks = []
+    cb = gpu.WRITE_FUNC(lambda ctx, data, size: chunks.append(C.string_at(data, size)))
+    for q in (1, 2, 3):
+        chunks.clear()
+        assert L.jpeg_gpu_encode_with_func(cb, None, q, 395, 348, 4, img.ctypes.data) == 1
+        want = oracle.oracle_encode(img, 0, q)
+        assert b"".join(chunks) == want
+        assert all(len(c) == 1023 for c in chunks[:-1]) and 0 < len(chunks[-1]) <= 1023   # jpeg_enc.h:487-490
+    # rejected exactly where the reference rejects (jpeg_enc.h:1223, :954, :958)
+    assert L.jpeg_gpu_encode_with_func(cb, None, 0, 8, 8, 3, img.ctypes.data) == 0
+    assert L.jpeg_gpu_encode_with_func(cb, None, 4, 8, 8, 3, img.ctypes.data) == 0
+    assert L.jpeg_gpu_encode_with_func(cb, None, 3, 8, 8, 1, img.ctypes.data) == 0
+    assert L.jpeg_gpu_encode_with_func(cb, None, 3, 70000, 8, 3, img.ctypes.data) == 0
+    p = str(tmp_path / "a.jpg").encode()
+    rgb = np.ascontiguousarray(img[..., :3])
+    assert L.jpeg_gpu_encode_to_file(p, 395, 348, 3, rgb.ctypes.data) == 1                # quality 3, jpeg_enc.h:1183
+    assert open(p, "rb").read() == oracle.oracle_encode(rgb, 0, 3)
+    assert L.jpeg_gpu_encode_to_file_at_quality(p, 1, 395, 348, 3, rgb.ctypes.data) == 1
+    assert open(p, "rb").read() == oracle.oracle_encode(rgb, 0, 1)
+    assert L.jpeg_gpu_encode_to_file_at_quality(p, 9, 395, 348, 3, rgb.ctypes.data) == 0  # and leaves a 0-byte file,
+    assert os.path.getsize(p) == 0                                                          # as the reference does
+    assert L.jpeg_gpu_encode_to_file(b"/nonexistent-dir/x.jpg", 8, 8, 3, rgb.ctypes.data) == 0
+
+
+def test_cpp_host_layer_like_reference_tests_cpp(gpu, fixture_pixels, tmp_path):
+    """tests.cpp:98-108 for one fixture, through the C++ Image façade: read .bmp, write .jpg."""
+    exe = os.path.join(os.path.dirname(gpu.LIB_PATH), "write_jpg_like_reference")
+    assert os.path.exists(exe), "built by imagecodecs_b200.build"
+    cat = fixture_pixels["cat_bgr"]                       # top-down, B,G,R
+    h, w, _ = cat.shape
+    pad = w % 4
+    rows = b"".join(cat[y].tobytes() + b"\0" * pad for y in range(h - 1, -1, -1))
+    import struct
+    hdr = b"BM" + struct.pack("<IIIIiiHHIIiiII", 54 + len(rows), 0, 54, 40, w, h, 1, 24, 0, len(rows), 0, 0, 0, 0)
+    bmp = tmp_path / "cat.bmp"; bmp.write_bytes(hdr + rows)
+    out = tmp_path / "cat.jpg"
+    r = subprocess.run([exe, str(bmp), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "395x348x3", r.stderr
+    got = out.read_bytes()
+    assert len(got) == 152466 and sha(got) == "0ab72a0e4a3dffd20f8aca2e58237c92ce7a0d8c0d8ec7b92cdbe2cdffc5547d"
+    r = subprocess.run([exe, str(bmp), str(tmp_path / "cat.png")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Cannot parse filetype" in r.stderr
