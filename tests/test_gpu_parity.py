@@ -85,6 +85,7 @@ def test_stage_parity(gpu):
     for (qm, q, sub, nc) in [(0, 3, 0, 3), (0, 2, 0, 4), (1, 75, 1, 3), (1, 85, 0, 1)]:
         batch = oracle.synth_batch(2, 203, 117, nc, "noise" if q == 3 else "photo")
         dev = torch.from_numpy(batch).cuda()
+        torch.cuda.synchronize()
         plan = gpu.Plan.for_arrays([dev[0], dev[1]], qm, q, sub, device=0)
         nb = plan.num_blocks
         coefs = torch.zeros(nb * 64, dtype=torch.int16, device="cuda")
@@ -179,6 +180,7 @@ def test_device_resident_pixels_and_plan_reuse(gpu):
     import torch
     from imagecodecs_b200.synth import synth_batch
     dev = synth_batch(6, 1920, 1080, 3, device="cuda")
+    torch.cuda.synchronize()
     plan = gpu.Plan.for_arrays([dev[i] for i in range(6)], 1, 75, 1, device=0)
     plan.run(); a = plan.fetch()
     plan.run(); b = plan.fetch()            # same plan, second launch: state is reset correctly
@@ -188,6 +190,7 @@ def test_device_resident_pixels_and_plan_reuse(gpu):
         assert a[i] == oracle.oracle_encode(host[i], 1, 75, 1)
     # re-point image 0 at other pixels of the same geometry
     other = synth_batch(1, 1920, 1080, 3, first=100, device="cuda")
+    torch.cuda.synchronize()     # the plan runs on the library's own stream: order it after torch's
     plan.set_pixels(0, other.data_ptr()); plan.run(); c = plan.fetch(); plan.close()
     assert c[0] == oracle.oracle_encode(other[0].cpu().numpy(), 1, 75, 1) and c[1:] == a[1:]
 
@@ -206,6 +209,7 @@ def test_full_size_16k_gray_roundtrip(gpu):
     import torch
     from imagecodecs_b200.synth import synth_batch
     dev = synth_batch(1, 16384, 16384, 1, device="cuda")
+    torch.cuda.synchronize()
     plan = gpu.Plan.for_arrays([dev[0]], 1, 85, 0, device=0)
     plan.run(); f = plan.fetch()[0]; plan.close()
     host = dev[0].cpu().numpy()
@@ -221,6 +225,7 @@ def test_16k_rgb_native_twin(gpu):
     import torch
     from imagecodecs_b200.synth import synth_batch
     dev = synth_batch(1, 16384, 16384, 3, device="cuda", chunk=1)
+    torch.cuda.synchronize()
     plan = gpu.Plan.for_arrays([dev[0]], 0, 2, 0, device=0)
     plan.run(); f = plan.fetch()[0]; plan.close()
     host = dev[0].cpu().numpy()
