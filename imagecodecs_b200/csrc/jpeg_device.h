@@ -42,6 +42,8 @@ JG_DEV void cta_sync() { __syncthreads(); }
 JG_DEV unsigned warp_ballot(int pred) { return __ballot_sync(0xffffffffu, pred); }
 JG_DEV unsigned warp_shfl_u32(unsigned v, int lane) { return __shfl_sync(0xffffffffu, v, lane); }
 JG_DEV unsigned warp_shfl_up_u32(unsigned v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+JG_DEV void warp_sync() { __syncwarp(); }
+JG_DEV float warp_shfl_xor_f32(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 JG_DEV unsigned long long warp_shfl_u64(unsigned long long v, int lane) { return __shfl_sync(0xffffffffu, v, lane); }
 JG_DEV unsigned long long warp_shfl_xor_u64(unsigned long long v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 

@@ -134,7 +134,7 @@ bool geometry_of(const jpeg_gpu_image& im, Geometry* g)
     g->mcus_x = (im.width + g->mcu - 1) / g->mcu;
     g->mcus_y = (im.height + g->mcu - 1) / g->mcu;
     g->n_mcus = g->mcus_x * g->mcus_y;
-    const int M = kBlocksPerTile / g->bpm;
+    const int M = mcus_per_tile(g->layout);
     g->n_tiles = (g->n_mcus + M - 1) / M;
     g->n_blocks = (size_t)g->n_mcus * g->bpm;
     return true;

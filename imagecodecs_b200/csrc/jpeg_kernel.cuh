@@ -6,34 +6,37 @@
 // (:1160-1167).  Output bytes are identical to the reference's for its native modes.
 //
 // Work decomposition
-//   tile   = 192 consecutive 8x8 data units (blocks) of ONE image in stream order
-//            (4:4:4: 64 MCUs x {Y,Cb,Cr}; 4:2:0: 32 MCUs x {Y00,Y01,Y10,Y11,Cb,Cr}; gray: 192).
-//   CTA    = 192 threads, one thread per block, warps are component-uniform.  CTAs are
-//            persistent and draw tiles from an atomic ticket, so a tile's predecessors are
-//            always resident or finished (what makes the look-back below deadlock-free).
-//   thread = colour conversion + AAN FDCT + quantise + zigzag entirely in registers
-//            (64 coefficients, statically indexed), then two walks over them: one that
-//            only sizes the block, one that packs its bits at the block's exact offset.
+//   tile   = the blocks (8x8 data units) of 63 / 31 / 191 consecutive MCUs of ONE image
+//            (4:4:4 / 4:2:0 / gray) in stream order, plus one extra "slot" for the MCU that
+//            precedes the tile: it is transformed like the others but only its DC values are
+//            kept (they seed the DC prediction), so no CTA ever waits for another CTA's DCs.
+//   CTA    = 256 threads, persistent; tiles are drawn from an atomic ticket, so a tile's
+//            predecessors are always resident or finished (what makes the look-backs safe).
 //
 // Per tile:
-//   1. stage   pixels of the tile's MCUs (+ the MCU before it) -> shared memory, edge
-//              replication applied here (jpeg_enc.h:1106-1111)
-//   2. xform   P2+P3+P4 of SURVEY 8a in registers; DC of the preceding MCU is recomputed
-//              (DC-only transform) instead of being communicated between CTAs
-//   3. size    per-block bit count (P5-P7), CTA exclusive scan in stream order
-//   4. pack    every thread ORs/stores its bits into the tile's window in shared memory
-//   5. chain   decoupled look-back over tiles (#1): exclusive BIT offset of the tile in its
-//              image; the descriptor also carries the tile's last 7 bits so the successor can
-//              complete the byte the two tiles share
-//   6. stuff   count 0xFF bytes this tile owns, decoupled look-back (#2) over those counts:
-//              exclusive BYTE offset in the stuffed stream; emit 0xFF00 (jpeg_enc.h:634-638)
-//   7. write   coalesced copy of the stuffed bytes to the image's scan; the last tile pads
-//              with zero bits (jpeg_enc.h:1161-1164) and appends EOI (:1166-1167)
-// HBM traffic is therefore: every pixel read once (+1/64 for the predecessor MCU), every
-// output byte written once.  Nothing else touches DRAM except two 8-byte descriptors per tile.
+//   1. transform  lane groups of 8 (16 for 4:2:0) own one MCU: each lane loads ONE pixel row
+//                 straight from global memory (edge replication jpeg_enc.h:1106-1111 applied
+//                 on the way), converts it to Y/Cb/Cr once for all components (:1118-1120),
+//                 runs the AAN row pass (:668-709), exchanges the 8x8 through a padded
+//                 shared-memory tile, runs the column pass (:718-759), quantises (:808-816)
+//                 and scatters int16 coefficients to shared memory in zigzag order.
+//   2. size       one thread per block walks its 63 AC coefficients: bits of the block
+//                 (P5-P7 of SURVEY 8a); CTA exclusive scan in stream order; the tile's bit
+//                 count is published at once.
+//   3. pack       second walk: every thread ORs/stores its codes at its exact bit offset of the
+//                 tile window in shared memory.
+//   4. chain #1   decoupled look-back over tiles: exclusive BIT offset of the tile in its
+//                 image; the predecessor's last 7 bits complete the byte the two tiles share.
+//   5. stuff      count the 0xFF bytes this tile owns, publish, emit 0xFF00 (jpeg_enc.h:634-638)
+//                 into shared memory, THEN look back over the counts (chain #2): the stuffed
+//                 BYTE offset.  Publishing early and consuming late hides the chain latency.
+//   6. write      coalesced copy to the image's scan; the last tile pads with zero bits
+//                 (jpeg_enc.h:1161-1164) and appends EOI (:1166-1167).
+// HBM traffic: every pixel read once (+1/63 for the predecessor slot), every output byte
+// written once, three 8-byte descriptors per tile.
 //
 // A tile whose bits do not fit the shared-memory window (pathological content) is processed
-// as several "groups" of blocks with the walks repeated; same bytes, lower speed.
+// as several "groups" of blocks with the pack walk repeated; same bytes, lower speed.
 #pragma once
 #include "jpeg_device.h"
 #include "jpeg_launch.h"
@@ -41,29 +44,37 @@
 
 namespace jg {
 
-template <int LAYOUT, int NC>
+constexpr int kTileFloats = 72;   // one 8x8 float tile with rows padded to 9 (bank-conflict free both ways)
+constexpr int kCoefStride = 66;   // int16 per block in shared memory (33 words: conflict-free block walks)
+
+template <int LAYOUT>
 struct Geo {
     static constexpr int BPM = LAYOUT == LAYOUT_444 ? 3 : (LAYOUT == LAYOUT_420 ? 6 : 1);  // blocks per MCU
-    static constexpr int MCU_W = LAYOUT == LAYOUT_420 ? 16 : 8;
-    static constexpr int MCU_H = MCU_W;
-    static constexpr int M = kBlocksPerTile / BPM;  // MCUs per tile
-    static constexpr int SLOTS = M + 1;             // slot 0 = the MCU preceding the tile
-    static constexpr int ROWB = MCU_W * NC;         // bytes of one MCU pixel row
-    static constexpr int WPR = ROWB / 4;            // ... in 32-bit words
-    static constexpr int STAGE_WORDS = MCU_H * SLOTS * WPR;  // layout [row][slot][WPR]
+    static constexpr int MCU = LAYOUT == LAYOUT_420 ? 16 : 8;                               // MCU edge in pixels
+    static constexpr int M = mcus_per_tile(LAYOUT);        // MCUs per tile
+    static constexpr int SLOTS = M + 1;                    // slot 0 = the MCU preceding the tile
+    static constexpr int LANES = LAYOUT == LAYOUT_420 ? 16 : 8;   // lanes that share one MCU
+    static constexpr int GROUPS = kThreads / LANES;
+    static constexpr int ITERS = SLOTS / GROUPS;
+    static constexpr int TILES = LAYOUT == LAYOUT_420 ? 6 : 1;    // exchange tiles per lane group
+    static_assert(SLOTS % GROUPS == 0, "slots must divide evenly among the lane groups");
+    static_assert(M * BPM <= kBlocksPerTile, "tile too large");
 };
 
 template <int LAYOUT, int NC>
 struct Smem {
-    using G = Geo<LAYOUT, NC>;
-    static constexpr int A_WORDS = (G::STAGE_WORDS > kWinWordsMax + 8 ? G::STAGE_WORDS : kWinWordsMax + 8);
-    alignas(16) uint32_t a[A_WORDS];               // pixel staging, then the unstuffed window
-    alignas(16) uint8_t sbuf[kWinWordsMax * 8 + 64];  // stuffed bytes of one group (worst case 2x)
+    using G = Geo<LAYOUT>;
+    static constexpr int SCRATCH = G::GROUPS * G::TILES * kTileFloats;
+    static constexpr int R1_WORDS = SCRATCH > kWinWordsMax + 8 ? SCRATCH : kWinWordsMax + 8;
+    alignas(16) uint32_t r1[R1_WORDS];                        // transform exchange tiles, then the unstuffed window
+    alignas(16) uint8_t sbuf[2 * kSubBytes + 64];             // stuffed bytes of one piece (worst case 2x)
+    alignas(16) int16_t coef[kBlocksPerTile * kCoefStride];   // quantised coefficients, zigzag order
     uint32_t huff_ac[2][256];
     uint32_t huff_dc[2][16];
     uint32_t bits_s[kBlocksPerTile];      // bits per block, stream order
-    uint32_t off_s[kBlocksPerTile + 1];   // exclusive scan of bits_s; [192] = total
+    uint32_t off_s[kThreads + 1];         // exclusive scan of bits_s; entries >= nblk hold the total
     int dc_s[kBlocksPerTile];             // quantised DC per block, stream order
+    int pred_dc[4];                       // DCs of the MCU preceding the tile, per component
     uint16_t gstart[kBlocksPerTile + 2];  // group boundaries (block indices)
     uint32_t warp_tmp[kWarps];
     // tile-wide scalars (written by one thread, read after a barrier)
@@ -75,116 +86,82 @@ struct Smem {
     unsigned long long ff_base;           // exclusive stuffed-FF count
 };
 
-// ------------------------------------------------------------------------------------------
-// zigzag: position in scan order of natural index i (jpeg_enc.h:376-386)
-// ------------------------------------------------------------------------------------------
-JG_DEV constexpr int zz_of(int i)
+// per-lane constants: the lane's column u = tid & 7 of every coefficient matrix it finishes
+struct LaneConst {
+    float pq_l[8], pq_c[8];   // reciprocal quantisers of column u: [v] = pqt[8v+u], luma / chroma
+    unsigned zz_lo, zz_hi;    // zigzag positions of (v,u), v = 0..7, one byte each
+};
+
+JG_DEV int zz_of(int i)   // jpeg_enc.h:376-386: position in scan order of natural index i
 {
-    constexpr unsigned char t[64] = JG_ZZ_INIT;
+    const unsigned char t[64] = JG_ZZ_INIT;
     return t[i];
 }
 
 // ------------------------------------------------------------------------------------------
-// sample fetch + colour conversion (jpeg_enc.h:1114-1124), operation order preserved
+// pixels: one row segment of NPX pixels starting at column x0 of row y, as little-endian words
 // ------------------------------------------------------------------------------------------
+template <int NC, int NPX>
+JG_DEV void load_segment(const ImageDesc& im, int x0, int y, uint32_t (&w)[NPX * NC / 4])
+{
+    const uint8_t* row = im.px + (size_t)y * (size_t)im.stride;
+    if (im.aligned4 && x0 + NPX <= im.w) {
+        const uint8_t* p = row + (size_t)x0 * NC;
+#pragma unroll
+        for (int i = 0; i < NPX * NC / 4; ++i) w[i] = ldg_u32(p + 4 * i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NPX * NC / 4; ++i) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int bo = 4 * i + b;
+                const int px = bo / NC, ch = bo - px * NC;
+                int x = x0 + px;
+                if (x >= im.w) x = im.w - 1;                     // replicate the last column
+                v |= ldg_u8(row + (size_t)x * NC + ch) << (8 * b);
+            }
+            w[i] = v;
+        }
+    }
+}
+
 JG_DEV unsigned byte_of(const uint32_t* w, int idx) { return (w[idx >> 2] >> ((idx & 3) * 8)) & 0xffu; }
 
-// Chroma weights of one component.  Cb and Cr share ONE code path (keeps the kernel small);
-// x - y == x + (-y) and (-c)*g == -(c*g) exactly in IEEE arithmetic, so
-//   Cb = (-0.1687f*r - 0.3313f*g) + 0.5f*b   and   Cr = (0.5f*r - 0.4187f*g) - 0.0813f*b
-// are both ((k0*r + k1*g) + k2*b) with the signs folded into the constants.
-struct ChromaK { float k0, k1, k2; };
-JG_DEV ChromaK chroma_k(int comp)
+template <int NC>
+JG_DEV void rgb_of(const uint32_t* w, int i, float& r, float& g, float& b)
 {
-    ChromaK k;
-    if (comp == 1) { k.k0 = -0.1687f; k.k1 = -0.3313f; k.k2 = 0.5f; }
-    else { k.k0 = 0.5f; k.k1 = -0.4187f; k.k2 = -0.0813f; }
-    return k;
-}
-
-template <int CLS>   // 0 = luma, 1 = chroma
-JG_DEV float ycc(float r, float g, float b, const ChromaK& k)
-{
-    if (CLS == 0) return f_sub(f_add(f_add(f_mul(0.299f, r), f_mul(0.587f, g)), f_mul(0.114f, b)), 128.0f);
-    return f_add(f_add(f_mul(k.k0, r), f_mul(k.k1, g)), f_mul(k.k2, b));
-}
-
-template <int NC, int CLS>
-JG_DEV float sample_of(const uint32_t* w, int i, const ChromaK& k)
-{
-    float r, g, b;
     if (NC == 4) {
         const uint32_t v = w[i];
         r = u8_to_f(v & 0xffu); g = u8_to_f((v >> 8) & 0xffu); b = u8_to_f((v >> 16) & 0xffu);
     } else {
         r = u8_to_f(byte_of(w, 3 * i)); g = u8_to_f(byte_of(w, 3 * i + 1)); b = u8_to_f(byte_of(w, 3 * i + 2));
     }
-    return ycc<CLS>(r, g, b, k);
 }
 
-template <int N>
-JG_DEV void lds_words(const uint32_t* p, uint32_t (&w)[N])
-{
-    // p is 8-byte aligned for every caller (row segments are multiples of 8 bytes)
-#pragma unroll
-    for (int i = 0; i < N / 2; ++i) {
-        const uint2 v = reinterpret_cast<const uint2*>(p)[i];
-        w[2 * i] = v.x; w[2 * i + 1] = v.y;
-    }
-}
-
-// Row r (0..7) of the thread's 8x8 block, as 8 level-shifted / colour-converted samples.
-// q: quadrant of the Y block inside a 4:2:0 MCU (ignored otherwise).
-template <int LAYOUT, int NC, int CLS>
-JG_DEV void fetch_row(const uint32_t* stage, int slot, int q, int r, const ChromaK& ck, float (&s)[8])
-{
-    using G = Geo<LAYOUT, NC>;
-    if (LAYOUT == LAYOUT_GRAY) {
-        uint32_t w[2];
-        lds_words<2>(stage + (r * G::SLOTS + slot) * G::WPR, w);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s[i] = f_sub(u8_to_f(byte_of(w, i)), 128.0f);
-    } else if (LAYOUT == LAYOUT_444 || CLS == 0) {
-        constexpr int W8 = 8 * NC / 4;  // words of 8 pixels
-        const int row = LAYOUT == LAYOUT_420 ? r + 8 * (q >> 1) : r;
-        const int xoff = LAYOUT == LAYOUT_420 ? (q & 1) * W8 : 0;
-        uint32_t w[W8];
-        lds_words<W8>(stage + (row * G::SLOTS + slot) * G::WPR + xoff, w);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s[i] = sample_of<NC, CLS>(w, i, ck);
-    } else {
-        // 4:2:0 chroma: ((a+b)+(c+d))*0.25f over the 2x2 float Cb/Cr values (extended mode)
-        constexpr int W16 = 16 * NC / 4;
-        uint32_t w0[W16], w1[W16];
-        lds_words<W16>(stage + ((2 * r) * G::SLOTS + slot) * G::WPR, w0);
-        lds_words<W16>(stage + ((2 * r + 1) * G::SLOTS + slot) * G::WPR, w1);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float a = sample_of<NC, CLS>(w0, 2 * i, ck), b = sample_of<NC, CLS>(w0, 2 * i + 1, ck);
-            const float c = sample_of<NC, CLS>(w1, 2 * i, ck), d = sample_of<NC, CLS>(w1, 2 * i + 1, ck);
-            s[i] = f_mul(f_add(f_add(a, b), f_add(c, d)), 0.25f);
-        }
-    }
-}
+// jpeg_enc.h:1118-1120, C's left-to-right evaluation made explicit
+JG_DEV float rgb_y(float r, float g, float b) { return f_sub(f_add(f_add(f_mul(0.299f, r), f_mul(0.587f, g)), f_mul(0.114f, b)), 128.0f); }
+JG_DEV float rgb_cb(float r, float g, float b) { return f_add(f_sub(f_mul(-0.1687f, r), f_mul(0.3313f, g)), f_mul(0.5f, b)); }
+JG_DEV float rgb_cr(float r, float g, float b) { return f_sub(f_sub(f_mul(0.5f, r), f_mul(0.4187f, g)), f_mul(0.0813f, b)); }
 
 // ------------------------------------------------------------------------------------------
 // AAN forward DCT, one 8-point pass (jpeg_enc.h:668-709 rows, :718-759 columns)
 // ------------------------------------------------------------------------------------------
-JG_DEV void aan8(float& d0, float& d1, float& d2, float& d3, float& d4, float& d5, float& d6, float& d7)
+JG_DEV void aan8(float (&d)[8])
 {
     const float c4 = 0.707106781f, c6 = 0.382683433f, c2m6 = 0.541196100f, c2p6 = 1.306562965f;
-    const float t0 = f_add(d0, d7), t7 = f_sub(d0, d7);
-    const float t1 = f_add(d1, d6), t6 = f_sub(d1, d6);
-    const float t2 = f_add(d2, d5), t5 = f_sub(d2, d5);
-    const float t3 = f_add(d3, d4), t4 = f_sub(d3, d4);
+    const float t0 = f_add(d[0], d[7]), t7 = f_sub(d[0], d[7]);
+    const float t1 = f_add(d[1], d[6]), t6 = f_sub(d[1], d[6]);
+    const float t2 = f_add(d[2], d[5]), t5 = f_sub(d[2], d[5]);
+    const float t3 = f_add(d[3], d[4]), t4 = f_sub(d[3], d[4]);
 
     const float e0 = f_add(t0, t3), e3 = f_sub(t0, t3);
     const float e1 = f_add(t1, t2), e2 = f_sub(t1, t2);
-    d0 = f_add(e0, e1);
-    d4 = f_sub(e0, e1);
+    d[0] = f_add(e0, e1);
+    d[4] = f_sub(e0, e1);
     const float z1 = f_mul(f_add(e2, e3), c4);
-    d2 = f_add(e3, z1);
-    d6 = f_sub(e3, z1);
+    d[2] = f_add(e3, z1);
+    d[6] = f_sub(e3, z1);
 
     const float o0 = f_add(t4, t5), o1 = f_add(t5, t6), o2 = f_add(t6, t7);
     const float z5 = f_mul(f_sub(o0, o2), c6);
@@ -192,17 +169,10 @@ JG_DEV void aan8(float& d0, float& d1, float& d2, float& d3, float& d4, float& d
     const float z4 = f_add(f_mul(c2p6, o2), z5);
     const float z3 = f_mul(o1, c4);
     const float z11 = f_add(t7, z3), z13 = f_sub(t7, z3);
-    d5 = f_add(z13, z2);
-    d3 = f_sub(z13, z2);
-    d1 = f_add(z11, z4);
-    d7 = f_sub(z11, z4);
-}
-
-// the DC output of aan8 only: ((d0+d7)+(d3+d4)) + ((d1+d6)+(d2+d5))
-JG_DEV float aan8_dc(const float (&d)[8])
-{
-    const float t0 = f_add(d[0], d[7]), t1 = f_add(d[1], d[6]), t2 = f_add(d[2], d[5]), t3 = f_add(d[3], d[4]);
-    return f_add(f_add(t0, t3), f_add(t1, t2));
+    d[5] = f_add(z13, z2);
+    d[3] = f_sub(z13, z2);
+    d[1] = f_add(z11, z4);
+    d[7] = f_sub(z11, z4);
 }
 
 // jpeg_enc.h:808-816: v*pqt, floorf((v + 1024) + 0.5f) - 1024, (int)
@@ -213,42 +183,149 @@ JG_DEV int quantise(float v, float pq)
     return f_floor_i(v) - 1024;
 }
 
-// samples -> 64 quantised coefficients in ZIGZAG order, all in registers
-template <int LAYOUT, int NC, int CLS>
-JG_DEV void transform_block(const uint32_t* stage, int slot, int q, const ChromaK& ck, const QuantSet& Q, int (&c)[64])
+// row pass of one 8-sample row, result into row `r` of an exchange tile
+JG_DEV void row_pass_store(float (&s)[8], float* tile, int r)
 {
-    float d[64];
+    aan8(s);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        float s[8];
-        fetch_row<LAYOUT, NC, CLS>(stage, slot, q, r, ck, s);
-        aan8(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d[8 * r + i] = s[i];
-    }
-#pragma unroll
-    for (int x = 0; x < 8; ++x)
-        aan8(d[x], d[8 + x], d[16 + x], d[24 + x], d[32 + x], d[40 + x], d[48 + x], d[56 + x]);
-#pragma unroll
-    for (int i = 0; i < 64; ++i) c[zz_of(i)] = quantise(d[i], CLS == 0 ? Q.luma[i] : Q.chroma[i]);
+    for (int i = 0; i < 8; ++i) tile[r * 9 + i] = s[i];
 }
 
-// quantised DC of a block without the other 63 outputs (same roundings as transform_block)
-template <int LAYOUT, int NC, int CLS>
-JG_DEV int transform_dc_only(const uint32_t* stage, int slot, int q, const ChromaK& ck, const QuantSet& Q)
+// column u of an exchange tile: column pass, quantise, scatter to zigzag order.
+// blk < 0: the block belongs to the predecessor slot, only its DC is kept (in *pred_dc).
+template <int LAYOUT, int NC>
+JG_DEV void column_pass(Smem<LAYOUT, NC>& S, const float* tile, int u, bool chroma, int blk, int* pred_dc, const LaneConst& LC)
 {
-    float col[8];
-#pragma unroll 1
-    for (int r = 0; r < 8; ++r) {
-        float s[8];
-        fetch_row<LAYOUT, NC, CLS>(stage, slot, q, r, ck, s);
-        col[r] = aan8_dc(s);
+    float c[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) c[v] = tile[v * 9 + u];
+    aan8(c);
+    if (blk >= 0) {
+        int16_t* dst = S.coef + blk * kCoefStride;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const int k = quantise(c[v], chroma ? LC.pq_c[v] : LC.pq_l[v]);
+            const unsigned zz = ((v < 4 ? LC.zz_lo : LC.zz_hi) >> (8 * (v & 3))) & 0xffu;
+            dst[zz] = (int16_t)k;
+            if (v == 0 && u == 0) S.dc_s[blk] = k;
+        }
+    } else if (u == 0 && pred_dc != nullptr) {
+        *pred_dc = quantise(c[0], chroma ? LC.pq_c[0] : LC.pq_l[0]);
     }
-    return quantise(aan8_dc(col), CLS == 0 ? Q.luma[0] : Q.chroma[0]);
 }
 
 // ------------------------------------------------------------------------------------------
-// entropy coding of one block (jpeg_enc.h:831-888)
+// stage 1: transform all slots of the tile
+// ------------------------------------------------------------------------------------------
+template <int LAYOUT, int NC>
+JG_DEV void transform_tile(Smem<LAYOUT, NC>& S, const ImageDesc& im, int m0, int nM, const LaneConst& LC)
+{
+    using G = Geo<LAYOUT>;
+    const int t = JG_TID;
+    float* scratch = reinterpret_cast<float*>(S.r1);
+    const int u = t & 7;
+    const int grp = t / G::LANES;
+
+#pragma unroll 1
+    for (int it = 0; it < G::ITERS; ++it) {
+        const int slot = it * G::GROUPS + grp;
+        const int m = m0 - 1 + slot;
+        const bool valid = slot == 0 ? (m0 > 0) : (slot <= nM);
+        int my = 0, mx = 0;
+        if (valid) { my = m / im.mcus_x; mx = m - my * im.mcus_x; }
+
+        if (LAYOUT == LAYOUT_GRAY) {
+            float* tile = scratch + grp * kTileFloats;
+            if (valid) {
+                int y = my * 8 + u; if (y >= im.h) y = im.h - 1;          // replicate the last row
+                uint32_t w[2];
+                load_segment<1, 8>(im, mx * 8, y, w);
+                float s[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s[i] = f_sub(u8_to_f(byte_of(w, i)), 128.0f);
+                row_pass_store(s, tile, u);
+            }
+            warp_sync();
+            if (valid) column_pass(S, tile, u, false, slot - 1, &S.pred_dc[0], LC);
+            warp_sync();
+        } else if (LAYOUT == LAYOUT_444) {
+            float* tile = scratch + grp * kTileFloats;
+            float R[8], Gc[8], B[8];
+            if (valid) {
+                int y = my * 8 + u; if (y >= im.h) y = im.h - 1;
+                uint32_t w[8 * NC / 4];
+                load_segment<NC, 8>(im, mx * 8, y, w);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rgb_of<NC>(w, i, R[i], Gc[i], B[i]);
+            }
+#pragma unroll
+            for (int comp = 0; comp < 3; ++comp) {
+                if (valid) {
+                    float s[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        s[i] = comp == 0 ? rgb_y(R[i], Gc[i], B[i]) : (comp == 1 ? rgb_cb(R[i], Gc[i], B[i]) : rgb_cr(R[i], Gc[i], B[i]));
+                    row_pass_store(s, tile, u);
+                }
+                warp_sync();
+                if (valid) column_pass(S, tile, u, comp != 0, slot >= 1 ? (slot - 1) * 3 + comp : -1, &S.pred_dc[comp], LC);
+                warp_sync();
+            }
+        } else {
+            // 4:2:0: 16 lanes per MCU, lane r16 owns pixel row r16 (16 pixels)
+            const int r16 = t & 15;
+            float* base = scratch + grp * (6 * kTileFloats);
+            float cbs[8], crs[8];            // horizontal pair sums (a+b) of this row
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { cbs[i] = 0.0f; crs[i] = 0.0f; }
+            if (valid) {
+                int y = my * 16 + r16; if (y >= im.h) y = im.h - 1;
+                uint32_t w[16 * NC / 4];
+                load_segment<NC, 16>(im, mx * 16, y, w);
+#pragma unroll
+                for (int hx = 0; hx < 2; ++hx) {
+                    float R[8], Gc[8], B[8], s[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        rgb_of<NC>(w, 8 * hx + i, R[i], Gc[i], B[i]);
+                        s[i] = rgb_y(R[i], Gc[i], B[i]);
+                    }
+                    row_pass_store(s, base + ((r16 >> 3) * 2 + hx) * kTileFloats, r16 & 7);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        cbs[4 * hx + i] = f_add(rgb_cb(R[2 * i], Gc[2 * i], B[2 * i]), rgb_cb(R[2 * i + 1], Gc[2 * i + 1], B[2 * i + 1]));
+                        crs[4 * hx + i] = f_add(rgb_cr(R[2 * i], Gc[2 * i], B[2 * i]), rgb_cr(R[2 * i + 1], Gc[2 * i + 1], B[2 * i + 1]));
+                    }
+                }
+            }
+            // vertical pairs live in neighbouring lanes: the even lane finishes Cb, the odd lane Cr;
+            // sample = ((a+b) + (c+d)) * 0.25f with (a+b) from the even row (extended mode)
+            const bool even = (r16 & 1) == 0;
+            float samp[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float other = warp_shfl_xor_f32(even ? crs[i] : cbs[i], 1);
+                samp[i] = even ? f_mul(f_add(cbs[i], other), 0.25f) : f_mul(f_add(other, crs[i]), 0.25f);
+            }
+            if (valid) row_pass_store(samp, base + (4 + (r16 & 1)) * kTileFloats, r16 >> 1);
+            warp_sync();
+            if (valid) {
+#pragma unroll
+                for (int k3 = 0; k3 < 3; ++k3) {
+                    const int tl = (r16 >> 3) + 2 * k3;          // tiles {0,2,4} for lanes 0-7, {1,3,5} for lanes 8-15
+                    const int comp = tl < 4 ? 0 : tl - 3;
+                    // of the predecessor MCU only Y11 (tile 3), Cb and Cr matter
+                    int* pd = (tl >= 3) ? &S.pred_dc[comp] : nullptr;
+                    column_pass(S, base + tl * kTileFloats, u, k3 == 2, slot >= 1 ? (slot - 1) * 6 + tl : -1, pd, LC);
+                }
+            }
+            warp_sync();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// entropy coding of one block (jpeg_enc.h:831-888); cz = 64 coefficients in zigzag order
 // ------------------------------------------------------------------------------------------
 JG_DEV unsigned category(int v)  // jpeg_enc.h:598-608; v != 0
 {
@@ -261,7 +338,7 @@ JG_DEV unsigned amplitude(int v, unsigned cat)  // jpeg_enc.h:601-609: (v<0 ? v-
 }
 
 // walk 1: size only
-JG_DEV unsigned block_bits(const int (&c)[64], int diff, const uint32_t* ac, const uint32_t* dc)
+JG_DEV unsigned block_bits(const int16_t* cz, int diff, const uint32_t* ac, const uint32_t* dc)
 {
     const unsigned zrl_len = ac[0xF0] & 0xffu;
     const unsigned dcat = diff ? category(diff) : 0u;
@@ -269,7 +346,7 @@ JG_DEV unsigned block_bits(const int (&c)[64], int diff, const uint32_t* ac, con
     int last = 0;
 #pragma unroll
     for (int k = 1; k < 64; ++k) {
-        const int v = c[k];
+        const int v = cz[k];
         if (v != 0) {
             unsigned run = (unsigned)(k - 1 - last);
             last = k;
@@ -317,7 +394,7 @@ struct BitPacker {
 };
 
 // walk 2: emit the block's bits at `bitpos` of `buf`
-JG_DEV void block_pack(const int (&c)[64], int diff, const uint32_t* ac, const uint32_t* dc, uint32_t* buf, unsigned bitpos)
+JG_DEV void block_pack(const int16_t* cz, int diff, const uint32_t* ac, const uint32_t* dc, uint32_t* buf, unsigned bitpos)
 {
     BitPacker bp;
     bp.init(buf, bitpos);
@@ -331,7 +408,7 @@ JG_DEV void block_pack(const int (&c)[64], int diff, const uint32_t* ac, const u
     int last = 0;
 #pragma unroll
     for (int k = 1; k < 64; ++k) {
-        const int v = c[k];
+        const int v = cz[k];
         if (v != 0) {
             unsigned run = (unsigned)(k - 1 - last);
             last = k;
@@ -348,7 +425,7 @@ JG_DEV void block_pack(const int (&c)[64], int diff, const uint32_t* ac, const u
 // ------------------------------------------------------------------------------------------
 // CTA-wide helpers
 // ------------------------------------------------------------------------------------------
-// exclusive scan over the 192 threads; contains two barriers
+// exclusive scan over the CTA's threads; contains two barriers
 JG_DEV unsigned cta_scan_excl(unsigned v, uint32_t* warp_tmp, unsigned& total)
 {
     const int lane = JG_TID & 31, wid = JG_TID >> 5;
@@ -380,15 +457,12 @@ JG_DEV unsigned long long warp_sum_u64(unsigned long long v)
 }
 
 // Decoupled look-back (Merrill & Garland) executed by one full warp.  desc[i] holds
-// status[63:62] | payload.  Tiles before `first` do not exist (image start): they count
-// as PREFIX 0.  Returns the exclusive prefix of tile g; *nearest receives desc[g-1].
-// On timeout sets *err and returns 0 (all lanes agree).
-JG_DEV unsigned long long lookback(const unsigned long long* desc, int g, int first, unsigned long long value_mask,
-                                   unsigned long long* nearest, unsigned* err_flag, int* timed_out)
+// status[63:62] | value.  Tiles before `first` do not exist (image start): they count as
+// PREFIX 0.  Returns the exclusive prefix of tile g.  On timeout sets *timed_out (all lanes agree).
+JG_DEV unsigned long long lookback(const unsigned long long* desc, int g, int first, unsigned* err_flag, int* timed_out)
 {
     const int lane = JG_TID & 31;
     unsigned long long running = 0;
-    bool first_round = true;
     *timed_out = 0;
     for (int base = g - 1;; base -= 32) {
         const int idx = base - lane;
@@ -402,10 +476,9 @@ JG_DEV unsigned long long lookback(const unsigned long long* desc, int g, int fi
             if (warp_ballot(spins == 0xffffffffu) != 0u) { *timed_out = 1; return 0; }
             backoff();
         }
-        if (first_round) { *nearest = warp_shfl_u64(w, 0); first_round = false; }
         const unsigned pmask = warp_ballot((w >> 62) == 2u);
         const int stop = pmask ? i_ffs(pmask) - 1 : 32;   // nearest tile that already knows its prefix
-        running += warp_sum_u64(lane <= stop ? (w & value_mask) : 0ull);
+        running += warp_sum_u64(lane <= stop ? (w & kCountMask) : 0ull);
         if (pmask) return running;
     }
 }
@@ -427,64 +500,12 @@ JG_DEV unsigned xword(const uint32_t* L, int i, unsigned k, unsigned hb)
     return (hi << (32u - k)) | (L[i] >> k);
 }
 
-// ------------------------------------------------------------------------------------------
-// stage 1: pixels -> shared memory
-// ------------------------------------------------------------------------------------------
-template <int LAYOUT, int NC>
-JG_DEV void stage_tile(uint32_t* stage, const ImageDesc& im, int m0, int nM)
+// 0xFF bytes among the first `valid` (1..4) bytes of MSB-first word x
+JG_DEV unsigned count_ff(unsigned x, unsigned valid)
 {
-    using G = Geo<LAYOUT, NC>;
-    constexpr int COLS = G::SLOTS * G::WPR;
-    for (int col = JG_TID; col < COLS; col += kThreads) {
-        const int j = col / G::WPR, wd = col - j * G::WPR;
-        const int m = m0 - 1 + j;
-        if (m < 0 || j > nM) continue;
-        const int my = m / im.mcus_x, mx = m - my * im.mcus_x;
-        const int y0 = my * G::MCU_H;
-        const int xb = mx * G::ROWB + wd * 4;  // byte offset of this word inside a pixel row
-        uint32_t* dst = stage + j * G::WPR + wd;
-        if (im.aligned4 && (mx + 1) * G::MCU_W <= im.w) {
-            uint32_t v[G::MCU_H];
-#pragma unroll
-            for (int r = 0; r < G::MCU_H; ++r) {
-                const int y = (y0 + r < im.h) ? y0 + r : im.h - 1;   // replicate the last row
-                v[r] = ldg_u32(im.px + (size_t)y * (size_t)im.stride + (size_t)xb);
-            }
-#pragma unroll
-            for (int r = 0; r < G::MCU_H; ++r) dst[r * (G::SLOTS * G::WPR)] = v[r];
-        } else {
-            for (int r = 0; r < G::MCU_H; ++r) {
-                const int y = (y0 + r < im.h) ? y0 + r : im.h - 1;
-                const uint8_t* row = im.px + (size_t)y * (size_t)im.stride;
-                uint32_t v = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int bo = xb + b;
-                    int x = bo / NC;
-                    const int ch = bo - x * NC;
-                    if (x >= im.w) x = im.w - 1;                      // replicate the last column
-                    v |= (uint32_t)ldg_u8(row + (size_t)x * NC + ch) << (8 * b);
-                }
-                dst[r * (G::SLOTS * G::WPR)] = v;
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// per-thread compute for one table class (0 = luma, 1 = chroma); leaves the coefficients in `c`
-// ------------------------------------------------------------------------------------------
-template <int LAYOUT, int NC, int CLS>
-JG_DEV void thread_transform(Smem<LAYOUT, NC>& S, const QuantSet& Q, int comp, bool active, int slot, int q, int s,
-                             bool pred_outside, bool have_prev_mcu, int pred_q, int (&c)[64], int& outside_dc)
-{
-    outside_dc = 0;
-    if (active) {
-        const ChromaK ck = chroma_k(comp);
-        transform_block<LAYOUT, NC, CLS>(S.a, slot, q, ck, Q, c);
-        S.dc_s[s] = c[0];
-        if (pred_outside && have_prev_mcu) outside_dc = transform_dc_only<LAYOUT, NC, CLS>(S.a, 0, pred_q, ck, Q);
-    }
+    unsigned m = v_cmpeq4(x, 0xffffffffu);
+    if (valid < 4u) m &= 0xffffffffu << (8u * (4u - valid));
+    return (unsigned)i_popc(m) >> 3;
 }
 
 // byte offset `o` of a little-endian byte array held as aligned words
@@ -494,11 +515,15 @@ JG_DEV unsigned word_at_byte(const uint32_t* w, unsigned o)
     return sh ? (w[i] >> sh) | (w[i + 1] << (32u - sh)) : w[i];
 }
 
+// ------------------------------------------------------------------------------------------
+// one tile
+// ------------------------------------------------------------------------------------------
 template <int LAYOUT, int NC>
-JG_DEV void encode_tile(const LaunchParams& P, const QuantSet& Q, Smem<LAYOUT, NC>& S, const int g)
+JG_DEV void encode_tile(const LaunchParams& P, Smem<LAYOUT, NC>& S, const LaneConst& LC, const int g)
 {
-    using G = Geo<LAYOUT, NC>;
+    using G = Geo<LAYOUT>;
     const int t = JG_TID;
+    uint32_t* win = S.r1;
 
     // ---- which image, which MCUs -------------------------------------------------------
     int img_idx;
@@ -519,64 +544,47 @@ JG_DEV void encode_tile(const LaunchParams& P, const QuantSet& Q, Smem<LAYOUT, N
     const int nblk = nM * G::BPM;
     const bool first_tile = lt == 0, last_tile = lt == im.n_tiles - 1;
 
-    // ---- 1. stage ----------------------------------------------------------------------
-    stage_tile<LAYOUT, NC>(S.a, im, m0, nM);
+    // ---- 1. transform -------------------------------------------------------------------
+    if (t < 4) S.pred_dc[t] = 0;          // jpeg_enc.h:1085-1087: predictors start at 0
     cta_sync();
+    transform_tile<LAYOUT, NC>(S, im, m0, nM, LC);
+    cta_sync();   // coefficients + DCs complete; the exchange tiles are dead from here on
 
-    // ---- 2. transform: thread -> (MCU slot, component, quadrant), stream index s ---------
-    int comp, ml, q = 0, s, pred_s, pred_q = 0;
-    bool pred_outside;
-    if (LAYOUT == LAYOUT_444) {
-        comp = t >> 6; ml = t & 63; s = ml * 3 + comp;
-        pred_s = s - 3; pred_outside = ml == 0;
-    } else if (LAYOUT == LAYOUT_420) {
-        if (t < 128) {
-            comp = 0; ml = (t & 63) >> 1; q = ((t >> 6) << 1) | (t & 1); s = ml * 6 + q;
-            pred_s = q ? s - 1 : s - 3; pred_outside = (q == 0) && (ml == 0); pred_q = 3;
-        } else {
-            comp = 1 + ((t - 128) >> 5); ml = (t - 128) & 31; s = ml * 6 + 3 + comp;
-            pred_s = s - 6; pred_outside = ml == 0;
-        }
-    } else {
-        comp = 0; ml = t; s = t; pred_s = s - 1; pred_outside = ml == 0;
+    // ---- 2. size: thread t owns block t of the tile (stream order) --------------------------
+    const bool active = t < nblk;
+    const int s = t;
+    int comp = 0, pred_s = s - 1;
+    if (LAYOUT == LAYOUT_444) { comp = s % 3; pred_s = s - 3; }
+    else if (LAYOUT == LAYOUT_420) {
+        const int j = s % 6;
+        comp = j < 4 ? 0 : j - 3;
+        pred_s = j >= 4 ? s - 6 : (j == 0 ? s - 3 : s - 1);      // Y00 follows the previous MCU's Y11
     }
-    const bool active = ml < nM;
     const int cls = comp ? 1 : 0;
-    int c[64];
-    int outside_dc;
-    if (cls == 0) thread_transform<LAYOUT, NC, 0>(S, Q, comp, active, ml + 1, q, s, pred_outside, m0 > 0, pred_q, c, outside_dc);
-    else thread_transform<LAYOUT, NC, 1>(S, Q, comp, active, ml + 1, q, s, pred_outside, m0 > 0, pred_q, c, outside_dc);
-    cta_sync();   // dc_s complete; staging area dead from here on
-
-    // ---- 3. size ------------------------------------------------------------------------
     const uint32_t* hac = S.huff_ac[cls];
     const uint32_t* hdc = S.huff_dc[cls];
+    const int16_t* cz = S.coef + s * kCoefStride;
     int diff = 0;
+    unsigned my_bits = 0;
     if (active) {
-        const int pred = pred_outside ? outside_dc : S.dc_s[pred_s];   // jpeg_enc.h:834-835
-        diff = c[0] - pred;
-        const unsigned my_bits = block_bits(c, diff, hac, hdc);
+        const int pred = pred_s >= 0 ? S.dc_s[pred_s] : S.pred_dc[comp];   // jpeg_enc.h:834-835
+        diff = S.dc_s[s] - pred;
+        my_bits = block_bits(cz, diff, hac, hdc);
         S.bits_s[s] = my_bits;
         if (P.dbg_bits) P.dbg_bits[im.first_block + (unsigned long long)(m0 * G::BPM + s)] = my_bits;
         if (P.dbg_coefs) {
             int16_t* dst = P.dbg_coefs + (im.first_block + (unsigned long long)(m0 * G::BPM + s)) * 64ull;
-#pragma unroll
-            for (int i = 0; i < 64; ++i) dst[i] = (int16_t)c[i];
+            for (int i = 0; i < 64; ++i) dst[i] = cz[i];
         }
     }
-    cta_sync();
     unsigned T;
-    {
-        const unsigned v = t < nblk ? S.bits_s[t] : 0u;
-        const unsigned ex = cta_scan_excl(v, S.warp_tmp, T);
-        S.off_s[t] = ex;
-        if (t == 0) S.off_s[kBlocksPerTile] = T;
-    }
+    S.off_s[t] = cta_scan_excl(my_bits, S.warp_tmp, T);
     // Publish the tile's bit count NOW, before packing: successors can then resolve their
     // look-back while we are still busy (the look-back needs every predecessor's count).
     const unsigned cap_bits = (unsigned)P.win_words * 32u - 64u;
     if (t == 0) {
         st_flag64(P.desc_bits + g, (first_tile ? kStatusPrefix : kStatusAgg) | (unsigned long long)T);
+        S.off_s[kThreads] = T;
         S.n_groups = 1;
     }
     cta_sync();   // off_s visible
@@ -597,7 +605,7 @@ JG_DEV void encode_tile(const LaunchParams& P, const QuantSet& Q, Smem<LAYOUT, N
     }
     const int n_groups = S.n_groups;
 
-    // ---- 4..7 as a list of jobs with ONE pack call site ------------------------------------
+    // ---- 3..6 as a list of jobs with ONE pack call site ------------------------------------
     //   one group   : [ALL]
     //   many groups : [TAIL, COUNT_0..COUNT_{n-1}, EMIT_0..EMIT_{n-1}]   (walk 2 is repeated)
     const int n_jobs = n_groups == 1 ? 1 : 1 + 2 * n_groups;
@@ -617,23 +625,23 @@ JG_DEV void encode_tile(const LaunchParams& P, const QuantSet& Q, Smem<LAYOUT, N
         else if (is_tail) { b0 = nblk >= 2 ? nblk - 2 : 0; b1 = nblk; }   // only to learn the last 7 bits
         else { b0 = S.gstart[j]; b1 = S.gstart[j + 1]; }
 
-        // ---- 4. pack blocks [b0,b1) at their offsets relative to block b0 ----------------------
+        // ---- 3. pack blocks [b0,b1) at their offsets relative to block b0 ----------------------
         const unsigned base = S.off_s[b0];
         const unsigned tg = S.off_s[b1] - base;
-        for (int i = t; i < (int)(tg >> 5) + 3; i += kThreads) S.a[i] = 0u;
+        for (int i = t; i < (int)(tg >> 5) + 3; i += kThreads) win[i] = 0u;
         cta_sync();
-        if (active && s >= b0 && s < b1) block_pack(c, diff, hac, hdc, S.a, S.off_s[s] - base);
+        if (active && s >= b0 && s < b1) block_pack(cz, diff, hac, hdc, win, S.off_s[s] - base);
         cta_sync();
 
-        // ---- 5. chain #1: publish our last 7 bits, learn our bit offset --------------------------
+        // ---- 4. chain #1: publish our last 7 bits, learn our bit offset --------------------------
         if (is_all || is_tail) {
             if (t < 32) {
-                const unsigned tail = tg >= 7u ? peek_bits(S.a, tg - 7u, 7u) : peek_bits(S.a, 0u, tg);
+                const unsigned tail = tg >= 7u ? peek_bits(win, tg - 7u, 7u) : peek_bits(win, 0u, tg);
                 if (t == 0) st_flag64(P.desc_tail + g, kStatusAgg | (unsigned long long)tail);
-                unsigned long long excl = 0, nearest = 0, ptail = 0;
+                unsigned long long excl = 0, ptail = 0;
                 int timed_out = 0;
                 if (!first_tile) {
-                    excl = lookback(P.desc_bits, g, im.first_tile, kCountMask, &nearest, P.error, &timed_out);
+                    excl = lookback(P.desc_bits, g, im.first_tile, P.error, &timed_out);
                     if (t == 0 && !timed_out) st_flag64(P.desc_bits + g, kStatusPrefix | (excl + T));
                     // the byte we share with the predecessor needs its last bits
                     unsigned spins = 0;
@@ -659,98 +667,103 @@ JG_DEV void encode_tile(const LaunchParams& P, const QuantSet& Q, Smem<LAYOUT, N
             if (is_tail) continue;
         }
 
-        // ---- 6. geometry of the byte-aligned stream X = (k head bits) ++ (group bits) ---------------
+        // ---- 5. geometry of the byte-aligned stream X = (k head bits) ++ (group bits) ---------------
         const bool final_group = last_tile && j == n_groups - 1;
         unsigned n_bytes = (k + tg) >> 3, k_out = (k + tg) & 7u, hb_out = 0;
         if (k_out) {
             if (final_group) { n_bytes += 1; k_out = 0; }             // zero padding, jpeg_enc.h:1161-1164
-            else if (tg >= k_out) hb_out = peek_bits(S.a, tg - k_out, k_out);
-            else hb_out = ((hb << tg) | peek_bits(S.a, 0u, tg)) & ((1u << k_out) - 1u);
+            else if (tg >= k_out) hb_out = peek_bits(win, tg - k_out, k_out);
+            else hb_out = ((hb << tg) | peek_bits(win, 0u, tg)) & ((1u << k_out) - 1u);
         }
-        // per-thread chunk of X words; the odd stride keeps the shared-memory banks apart
-        const unsigned cw = (((n_bytes + 3u) / 4u + kThreads - 1u) / kThreads) | 1u;
-        const unsigned w_lo = (unsigned)t * cw;
-        unsigned cnt = 0;
-        for (unsigned i = w_lo; i < w_lo + cw && i * 4u < n_bytes; ++i) {
-            unsigned m = v_cmpeq4(xword(S.a, (int)i, k, hb), 0xffffffffu);
-            const unsigned valid = n_bytes - i * 4u;
-            if (valid < 4u) m &= 0xffffffffu << (8u * (4u - valid));
-            cnt += (unsigned)i_popc(m) >> 3;
-        }
-        unsigned ff_group;
-        const unsigned ff_ex = cta_scan_excl(cnt, S.warp_tmp, ff_group);
-        if (!is_emit) ff_tile += ff_group;
-
-        // publish the stuffed-byte count as soon as it is complete
-        if ((is_all || (is_count && j == n_groups - 1)) && t == 0)
-            st_flag64(P.desc_ff + g, (first_tile ? kStatusPrefix : kStatusAgg) | (unsigned long long)ff_tile);
-
-        if (is_count) {
-            if (j == n_groups - 1) { k = k0; hb = hb0; } else { k = k_out; hb = hb_out; }
-            continue;
-        }
-
-        // ---- 7a. emit stuffed bytes into sbuf (position independent) ----------------------------------
-        {
-            unsigned o = w_lo * 4u + ff_ex;
-            for (unsigned i = w_lo; i < w_lo + cw && i * 4u < n_bytes; ++i) {
-                const unsigned x = xword(S.a, (int)i, k, hb);
-                const unsigned valid = n_bytes - i * 4u < 4u ? n_bytes - i * 4u : 4u;
-                for (unsigned b = 0; b < valid; ++b) {
-                    const unsigned byte = (x >> (24u - 8u * b)) & 0xffu;
-                    S.sbuf[o++] = (uint8_t)byte;
-                    if (byte == 0xffu) S.sbuf[o++] = 0;               // jpeg_enc.h:634-638
-                }
+        // 0xFF bytes of the whole group (thread t takes words t, t+256, ...)
+        if (!is_emit) {
+            unsigned cnt = 0;
+            for (unsigned i = (unsigned)t; i * 4u < n_bytes; i += kThreads)
+                cnt += count_ff(xword(win, (int)i, k, hb), n_bytes - i * 4u < 4u ? n_bytes - i * 4u : 4u);
+            unsigned ff_group;
+            cta_scan_excl(cnt, S.warp_tmp, ff_group);
+            ff_tile += ff_group;
+            // publish the stuffed-byte count as soon as it is complete
+            if ((is_all || j == n_groups - 1) && t == 0)
+                st_flag64(P.desc_ff + g, (first_tile ? kStatusPrefix : kStatusAgg) | (unsigned long long)ff_tile);
+            if (is_count) {
+                if (j == n_groups - 1) { k = k0; hb = hb0; } else { k = k_out; hb = hb_out; }
+                continue;
             }
         }
-        // ---- 6b. chain #2 (after the emit, so predecessors had time to publish) ---------------------------
-        if (!have_pos) {
-            if (t < 32) {
-                unsigned long long excl = 0, nearest = 0;
-                int timed_out = 0;
-                if (!first_tile) {
-                    excl = lookback(P.desc_ff, g, im.first_tile, kCountMask, &nearest, P.error, &timed_out);
-                    if (t == 0 && !timed_out) st_flag64(P.desc_ff + g, kStatusPrefix | (excl + ff_tile));
-                }
-                if (t == 0) {
-                    S.ff_base = excl;
-                    S.abort = timed_out;
-                    if (timed_out) gmem_atomic_or(P.error, 1u);
-                }
-            }
-            cta_sync();   // also orders the sbuf writes above
-            if (S.abort) return;
-            pos = (bit_base >> 3) + S.ff_base;   // byte position of the tile's first owned byte
-            have_pos = true;
-        } else {
-            cta_sync();
-        }
 
-        // ---- 7b. copy out: bytes to the first 16B boundary, aligned 16B stores, tail bytes ------------------
-        const unsigned out_bytes = n_bytes + ff_group;
-        if (pos + out_bytes + (last_tile ? 2u : 0u) > im.out_cap) {
-            overflow = true;
-        } else {
-            uint8_t* dst = im.out + pos;
-            unsigned head = (16u - (unsigned)((size_t)dst & 15u)) & 15u;
-            if (head > out_bytes) head = out_bytes;
-            const unsigned nvec = (out_bytes - head) >> 4;
-            const unsigned tail0 = head + (nvec << 4);
-            const uint32_t* sw = reinterpret_cast<const uint32_t*>(S.sbuf);
-            if ((unsigned)t < head) dst[t] = S.sbuf[t];
-            uint4* dst4 = reinterpret_cast<uint4*>(dst + head);
-            for (unsigned i = (unsigned)t; i < nvec; i += kThreads) {
-                const unsigned o = head + (i << 4);
-                uint4 v;
-                v.x = word_at_byte(sw, o); v.y = word_at_byte(sw, o + 4u);
-                v.z = word_at_byte(sw, o + 8u); v.w = word_at_byte(sw, o + 12u);
-                dst4[i] = v;
+        // ---- 5b/6. stuffed bytes, one piece of kSubBytes unstuffed bytes at a time ------------------------
+        for (unsigned c0 = 0; c0 < n_bytes; c0 += kSubBytes) {
+            const unsigned nb = n_bytes - c0 < (unsigned)kSubBytes ? n_bytes - c0 : (unsigned)kSubBytes;
+            const unsigned nw = (nb + 3u) >> 2;
+            // contiguous per-thread chunks; the odd stride keeps the shared-memory banks apart
+            const unsigned cw = ((nw + kThreads - 1u) / kThreads) | 1u;
+            const unsigned w_lo = (unsigned)t * cw, w_hi = w_lo + cw < nw ? w_lo + cw : nw;
+            unsigned cnt = 0;
+            for (unsigned i = w_lo; i < w_hi; ++i)
+                cnt += count_ff(xword(win, (int)(c0 / 4u + i), k, hb), nb - i * 4u < 4u ? nb - i * 4u : 4u);
+            unsigned ff_piece;
+            const unsigned ff_ex = cta_scan_excl(cnt, S.warp_tmp, ff_piece);
+            {
+                unsigned o = w_lo * 4u + ff_ex;
+                for (unsigned i = w_lo; i < w_hi; ++i) {
+                    const unsigned x = xword(win, (int)(c0 / 4u + i), k, hb);
+                    const unsigned valid = nb - i * 4u < 4u ? nb - i * 4u : 4u;
+                    for (unsigned b = 0; b < valid; ++b) {
+                        const unsigned byte = (x >> (24u - 8u * b)) & 0xffu;
+                        S.sbuf[o++] = (uint8_t)byte;
+                        if (byte == 0xffu) S.sbuf[o++] = 0;               // jpeg_enc.h:634-638
+                    }
+                }
             }
-            if (tail0 + (unsigned)t < out_bytes) dst[tail0 + t] = S.sbuf[tail0 + t];
+            // chain #2 (after the first emit, so predecessors had time to publish)
+            if (!have_pos) {
+                if (t < 32) {
+                    unsigned long long excl = 0;
+                    int timed_out = 0;
+                    if (!first_tile) {
+                        excl = lookback(P.desc_ff, g, im.first_tile, P.error, &timed_out);
+                        if (t == 0 && !timed_out) st_flag64(P.desc_ff + g, kStatusPrefix | (excl + ff_tile));
+                    }
+                    if (t == 0) {
+                        S.ff_base = excl;
+                        S.abort = timed_out;
+                        if (timed_out) gmem_atomic_or(P.error, 1u);
+                    }
+                }
+                cta_sync();   // also orders the sbuf writes above
+                if (S.abort) return;
+                pos = (bit_base >> 3) + S.ff_base;   // byte position of the tile's first owned byte
+                have_pos = true;
+            } else {
+                cta_sync();
+            }
+            // copy out: bytes to the first 16B boundary, aligned 16B stores, tail bytes
+            const unsigned out_bytes = nb + ff_piece;
+            if (pos + out_bytes + (last_tile ? 2u : 0u) > im.out_cap) {
+                overflow = true;
+            } else {
+                uint8_t* dst = im.out + pos;
+                unsigned head = (16u - (unsigned)((size_t)dst & 15u)) & 15u;
+                if (head > out_bytes) head = out_bytes;
+                const unsigned nvec = (out_bytes - head) >> 4;
+                const unsigned tail0 = head + (nvec << 4);
+                const uint32_t* sw = reinterpret_cast<const uint32_t*>(S.sbuf);
+                if ((unsigned)t < head) dst[t] = S.sbuf[t];
+                uint4* dst4 = reinterpret_cast<uint4*>(dst + head);
+                for (unsigned i = (unsigned)t; i < nvec; i += kThreads) {
+                    const unsigned o = head + (i << 4);
+                    uint4 v;
+                    v.x = word_at_byte(sw, o); v.y = word_at_byte(sw, o + 4u);
+                    v.z = word_at_byte(sw, o + 8u); v.w = word_at_byte(sw, o + 12u);
+                    dst4[i] = v;
+                }
+                if (tail0 + (unsigned)t < out_bytes) dst[tail0 + t] = S.sbuf[tail0 + t];
+            }
+            pos += out_bytes;
+            cta_sync();   // sbuf is reused by the next piece, the window by the next group
         }
-        pos += out_bytes;
         k = k_out; hb = hb_out;
-        if (job + 1 < n_jobs) cta_sync();   // sbuf / window are reused by the next group
     }
     if (t == 0) {
         if (last_tile) {
@@ -765,7 +778,7 @@ JG_DEV void encode_tile(const LaunchParams& P, const QuantSet& Q, Smem<LAYOUT, N
 // the kernel
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT, int NC>
-JG_KERNEL(kThreads, 2)
+JG_KERNEL(kThreads, 3)
 void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTANT QuantSet Q)
 {
     JG_DYNAMIC_SMEM(smem_raw);
@@ -773,6 +786,18 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
     const int t = JG_TID;
     for (int i = t; i < 512; i += kThreads) (&S.huff_ac[0][0])[i] = (&P.huff->ac[0][0])[i];
     if (t < 32) (&S.huff_dc[0][0])[t] = (&P.huff->dc[0][0])[t];
+    LaneConst LC;
+    {
+        const int u = t & 7;
+        LC.zz_lo = 0; LC.zz_hi = 0;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            LC.pq_l[v] = Q.luma[8 * v + u];
+            LC.pq_c[v] = Q.chroma[8 * v + u];
+            const unsigned z = (unsigned)zz_of(8 * v + u);
+            if (v < 4) LC.zz_lo |= z << (8 * v); else LC.zz_hi |= z << (8 * (v - 4));
+        }
+    }
     for (;;) {
         cta_sync();   // everyone is done with the previous tile's shared state
         if (t == 0) {
@@ -782,7 +807,7 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
         cta_sync();
         const int g = S.tile;
         if (g >= P.n_tiles || S.abort) break;
-        encode_tile<LAYOUT, NC>(P, Q, S, g);
+        encode_tile<LAYOUT, NC>(P, S, LC, g);
     }
 }
 

@@ -13,9 +13,14 @@
 
 namespace jg {
 
-constexpr int kThreads = 192;
-constexpr int kBlocksPerTile = 192;
+constexpr int kThreads = 256;
+constexpr int kBlocksPerTile = 192;   // array bound; a tile holds mcus_per_tile(layout) * blocks-per-MCU <= 191 blocks
 constexpr int kWarps = kThreads / 32;
+constexpr int kSubBytes = 4096;       // stuffed output is produced in pieces of this many unstuffed bytes
+
+// MCUs per tile.  One extra "slot" per tile holds the MCU that precedes the tile (its DCs seed the
+// DC prediction), so slots = MCUs + 1 divides evenly among the CTA's lane groups.
+constexpr int mcus_per_tile(int layout) { return layout == LAYOUT_444 ? 63 : (layout == LAYOUT_420 ? 31 : 191); }
 constexpr int kWinWordsMax = 4096;   // 16 KB of unstuffed scan per group
 constexpr int kWinWordsMin = 64;     // must hold one worst-case block (1658 bits) + slack
 constexpr unsigned kSpinLimit = 1u << 24;

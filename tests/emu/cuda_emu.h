@@ -83,6 +83,13 @@ JG_DEV unsigned warp_shfl_up_u32(unsigned v, int d)
     const int lane = emu::tls.tid & 31;
     return (unsigned)warp_exchange(v, lane - d >= 0 ? lane - d : lane);
 }
+JG_DEV void warp_sync() { emu::warp_barrier(); }
+JG_DEV float warp_shfl_xor_f32(float v, int m)
+{
+    unsigned bits; memcpy(&bits, &v, 4);
+    bits = (unsigned)warp_exchange(bits, (emu::tls.tid & 31) ^ m);
+    float r; memcpy(&r, &bits, 4); return r;
+}
 JG_DEV unsigned long long warp_shfl_u64(unsigned long long v, int lane) { return warp_exchange(v, lane); }
 JG_DEV unsigned long long warp_shfl_xor_u64(unsigned long long v, int m)
 {

@@ -70,7 +70,7 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
     const int bpm = layout == LAYOUT_444 ? 3 : (layout == LAYOUT_420 ? 6 : 1);
     const int mcus_x = (w + mcu - 1) / mcu, mcus_y = (h + mcu - 1) / mcu;
     const int n_mcus = mcus_x * mcus_y;
-    const int M = kBlocksPerTile / bpm;
+    const int M = mcus_per_tile(layout);
     const int tiles = (n_mcus + M - 1) / M;
     if (stride == 0) stride = w * ncomp;
 
