@@ -57,6 +57,8 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ, "kernel_%d_%d.o" % (layout, nc))
         jobs.append((obj, [_nvcc()] + NVCC_FLAGS + ["-Xptxas", "-v", "-DJG_LAYOUT=%d" % layout, "-DJG_NC=%d" % nc,
                                                    "-c", os.path.join(CSRC, "jpeg_kernel_inst.cu"), "-o", obj]))
+    jobs.append((os.path.join(OBJ, "jpeg_stuff.o"), [_nvcc()] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", os.path.join(CSRC, "jpeg_stuff.cu"),
+                                                                 "-o", os.path.join(OBJ, "jpeg_stuff.o")]))
     for src in ("jpeg_gpu_api.cpp", "jpeg_host.cpp", "codecs_jpeg.cpp"):
         if not os.path.exists(os.path.join(CSRC, src)):
             continue

@@ -73,6 +73,7 @@ struct Device {
     int id = -1;
     int sm_count = 0;
     int ctas_per_sm[5] = {0, 0, 0, 0, 0};
+    int stuff_ctas_per_sm = 0;
     HuffLut* d_huff = nullptr;
     cudaStream_t stream = nullptr;   // used when the caller gives none
 };
@@ -95,6 +96,8 @@ bool init_device(Device& d, int id)
         JG_CUDA(kSpecs[i].prepare(&d.ctas_per_sm[i]));
         if (d.ctas_per_sm[i] < 1) { set_error("kernel spec %d does not fit an SM", i); return false; }
     }
+    JG_CUDA(stuff_prepare(&d.stuff_ctas_per_sm));
+    if (d.stuff_ctas_per_sm < 1) { set_error("stuffing kernel does not fit an SM"); return false; }
     HuffLut lut;
     build_huff_lut(&lut);
     JG_CUDA(cudaMalloc(&d.d_huff, sizeof(HuffLut)));
@@ -178,7 +181,10 @@ struct jpeg_gpu_plan {
         QuantSet quant;
         std::vector<int> items;
         int n_tiles = 0, tiles_per_image = 0;
-        size_t state_off = 0;     // offset of {ticket, error, pad, desc_bits[], desc_ff[]} in d_state
+        size_t state_off = 0;     // offset of {ticket, ticket2, error, pad, desc_bits[], desc_tail[], desc_ff[]} in d_state
+        size_t max_chunks = 0;    // upper bound of stuffing chunks (from the capacities)
+        unsigned long long* d_raw_bytes = nullptr;    // into d_aux
+        unsigned* d_first_chunk = nullptr;
         ImageDesc* d_images = nullptr;
         unsigned long long* d_scan_bytes = nullptr;   // into d_results
         unsigned* d_status = nullptr;
@@ -190,6 +196,8 @@ struct jpeg_gpu_plan {
     std::vector<Item> items;
     std::vector<Group> groups;
     uint8_t* d_arena = nullptr;      size_t arena_bytes = 0;
+    uint8_t* d_raw = nullptr;        // unstuffed scans, same layout as the arena
+    uint8_t* d_aux = nullptr;        // raw_bytes u64[n] + first_chunk u32[n + groups]
     uint8_t* d_pixels = nullptr;     size_t pixels_bytes = 0;
     uint8_t* d_state = nullptr;      size_t state_bytes = 0;    // zeroed before every run
     uint8_t* d_results = nullptr;    size_t results_bytes = 0;  // scan_bytes[n] u64, status[n] u32
@@ -268,7 +276,10 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
         g.n_tiles = tiles;
         g.tiles_per_image = uniform ? t0 : 0;
         g.state_off = state;
-        state += 16 + (size_t)tiles * 24;
+        size_t chunks = 1;
+        for (int idx : g.items) chunks += (p->items[idx].scan_cap + kChunkBytes - 1) / kChunkBytes;
+        g.max_chunks = chunks;
+        state += 16 + (size_t)tiles * 16 + chunks * 8;
         g.result_off = res_index;
         res_index += g.items.size();
     }
@@ -278,6 +289,8 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
     if (nres == 0) return true;
 
     JG_CUDA(cudaMalloc(&p->d_arena, std::max<size_t>(arena, 256)));
+    JG_CUDA(cudaMalloc(&p->d_raw, std::max<size_t>(arena, 256)));
+    JG_CUDA(cudaMalloc(&p->d_aux, nres * 8 + (nres + p->groups.size()) * 4 + 16));
     if (pixels) JG_CUDA(cudaMalloc(&p->d_pixels, pixels));
     JG_CUDA(cudaMalloc(&p->d_state, state));
     JG_CUDA(cudaMalloc(&p->d_results, p->results_bytes));
@@ -289,6 +302,8 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
         g.d_images = p->d_images + g.result_off;
         g.d_scan_bytes = reinterpret_cast<unsigned long long*>(p->d_results) + g.result_off;
         g.d_status = reinterpret_cast<unsigned*>(p->d_results + nres * 8) + g.result_off;
+        g.d_raw_bytes = reinterpret_cast<unsigned long long*>(p->d_aux) + g.result_off;
+        g.d_first_chunk = reinterpret_cast<unsigned*>(p->d_aux + nres * 8) + g.result_off + (&g - &p->groups[0]);
         int tile = 0;
         for (size_t k = 0; k < g.items.size(); ++k) {
             jpeg_gpu_plan::Item& it = p->items[g.items[k]];
@@ -296,6 +311,8 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
             else it.d_pixels = it.img.pixels;
             ImageDesc& d = p->h_images[g.result_off + k];
             d.px = it.d_pixels;
+            d.raw = p->d_raw + it.arena_off;
+            d.raw_cap = it.scan_cap;
             d.out = p->d_arena + it.arena_off;
             d.out_cap = it.scan_cap;
             d.first_block = it.first_block;
@@ -337,9 +354,12 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
         uint8_t* st = p->d_state + g.state_off;
         P.ticket = reinterpret_cast<unsigned*>(st);
         P.error = reinterpret_cast<unsigned*>(st + 4);
+        P.ticket2 = reinterpret_cast<unsigned*>(st + 8);
         P.desc_bits = reinterpret_cast<unsigned long long*>(st + 16);
         P.desc_tail = P.desc_bits + g.n_tiles;
         P.desc_ff = P.desc_tail + g.n_tiles;
+        P.raw_bytes = g.d_raw_bytes;
+        P.first_chunk = g.d_first_chunk;
         P.scan_bytes = g.d_scan_bytes;
         P.img_status = g.d_status;
         P.huff = dev.d_huff;
@@ -347,6 +367,7 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
         P.dbg_bits = p->dbg_bits;
         const int grid = std::min(g.n_tiles, dev.sm_count * dev.ctas_per_sm[g.spec]);
         JG_CUDA(kSpecs[g.spec].launch(grid, s, P, g.quant));
+        JG_CUDA(stuff_launch(dev.sm_count * dev.stuff_ctas_per_sm, s, P));
     }
     p->fetched_results = false;
     return true;
@@ -371,7 +392,7 @@ void plan_free(jpeg_gpu_plan* p)
 {
     if (!p) return;
     if (p->dev_index < (int)g_devices.size()) cudaSetDevice(g_devices[p->dev_index].id);
-    cudaFree(p->d_arena); cudaFree(p->d_pixels); cudaFree(p->d_state); cudaFree(p->d_results);
+    cudaFree(p->d_arena); cudaFree(p->d_raw); cudaFree(p->d_aux); cudaFree(p->d_pixels); cudaFree(p->d_state); cudaFree(p->d_results);
     cudaFree(p->d_images);
     if (p->h_results) cudaFreeHost(p->h_results);
     delete p;
@@ -508,7 +529,7 @@ int jpeg_gpu_plan_run(jpeg_gpu_plan* p, void* stream)
     return plan_run(p, s) ? 1 : 0;
 }
 
-int jpeg_gpu_plan_launches(const jpeg_gpu_plan* p) { return p ? (int)p->groups.size() : 0; }
+int jpeg_gpu_plan_launches(const jpeg_gpu_plan* p) { return p ? 3 * (int)p->groups.size() : 0; }   // encode + plan + stuff
 
 size_t jpeg_gpu_plan_num_blocks(const jpeg_gpu_plan* p) { return p ? p->n_blocks : 0; }
 

@@ -65,9 +65,8 @@ template <int LAYOUT, int NC>
 struct Smem {
     using G = Geo<LAYOUT>;
     static constexpr int SCRATCH = G::GROUPS * G::TILES * kTileFloats;
-    static constexpr int R1_WORDS = SCRATCH > kWinWordsMax + 8 ? SCRATCH : kWinWordsMax + 8;
-    alignas(16) uint32_t r1[R1_WORDS];                        // transform exchange tiles, then the unstuffed window
-    alignas(16) uint8_t sbuf[2 * kSubBytes + 64];             // stuffed bytes of one piece (worst case 2x)
+    alignas(16) uint32_t r1[SCRATCH];                         // transform exchange tiles
+    alignas(16) uint32_t win[kWinWordsMax + 8];               // the tile's packed bits; survives into the next iteration
     alignas(16) int16_t coef[kBlocksPerTile * kCoefStride];   // quantised coefficients, zigzag order
     uint32_t huff_ac[2][256];
     uint32_t huff_dc[2][16];
@@ -83,7 +82,6 @@ struct Smem {
     int n_groups;
     unsigned pred_tail;                   // last 7 bits of the preceding tile
     unsigned long long bit_base;          // exclusive bit offset of the tile in its image
-    unsigned long long ff_base;           // exclusive stuffed-FF count
 };
 
 // per-lane constants: the lane's column u = tid & 7 of every coefficient matrix it finishes
@@ -500,32 +498,105 @@ JG_DEV unsigned xword(const uint32_t* L, int i, unsigned k, unsigned hb)
     return (hi << (32u - k)) | (L[i] >> k);
 }
 
-// 0xFF bytes among the first `valid` (1..4) bytes of MSB-first word x
-JG_DEV unsigned count_ff(unsigned x, unsigned valid)
+// ------------------------------------------------------------------------------------------
+// a tile's identity (CTA-uniform, lives in registers across loop iterations)
+// ------------------------------------------------------------------------------------------
+struct TileCtx {
+    int g;                   // launch-wide tile index, -1 = none
+    int img_idx;
+    int first_tile_of_img;   // launch-wide index of the image's first tile
+    int nblk;
+    unsigned T;              // bits of the tile
+    bool first, last;
+    uint8_t* raw;            // the image's unstuffed scan
+    unsigned long long raw_cap;
+};
+
+// Copy bytes [0, n_bytes) of the byte-aligned stream X = (k head bits) ++ L to dst (any
+// alignment).  Every byte is written exactly once and nothing outside the range is touched:
+// the bytes up to the second 16-byte boundary and after the last one go out singly, the rest
+// as aligned 16-byte vectors (X words are MSB-first, memory wants them byte-swapped).
+JG_DEV void copy_stream_out(const uint32_t* L, unsigned k, unsigned hb, unsigned n_bytes, uint8_t* dst)
 {
-    unsigned m = v_cmpeq4(x, 0xffffffffu);
-    if (valid < 4u) m &= 0xffffffffu << (8u * (4u - valid));
-    return (unsigned)i_popc(m) >> 3;
+    const unsigned t = (unsigned)JG_TID;
+    const unsigned d = (unsigned)((size_t)dst & 15u);
+    uint8_t* A = dst - d;                         // 16-byte aligned; V = d pad bytes ++ X starts here
+    const unsigned total = d + n_bytes;
+    auto xbyte = [&](unsigned j) { return (xword(L, (int)(j >> 2), k, hb) >> (24u - 8u * (j & 3u))) & 0xffu; };
+    // head: V bytes [d, min(total, 32))
+    if (t >= d && t < 32u && t < total) A[t] = (uint8_t)xbyte(t - d);
+    // body: whole vectors v >= 2 (V byte 16v is X byte 16v - d, bit 8(16v-d) - k of L: never negative here)
+    const unsigned nvec = total >> 4;
+    for (unsigned v = 2u + t; v < nvec; v += kThreads) {
+        const unsigned p = 8u * (16u * v - d) - k;      // bit position in L of the vector's first bit
+        const unsigned i = p >> 5, sft = p & 31u;
+        uint32_t w[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) w[q] = L[i + q];
+        uint4 o;
+        o.x = bswap32(sft ? (w[0] << sft) | (w[1] >> (32u - sft)) : w[0]);
+        o.y = bswap32(sft ? (w[1] << sft) | (w[2] >> (32u - sft)) : w[1]);
+        o.z = bswap32(sft ? (w[2] << sft) | (w[3] >> (32u - sft)) : w[2]);
+        o.w = bswap32(sft ? (w[3] << sft) | (w[4] >> (32u - sft)) : w[3]);
+        *reinterpret_cast<uint4*>(A + 16u * v) = o;
+    }
+    // tail: V bytes [max(32, 16*nvec), total)
+    const unsigned tail0 = nvec >= 2u ? nvec << 4 : 32u;
+    if (tail0 + t < total) A[tail0 + t] = (uint8_t)xbyte(tail0 + t - d);
 }
 
-// byte offset `o` of a little-endian byte array held as aligned words
-JG_DEV unsigned word_at_byte(const uint32_t* w, unsigned o)
-{
-    const unsigned i = o >> 2, sh = (o & 3u) * 8u;
-    return sh ? (w[i] >> sh) | (w[i + 1] << (32u - sh)) : w[i];
-}
-
-// ------------------------------------------------------------------------------------------
-// one tile
-// ------------------------------------------------------------------------------------------
+// Learn the tile's bit offset (look-back over desc_bits) and the predecessor's last bits.
+// Executed by warp 0; results go to S.bit_base / S.pred_tail / S.abort.
 template <int LAYOUT, int NC>
-JG_DEV void encode_tile(const LaunchParams& P, Smem<LAYOUT, NC>& S, const LaneConst& LC, const int g)
+JG_DEV void chain_bits(const LaunchParams& P, Smem<LAYOUT, NC>& S, const TileCtx& c)
+{
+    const int t = JG_TID;
+    if (t < 32) {
+        unsigned long long excl = 0, ptail = 0;
+        int timed_out = 0;
+        if (!c.first) {
+            excl = lookback(P.desc_bits, c.g, c.first_tile_of_img, P.error, &timed_out);
+            if (t == 0 && !timed_out) st_flag64(P.desc_bits + c.g, kStatusPrefix | (excl + c.T));
+            unsigned spins = 0;      // the byte we share with the predecessor needs its last bits
+            while (!timed_out && ((ptail = ld_flag64(P.desc_tail + c.g - 1)) >> 62) == 0) {
+                if (++spins > kSpinLimit || ld_flag32(P.error) != 0u) timed_out = 1;
+                backoff();
+            }
+            timed_out = warp_ballot(timed_out) != 0u;
+        }
+        if (t == 0) {
+            S.bit_base = excl;
+            S.pred_tail = (unsigned)ptail & 0x7fu;
+            S.abort = timed_out;
+            if (timed_out) gmem_atomic_or(P.error, 1u);
+        }
+    }
+}
+
+// Write the window (tg bits) as the next piece of the image's unstuffed scan.
+// k/hb: bits of the first byte that precede the window (carry in); updated to the carry out.
+template <int LAYOUT, int NC>
+JG_DEV void flush_window(const LaunchParams& P, Smem<LAYOUT, NC>& S, const TileCtx& c, unsigned tg, bool final_piece,
+                         unsigned& k, unsigned& hb, unsigned long long& pos, bool& overflow)
+{
+    unsigned n_bytes = (k + tg) >> 3, k_out = (k + tg) & 7u, hb_out = 0;
+    if (k_out) {
+        if (final_piece) { n_bytes += 1; k_out = 0; }                 // zero padding, jpeg_enc.h:1161-1164
+        else if (tg >= k_out) hb_out = peek_bits(S.win, tg - k_out, k_out);
+        else hb_out = ((hb << tg) | peek_bits(S.win, 0u, tg)) & ((1u << k_out) - 1u);
+    }
+    if (pos + n_bytes > c.raw_cap) overflow = true;
+    else copy_stream_out(S.win, k, hb, n_bytes, c.raw + pos);
+    pos += n_bytes;
+    k = k_out; hb = hb_out;
+}
+
+// ---- front half of a tile: transform, size, scan, publish the bit count -----------------------
+template <int LAYOUT, int NC>
+JG_DEV void tile_front(const LaunchParams& P, Smem<LAYOUT, NC>& S, const LaneConst& LC, const int g, TileCtx& c, int& diff)
 {
     using G = Geo<LAYOUT>;
     const int t = JG_TID;
-    uint32_t* win = S.r1;
-
-    // ---- which image, which MCUs -------------------------------------------------------
     int img_idx;
     if (P.tiles_per_image > 0) {
         img_idx = g / P.tiles_per_image;
@@ -541,17 +612,15 @@ JG_DEV void encode_tile(const LaunchParams& P, Smem<LAYOUT, NC>& S, const LaneCo
     const int lt = g - im.first_tile;
     const int m0 = lt * G::M;
     const int nM = (im.n_mcus - m0 < G::M) ? im.n_mcus - m0 : G::M;
-    const int nblk = nM * G::BPM;
-    const bool first_tile = lt == 0, last_tile = lt == im.n_tiles - 1;
+    c.g = g; c.img_idx = img_idx; c.first_tile_of_img = im.first_tile; c.nblk = nM * G::BPM;
+    c.first = lt == 0; c.last = lt == im.n_tiles - 1; c.raw = im.raw; c.raw_cap = im.raw_cap;
 
-    // ---- 1. transform -------------------------------------------------------------------
     if (t < 4) S.pred_dc[t] = 0;          // jpeg_enc.h:1085-1087: predictors start at 0
     cta_sync();
     transform_tile<LAYOUT, NC>(S, im, m0, nM, LC);
-    cta_sync();   // coefficients + DCs complete; the exchange tiles are dead from here on
+    cta_sync();   // coefficients + DCs complete
 
-    // ---- 2. size: thread t owns block t of the tile (stream order) --------------------------
-    const bool active = t < nblk;
+    // thread t owns block t of the tile (stream order)
     const int s = t;
     int comp = 0, pred_s = s - 1;
     if (LAYOUT == LAYOUT_444) { comp = s % 3; pred_s = s - 3; }
@@ -561,15 +630,13 @@ JG_DEV void encode_tile(const LaunchParams& P, Smem<LAYOUT, NC>& S, const LaneCo
         pred_s = j >= 4 ? s - 6 : (j == 0 ? s - 3 : s - 1);      // Y00 follows the previous MCU's Y11
     }
     const int cls = comp ? 1 : 0;
-    const uint32_t* hac = S.huff_ac[cls];
-    const uint32_t* hdc = S.huff_dc[cls];
     const int16_t* cz = S.coef + s * kCoefStride;
-    int diff = 0;
     unsigned my_bits = 0;
-    if (active) {
+    diff = 0;
+    if (s < c.nblk) {
         const int pred = pred_s >= 0 ? S.dc_s[pred_s] : S.pred_dc[comp];   // jpeg_enc.h:834-835
         diff = S.dc_s[s] - pred;
-        my_bits = block_bits(cz, diff, hac, hdc);
+        my_bits = block_bits(cz, diff, S.huff_ac[cls], S.huff_dc[cls]);
         S.bits_s[s] = my_bits;
         if (P.dbg_bits) P.dbg_bits[im.first_block + (unsigned long long)(m0 * G::BPM + s)] = my_bits;
         if (P.dbg_coefs) {
@@ -579,203 +646,55 @@ JG_DEV void encode_tile(const LaunchParams& P, Smem<LAYOUT, NC>& S, const LaneCo
     }
     unsigned T;
     S.off_s[t] = cta_scan_excl(my_bits, S.warp_tmp, T);
-    // Publish the tile's bit count NOW, before packing: successors can then resolve their
-    // look-back while we are still busy (the look-back needs every predecessor's count).
-    const unsigned cap_bits = (unsigned)P.win_words * 32u - 64u;
+    c.T = T;
+    // Publish the tile's bit count NOW: it is consumed (by us and by every successor) one
+    // loop iteration later, so the look-back practically never waits.
     if (t == 0) {
-        st_flag64(P.desc_bits + g, (first_tile ? kStatusPrefix : kStatusAgg) | (unsigned long long)T);
+        st_flag64(P.desc_bits + g, (c.first ? kStatusPrefix : kStatusAgg) | (unsigned long long)T);
         S.off_s[kThreads] = T;
         S.n_groups = 1;
     }
     cta_sync();   // off_s visible
+    const unsigned cap_bits = (unsigned)P.win_words * 32u - 64u;
     if (T > cap_bits) {   // pathological tile: split into groups that fit the window
         if (t == 0) {
             int ng = 0;
             unsigned gbase = 0;
             S.gstart[0] = 0;
-            for (int b = 0; b < nblk; ++b) {
+            for (int b = 0; b < c.nblk; ++b) {
                 const unsigned end = S.off_s[b] + S.bits_s[b];
                 if (end - gbase > cap_bits) { ++ng; S.gstart[ng] = (uint16_t)b; gbase = S.off_s[b]; }
             }
             ++ng;
-            S.gstart[ng] = (uint16_t)nblk;
+            S.gstart[ng] = (uint16_t)c.nblk;
             S.n_groups = ng;
         }
         cta_sync();
     }
-    const int n_groups = S.n_groups;
+}
 
-    // ---- 3..6 as a list of jobs with ONE pack call site ------------------------------------
-    //   one group   : [ALL]
-    //   many groups : [TAIL, COUNT_0..COUNT_{n-1}, EMIT_0..EMIT_{n-1}]   (walk 2 is repeated)
-    const int n_jobs = n_groups == 1 ? 1 : 1 + 2 * n_groups;
-    unsigned long long bit_base = 0, pos = 0;
-    unsigned k0 = 0, hb0 = 0, k = 0, hb = 0;
-    unsigned ff_tile = 0;
-    bool overflow = false, have_pos = false;
-
-    for (int job = 0; job < n_jobs; ++job) {
-        const bool is_all = n_groups == 1;
-        const bool is_tail = !is_all && job == 0;
-        const bool is_count = !is_all && job >= 1 && job <= n_groups;
-        const bool is_emit = !is_all && job > n_groups;
-        const int j = is_all ? 0 : (is_count ? job - 1 : (is_emit ? job - 1 - n_groups : 0));
-        int b0, b1;
-        if (is_all) { b0 = 0; b1 = nblk; }
-        else if (is_tail) { b0 = nblk >= 2 ? nblk - 2 : 0; b1 = nblk; }   // only to learn the last 7 bits
-        else { b0 = S.gstart[j]; b1 = S.gstart[j + 1]; }
-
-        // ---- 3. pack blocks [b0,b1) at their offsets relative to block b0 ----------------------
-        const unsigned base = S.off_s[b0];
-        const unsigned tg = S.off_s[b1] - base;
-        for (int i = t; i < (int)(tg >> 5) + 3; i += kThreads) win[i] = 0u;
-        cta_sync();
-        if (active && s >= b0 && s < b1) block_pack(cz, diff, hac, hdc, win, S.off_s[s] - base);
-        cta_sync();
-
-        // ---- 4. chain #1: publish our last 7 bits, learn our bit offset --------------------------
-        if (is_all || is_tail) {
-            if (t < 32) {
-                const unsigned tail = tg >= 7u ? peek_bits(win, tg - 7u, 7u) : peek_bits(win, 0u, tg);
-                if (t == 0) st_flag64(P.desc_tail + g, kStatusAgg | (unsigned long long)tail);
-                unsigned long long excl = 0, ptail = 0;
-                int timed_out = 0;
-                if (!first_tile) {
-                    excl = lookback(P.desc_bits, g, im.first_tile, P.error, &timed_out);
-                    if (t == 0 && !timed_out) st_flag64(P.desc_bits + g, kStatusPrefix | (excl + T));
-                    // the byte we share with the predecessor needs its last bits
-                    unsigned spins = 0;
-                    while (!timed_out && ((ptail = ld_flag64(P.desc_tail + g - 1)) >> 62) == 0) {
-                        if (++spins > kSpinLimit || ld_flag32(P.error) != 0u) timed_out = 1;
-                        backoff();
-                    }
-                    timed_out = warp_ballot(timed_out) != 0u;
-                }
-                if (t == 0) {
-                    S.bit_base = excl;
-                    S.pred_tail = (unsigned)ptail & 0x7fu;
-                    S.abort = timed_out;
-                    if (timed_out) gmem_atomic_or(P.error, 1u);
-                }
-            }
-            cta_sync();
-            if (S.abort) return;
-            bit_base = S.bit_base;
-            k0 = (unsigned)(bit_base & 7ull);            // bits of our first byte owned by the predecessor
-            hb0 = S.pred_tail & ((1u << k0) - 1u);
-            k = k0; hb = hb0;
-            if (is_tail) continue;
-        }
-
-        // ---- 5. geometry of the byte-aligned stream X = (k head bits) ++ (group bits) ---------------
-        const bool final_group = last_tile && j == n_groups - 1;
-        unsigned n_bytes = (k + tg) >> 3, k_out = (k + tg) & 7u, hb_out = 0;
-        if (k_out) {
-            if (final_group) { n_bytes += 1; k_out = 0; }             // zero padding, jpeg_enc.h:1161-1164
-            else if (tg >= k_out) hb_out = peek_bits(win, tg - k_out, k_out);
-            else hb_out = ((hb << tg) | peek_bits(win, 0u, tg)) & ((1u << k_out) - 1u);
-        }
-        // 0xFF bytes of the whole group (thread t takes words t, t+256, ...)
-        if (!is_emit) {
-            unsigned cnt = 0;
-            for (unsigned i = (unsigned)t; i * 4u < n_bytes; i += kThreads)
-                cnt += count_ff(xword(win, (int)i, k, hb), n_bytes - i * 4u < 4u ? n_bytes - i * 4u : 4u);
-            unsigned ff_group;
-            cta_scan_excl(cnt, S.warp_tmp, ff_group);
-            ff_tile += ff_group;
-            // publish the stuffed-byte count as soon as it is complete
-            if ((is_all || j == n_groups - 1) && t == 0)
-                st_flag64(P.desc_ff + g, (first_tile ? kStatusPrefix : kStatusAgg) | (unsigned long long)ff_tile);
-            if (is_count) {
-                if (j == n_groups - 1) { k = k0; hb = hb0; } else { k = k_out; hb = hb_out; }
-                continue;
-            }
-        }
-
-        // ---- 5b/6. stuffed bytes, one piece of kSubBytes unstuffed bytes at a time ------------------------
-        for (unsigned c0 = 0; c0 < n_bytes; c0 += kSubBytes) {
-            const unsigned nb = n_bytes - c0 < (unsigned)kSubBytes ? n_bytes - c0 : (unsigned)kSubBytes;
-            const unsigned nw = (nb + 3u) >> 2;
-            // contiguous per-thread chunks; the odd stride keeps the shared-memory banks apart
-            const unsigned cw = ((nw + kThreads - 1u) / kThreads) | 1u;
-            const unsigned w_lo = (unsigned)t * cw, w_hi = w_lo + cw < nw ? w_lo + cw : nw;
-            unsigned cnt = 0;
-            for (unsigned i = w_lo; i < w_hi; ++i)
-                cnt += count_ff(xword(win, (int)(c0 / 4u + i), k, hb), nb - i * 4u < 4u ? nb - i * 4u : 4u);
-            unsigned ff_piece;
-            const unsigned ff_ex = cta_scan_excl(cnt, S.warp_tmp, ff_piece);
-            {
-                unsigned o = w_lo * 4u + ff_ex;
-                for (unsigned i = w_lo; i < w_hi; ++i) {
-                    const unsigned x = xword(win, (int)(c0 / 4u + i), k, hb);
-                    const unsigned valid = nb - i * 4u < 4u ? nb - i * 4u : 4u;
-                    for (unsigned b = 0; b < valid; ++b) {
-                        const unsigned byte = (x >> (24u - 8u * b)) & 0xffu;
-                        S.sbuf[o++] = (uint8_t)byte;
-                        if (byte == 0xffu) S.sbuf[o++] = 0;               // jpeg_enc.h:634-638
-                    }
-                }
-            }
-            // chain #2 (after the first emit, so predecessors had time to publish)
-            if (!have_pos) {
-                if (t < 32) {
-                    unsigned long long excl = 0;
-                    int timed_out = 0;
-                    if (!first_tile) {
-                        excl = lookback(P.desc_ff, g, im.first_tile, P.error, &timed_out);
-                        if (t == 0 && !timed_out) st_flag64(P.desc_ff + g, kStatusPrefix | (excl + ff_tile));
-                    }
-                    if (t == 0) {
-                        S.ff_base = excl;
-                        S.abort = timed_out;
-                        if (timed_out) gmem_atomic_or(P.error, 1u);
-                    }
-                }
-                cta_sync();   // also orders the sbuf writes above
-                if (S.abort) return;
-                pos = (bit_base >> 3) + S.ff_base;   // byte position of the tile's first owned byte
-                have_pos = true;
-            } else {
-                cta_sync();
-            }
-            // copy out: bytes to the first 16B boundary, aligned 16B stores, tail bytes
-            const unsigned out_bytes = nb + ff_piece;
-            if (pos + out_bytes + (last_tile ? 2u : 0u) > im.out_cap) {
-                overflow = true;
-            } else {
-                uint8_t* dst = im.out + pos;
-                unsigned head = (16u - (unsigned)((size_t)dst & 15u)) & 15u;
-                if (head > out_bytes) head = out_bytes;
-                const unsigned nvec = (out_bytes - head) >> 4;
-                const unsigned tail0 = head + (nvec << 4);
-                const uint32_t* sw = reinterpret_cast<const uint32_t*>(S.sbuf);
-                if ((unsigned)t < head) dst[t] = S.sbuf[t];
-                uint4* dst4 = reinterpret_cast<uint4*>(dst + head);
-                for (unsigned i = (unsigned)t; i < nvec; i += kThreads) {
-                    const unsigned o = head + (i << 4);
-                    uint4 v;
-                    v.x = word_at_byte(sw, o); v.y = word_at_byte(sw, o + 4u);
-                    v.z = word_at_byte(sw, o + 8u); v.w = word_at_byte(sw, o + 12u);
-                    dst4[i] = v;
-                }
-                if (tail0 + (unsigned)t < out_bytes) dst[tail0 + t] = S.sbuf[tail0 + t];
-            }
-            pos += out_bytes;
-            cta_sync();   // sbuf is reused by the next piece, the window by the next group
-        }
-        k = k_out; hb = hb_out;
+// ---- back half of a (single-window) tile, run one iteration later: offset + write -------------
+template <int LAYOUT, int NC>
+JG_DEV bool tile_back(const LaunchParams& P, Smem<LAYOUT, NC>& S, const TileCtx& c)
+{
+    chain_bits(P, S, c);
+    cta_sync();
+    if (S.abort) return false;
+    const unsigned long long bit_base = S.bit_base;
+    unsigned k = (unsigned)(bit_base & 7ull);          // bits of our first byte owned by the predecessor
+    unsigned hb = S.pred_tail & ((1u << k) - 1u);
+    unsigned long long pos = bit_base >> 3;
+    bool overflow = false;
+    flush_window(P, S, c, c.T, c.last, k, hb, pos, overflow);
+    if (JG_TID == 0) {
+        if (c.last) P.raw_bytes[c.img_idx] = pos;
+        if (overflow) gmem_atomic_or(P.img_status + c.img_idx, 1u);
     }
-    if (t == 0) {
-        if (last_tile) {
-            if (!overflow) { im.out[pos] = 0xFF; im.out[pos + 1] = 0xD9; }    // EOI, jpeg_enc.h:1166-1167
-            P.scan_bytes[img_idx] = pos + 2;
-        }
-        if (overflow) gmem_atomic_or(P.img_status + img_idx, 1u);
-    }
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------
-// the kernel
+// kernel 1: pixels -> unstuffed entropy-coded bits
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT, int NC>
 JG_KERNEL(kThreads, 3)
@@ -798,16 +717,77 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
             if (v < 4) LC.zz_lo |= z << (8 * v); else LC.zz_hi |= z << (8 * (v - 4));
         }
     }
+    TileCtx prev;
+    prev.g = -1;
     for (;;) {
-        cta_sync();   // everyone is done with the previous tile's shared state
+        cta_sync();   // everyone is done with the previous iteration's shared state
         if (t == 0) {
             S.tile = (int)gmem_atomic_add(P.ticket, 1u);
             S.abort = ld_flag32(P.error) != 0u;
         }
         cta_sync();
         const int g = S.tile;
-        if (g >= P.n_tiles || S.abort) break;
-        encode_tile<LAYOUT, NC>(P, S, LC, g);
+        const bool have = g < P.n_tiles;
+        if (S.abort) break;
+
+        // software pipeline: front of tile g, THEN the back of the tile packed last iteration
+        TileCtx cur;
+        cur.g = -1;
+        int diff = 0;
+        if (have) tile_front<LAYOUT, NC>(P, S, LC, g, cur, diff);
+        if (prev.g >= 0) {
+            if (!tile_back<LAYOUT, NC>(P, S, prev)) break;
+            prev.g = -1;
+        }
+        if (!have) break;
+
+        // pack.  One window: [ALL] (written out next iteration).  Several: [TAIL, GROUP_0..n-1]
+        // written out right away (walk 2 repeated per group; pathological content only).
+        const int n_groups = S.n_groups;
+        const int n_jobs = n_groups == 1 ? 1 : 1 + n_groups;
+        const int s = t;
+        const int cls = (LAYOUT == LAYOUT_444) ? (s % 3 != 0) : (LAYOUT == LAYOUT_420 ? (s % 6 >= 4) : 0);
+        unsigned k = 0, hb = 0;
+        unsigned long long pos = 0;
+        bool overflow = false;
+        cta_sync();   // the window is free again (tile_back has read it)
+        for (int job = 0; job < n_jobs; ++job) {
+            int b0 = 0, b1 = cur.nblk;
+            if (n_groups > 1) {
+                if (job == 0) b0 = cur.nblk >= 2 ? cur.nblk - 2 : 0;        // only to learn the last 7 bits
+                else { b0 = S.gstart[job - 1]; b1 = S.gstart[job]; }
+            }
+            const unsigned base = S.off_s[b0];
+            const unsigned tg = S.off_s[b1] - base;
+            for (int i = t; i < (int)(tg >> 5) + 8; i += kThreads) S.win[i] = 0u;
+            cta_sync();
+            if (s >= b0 && s < b1)
+                block_pack(S.coef + s * kCoefStride, diff, S.huff_ac[cls], S.huff_dc[cls], S.win, S.off_s[s] - base);
+            cta_sync();
+            if (job == 0 && t == 0) {
+                const unsigned tail = tg >= 7u ? peek_bits(S.win, tg - 7u, 7u) : peek_bits(S.win, 0u, tg);
+                st_flag64(P.desc_tail + g, kStatusAgg | (unsigned long long)tail);
+            }
+            if (n_groups == 1) break;               // deferred: tile_back() next iteration
+            if (job == 0) {
+                chain_bits(P, S, cur);
+                cta_sync();
+                if (S.abort) break;
+                k = (unsigned)(S.bit_base & 7ull);
+                hb = S.pred_tail & ((1u << k) - 1u);
+                pos = S.bit_base >> 3;
+            } else {
+                flush_window(P, S, cur, tg, cur.last && job == n_groups, k, hb, pos, overflow);
+                cta_sync();   // the window is reused by the next group
+            }
+        }
+        if (S.abort) break;
+        if (n_groups == 1) {
+            prev = cur;
+        } else if (t == 0) {
+            if (cur.last) P.raw_bytes[cur.img_idx] = pos;
+            if (overflow) gmem_atomic_or(P.img_status + cur.img_idx, 1u);
+        }
     }
 }
 

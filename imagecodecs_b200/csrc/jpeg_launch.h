@@ -16,7 +16,7 @@ namespace jg {
 constexpr int kThreads = 256;
 constexpr int kBlocksPerTile = 192;   // array bound; a tile holds mcus_per_tile(layout) * blocks-per-MCU <= 191 blocks
 constexpr int kWarps = kThreads / 32;
-constexpr int kSubBytes = 4096;       // stuffed output is produced in pieces of this many unstuffed bytes
+constexpr int kChunkBytes = 4096;     // unstuffed bytes one stuffing step handles (16 per thread)
 
 // MCUs per tile.  One extra "slot" per tile holds the MCU that precedes the tile (its DCs seed the
 // DC prediction), so slots = MCUs + 1 divides evenly among the CTA's lane groups.
@@ -31,7 +31,9 @@ constexpr unsigned long long kCountMask = (1ull << 62) - 1;  // descriptors: sta
 
 struct ImageDesc {
     const uint8_t* px;               // device pixels
+    uint8_t* raw;                    // device scratch: the image's entropy-coded bits BEFORE 0xFF00 stuffing
     uint8_t* out;                    // device destination of the entropy-coded segment (+EOI)
+    unsigned long long raw_cap;      // bytes available at `raw`
     unsigned long long out_cap;      // bytes available at `out`
     unsigned long long first_block;  // index of the image's first block in the debug dumps
     int w, h;
@@ -43,24 +45,30 @@ struct ImageDesc {
     int aligned4;    // px and stride are multiples of 4 (word loads allowed)
 };
 
+// One parameter block for the three kernels of a launch group:
+//   encode_tiles_kernel  pixels -> unstuffed bits (raw), bits chained over tiles
+//   plan_chunks_kernel   raw sizes -> chunk table of the stuffing pass
+//   stuff_kernel         raw -> final scan with 0xFF00 stuffing + EOI, bytes chained over chunks
 struct LaunchParams {
     const ImageDesc* images;
     int n_images;
     int n_tiles;
     int tiles_per_image;             // > 0 when every image of the launch has this many tiles
     int win_words;                   // window size actually used (<= kWinWordsMax)
-    unsigned* ticket;                // zeroed before the launch
-    unsigned long long* desc_bits;   // [n_tiles], zeroed before the launch: bits of the tile / inclusive prefix
-    unsigned long long* desc_tail;   // [n_tiles], zeroed before the launch: the tile's last 7 bits
-    unsigned long long* desc_ff;     // [n_tiles], zeroed before the launch
+    unsigned* ticket;                // zeroed before the launch (encode)
+    unsigned* ticket2;               // zeroed before the launch (stuff)
+    unsigned* error;                 // OUT: non-zero if a look-back timed out
+    unsigned long long* desc_bits;   // [n_tiles], zeroed: bits of the tile -> inclusive bit prefix
+    unsigned long long* desc_tail;   // [n_tiles], zeroed: the tile's last 7 bits
+    unsigned long long* desc_ff;     // [max_chunks], zeroed: 0xFF bytes of the chunk -> inclusive count
+    unsigned long long* raw_bytes;   // [n_images] bytes of unstuffed scan (encode -> plan/stuff)
+    unsigned* first_chunk;           // [n_images + 1] chunk table (plan -> stuff)
     unsigned long long* scan_bytes;  // [n_images] OUT: bytes of scan + EOI
     unsigned* img_status;            // [n_images] OUT: bit0 = capacity exceeded
-    unsigned* error;                 // OUT: non-zero if a look-back timed out
     const HuffLut* huff;
     int16_t* dbg_coefs;              // optional [blocks*64], zigzag order
     uint32_t* dbg_bits;              // optional [blocks]
 };
-
 
 #if !defined(JG_EMULATE)
 // one set per (layout, channels) specialisation; see jpeg_kernel_inst.cu
@@ -74,6 +82,10 @@ JG_DECLARE_SPEC(1, 3)
 JG_DECLARE_SPEC(1, 4)
 JG_DECLARE_SPEC(2, 1)
 #undef JG_DECLARE_SPEC
+// layout-independent second pass (jpeg_stuff.cu)
+size_t stuff_smem_bytes();
+cudaError_t stuff_prepare(int* ctas_per_sm);
+cudaError_t stuff_launch(int grid, cudaStream_t stream, const LaunchParams& P);
 #endif
 
 }  // namespace jg

@@ -46,6 +46,7 @@ JG_DEV float u8_to_f(unsigned v) { return (float)v; }
 JG_DEV int i_clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 JG_DEV int i_ffs(unsigned v) { return __builtin_ffs((int)v); }
 JG_DEV int i_popc(unsigned v) { return __builtin_popcount(v); }
+JG_DEV unsigned bswap32(unsigned v) { return __builtin_bswap32(v); }
 JG_DEV unsigned v_cmpeq4(unsigned a, unsigned b)
 {
     unsigned r = 0;

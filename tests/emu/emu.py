@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _SO = os.path.join(_HERE, "libjpeg_emu.so")
 _SRC = [os.path.join(_HERE, "emu_driver.cpp"), os.path.join(_HERE, "cuda_emu.h"),
+        os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_stuff.cuh"),
         os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_kernel.cuh"),
         os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_device.h"),
         os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_tables.h"),

@@ -1,10 +1,12 @@
-// tests/emu/emu_driver.cpp -- TEST INFRASTRUCTURE.  Runs the product's kernel source
-// (imagecodecs_b200/csrc/jpeg_kernel.cuh) on CPU threads through cuda_emu.h and exposes
-// one C function the CPU test-suite calls.  See cuda_emu.h for why this exists.
+// tests/emu/emu_driver.cpp -- TEST INFRASTRUCTURE.  Runs the product's kernel sources
+// (imagecodecs_b200/csrc/jpeg_kernel.cuh, jpeg_stuff.cuh) on CPU threads through cuda_emu.h and
+// exposes one C function the CPU test-suite calls.  See cuda_emu.h for why this exists.
 #define JG_EMULATE 1
-#include "jpeg_kernel.cuh"
+#include "jpeg_stuff.cuh"
 
 #include <stdlib.h>
+
+#include <functional>
 #include <vector>
 
 namespace jg {
@@ -20,9 +22,7 @@ using namespace jg;
 struct ThreadArg {
     emu::Cta* cta;
     int tid;
-    int layout, nc;
-    const LaunchParams* P;
-    const QuantSet* Q;
+    const std::function<void()>* body;
 };
 
 void* thread_main(void* p)
@@ -30,12 +30,33 @@ void* thread_main(void* p)
     ThreadArg* a = (ThreadArg*)p;
     emu::tls.tid = a->tid;
     emu::tls.cta = a->cta;
-    if (a->layout == LAYOUT_444 && a->nc == 3) encode_tiles_kernel<LAYOUT_444, 3>(*a->P, *a->Q);
-    else if (a->layout == LAYOUT_444 && a->nc == 4) encode_tiles_kernel<LAYOUT_444, 4>(*a->P, *a->Q);
-    else if (a->layout == LAYOUT_420 && a->nc == 3) encode_tiles_kernel<LAYOUT_420, 3>(*a->P, *a->Q);
-    else if (a->layout == LAYOUT_420 && a->nc == 4) encode_tiles_kernel<LAYOUT_420, 4>(*a->P, *a->Q);
-    else encode_tiles_kernel<LAYOUT_GRAY, 1>(*a->P, *a->Q);
+    (*a->body)();
     return nullptr;
+}
+
+// "launch" n_ctas CTAs of kThreads threads that all run concurrently
+void launch(int n_ctas, size_t smem_bytes, const std::function<void()>& body)
+{
+    std::vector<emu::Cta> ctas(n_ctas);
+    std::vector<ThreadArg> args((size_t)n_ctas * kThreads);
+    std::vector<pthread_t> th((size_t)n_ctas * kThreads);
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 256 * 1024);
+    for (int c = 0; c < n_ctas; ++c) {
+        emu::Cta& cta = ctas[c];
+        cta.nthreads = kThreads;
+        cta.smem = (unsigned char*)aligned_alloc(64, (smem_bytes + 63) / 64 * 64);
+        pthread_barrier_init(&cta.bar, nullptr, kThreads);
+        for (int wv = 0; wv < kThreads / 32; ++wv) pthread_barrier_init(&cta.wbar[wv], nullptr, 32);
+        for (int t = 0; t < kThreads; ++t) {
+            ThreadArg& a = args[(size_t)c * kThreads + t];
+            a.cta = &cta; a.tid = t; a.body = &body;
+            pthread_create(&th[(size_t)c * kThreads + t], &attr, thread_main, &a);
+        }
+    }
+    for (auto& x : th) pthread_join(x, nullptr);
+    for (auto& cta : ctas) free(cta.smem);
 }
 
 size_t smem_bytes(int layout, int nc)
@@ -74,10 +95,14 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
     const int tiles = (n_mcus + M - 1) / M;
     if (stride == 0) stride = w * ncomp;
 
+    const size_t raw_cap = (scan_cap + 255) / 256 * 256;
+    uint8_t* raw = (uint8_t*)aligned_alloc(256, raw_cap * n_images);
     std::vector<ImageDesc> imgs(n_images);
     for (int i = 0; i < n_images; ++i) {
         ImageDesc& d = imgs[i];
         d.px = pixels + (size_t)i * stride * h;
+        d.raw = raw + (size_t)i * raw_cap;
+        d.raw_cap = scan_cap;
         d.out = scan_out + (size_t)i * scan_cap;
         d.out_cap = scan_cap;
         d.first_block = (unsigned long long)i * n_mcus * bpm;
@@ -86,40 +111,33 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
         d.aligned4 = ((size_t)d.px % 4 == 0) && (stride % 4 == 0);
     }
     const int n_tiles = tiles * n_images;
-    std::vector<unsigned long long> desc_bits(n_tiles, 0), desc_tail(n_tiles, 0), desc_ff(n_tiles, 0);
-    unsigned ticket = 0, error = 0;
+    const size_t max_chunks = (size_t)n_images * ((scan_cap + kChunkBytes - 1) / kChunkBytes) + 1;
+    std::vector<unsigned long long> desc_bits(n_tiles, 0), desc_tail(n_tiles, 0), desc_ff(max_chunks, 0), raw_bytes(n_images, 0);
+    std::vector<unsigned> first_chunk(n_images + 1, 0);
+    unsigned ticket = 0, ticket2 = 0, error = 0;
     for (int i = 0; i < n_images; ++i) { scan_bytes[i] = 0; img_status[i] = 0; }
 
     LaunchParams P;
     P.images = imgs.data(); P.n_images = n_images; P.n_tiles = n_tiles;
     P.tiles_per_image = (n_images % 2) ? tiles : 0;   // exercise both tile->image paths
     P.win_words = win_words ? win_words : kWinWordsMax;
-    P.ticket = &ticket; P.desc_bits = desc_bits.data(); P.desc_tail = desc_tail.data(); P.desc_ff = desc_ff.data();
-    P.scan_bytes = scan_bytes; P.img_status = img_status; P.error = &error; P.huff = &lut;
+    P.ticket = &ticket; P.ticket2 = &ticket2; P.error = &error;
+    P.desc_bits = desc_bits.data(); P.desc_tail = desc_tail.data(); P.desc_ff = desc_ff.data();
+    P.raw_bytes = raw_bytes.data(); P.first_chunk = first_chunk.data();
+    P.scan_bytes = scan_bytes; P.img_status = img_status; P.huff = &lut;
     P.dbg_coefs = dbg_coefs; P.dbg_bits = dbg_bits;
 
-    if (n_ctas > n_tiles) n_ctas = n_tiles;
-    std::vector<emu::Cta> ctas(n_ctas);
-    std::vector<ThreadArg> args((size_t)n_ctas * kThreads);
-    std::vector<pthread_t> th((size_t)n_ctas * kThreads);
-    const size_t sb = smem_bytes(layout, ncomp);
-    pthread_attr_t attr;
-    pthread_attr_init(&attr);
-    pthread_attr_setstacksize(&attr, 256 * 1024);
-    for (int c = 0; c < n_ctas; ++c) {
-        emu::Cta& cta = ctas[c];
-        cta.nthreads = kThreads;
-        cta.smem = (unsigned char*)aligned_alloc(64, (sb + 63) / 64 * 64);
-        pthread_barrier_init(&cta.bar, nullptr, kThreads);
-        for (int wv = 0; wv < kThreads / 32; ++wv) pthread_barrier_init(&cta.wbar[wv], nullptr, 32);
-        for (int t = 0; t < kThreads; ++t) {
-            ThreadArg& a = args[(size_t)c * kThreads + t];
-            a.cta = &cta; a.tid = t; a.layout = layout; a.nc = ncomp; a.P = &P; a.Q = &Q;
-            pthread_create(&th[(size_t)c * kThreads + t], &attr, thread_main, &a);
-        }
-    }
-    for (auto& x : th) pthread_join(x, nullptr);
-    for (auto& cta : ctas) free(cta.smem);
+    const int nc = ncomp;
+    launch(n_ctas > n_tiles ? n_tiles : n_ctas, smem_bytes(layout, nc), [&] {
+        if (layout == LAYOUT_444 && nc == 3) encode_tiles_kernel<LAYOUT_444, 3>(P, Q);
+        else if (layout == LAYOUT_444 && nc == 4) encode_tiles_kernel<LAYOUT_444, 4>(P, Q);
+        else if (layout == LAYOUT_420 && nc == 3) encode_tiles_kernel<LAYOUT_420, 3>(P, Q);
+        else if (layout == LAYOUT_420 && nc == 4) encode_tiles_kernel<LAYOUT_420, 4>(P, Q);
+        else encode_tiles_kernel<LAYOUT_GRAY, 1>(P, Q);
+    });
+    if (!error) launch(1, sizeof(StuffSmem), [&] { plan_chunks_kernel(P); });
+    if (!error) launch(n_ctas, sizeof(StuffSmem), [&] { stuff_kernel(P); });
+    free(raw);
     return (int)error;
 }
 }
