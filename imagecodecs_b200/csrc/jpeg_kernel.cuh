@@ -20,23 +20,27 @@
 //                 runs the AAN row pass (:668-709), exchanges the 8x8 through a padded
 //                 shared-memory tile, runs the column pass (:718-759), quantises (:808-816)
 //                 and scatters int16 coefficients to shared memory in zigzag order.
-//   2. size       one thread per block walks its 63 AC coefficients: bits of the block
-//                 (P5-P7 of SURVEY 8a); CTA exclusive scan in stream order; the tile's bit
-//                 count is published at once.
-//   3. pack       second walk: every thread ORs/stores its codes at its exact bit offset of the
-//                 tile window in shared memory.
-//   4. chain #1   decoupled look-back over tiles: exclusive BIT offset of the tile in its
-//                 image; the predecessor's last 7 bits complete the byte the two tiles share.
-//   5. stuff      count the 0xFF bytes this tile owns, publish, emit 0xFF00 (jpeg_enc.h:634-638)
-//                 into shared memory, THEN look back over the counts (chain #2): the stuffed
-//                 BYTE offset.  Publishing early and consuming late hides the chain latency.
-//   6. write      coalesced copy to the image's scan; the last tile pads with zero bits
-//                 (jpeg_enc.h:1161-1164) and appends EOI (:1166-1167).
-// HBM traffic: every pixel read once (+1/63 for the predecessor slot), every output byte
-// written once, three 8-byte descriptors per tile.
+//   2. entropy    warp-cooperative, one pass (P5-P8 of SURVEY 8a).  A warp owns 24 consecutive
+//                 blocks; four at a time it compacts their nonzero coefficients (+ DC + EOB) into
+//                 a dense symbol queue, then codes 32 symbols per round with every lane busy:
+//                 category / run / Huffman lookup, warp scan of the code lengths, atomicOr of the
+//                 bits into the warp's own region.  No per-block size walk, no divergence between
+//                 sparse and dense blocks.
+//   3. publish    sum of the 8 warp bit counts = the tile's bit count, published at once.
+//   4. compact    (after the previous tile's write-out, below) the 8 regions are shifted into
+//                 the tile window; its last 7 bits are published for the successor.
+//   5. chain      ONE LOOP ITERATION LATER: decoupled look-back over the tiles' bit counts gives
+//                 the exclusive BIT offset of the tile in its image; the predecessor's last 7
+//                 bits complete the byte the two tiles share.  Because the counts were published
+//                 a whole iteration earlier the look-back practically never waits.
+//   6. write      the window goes to the image's UNSTUFFED scan (every byte written once, by the
+//                 tile that holds its last bit); the last tile pads with zero bits
+//                 (jpeg_enc.h:1161-1164).  0xFF00 stuffing + EOI are the second pass (jpeg_stuff.cuh).
+// HBM traffic of this kernel: every pixel read once (+1/63 for the predecessor slot), the
+// unstuffed scan written once, two 8-byte descriptors per tile.
 //
-// A tile whose bits do not fit the shared-memory window (pathological content) is processed
-// as several "groups" of blocks with the pack walk repeated; same bytes, lower speed.
+// A tile whose bits overflow a warp region or the window (pathological content) is redone in
+// six groups of 32 blocks; same bytes, lower speed.
 #pragma once
 #include "jpeg_device.h"
 #include "jpeg_launch.h"
@@ -45,7 +49,10 @@
 namespace jg {
 
 constexpr int kTileFloats = 72;   // one 8x8 float tile with rows padded to 9 (bank-conflict free both ways)
-constexpr int kCoefStride = 66;   // int16 per block in shared memory (33 words: conflict-free block walks)
+constexpr int kCoefStride = 72;   // int16 per block in shared memory (144 B: 16-byte aligned 8-coefficient reads)
+constexpr int kRegionWords = kWinWordsMax / kWarps;   // bits a warp may emit for its 24 blocks before the tile goes slow
+constexpr int kQueueEntries = 288;                     // 32 lanes x (8 coefficients + EOB)
+constexpr int kWarpBlocks = 24;                        // blocks per warp (8 x 24 = 192)
 
 template <int LAYOUT>
 struct Geo {
@@ -65,21 +72,19 @@ template <int LAYOUT, int NC>
 struct Smem {
     using G = Geo<LAYOUT>;
     static constexpr int SCRATCH = G::GROUPS * G::TILES * kTileFloats;
-    alignas(16) uint32_t r1[SCRATCH];                         // transform exchange tiles
+    static constexpr int ENTROPY = kWarps * (kRegionWords + kQueueEntries);
+    static constexpr int R1_WORDS = SCRATCH > ENTROPY ? SCRATCH : ENTROPY;
+    alignas(16) uint32_t r1[R1_WORDS];                        // transform exchange tiles; then per-warp regions + symbol queues
     alignas(16) uint32_t win[kWinWordsMax + 8];               // the tile's packed bits; survives into the next iteration
     alignas(16) int16_t coef[kBlocksPerTile * kCoefStride];   // quantised coefficients, zigzag order
-    uint32_t huff_ac[2][256];
-    uint32_t huff_dc[2][16];
-    uint32_t bits_s[kBlocksPerTile];      // bits per block, stream order
-    uint32_t off_s[kThreads + 1];         // exclusive scan of bits_s; entries >= nblk hold the total
-    int dc_s[kBlocksPerTile];             // quantised DC per block, stream order
+    uint32_t huff[2][272];                // [class][(run<<4)|cat] AC, [class][256+cat] DC; entry = code<<8 | length
     int pred_dc[4];                       // DCs of the MCU preceding the tile, per component
-    uint16_t gstart[kBlocksPerTile + 2];  // group boundaries (block indices)
+    uint32_t warp_bits[kWarps];           // bits emitted by each warp
     uint32_t warp_tmp[kWarps];
     // tile-wide scalars (written by one thread, read after a barrier)
     int tile;
     int abort;
-    int n_groups;
+    int slow;                             // a warp region overflowed: redo the tile in groups
     unsigned pred_tail;                   // last 7 bits of the preceding tile
     unsigned long long bit_base;          // exclusive bit offset of the tile in its image
 };
@@ -205,7 +210,6 @@ JG_DEV void column_pass(Smem<LAYOUT, NC>& S, const float* tile, int u, bool chro
             const int k = quantise(c[v], chroma ? LC.pq_c[v] : LC.pq_l[v]);
             const unsigned zz = ((v < 4 ? LC.zz_lo : LC.zz_hi) >> (8 * (v & 3))) & 0xffu;
             dst[zz] = (int16_t)k;
-            if (v == 0 && u == 0) S.dc_s[blk] = k;
         }
     } else if (u == 0 && pred_dc != nullptr) {
         *pred_dc = quantise(c[0], chroma ? LC.pq_c[0] : LC.pq_l[0]);
@@ -335,89 +339,176 @@ JG_DEV unsigned amplitude(int v, unsigned cat)  // jpeg_enc.h:601-609: (v<0 ? v-
     return (unsigned)(v + (v >> 31)) & ((1u << cat) - 1u);
 }
 
-// walk 1: size only
-JG_DEV unsigned block_bits(const int16_t* cz, int diff, const uint32_t* ac, const uint32_t* dc)
+// Stream-order predecessor of block `blk` with the same component, or -1 if it lies before the tile.
+template <int LAYOUT>
+JG_DEV void block_kind(int blk, int& comp, int& pred_blk)
 {
-    const unsigned zrl_len = ac[0xF0] & 0xffu;
-    const unsigned dcat = diff ? category(diff) : 0u;
-    unsigned n = (dc[dcat] & 0xffu) + dcat;
-    int last = 0;
-#pragma unroll
-    for (int k = 1; k < 64; ++k) {
-        const int v = cz[k];
-        if (v != 0) {
-            unsigned run = (unsigned)(k - 1 - last);
-            last = k;
-            n += (run >> 4) * zrl_len;   // one ZRL per 16 zeros (jpeg_enc.h:863-867)
-            run &= 15u;
-            const unsigned cat = category(v);
-            n += (ac[(run << 4) | cat] & 0xffu) + cat;
-        }
-    }
-    if (last != 63) n += ac[0] & 0xffu;  // EOB (jpeg_enc.h:884-887)
-    return n;
+    if (LAYOUT == LAYOUT_444) { comp = blk % 3; pred_blk = blk - 3; }
+    else if (LAYOUT == LAYOUT_420) {
+        const int j = blk % 6;
+        comp = j < 4 ? 0 : j - 3;
+        pred_blk = j >= 4 ? blk - 6 : (j == 0 ? blk - 3 : blk - 1);     // Y00 follows the previous MCU's Y11
+    } else { comp = 0; pred_blk = blk - 1; }
 }
 
-// MSB-first bit writer into a shared-memory word array that several threads fill
-// concurrently: a thread's first and last (partial) words are OR-ed atomically, the
-// words in between belong to it alone.  Replaces the serial cursor of jpeg_enc.h:613-643.
-struct BitPacker {
-    uint32_t* buf;
-    unsigned long long acc;  // pending bits, left-aligned
-    int fill;                // bits pending in acc (including the foreign bits of the head word)
-    int wi;                  // index of the word `acc`'s top half goes to
-    bool head;
-
-    JG_DEV void init(uint32_t* b, unsigned bitpos)
-    {
-        buf = b; acc = 0; fill = (int)(bitpos & 31u); wi = (int)(bitpos >> 5); head = true;
-    }
-    JG_DEV void flush()
-    {
-        const unsigned w = (unsigned)(acc >> 32);
-        if (head) { smem_atomic_or(buf + wi, w); head = false; }
-        else buf[wi] = w;
-        ++wi; acc <<= 32; fill -= 32;
-    }
-    JG_DEV void put(unsigned val, unsigned len)  // 1 <= len <= 26, val < 2^len
-    {
-        acc |= (unsigned long long)val << (64 - fill - (int)len);
-        fill += (int)len;
-        if (fill >= 32) flush();
-    }
-    JG_DEV void finish()
-    {
-        if (fill > 0) smem_atomic_or(buf + wi, (unsigned)(acc >> 32));
-    }
-};
-
-// walk 2: emit the block's bits at `bitpos` of `buf`
-JG_DEV void block_pack(const int16_t* cz, int diff, const uint32_t* ac, const uint32_t* dc, uint32_t* buf, unsigned bitpos)
+// One warp codes blocks [first, end) (at most 24) into `region` (zeroed, MSB-first words).
+// Symbol queue entry: value<<16 | EOB<<15 | DC<<14 | chroma<<13 | block-in-warp<<8 | zigzag position.
+// Returns the bits emitted; sets `overflow` if they did not fit region_words (the count stays right).
+template <int LAYOUT, int NC>
+JG_DEV unsigned encode_blocks_warp(const LaunchParams& P, Smem<LAYOUT, NC>& S, int first, int end, uint32_t* region,
+                                   unsigned region_words, uint32_t* queue, unsigned long long dbg_base, bool& overflow)
 {
-    BitPacker bp;
-    bp.init(buf, bitpos);
-    const unsigned zrl = ac[0xF0];
-    {
-        const unsigned cat = diff ? category(diff) : 0u;
-        const unsigned e = dc[cat];
-        const unsigned amp = diff ? amplitude(diff, cat) : 0u;
-        bp.put(((e >> 8) << cat) | amp, (e & 0xffu) + cat);
-    }
-    int last = 0;
-#pragma unroll
-    for (int k = 1; k < 64; ++k) {
-        const int v = cz[k];
-        if (v != 0) {
-            unsigned run = (unsigned)(k - 1 - last);
-            last = k;
-            while (run >= 16u) { bp.put(zrl >> 8, zrl & 0xffu); run -= 16u; }
-            const unsigned cat = category(v);
-            const unsigned e = ac[(run << 4) | cat];
-            bp.put(((e >> 8) << cat) | amplitude(v, cat), (e & 0xffu) + cat);
+    const int lane = JG_TID & 31, L = lane & 7, b4 = lane >> 3;
+    unsigned carry = 0;
+#pragma unroll 1
+    for (int b0 = first; b0 < end; b0 += 4) {
+        const int blk = b0 + b4;
+        const bool valid = blk < end;
+        // ---- compaction: my 8 coefficients (zigzag positions 8L..8L+7 of block blk) -----------------
+        uint4 w = {0u, 0u, 0u, 0u};
+        int comp = 0, pred_blk = -1;
+        if (valid) {
+            w = *reinterpret_cast<const uint4*>(S.coef + blk * kCoefStride + 8 * L);
+            block_kind<LAYOUT>(blk, comp, pred_blk);
         }
+        const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+        unsigned m8 = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (ww[q] & 0xffffu) m8 |= 1u << (2 * q);
+            if (ww[q] >> 16) m8 |= 2u << (2 * q);
+        }
+        int diff = 0;
+        if (valid && L == 0) {                              // DC: always coded, as a difference (jpeg_enc.h:834-844)
+            const int pred = pred_blk >= 0 ? (int)S.coef[pred_blk * kCoefStride] : S.pred_dc[comp];
+            diff = (int)(int16_t)(ww[0] & 0xffffu) - pred;
+            m8 |= 1u;
+        }
+        const unsigned eob = (valid && L == 7 && (ww[3] >> 16) == 0u) ? 1u : 0u;   // jpeg_enc.h:884-887
+        const unsigned cnt = (unsigned)i_popc(m8) + eob;
+        unsigned inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned n = warp_shfl_up_u32(inc, d);
+            if (lane >= d) inc += n;
+        }
+        const unsigned N = warp_shfl_u32(inc, 31);
+        unsigned at = inc - cnt;
+        const unsigned common = (comp ? 1u << 13 : 0u) | ((unsigned)(blk - first) << 8) | (unsigned)(8 * L);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (m8 & (1u << i)) {
+                int val = (int)(int16_t)((i & 1) ? (ww[i >> 1] >> 16) : (ww[i >> 1] & 0xffffu));
+                unsigned e = common + (unsigned)i;
+                if (i == 0 && L == 0) { val = diff; e |= 1u << 14; }
+                queue[at++] = ((unsigned)val << 16) | e;
+            }
+        }
+        if (eob) queue[at] = (1u << 15) | common | 7u;
+        warp_sync();
+
+        // ---- 32 symbols per round -------------------------------------------------------------------
+#pragma unroll 1
+        for (unsigned j0 = 0; j0 < N; j0 += 32) {
+            const unsigned j = j0 + (unsigned)lane;
+            unsigned long long sym = 0;
+            unsigned len = 0;
+            if (j < N) {
+                const unsigned e = queue[j];
+                const int v = (int)e >> 16;
+                const unsigned cls = (e >> 13) & 1u;
+                unsigned idx = 0, cat = 0, nz = 0;
+                if (!(e & 0x8000u)) {
+                    cat = category(v);                              // 0 for a zero DC difference
+                    if (e & 0x4000u) idx = 256u + cat;
+                    else {
+                        const unsigned run = (e & 63u) - (queue[j - 1] & 63u) - 1u;   // zeros since the previous symbol of the block
+                        nz = run >> 4;                              // one ZRL per 16 zeros (jpeg_enc.h:863-867)
+                        idx = ((run & 15u) << 4) | cat;
+                    }
+                }
+                const unsigned h = S.huff[cls][idx];
+                sym = (unsigned long long)(((h >> 8) << cat) | amplitude(v, cat));
+                len = (h & 0xffu) + cat;
+                if (nz) {
+                    const unsigned z = S.huff[cls][0xF0];
+                    for (unsigned q = 0; q < nz; ++q) { sym |= (unsigned long long)(z >> 8) << len; len += z & 0xffu; }
+                }
+                if (P.dbg_bits) gmem_atomic_add(P.dbg_bits + dbg_base + (unsigned long long)(first + (int)((e >> 8) & 31u)), len);
+            }
+            unsigned endb = len;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned n = warp_shfl_up_u32(endb, d);
+                if (lane >= d) endb += n;
+            }
+            const unsigned tot = warp_shfl_u32(endb, 31);
+            if (len) {
+                const unsigned start = carry + endb - len;
+                const unsigned long long al = sym << (64u - len);
+                const unsigned hi = (unsigned)(al >> 32), lo = (unsigned)al;
+                const unsigned sh = start & 31u, wi = start >> 5;
+                if (wi + 2u < region_words) {
+                    const unsigned w0 = hi >> sh;
+                    const unsigned w1 = sh ? (hi << (32u - sh)) | (lo >> sh) : lo;
+                    const unsigned w2 = sh ? lo << (32u - sh) : 0u;
+                    if (w0) smem_atomic_or(region + wi, w0);
+                    if (w1) smem_atomic_or(region + wi + 1, w1);
+                    if (w2) smem_atomic_or(region + wi + 2, w2);
+                } else overflow = true;
+            }
+            carry += tot;
+        }
+        warp_sync();   // the queue is rewritten by the next four blocks
     }
-    if (last != 63) { const unsigned e = ac[0]; bp.put(e >> 8, e & 0xffu); }
-    bp.finish();
+    return carry;
+}
+
+// Code blocks [b_lo, b_hi) of the tile, `per_warp` consecutive blocks per warp, into the warps'
+// regions.  Returns the bits of the range (CTA-uniform, after a barrier); raises S.slow if a
+// region overflowed (the bit count is right even then).
+template <int LAYOUT, int NC>
+JG_DEV unsigned encode_range(const LaunchParams& P, Smem<LAYOUT, NC>& S, int b_lo, int b_hi, int per_warp,
+                             unsigned long long dbg_base)
+{
+    const int t = JG_TID, lane = t & 31, wid = t >> 5;
+    uint32_t* region = S.r1 + wid * kRegionWords;
+    uint32_t* queue = S.r1 + kWarps * kRegionWords + wid * kQueueEntries;
+    for (int i = lane; i < kRegionWords; i += 32) region[i] = 0u;
+    warp_sync();
+    const int first = b_lo + wid * per_warp;
+    const int end = first + per_warp < b_hi ? first + per_warp : b_hi;
+    bool overflow = false;
+    const unsigned bits = first < end ? encode_blocks_warp<LAYOUT, NC>(P, S, first, end, region, kRegionWords, queue, dbg_base, overflow) : 0u;
+    if (lane == 0) S.warp_bits[wid] = bits;
+    if (overflow) S.slow = 1;
+    cta_sync();
+    unsigned total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) total += S.warp_bits[w];
+    return total;
+}
+
+// Shift the 8 warp regions (S.warp_bits[w] bits each) into the window, back to back.
+// Contains barriers; the window must not be in use.
+template <int LAYOUT, int NC>
+JG_DEV void compact_regions(Smem<LAYOUT, NC>& S, unsigned total_bits)
+{
+    const int t = JG_TID, lane = t & 31, wid = t >> 5;
+    for (int i = t; i < (int)(total_bits >> 5) + 8; i += kThreads) S.win[i] = 0u;
+    cta_sync();
+    unsigned off = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) if (w < wid) off += S.warp_bits[w];
+    const uint32_t* region = S.r1 + wid * kRegionWords;
+    const unsigned nwords = (S.warp_bits[wid] + 31u) >> 5;
+    const unsigned sh = off & 31u, d0 = off >> 5;
+    for (unsigned i = (unsigned)lane; i < nwords; i += 32) {
+        const unsigned v = region[i];
+        if (v >> sh) smem_atomic_or(S.win + d0 + i, v >> sh);
+        if (sh && (v << (32u - sh))) smem_atomic_or(S.win + d0 + i + 1, v << (32u - sh));
+    }
+    cta_sync();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -510,6 +601,7 @@ struct TileCtx {
     bool first, last;
     uint8_t* raw;            // the image's unstuffed scan
     unsigned long long raw_cap;
+    unsigned long long dbg_base;   // index of the tile's first block in the debug dumps
 };
 
 // Copy bytes [0, n_bytes) of the byte-aligned stream X = (k head bits) ++ L to dst (any
@@ -591,9 +683,9 @@ JG_DEV void flush_window(const LaunchParams& P, Smem<LAYOUT, NC>& S, const TileC
     k = k_out; hb = hb_out;
 }
 
-// ---- front half of a tile: transform, size, scan, publish the bit count -----------------------
+// ---- front half of a tile: transform, entropy-code into the warp regions, publish the bit count ----
 template <int LAYOUT, int NC>
-JG_DEV void tile_front(const LaunchParams& P, Smem<LAYOUT, NC>& S, const LaneConst& LC, const int g, TileCtx& c, int& diff)
+JG_DEV void tile_front(const LaunchParams& P, Smem<LAYOUT, NC>& S, const LaneConst& LC, const int g, TileCtx& c)
 {
     using G = Geo<LAYOUT>;
     const int t = JG_TID;
@@ -614,63 +706,22 @@ JG_DEV void tile_front(const LaunchParams& P, Smem<LAYOUT, NC>& S, const LaneCon
     const int nM = (im.n_mcus - m0 < G::M) ? im.n_mcus - m0 : G::M;
     c.g = g; c.img_idx = img_idx; c.first_tile_of_img = im.first_tile; c.nblk = nM * G::BPM;
     c.first = lt == 0; c.last = lt == im.n_tiles - 1; c.raw = im.raw; c.raw_cap = im.raw_cap;
+    c.dbg_base = im.first_block + (unsigned long long)(m0 * G::BPM);
 
     if (t < 4) S.pred_dc[t] = 0;          // jpeg_enc.h:1085-1087: predictors start at 0
+    if (t == 0) S.slow = 0;
     cta_sync();
     transform_tile<LAYOUT, NC>(S, im, m0, nM, LC);
-    cta_sync();   // coefficients + DCs complete
+    cta_sync();   // coefficients complete; the exchange tiles are dead, their space becomes regions + queues
 
-    // thread t owns block t of the tile (stream order)
-    const int s = t;
-    int comp = 0, pred_s = s - 1;
-    if (LAYOUT == LAYOUT_444) { comp = s % 3; pred_s = s - 3; }
-    else if (LAYOUT == LAYOUT_420) {
-        const int j = s % 6;
-        comp = j < 4 ? 0 : j - 3;
-        pred_s = j >= 4 ? s - 6 : (j == 0 ? s - 3 : s - 1);      // Y00 follows the previous MCU's Y11
+    if (P.dbg_coefs) {
+        for (int i = t; i < c.nblk * 64; i += kThreads)
+            P.dbg_coefs[c.dbg_base * 64ull + (unsigned long long)i] = S.coef[(i >> 6) * kCoefStride + (i & 63)];
     }
-    const int cls = comp ? 1 : 0;
-    const int16_t* cz = S.coef + s * kCoefStride;
-    unsigned my_bits = 0;
-    diff = 0;
-    if (s < c.nblk) {
-        const int pred = pred_s >= 0 ? S.dc_s[pred_s] : S.pred_dc[comp];   // jpeg_enc.h:834-835
-        diff = S.dc_s[s] - pred;
-        my_bits = block_bits(cz, diff, S.huff_ac[cls], S.huff_dc[cls]);
-        S.bits_s[s] = my_bits;
-        if (P.dbg_bits) P.dbg_bits[im.first_block + (unsigned long long)(m0 * G::BPM + s)] = my_bits;
-        if (P.dbg_coefs) {
-            int16_t* dst = P.dbg_coefs + (im.first_block + (unsigned long long)(m0 * G::BPM + s)) * 64ull;
-            for (int i = 0; i < 64; ++i) dst[i] = cz[i];
-        }
-    }
-    unsigned T;
-    S.off_s[t] = cta_scan_excl(my_bits, S.warp_tmp, T);
-    c.T = T;
+    c.T = encode_range<LAYOUT, NC>(P, S, 0, c.nblk, kWarpBlocks, c.dbg_base);
     // Publish the tile's bit count NOW: it is consumed (by us and by every successor) one
     // loop iteration later, so the look-back practically never waits.
-    if (t == 0) {
-        st_flag64(P.desc_bits + g, (c.first ? kStatusPrefix : kStatusAgg) | (unsigned long long)T);
-        S.off_s[kThreads] = T;
-        S.n_groups = 1;
-    }
-    cta_sync();   // off_s visible
-    const unsigned cap_bits = (unsigned)P.win_words * 32u - 64u;
-    if (T > cap_bits) {   // pathological tile: split into groups that fit the window
-        if (t == 0) {
-            int ng = 0;
-            unsigned gbase = 0;
-            S.gstart[0] = 0;
-            for (int b = 0; b < c.nblk; ++b) {
-                const unsigned end = S.off_s[b] + S.bits_s[b];
-                if (end - gbase > cap_bits) { ++ng; S.gstart[ng] = (uint16_t)b; gbase = S.off_s[b]; }
-            }
-            ++ng;
-            S.gstart[ng] = (uint16_t)c.nblk;
-            S.n_groups = ng;
-        }
-        cta_sync();
-    }
+    if (t == 0) st_flag64(P.desc_bits + g, (c.first ? kStatusPrefix : kStatusAgg) | (unsigned long long)c.T);
 }
 
 // ---- back half of a (single-window) tile, run one iteration later: offset + write -------------
@@ -703,8 +754,10 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
     JG_DYNAMIC_SMEM(smem_raw);
     Smem<LAYOUT, NC>& S = *reinterpret_cast<Smem<LAYOUT, NC>*>(smem_raw);
     const int t = JG_TID;
-    for (int i = t; i < 512; i += kThreads) (&S.huff_ac[0][0])[i] = (&P.huff->ac[0][0])[i];
-    if (t < 32) (&S.huff_dc[0][0])[t] = (&P.huff->dc[0][0])[t];
+    for (int i = t; i < 2 * 272; i += kThreads) {
+        const int cls = i / 272, k = i - cls * 272;
+        S.huff[cls][k] = k < 256 ? P.huff->ac[cls][k] : P.huff->dc[cls][k - 256];
+    }
     LaneConst LC;
     {
         const int u = t & 7;
@@ -730,63 +783,55 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
         const bool have = g < P.n_tiles;
         if (S.abort) break;
 
-        // software pipeline: front of tile g, THEN the back of the tile packed last iteration
+        // software pipeline: front of tile g, THEN the back of the tile compacted last iteration
         TileCtx cur;
         cur.g = -1;
-        int diff = 0;
-        if (have) tile_front<LAYOUT, NC>(P, S, LC, g, cur, diff);
+        if (have) tile_front<LAYOUT, NC>(P, S, LC, g, cur);
         if (prev.g >= 0) {
             if (!tile_back<LAYOUT, NC>(P, S, prev)) break;
             prev.g = -1;
         }
         if (!have) break;
+        cta_sync();   // the window is free again (tile_back has read it); S.slow is settled
 
-        // pack.  One window: [ALL] (written out next iteration).  Several: [TAIL, GROUP_0..n-1]
-        // written out right away (walk 2 repeated per group; pathological content only).
-        const int n_groups = S.n_groups;
-        const int n_jobs = n_groups == 1 ? 1 : 1 + n_groups;
-        const int s = t;
-        const int cls = (LAYOUT == LAYOUT_444) ? (s % 3 != 0) : (LAYOUT == LAYOUT_420 ? (s % 6 >= 4) : 0);
-        unsigned k = 0, hb = 0;
-        unsigned long long pos = 0;
-        bool overflow = false;
-        cta_sync();   // the window is free again (tile_back has read it)
-        for (int job = 0; job < n_jobs; ++job) {
-            int b0 = 0, b1 = cur.nblk;
-            if (n_groups > 1) {
-                if (job == 0) b0 = cur.nblk >= 2 ? cur.nblk - 2 : 0;        // only to learn the last 7 bits
-                else { b0 = S.gstart[job - 1]; b1 = S.gstart[job]; }
-            }
-            const unsigned base = S.off_s[b0];
-            const unsigned tg = S.off_s[b1] - base;
-            for (int i = t; i < (int)(tg >> 5) + 8; i += kThreads) S.win[i] = 0u;
-            cta_sync();
-            if (s >= b0 && s < b1)
-                block_pack(S.coef + s * kCoefStride, diff, S.huff_ac[cls], S.huff_dc[cls], S.win, S.off_s[s] - base);
-            cta_sync();
-            if (job == 0 && t == 0) {
-                const unsigned tail = tg >= 7u ? peek_bits(S.win, tg - 7u, 7u) : peek_bits(S.win, 0u, tg);
+        const unsigned cap_bits = (unsigned)P.win_words * 32u - 64u;
+        if (!S.slow && cur.T <= cap_bits) {
+            // regions -> window; written out next iteration by tile_back()
+            compact_regions<LAYOUT, NC>(S, cur.T);
+            if (t == 0) {
+                const unsigned tail = cur.T >= 7u ? peek_bits(S.win, cur.T - 7u, 7u) : peek_bits(S.win, 0u, cur.T);
                 st_flag64(P.desc_tail + g, kStatusAgg | (unsigned long long)tail);
             }
-            if (n_groups == 1) break;               // deferred: tile_back() next iteration
-            if (job == 0) {
-                chain_bits(P, S, cur);
-                cta_sync();
-                if (S.abort) break;
-                k = (unsigned)(S.bit_base & 7ull);
-                hb = S.pred_tail & ((1u << k) - 1u);
-                pos = S.bit_base >> 3;
-            } else {
-                flush_window(P, S, cur, tg, cur.last && job == n_groups, k, hb, pos, overflow);
-                cta_sync();   // the window is reused by the next group
-            }
-        }
-        if (S.abort) break;
-        if (n_groups == 1) {
             prev = cur;
-        } else if (t == 0) {
-            if (cur.last) P.raw_bytes[cur.img_idx] = pos;
-            if (overflow) gmem_atomic_or(P.img_status + cur.img_idx, 1u);
+        } else {
+            // pathological tile: six groups of 32 blocks (4 per warp, always fit), coded again and
+            // written out right away, not pipelined
+            chain_bits(P, S, cur);
+            cta_sync();
+            if (S.abort) break;
+            unsigned k = (unsigned)(S.bit_base & 7ull);
+            unsigned hb = S.pred_tail & ((1u << k) - 1u);
+            unsigned long long pos = S.bit_base >> 3;
+            bool overflow = false;
+            const int n_groups = (cur.nblk + 31) / 32;
+            uint32_t* keep_dbg = nullptr;
+            for (int gi = 0; gi < n_groups; ++gi) {
+                const int b_lo = gi * 32, b_hi = b_lo + 32 < cur.nblk ? b_lo + 32 : cur.nblk;
+                LaunchParams Q2 = P;
+                Q2.dbg_bits = keep_dbg;            // block sizes were already dumped by the first attempt
+                const unsigned tg = encode_range<LAYOUT, NC>(Q2, S, b_lo, b_hi, 4, cur.dbg_base);
+                compact_regions<LAYOUT, NC>(S, tg);
+                if (gi == n_groups - 1 && t == 0) {
+                    const unsigned tail = tg >= 7u ? peek_bits(S.win, tg - 7u, 7u) : peek_bits(S.win, 0u, tg);
+                    st_flag64(P.desc_tail + g, kStatusAgg | (unsigned long long)tail);
+                }
+                flush_window(P, S, cur, tg, cur.last && gi == n_groups - 1, k, hb, pos, overflow);
+                cta_sync();   // window + regions are reused by the next group
+            }
+            if (t == 0) {
+                if (cur.last) P.raw_bytes[cur.img_idx] = pos;
+                if (overflow) gmem_atomic_or(P.img_status + cur.img_idx, 1u);
+            }
         }
     }
 }

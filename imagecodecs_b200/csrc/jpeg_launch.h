@@ -21,7 +21,7 @@ constexpr int kChunkBytes = 4096;     // unstuffed bytes one stuffing step handl
 // MCUs per tile.  One extra "slot" per tile holds the MCU that precedes the tile (its DCs seed the
 // DC prediction), so slots = MCUs + 1 divides evenly among the CTA's lane groups.
 constexpr int mcus_per_tile(int layout) { return layout == LAYOUT_444 ? 63 : (layout == LAYOUT_420 ? 31 : 191); }
-constexpr int kWinWordsMax = 4096;   // 16 KB of unstuffed scan per group
+constexpr int kWinWordsMax = 3072;   // 12 KB tile window (unstuffed bits of one tile)
 constexpr int kWinWordsMin = 64;     // must hold one worst-case block (1658 bits) + slack
 constexpr unsigned kSpinLimit = 1u << 24;
 
