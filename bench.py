@@ -356,7 +356,7 @@ def run_ours(args):
 
 
 def plan_launches_per_step():
-    return 1   # one (layout, channels, quantiser) group -> one kernel launch per step
+    return 3   # one (layout, channels, quantiser) group -> encode + plan_chunks + stuff kernels per step
 
 
 def main():
