@@ -37,6 +37,8 @@ JG_DEV unsigned bswap32(unsigned v) { return __byte_perm(v, 0u, 0x0123u); }
 JG_DEV unsigned funnel_l(unsigned lo, unsigned hi, unsigned s) { return __funnelshift_l(lo, hi, s); }
 // per-byte compare: 0xff in every byte lane where a == b
 JG_DEV unsigned v_cmpeq4(unsigned a, unsigned b) { return __vcmpeq4(a, b); }
+// per-halfword compare: 0xffff in every halfword lane where a != b
+JG_DEV unsigned v_cmpne2(unsigned a, unsigned b) { return __vcmpne2(a, b); }
 
 // ---- CTA / warp collectives --------------------------------------------------------------
 JG_DEV void cta_sync() { __syncthreads(); }

@@ -51,7 +51,7 @@ namespace jg {
 constexpr int kTileFloats = 72;   // one 8x8 float tile with rows padded to 9 (bank-conflict free both ways)
 constexpr int kCoefStride = 72;   // int16 per block in shared memory (144 B: 16-byte aligned 8-coefficient reads)
 constexpr int kRegionWords = kWinWordsMax / kWarps;   // bits a warp may emit for its 24 blocks before the tile goes slow
-constexpr int kQueueEntries = 288;                     // 32 lanes x (8 coefficients + EOB)
+constexpr int kQueueEntries = 292;                     // 32 lanes x (8 coefficients + EOB) + pad
 constexpr int kWarpBlocks = 24;                        // blocks per warp (8 x 24 = 192)
 
 template <int LAYOUT>
@@ -78,6 +78,7 @@ struct Smem {
     alignas(16) uint32_t win[kWinWordsMax + 8];               // the tile's packed bits; survives into the next iteration
     alignas(16) int16_t coef[kBlocksPerTile * kCoefStride];   // quantised coefficients, zigzag order
     uint32_t huff[2][272];                // [class][(run<<4)|cat] AC, [class][256+cat] DC; entry = code<<8 | length
+    unsigned long long zrl[2][4];         // [class][n]: n ZRL codes back to back (<= 33 bits), bits<<8 | length
     int pred_dc[4];                       // DCs of the MCU preceding the tile, per component
     uint32_t warp_bits[kWarps];           // bits emitted by each warp
     uint32_t warp_tmp[kWarps];
@@ -353,10 +354,11 @@ JG_DEV void block_kind(int blk, int& comp, int& pred_blk)
 
 // One warp codes blocks [first, end) (at most 24) into `region` (zeroed, MSB-first words).
 // Symbol queue entry: value<<16 | EOB<<15 | DC<<14 | chroma<<13 | block-in-warp<<8 | zigzag position.
-// Returns the bits emitted; sets `overflow` if they did not fit region_words (the count stays right).
+// queue[-1] must be readable (one pad word).  Returns the bits emitted; sets `overflow` if they
+// did not fit region_words (the count stays right).
 template <int LAYOUT, int NC>
-JG_DEV unsigned encode_blocks_warp(const LaunchParams& P, Smem<LAYOUT, NC>& S, int first, int end, uint32_t* region,
-                                   unsigned region_words, uint32_t* queue, unsigned long long dbg_base, bool& overflow)
+JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint32_t* region, unsigned region_words,
+                                   uint32_t* queue, uint32_t* dbg_bits, bool& overflow)
 {
     const int lane = JG_TID & 31, L = lane & 7, b4 = lane >> 3;
     unsigned carry = 0;
@@ -375,8 +377,8 @@ JG_DEV unsigned encode_blocks_warp(const LaunchParams& P, Smem<LAYOUT, NC>& S, i
         unsigned m8 = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            if (ww[q] & 0xffffu) m8 |= 1u << (2 * q);
-            if (ww[q] >> 16) m8 |= 2u << (2 * q);
+            const unsigned ne = v_cmpne2(ww[q], 0u);        // 0xffff per non-zero halfword
+            m8 |= ((ne & 1u) | ((ne >> 15) & 2u)) << (2 * q);
         }
         int diff = 0;
         if (valid && L == 0) {                              // DC: always coded, as a difference (jpeg_enc.h:834-844)
@@ -393,49 +395,42 @@ JG_DEV unsigned encode_blocks_warp(const LaunchParams& P, Smem<LAYOUT, NC>& S, i
             if (lane >= d) inc += n;
         }
         const unsigned N = warp_shfl_u32(inc, 31);
-        unsigned at = inc - cnt;
+        uint32_t* qp = queue + (inc - cnt);
         const unsigned common = (comp ? 1u << 13 : 0u) | ((unsigned)(blk - first) << 8) | (unsigned)(8 * L);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             if (m8 & (1u << i)) {
-                int val = (int)(int16_t)((i & 1) ? (ww[i >> 1] >> 16) : (ww[i >> 1] & 0xffffu));
+                unsigned hv = (i & 1) ? (ww[i >> 1] & 0xffff0000u) : (ww[i >> 1] << 16);     // value in the top half
                 unsigned e = common + (unsigned)i;
-                if (i == 0 && L == 0) { val = diff; e |= 1u << 14; }
-                queue[at++] = ((unsigned)val << 16) | e;
+                if (i == 0 && L == 0) { hv = (unsigned)diff << 16; e |= 1u << 14; }
+                *qp++ = hv | e;
             }
         }
-        if (eob) queue[at] = (1u << 15) | common | 7u;
+        if (eob) *qp = (1u << 15) | common | 7u;
         warp_sync();
 
-        // ---- 32 symbols per round -------------------------------------------------------------------
+        // ---- 32 symbols per round, branch-free -------------------------------------------------------
 #pragma unroll 1
         for (unsigned j0 = 0; j0 < N; j0 += 32) {
             const unsigned j = j0 + (unsigned)lane;
-            unsigned long long sym = 0;
-            unsigned len = 0;
-            if (j < N) {
-                const unsigned e = queue[j];
-                const int v = (int)e >> 16;
-                const unsigned cls = (e >> 13) & 1u;
-                unsigned idx = 0, cat = 0, nz = 0;
-                if (!(e & 0x8000u)) {
-                    cat = category(v);                              // 0 for a zero DC difference
-                    if (e & 0x4000u) idx = 256u + cat;
-                    else {
-                        const unsigned run = (e & 63u) - (queue[j - 1] & 63u) - 1u;   // zeros since the previous symbol of the block
-                        nz = run >> 4;                              // one ZRL per 16 zeros (jpeg_enc.h:863-867)
-                        idx = ((run & 15u) << 4) | cat;
-                    }
-                }
-                const unsigned h = S.huff[cls][idx];
-                sym = (unsigned long long)(((h >> 8) << cat) | amplitude(v, cat));
-                len = (h & 0xffu) + cat;
-                if (nz) {
-                    const unsigned z = S.huff[cls][0xF0];
-                    for (unsigned q = 0; q < nz; ++q) { sym |= (unsigned long long)(z >> 8) << len; len += z & 0xffu; }
-                }
-                if (P.dbg_bits) gmem_atomic_add(P.dbg_bits + dbg_base + (unsigned long long)(first + (int)((e >> 8) & 31u)), len);
-            }
+            const unsigned e = queue[j];
+            const unsigned ep = queue[(int)j - 1];
+            const int v = (int)e >> 16;
+            const unsigned cls = (e >> 13) & 1u;
+            const unsigned cat = category(v) & 15u;             // 0 for EOB and for a zero DC difference
+            const unsigned run = ((e & 63u) - (ep & 63u) - 1u) & 63u;   // zeros since the previous symbol of the block
+            const bool special = (e & 0xC000u) != 0u;           // DC or EOB: no run
+            unsigned idx = ((run & 15u) << 4) | cat;
+            if (e & 0x4000u) idx = 256u + cat;
+            if (e & 0x8000u) idx = 0u;
+            const unsigned nz = special ? 0u : run >> 4;        // one ZRL per 16 zeros (jpeg_enc.h:863-867)
+            const unsigned h = S.huff[cls][idx];
+            const unsigned long long zp = S.zrl[cls][nz];       // nz ZRL codes: bits<<8 | length  (nz <= 3)
+            const unsigned slen = (h & 0xffu) + cat;
+            unsigned len = slen + (unsigned)(zp & 0xffull);
+            const unsigned long long sym = ((zp >> 8) << slen) | (unsigned long long)(((h >> 8) << cat) | amplitude(v, cat));
+            if (j >= N) len = 0u;
+            if (dbg_bits != nullptr && len) gmem_atomic_add(dbg_bits + ((e >> 8) & 31u), len);
             unsigned endb = len;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -449,12 +444,11 @@ JG_DEV unsigned encode_blocks_warp(const LaunchParams& P, Smem<LAYOUT, NC>& S, i
                 const unsigned hi = (unsigned)(al >> 32), lo = (unsigned)al;
                 const unsigned sh = start & 31u, wi = start >> 5;
                 if (wi + 2u < region_words) {
-                    const unsigned w0 = hi >> sh;
-                    const unsigned w1 = sh ? (hi << (32u - sh)) | (lo >> sh) : lo;
-                    const unsigned w2 = sh ? lo << (32u - sh) : 0u;
-                    if (w0) smem_atomic_or(region + wi, w0);
-                    if (w1) smem_atomic_or(region + wi + 1, w1);
-                    if (w2) smem_atomic_or(region + wi + 2, w2);
+                    smem_atomic_or(region + wi, hi >> sh);
+                    if (sh + len > 32u) {
+                        smem_atomic_or(region + wi + 1, sh ? (hi << (32u - sh)) | (lo >> sh) : lo);
+                        if (sh + len > 64u) smem_atomic_or(region + wi + 2, lo << (32u - sh));
+                    }
                 } else overflow = true;
             }
             carry += tot;
@@ -468,18 +462,18 @@ JG_DEV unsigned encode_blocks_warp(const LaunchParams& P, Smem<LAYOUT, NC>& S, i
 // regions.  Returns the bits of the range (CTA-uniform, after a barrier); raises S.slow if a
 // region overflowed (the bit count is right even then).
 template <int LAYOUT, int NC>
-JG_DEV unsigned encode_range(const LaunchParams& P, Smem<LAYOUT, NC>& S, int b_lo, int b_hi, int per_warp,
-                             unsigned long long dbg_base)
+JG_DEV unsigned encode_range(Smem<LAYOUT, NC>& S, int b_lo, int b_hi, int per_warp, uint32_t* dbg_bits)
 {
     const int t = JG_TID, lane = t & 31, wid = t >> 5;
     uint32_t* region = S.r1 + wid * kRegionWords;
-    uint32_t* queue = S.r1 + kWarps * kRegionWords + wid * kQueueEntries;
+    uint32_t* queue = S.r1 + kWarps * kRegionWords + wid * kQueueEntries + 1;    // [-1] is a pad word
     for (int i = lane; i < kRegionWords; i += 32) region[i] = 0u;
     warp_sync();
     const int first = b_lo + wid * per_warp;
     const int end = first + per_warp < b_hi ? first + per_warp : b_hi;
     bool overflow = false;
-    const unsigned bits = first < end ? encode_blocks_warp<LAYOUT, NC>(P, S, first, end, region, kRegionWords, queue, dbg_base, overflow) : 0u;
+    const unsigned bits = first < end ? encode_blocks_warp<LAYOUT, NC>(S, first, end, region, kRegionWords, queue,
+                                                                       dbg_bits ? dbg_bits + first : nullptr, overflow) : 0u;
     if (lane == 0) S.warp_bits[wid] = bits;
     if (overflow) S.slow = 1;
     cta_sync();
@@ -718,7 +712,7 @@ JG_DEV void tile_front(const LaunchParams& P, Smem<LAYOUT, NC>& S, const LaneCon
         for (int i = t; i < c.nblk * 64; i += kThreads)
             P.dbg_coefs[c.dbg_base * 64ull + (unsigned long long)i] = S.coef[(i >> 6) * kCoefStride + (i & 63)];
     }
-    c.T = encode_range<LAYOUT, NC>(P, S, 0, c.nblk, kWarpBlocks, c.dbg_base);
+    c.T = encode_range<LAYOUT, NC>(S, 0, c.nblk, kWarpBlocks, P.dbg_bits ? P.dbg_bits + c.dbg_base : nullptr);
     // Publish the tile's bit count NOW: it is consumed (by us and by every successor) one
     // loop iteration later, so the look-back practically never waits.
     if (t == 0) st_flag64(P.desc_bits + g, (c.first ? kStatusPrefix : kStatusAgg) | (unsigned long long)c.T);
@@ -757,6 +751,13 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
     for (int i = t; i < 2 * 272; i += kThreads) {
         const int cls = i / 272, k = i - cls * 272;
         S.huff[cls][k] = k < 256 ? P.huff->ac[cls][k] : P.huff->dc[cls][k - 256];
+    }
+    if (t < 8) {      // n = t & 3 ZRL codes back to back (the luma ZRL has 11 bits: up to 33 bits)
+        const int cls = t >> 2, n = t & 3;
+        const unsigned z = P.huff->ac[cls][0xF0];
+        unsigned long long bits = 0, len = 0;
+        for (int q = 0; q < n; ++q) { bits = (bits << (z & 0xffu)) | (z >> 8); len += z & 0xffu; }
+        S.zrl[cls][n] = (bits << 8) | len;
     }
     LaneConst LC;
     {
@@ -804,8 +805,19 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
             }
             prev = cur;
         } else {
-            // pathological tile: six groups of 32 blocks (4 per warp, always fit), coded again and
-            // written out right away, not pipelined
+            // pathological tile: groups of 32 blocks (4 per warp, always fit), coded again and written
+            // out right away, not pipelined.  The last group goes first, only to learn the tile's
+            // last 7 bits: successors must not wait for our whole slow pass.
+            const int n_groups = (cur.nblk + 31) / 32;
+            {
+                const int b_lo = (n_groups - 1) * 32;
+                const unsigned tg = encode_range<LAYOUT, NC>(S, b_lo, cur.nblk, 4, nullptr);
+                compact_regions<LAYOUT, NC>(S, tg);
+                if (t == 0) {
+                    const unsigned tail = tg >= 7u ? peek_bits(S.win, tg - 7u, 7u) : peek_bits(S.win, 0u, tg);
+                    st_flag64(P.desc_tail + g, kStatusAgg | (unsigned long long)tail);
+                }
+            }
             chain_bits(P, S, cur);
             cta_sync();
             if (S.abort) break;
@@ -813,18 +825,10 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
             unsigned hb = S.pred_tail & ((1u << k) - 1u);
             unsigned long long pos = S.bit_base >> 3;
             bool overflow = false;
-            const int n_groups = (cur.nblk + 31) / 32;
-            uint32_t* keep_dbg = nullptr;
             for (int gi = 0; gi < n_groups; ++gi) {
                 const int b_lo = gi * 32, b_hi = b_lo + 32 < cur.nblk ? b_lo + 32 : cur.nblk;
-                LaunchParams Q2 = P;
-                Q2.dbg_bits = keep_dbg;            // block sizes were already dumped by the first attempt
-                const unsigned tg = encode_range<LAYOUT, NC>(Q2, S, b_lo, b_hi, 4, cur.dbg_base);
+                const unsigned tg = encode_range<LAYOUT, NC>(S, b_lo, b_hi, 4, nullptr);   // block sizes were dumped by the first attempt
                 compact_regions<LAYOUT, NC>(S, tg);
-                if (gi == n_groups - 1 && t == 0) {
-                    const unsigned tail = tg >= 7u ? peek_bits(S.win, tg - 7u, 7u) : peek_bits(S.win, 0u, tg);
-                    st_flag64(P.desc_tail + g, kStatusAgg | (unsigned long long)tail);
-                }
                 flush_window(P, S, cur, tg, cur.last && gi == n_groups - 1, k, hb, pos, overflow);
                 cta_sync();   // window + regions are reused by the next group
             }

@@ -47,6 +47,10 @@ JG_DEV int i_clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 JG_DEV int i_ffs(unsigned v) { return __builtin_ffs((int)v); }
 JG_DEV int i_popc(unsigned v) { return __builtin_popcount(v); }
 JG_DEV unsigned bswap32(unsigned v) { return __builtin_bswap32(v); }
+JG_DEV unsigned v_cmpne2(unsigned a, unsigned b)
+{
+    return (((a ^ b) & 0xffffu) ? 0xffffu : 0u) | (((a ^ b) >> 16) ? 0xffff0000u : 0u);
+}
 JG_DEV unsigned v_cmpeq4(unsigned a, unsigned b)
 {
     unsigned r = 0;

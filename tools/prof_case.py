@@ -1,0 +1,33 @@
+"""Run one encode configuration a few times (for ncu / quick timing).
+usage: python tools/prof_case.py --w 1920 --h 1080 --n 64 --qmode 1 --q 75 --sub 1 [--kind photo] [--steps 5]"""
+import argparse, ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import imagecodecs_b200 as jg
+from imagecodecs_b200.synth import synth_batch
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--w", type=int, default=1920); ap.add_argument("--h", type=int, default=1080)
+ap.add_argument("--n", type=int, default=64); ap.add_argument("--nc", type=int, default=3)
+ap.add_argument("--qmode", type=int, default=1); ap.add_argument("--q", type=int, default=75)
+ap.add_argument("--sub", type=int, default=1); ap.add_argument("--kind", default="photo")
+ap.add_argument("--steps", type=int, default=5)
+a = ap.parse_args()
+jg.init([0])
+px = synth_batch(a.n, a.w, a.h, a.nc, a.kind, device="cuda")
+stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+sp = C.c_void_p(stream.cuda_stream)
+torch.cuda.synchronize()
+plan = jg.Plan.for_arrays([px[i] for i in range(a.n)], a.qmode, a.q, a.sub, device=0)
+for _ in range(3): plan.run(sp)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(stream)
+for _ in range(a.steps): plan.run(sp)
+e1.record(stream); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.steps
+mp = a.n * a.w * a.h / 1e6
+sz = sum(plan.encoded_size(i) for i in range(a.n))
+print("%dx%dx%d n=%d qmode=%d q=%d sub=%d %s: %.3f ms/step  %.1f GP/s  out %.3f B/px  roofline %.4f" % (
+    a.w, a.h, a.nc, a.n, a.qmode, a.q, a.sub, a.kind, ms, mp / ms, sz / (a.n * a.w * a.h),
+    (a.n * a.w * a.h * a.nc + sz) / (ms * 1e-3) / 6550.1e9))
