@@ -677,23 +677,24 @@ JG_DEV void flush_window(const LaunchParams& P, Smem<LAYOUT, NC>& S, const TileC
     k = k_out; hb = hb_out;
 }
 
+JG_DEV int image_of_tile(const LaunchParams& P, int g)
+{
+    if (P.tiles_per_image > 0) return g / P.tiles_per_image;
+    int lo = 0, hi = P.n_images - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (P.images[mid].first_tile <= g) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
 // ---- front half of a tile: transform, entropy-code into the warp regions, publish the bit count ----
 template <int LAYOUT, int NC>
 JG_DEV void tile_front(const LaunchParams& P, Smem<LAYOUT, NC>& S, const LaneConst& LC, const int g, TileCtx& c)
 {
     using G = Geo<LAYOUT>;
     const int t = JG_TID;
-    int img_idx;
-    if (P.tiles_per_image > 0) {
-        img_idx = g / P.tiles_per_image;
-    } else {
-        int lo = 0, hi = P.n_images - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (P.images[mid].first_tile <= g) lo = mid; else hi = mid - 1;
-        }
-        img_idx = lo;
-    }
+    const int img_idx = image_of_tile(P, g);
     const ImageDesc im = P.images[img_idx];
     const int lt = g - im.first_tile;
     const int m0 = lt * G::M;
