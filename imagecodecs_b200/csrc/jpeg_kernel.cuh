@@ -51,7 +51,7 @@ namespace jg {
 constexpr int kTileFloats = 72;   // one 8x8 float tile with rows padded to 9 (bank-conflict free both ways)
 constexpr int kCoefStride = 72;   // int16 per block in shared memory (144 B: 16-byte aligned 8-coefficient reads)
 constexpr int kRegionWords = kWinWordsMax / kWarps;   // bits a warp may emit for its 24 blocks before the tile goes slow
-constexpr int kQueueEntries = 292;                     // 32 lanes x (8 coefficients + EOB) + pad
+constexpr int kQueueEntries = 360;                     // 31 carried + 32 lanes x (8 coefficients + EOB) + 32 read-ahead + pad
 constexpr int kWarpBlocks = 24;                        // blocks per warp (8 x 24 = 192)
 
 template <int LAYOUT>
@@ -362,6 +362,7 @@ JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint
 {
     const int lane = JG_TID & 31, L = lane & 7, b4 = lane >> 3;
     unsigned carry = 0;
+    unsigned left = 0;      // symbols queued but not yet coded (an incomplete round is carried to the next step)
 #pragma unroll 1
     for (int b0 = first; b0 < end; b0 += 4) {
         const int blk = b0 + b4;
@@ -395,7 +396,7 @@ JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint
             if (lane >= d) inc += n;
         }
         const unsigned N = warp_shfl_u32(inc, 31);
-        uint32_t* qp = queue + (inc - cnt);
+        uint32_t* qp = queue + left + (inc - cnt);
         const unsigned common = (comp ? 1u << 13 : 0u) | ((unsigned)(blk - first) << 8) | (unsigned)(8 * L);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -409,9 +410,11 @@ JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint
         if (eob) *qp = (1u << 15) | common | 7u;
         warp_sync();
 
-        // ---- 32 symbols per round, branch-free -------------------------------------------------------
+        // ---- 32 symbols per round, branch-free; only full rounds except at the very end ---------------
+        const unsigned M = left + N;
+        const unsigned full = (b0 + 4 >= end) ? M : (M & ~31u);
 #pragma unroll 1
-        for (unsigned j0 = 0; j0 < N; j0 += 32) {
+        for (unsigned j0 = 0; j0 < full; j0 += 32) {
             const unsigned j = j0 + (unsigned)lane;
             const unsigned e = queue[j];
             const unsigned ep = queue[(int)j - 1];
@@ -429,7 +432,7 @@ JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint
             const unsigned slen = (h & 0xffu) + cat;
             unsigned len = slen + (unsigned)(zp & 0xffull);
             const unsigned long long sym = ((zp >> 8) << slen) | (unsigned long long)(((h >> 8) << cat) | amplitude(v, cat));
-            if (j >= N) len = 0u;
+            if (j >= full) len = 0u;
             if (dbg_bits != nullptr && len) gmem_atomic_add(dbg_bits + ((e >> 8) & 31u), len);
             unsigned endb = len;
 #pragma unroll
@@ -453,7 +456,16 @@ JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint
             }
             carry += tot;
         }
-        warp_sync();   // the queue is rewritten by the next four blocks
+        // move the incomplete round to the front; queue[-1] keeps the symbol before it (for its run)
+        left = M - full;
+        if (left && full) {
+            const unsigned keep = queue[full + (unsigned)lane];
+            const unsigned before = queue[full - 1u];
+            warp_sync();
+            if ((unsigned)lane < left) queue[lane] = keep;
+            if (lane == 0) queue[-1] = before;
+        }
+        warp_sync();   // the queue is appended to by the next four blocks
     }
     return carry;
 }
