@@ -52,6 +52,8 @@ JG_DEV unsigned long long warp_shfl_xor_u64(unsigned long long v, int m) { retur
 
 // ---- memory ------------------------------------------------------------------------------
 JG_DEV uint32_t ldg_u32(const void* p) { return __ldg(reinterpret_cast<const unsigned*>(p)); }
+JG_DEV uint2 ldg_u64(const void* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+JG_DEV uint4 ldg_u128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 JG_DEV uint32_t ldg_u8(const void* p) { return __ldg(reinterpret_cast<const unsigned char*>(p)); }
 JG_DEV void smem_atomic_or(unsigned* p, unsigned v) { atomicOr(p, v); }
 JG_DEV unsigned gmem_atomic_add(unsigned* p, unsigned v) { return atomicAdd(p, v); }

@@ -159,6 +159,13 @@ size_t default_scan_bytes(const jpeg_gpu_image& im, const Geometry& g)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// largest power of two <= 16 dividing both the base address and the row pitch
+int alignment_of(const void* px, int stride)
+{
+    const size_t v = (size_t)px | (size_t)stride | 16u;
+    return (int)(v & (~v + 1));
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -319,7 +326,7 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
             d.w = it.img.width; d.h = it.img.height; d.stride = it.img.stride;
             d.mcus_x = it.geo.mcus_x; d.n_mcus = it.geo.n_mcus;
             d.first_tile = tile; d.n_tiles = it.geo.n_tiles;
-            d.aligned4 = ((size_t)d.px % 4 == 0) && (d.stride % 4 == 0);
+            d.align = alignment_of(d.px, d.stride);
             tile += it.geo.n_tiles;
         }
     }
@@ -505,7 +512,7 @@ int jpeg_gpu_plan_set_pixels(jpeg_gpu_plan* p, int i, const uint8_t* device_pixe
     it.d_pixels = device_pixels;
     ImageDesc& d = p->h_images[p->groups[it.group].result_off + it.index_in_group];
     d.px = device_pixels;
-    d.aligned4 = ((size_t)d.px % 4 == 0) && (d.stride % 4 == 0);
+    d.align = alignment_of(d.px, d.stride);
     p->images_dirty = true;
     return 1;
 }

@@ -86,8 +86,6 @@ struct Smem {
     int tile;
     int abort;
     int slow;                             // a warp region overflowed: redo the tile in groups
-    unsigned pred_tail;                   // last 7 bits of the preceding tile
-    unsigned long long bit_base;          // exclusive bit offset of the tile in its image
 };
 
 // per-lane constants: the lane's column u = tid & 7 of every coefficient matrix it finishes
@@ -108,14 +106,30 @@ JG_DEV int zz_of(int i)   // jpeg_enc.h:376-386: position in scan order of natur
 template <int NC, int NPX>
 JG_DEV void load_segment(const ImageDesc& im, int x0, int y, uint32_t (&w)[NPX * NC / 4])
 {
+    constexpr int BYTES = NPX * NC;
     const uint8_t* row = im.px + (size_t)y * (size_t)im.stride;
-    if (im.aligned4 && x0 + NPX <= im.w) {
+    if (x0 + NPX <= im.w && im.align >= 4) {
         const uint8_t* p = row + (size_t)x0 * NC;
+        // widest load the segment size and the image's alignment allow: fewer, fatter requests
+        if (BYTES % 16 == 0 && im.align >= 16) {
 #pragma unroll
-        for (int i = 0; i < NPX * NC / 4; ++i) w[i] = ldg_u32(p + 4 * i);
+            for (int i = 0; i < BYTES / 16; ++i) {
+                const uint4 v = ldg_u128(p + 16 * i);
+                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            }
+        } else if (BYTES % 8 == 0 && im.align >= 8) {
+#pragma unroll
+            for (int i = 0; i < BYTES / 8; ++i) {
+                const uint2 v = ldg_u64(p + 8 * i);
+                w[2 * i] = v.x; w[2 * i + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < BYTES / 4; ++i) w[i] = ldg_u32(p + 4 * i);
+        }
     } else {
 #pragma unroll
-        for (int i = 0; i < NPX * NC / 4; ++i) {
+        for (int i = 0; i < BYTES / 4; ++i) {
             uint32_t v = 0;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
@@ -644,31 +658,28 @@ JG_DEV void copy_stream_out(const uint32_t* L, unsigned k, unsigned hb, unsigned
 }
 
 // Learn the tile's bit offset (look-back over desc_bits) and the predecessor's last bits.
-// Executed by warp 0; results go to S.bit_base / S.pred_tail / S.abort.
+// EVERY warp resolves the chain for itself (same descriptors, same answer): nobody waits at a
+// barrier for one designated warp.  Warp 0 publishes the inclusive prefix.  On a timeout the
+// error flag is raised (checked CTA-uniformly at the next barrier).
 template <int LAYOUT, int NC>
-JG_DEV void chain_bits(const LaunchParams& P, Smem<LAYOUT, NC>& S, const TileCtx& c)
+JG_DEV void chain_bits(const LaunchParams& P, Smem<LAYOUT, NC>& S, const TileCtx& c, unsigned long long& bit_base, unsigned& pred_tail)
 {
     const int t = JG_TID;
-    if (t < 32) {
-        unsigned long long excl = 0, ptail = 0;
-        int timed_out = 0;
-        if (!c.first) {
-            excl = lookback(P.desc_bits, c.g, c.first_tile_of_img, P.error, &timed_out);
-            if (t == 0 && !timed_out) st_flag64(P.desc_bits + c.g, kStatusPrefix | (excl + c.T));
-            unsigned spins = 0;      // the byte we share with the predecessor needs its last bits
-            while (!timed_out && ((ptail = ld_flag64(P.desc_tail + c.g - 1)) >> 62) == 0) {
-                if (++spins > kSpinLimit || ld_flag32(P.error) != 0u) timed_out = 1;
-                backoff();
-            }
-            timed_out = warp_ballot(timed_out) != 0u;
+    unsigned long long excl = 0, ptail = 0;
+    int timed_out = 0;
+    if (!c.first) {
+        excl = lookback(P.desc_bits, c.g, c.first_tile_of_img, P.error, &timed_out);
+        if (t == 0 && !timed_out) st_flag64(P.desc_bits + c.g, kStatusPrefix | (excl + c.T));
+        unsigned spins = 0;      // the byte we share with the predecessor needs its last bits
+        while (!timed_out && ((ptail = ld_flag64(P.desc_tail + c.g - 1)) >> 62) == 0) {
+            if (++spins > kSpinLimit || ld_flag32(P.error) != 0u) timed_out = 1;
+            backoff();
         }
-        if (t == 0) {
-            S.bit_base = excl;
-            S.pred_tail = (unsigned)ptail & 0x7fu;
-            S.abort = timed_out;
-            if (timed_out) gmem_atomic_or(P.error, 1u);
-        }
+        timed_out = warp_ballot(timed_out) != 0u;
     }
+    if (timed_out) { S.abort = 1; if ((t & 31) == 0) gmem_atomic_or(P.error, 1u); excl = 0; ptail = 0; }
+    bit_base = excl;
+    pred_tail = (unsigned)ptail & 0x7fu;
 }
 
 // Write the window (tg bits) as the next piece of the image's unstuffed scan.
@@ -733,14 +744,13 @@ JG_DEV void tile_front(const LaunchParams& P, Smem<LAYOUT, NC>& S, const LaneCon
 
 // ---- back half of a (single-window) tile, run one iteration later: offset + write -------------
 template <int LAYOUT, int NC>
-JG_DEV bool tile_back(const LaunchParams& P, Smem<LAYOUT, NC>& S, const TileCtx& c)
+JG_DEV void tile_back(const LaunchParams& P, Smem<LAYOUT, NC>& S, const TileCtx& c)
 {
-    chain_bits(P, S, c);
-    cta_sync();
-    if (S.abort) return false;
-    const unsigned long long bit_base = S.bit_base;
+    unsigned long long bit_base;
+    unsigned pred_tail;
+    chain_bits(P, S, c, bit_base, pred_tail);
     unsigned k = (unsigned)(bit_base & 7ull);          // bits of our first byte owned by the predecessor
-    unsigned hb = S.pred_tail & ((1u << k) - 1u);
+    unsigned hb = pred_tail & ((1u << k) - 1u);
     unsigned long long pos = bit_base >> 3;
     bool overflow = false;
     flush_window(P, S, c, c.T, c.last, k, hb, pos, overflow);
@@ -748,7 +758,6 @@ JG_DEV bool tile_back(const LaunchParams& P, Smem<LAYOUT, NC>& S, const TileCtx&
         if (c.last) P.raw_bytes[c.img_idx] = pos;
         if (overflow) gmem_atomic_or(P.img_status + c.img_idx, 1u);
     }
-    return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -802,11 +811,11 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
         cur.g = -1;
         if (have) tile_front<LAYOUT, NC>(P, S, LC, g, cur);
         if (prev.g >= 0) {
-            if (!tile_back<LAYOUT, NC>(P, S, prev)) break;
+            tile_back<LAYOUT, NC>(P, S, prev);
             prev.g = -1;
         }
-        if (!have) break;
-        cta_sync();   // the window is free again (tile_back has read it); S.slow is settled
+        cta_sync();   // the window is free again (tile_back has read it); S.slow / S.abort are settled
+        if (S.abort || !have) break;
 
         const unsigned cap_bits = (unsigned)P.win_words * 32u - 64u;
         if (!S.slow && cur.T <= cap_bits) {
@@ -831,12 +840,14 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
                     st_flag64(P.desc_tail + g, kStatusAgg | (unsigned long long)tail);
                 }
             }
-            chain_bits(P, S, cur);
+            unsigned long long bit_base;
+            unsigned pred_tail;
+            chain_bits(P, S, cur, bit_base, pred_tail);
             cta_sync();
             if (S.abort) break;
-            unsigned k = (unsigned)(S.bit_base & 7ull);
-            unsigned hb = S.pred_tail & ((1u << k) - 1u);
-            unsigned long long pos = S.bit_base >> 3;
+            unsigned k = (unsigned)(bit_base & 7ull);
+            unsigned hb = pred_tail & ((1u << k) - 1u);
+            unsigned long long pos = bit_base >> 3;
             bool overflow = false;
             for (int gi = 0; gi < n_groups; ++gi) {
                 const int b_lo = gi * 32, b_hi = b_lo + 32 < cur.nblk ? b_lo + 32 : cur.nblk;

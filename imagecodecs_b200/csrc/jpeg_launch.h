@@ -42,7 +42,7 @@ struct ImageDesc {
     int n_mcus;
     int first_tile;  // launch-local index of the image's first tile
     int n_tiles;
-    int aligned4;    // px and stride are multiples of 4 (word loads allowed)
+    int align;       // largest power of two (<= 16) dividing both px and stride: widest legal vector load
 };
 
 // One parameter block for the three kernels of a launch group:

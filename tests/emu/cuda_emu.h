@@ -102,6 +102,8 @@ JG_DEV unsigned long long warp_shfl_xor_u64(unsigned long long v, int m)
 }
 
 JG_DEV uint32_t ldg_u32(const void* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+JG_DEV uint2 ldg_u64(const void* p) { uint2 v; memcpy(&v, p, 8); return v; }
+JG_DEV uint4 ldg_u128(const void* p) { uint4 v; memcpy(&v, p, 16); return v; }
 JG_DEV uint32_t ldg_u8(const void* p) { return *(const unsigned char*)p; }
 JG_DEV void smem_atomic_or(unsigned* p, unsigned v) { __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 JG_DEV unsigned gmem_atomic_add(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

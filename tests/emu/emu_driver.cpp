@@ -108,7 +108,7 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
         d.first_block = (unsigned long long)i * n_mcus * bpm;
         d.w = w; d.h = h; d.stride = stride; d.mcus_x = mcus_x; d.n_mcus = n_mcus;
         d.first_tile = i * tiles; d.n_tiles = tiles;
-        d.aligned4 = ((size_t)d.px % 4 == 0) && (stride % 4 == 0);
+        { const size_t v = (size_t)d.px | (size_t)stride | 16u; d.align = (int)(v & (~v + 1)); }
     }
     const int n_tiles = tiles * n_images;
     const size_t max_chunks = (size_t)n_images * ((scan_cap + kChunkBytes - 1) / kChunkBytes) + 1;
