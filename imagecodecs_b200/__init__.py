@@ -49,6 +49,8 @@ SYMBOLS = {
     "jpeg_gpu_plan_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "jpeg_gpu_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "jpeg_gpu_plan_launches": (C.c_int, [C.c_void_p]),
+    "jpeg_gpu_plan_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "jpeg_gpu_plan_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "jpeg_gpu_plan_fetch": (C.c_int, [C.c_void_p, C.POINTER(Output), C.c_int, C.c_void_p]),
     "jpeg_gpu_plan_encoded_size": (C.c_size_t, [C.c_void_p, C.c_int]),
     "jpeg_gpu_plan_num_blocks": (C.c_size_t, [C.c_void_p]),
@@ -193,6 +195,17 @@ class Plan:
     def upload(self, i, host_ptr, stream=None):
         if not self._L.jpeg_gpu_plan_upload(self._h, i, host_ptr, stream):
             raise JpegGpuError("upload failed: " + last_error())
+
+    def enable_timing(self, on=True):
+        if not self._L.jpeg_gpu_plan_enable_timing(self._h, 1 if on else 0):
+            raise JpegGpuError("enable_timing failed: " + last_error())
+
+    def kernel_times(self):
+        """(encode_ms, stuff_ms) of the last completed run (needs enable_timing)."""
+        a, b = C.c_float(0), C.c_float(0)
+        if not self._L.jpeg_gpu_plan_kernel_times(self._h, C.byref(a), C.byref(b)):
+            raise JpegGpuError("kernel_times unavailable")
+        return a.value, b.value
 
     def attach_debug(self, coefs_ptr, bits_ptr):
         self._L.jpeg_gpu_plan_attach_debug(self._h, coefs_ptr, bits_ptr)

@@ -217,6 +217,8 @@ struct jpeg_gpu_plan {
     size_t n_blocks = 0;
     int n_valid = 0;
     bool fetched_results = false;
+    bool timing = false;
+    std::vector<cudaEvent_t> events;   // per group: before encode, after encode, after stuff
 };
 
 namespace {
@@ -373,8 +375,12 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
         P.dbg_coefs = p->dbg_coefs;
         P.dbg_bits = p->dbg_bits;
         const int grid = std::min(g.n_tiles, dev.sm_count * dev.ctas_per_sm[g.spec]);
+        const size_t gi = (size_t)(&g - &p->groups[0]);
+        if (p->timing) JG_CUDA(cudaEventRecord(p->events[3 * gi], s));
         JG_CUDA(kSpecs[g.spec].launch(grid, s, P, g.quant));
+        if (p->timing) JG_CUDA(cudaEventRecord(p->events[3 * gi + 1], s));
         JG_CUDA(stuff_launch(dev.sm_count * dev.stuff_ctas_per_sm, s, P));
+        if (p->timing) JG_CUDA(cudaEventRecord(p->events[3 * gi + 2], s));
     }
     p->fetched_results = false;
     return true;
@@ -402,6 +408,7 @@ void plan_free(jpeg_gpu_plan* p)
     cudaFree(p->d_arena); cudaFree(p->d_raw); cudaFree(p->d_aux); cudaFree(p->d_pixels); cudaFree(p->d_state); cudaFree(p->d_results);
     cudaFree(p->d_images);
     if (p->h_results) cudaFreeHost(p->h_results);
+    for (cudaEvent_t e : p->events) cudaEventDestroy(e);
     delete p;
 }
 
@@ -534,6 +541,35 @@ int jpeg_gpu_plan_run(jpeg_gpu_plan* p, void* stream)
     if (!p) return 0;
     cudaStream_t s = stream ? (cudaStream_t)stream : g_devices[p->dev_index].stream;
     return plan_run(p, s) ? 1 : 0;
+}
+
+int jpeg_gpu_plan_enable_timing(jpeg_gpu_plan* p, int enable)
+{
+    if (!p) return 0;
+    if (enable && p->events.empty()) {
+        if (cudaSetDevice(g_devices[p->dev_index].id) != cudaSuccess) return 0;
+        p->events.resize(3 * p->groups.size());
+        for (auto& e : p->events)
+            if (cudaEventCreate(&e) != cudaSuccess) { set_error("cudaEventCreate failed"); return 0; }
+    }
+    p->timing = enable != 0;
+    return 1;
+}
+
+int jpeg_gpu_plan_kernel_times(jpeg_gpu_plan* p, float* encode_ms, float* stuff_ms)
+{
+    if (!p || !p->timing || p->events.empty()) return 0;
+    float enc = 0.f, stf = 0.f;
+    for (size_t gi = 0; gi < p->groups.size(); ++gi) {
+        float a = 0.f, b = 0.f;
+        if (cudaEventSynchronize(p->events[3 * gi + 2]) != cudaSuccess) return 0;
+        if (cudaEventElapsedTime(&a, p->events[3 * gi], p->events[3 * gi + 1]) != cudaSuccess) return 0;
+        if (cudaEventElapsedTime(&b, p->events[3 * gi + 1], p->events[3 * gi + 2]) != cudaSuccess) return 0;
+        enc += a; stf += b;
+    }
+    if (encode_ms) *encode_ms = enc;
+    if (stuff_ms) *stuff_ms = stf;
+    return 1;
 }
 
 int jpeg_gpu_plan_launches(const jpeg_gpu_plan* p) { return p ? 3 * (int)p->groups.size() : 0; }   // encode + plan + stuff

@@ -121,6 +121,11 @@ JPEG_GPU_API int jpeg_gpu_plan_set_pixels(jpeg_gpu_plan* plan, int i, const uint
 JPEG_GPU_API int jpeg_gpu_plan_upload(jpeg_gpu_plan* plan, int i, const uint8_t* host_pixels, void* stream);
 /* Enqueue the encode of every image of the plan on `stream` (cudaStream_t, may be NULL). */
 JPEG_GPU_API int jpeg_gpu_plan_run(jpeg_gpu_plan* plan, void* stream);
+/* With timing enabled every run records CUDA events around its kernels; after the run has
+ * completed, kernel_times returns the device time of the encode kernels (pass 1) and of the
+ * plan+stuff kernels (pass 2) of the LAST run, in milliseconds.  Returns 0 if unavailable. */
+JPEG_GPU_API int jpeg_gpu_plan_enable_timing(jpeg_gpu_plan* plan, int enable);
+JPEG_GPU_API int jpeg_gpu_plan_kernel_times(jpeg_gpu_plan* plan, float* encode_ms, float* stuff_ms);
 /* Number of kernel launches one jpeg_gpu_plan_run enqueues. */
 JPEG_GPU_API int jpeg_gpu_plan_launches(const jpeg_gpu_plan* plan);
 /* Wait for `stream`, then deliver headers + scans into outs[] (host or device buffers). */
