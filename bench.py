@@ -29,7 +29,6 @@ W, H, NC = 1920, 1080, 3
 BATCH = 256
 QMODE, QUALITY, SUB = 1, 75, 1          # IJG 75, 4:2:0
 TWIN_QMODE, TWIN_QUALITY, TWIN_SUB = 0, 2, 0   # byte-pinned native twin: tje quality 2, 4:4:4
-E2E_CHUNKS = 8
 METRIC = "jpeg_encode_mp_per_s"
 UNIT = "MP/s"
 
@@ -276,35 +275,22 @@ def run_ours(args):
         except Exception as e:   # the bench still reports, but says so
             parity = "check failed: %r" % (e,)
 
-    # ---- end to end: pinned host pixels -> C ABI -> host JPEG files -----------------------------
-    # The batch goes through E2E_CHUNKS plans on separate streams, so the upload of one chunk
-    # overlaps the kernels and the download of the others (PCIe is the bottleneck of this path).
+    # ---- end to end: pinned host pixels -> ONE C-ABI call -> host JPEG files --------------------
+    # jpeg_gpu_encode_batch is the call a user of the library makes: it uploads, encodes and
+    # downloads (internally in chunks on a ring of streams, so the PCIe copies overlap the kernels).
     host_px = pixels.cpu().pin_memory()
     img_bytes = W * H * NC
     cap = max(sizes) + 4096
     host_out = torch.empty((BATCH, cap), dtype=torch.uint8).pin_memory()
-    per = BATCH // E2E_CHUNKS
-    eplans, estreams, eouts = [], [], []
-    for c in range(E2E_CHUNKS):
-        descs = [jg.Image(0, W, H, NC, 0, QMODE, QUALITY, SUB, 0) for _ in range(per)]
-        eplans.append(jg.Plan(descs, device=0))
-        estreams.append(torch.cuda.Stream(device=dev))
-        o = (jg.Output * per)()
-        for i in range(per):
-            o[i] = jg.Output(host_out[c * per + i].data_ptr(), cap, 0, 0)
-        eouts.append(o)
-    base = host_px.data_ptr()
+    e_imgs = (jg.Image * BATCH)(*[jg.Image(host_px[i].data_ptr(), W, H, NC, 0, QMODE, QUALITY, SUB, 0) for i in range(BATCH)])
+    e_outs = (jg.Output * BATCH)(*[jg.Output(host_out[i].data_ptr(), cap, 0, 0) for i in range(BATCH)])
+    e_opts = jg.BatchOpts(0, 0, None, 0)
+    L = jg.lib()
 
     def e2e_step():
-        for c in range(E2E_CHUNKS):
-            sp = C.c_void_p(estreams[c].cuda_stream)
-            for i in range(per):
-                eplans[c].upload(i, base + (c * per + i) * img_bytes, sp)
-            eplans[c].run(sp)
-        for c in range(E2E_CHUNKS):       # synchronises stream c: headers + scans are in host memory after this
-            ok = eplans[c].fetch_into(eouts[c], 0, C.c_void_p(estreams[c].cuda_stream))
-            if ok != per:
-                raise RuntimeError("e2e step encoded %d of %d" % (ok, per))
+        ok = L.jpeg_gpu_encode_batch(e_imgs, BATCH, e_outs, C.byref(e_opts))   # returns with the files in host memory
+        if ok != BATCH:
+            raise RuntimeError("e2e step encoded %d of %d: %s" % (ok, BATCH, jg.last_error()))
 
     for _ in range(max(1, min(args.warmup, 3))):
         e2e_step()
@@ -317,15 +303,13 @@ def run_ours(args):
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     barrier()
     e2e_ms = max_over_ranks(e2e_ms)
-    d2h = int(sum(eouts[c][i].size for c in range(E2E_CHUNKS) for i in range(per)) - BATCH * hdr_len)
+    d2h = int(sum(e_outs[i].size for i in range(BATCH)) - BATCH * hdr_len)
     e2e = {"value": round(world * mp_per_step / (e2e_ms * 1e-3), 2), "unit": UNIT,
            "h2d_bytes_per_step": BATCH * img_bytes, "d2h_bytes_per_step": d2h,
            "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
-           "api": "per %d-image chunk: jpeg_gpu_plan_upload x%d + jpeg_gpu_plan_run + jpeg_gpu_plan_fetch, %d chunks on %d streams (pinned host in/out)" % (per, per, E2E_CHUNKS, E2E_CHUNKS)}
+           "api": "jpeg_gpu_encode_batch(256 host images) -> 256 host JPEG files, pinned buffers, one call per step"}
     if rank == 0 and parity is True:
-        parity = bytes(host_out[0][:eouts[0][0].size].numpy().tobytes()) == files[0]
-    for pl in eplans:
-        pl.close()
+        parity = bytes(host_out[0][:e_outs[0].size].numpy().tobytes()) == files[0]
 
     # ---- byte-pinned native twin of the same shape (tje quality 2, 4:4:4), device-timed ----------
     twin = None

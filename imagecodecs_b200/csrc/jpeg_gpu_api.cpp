@@ -76,6 +76,12 @@ struct Device {
     int stuff_ctas_per_sm = 0;
     HuffLut* d_huff = nullptr;
     cudaStream_t stream = nullptr;   // used when the caller gives none
+    cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};   // chunk pipeline of jpeg_gpu_encode_batch
+    // Caching allocator: plans come and go per call, cudaMalloc / cudaMallocHost must not.
+    std::mutex* pool_mutex = nullptr;
+    std::multimap<size_t, void*>* pool_dev = nullptr;    // free device blocks by size
+    std::multimap<size_t, void*>* pool_host = nullptr;   // free pinned host blocks by size
+    size_t pooled_bytes = 0;
 };
 
 std::mutex g_mutex;
@@ -103,7 +109,63 @@ bool init_device(Device& d, int id)
     JG_CUDA(cudaMalloc(&d.d_huff, sizeof(HuffLut)));
     JG_CUDA(cudaMemcpy(d.d_huff, &lut, sizeof(HuffLut), cudaMemcpyHostToDevice));
     JG_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    for (auto& ps : d.pipe) JG_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    d.pool_mutex = new std::mutex();
+    d.pool_dev = new std::multimap<size_t, void*>();
+    d.pool_host = new std::multimap<size_t, void*>();
     return true;
+}
+
+// size classes: powers of two from 64 KB, so that a freed block fits the next request of its kind
+size_t pool_class(size_t bytes)
+{
+    size_t c = 64 * 1024;
+    while (c < bytes) c <<= 1;
+    return c;
+}
+
+constexpr size_t kPoolLimit = 24ull << 30;   // keep at most this much idle device memory cached per GPU
+
+bool pool_alloc(Device& d, size_t bytes, bool host, void** out)
+{
+    const size_t c = pool_class(bytes);
+    {
+        std::lock_guard<std::mutex> lk(*d.pool_mutex);
+        auto& m = host ? *d.pool_host : *d.pool_dev;
+        auto f = m.find(c);
+        if (f != m.end()) {
+            *out = f->second;
+            m.erase(f);
+            if (!host) d.pooled_bytes -= c;
+            return true;
+        }
+    }
+    cudaError_t e = host ? cudaMallocHost(out, c) : cudaMalloc(out, c);
+    if (e != cudaSuccess && !host) {
+        // out of memory: drop the cache and try once more
+        std::lock_guard<std::mutex> lk(*d.pool_mutex);
+        for (auto& kv : *d.pool_dev) cudaFree(kv.second);
+        d.pool_dev->clear();
+        d.pooled_bytes = 0;
+        (void)cudaGetLastError();
+        e = cudaMalloc(out, c);
+    }
+    if (e != cudaSuccess) {
+        set_error("%s of %zu bytes failed: %s", host ? "cudaMallocHost" : "cudaMalloc", c, cudaGetErrorString(e));
+        *out = nullptr;
+        return false;
+    }
+    return true;
+}
+
+void pool_free(Device& d, void* p, size_t bytes, bool host)
+{
+    if (!p) return;
+    const size_t c = pool_class(bytes);
+    std::lock_guard<std::mutex> lk(*d.pool_mutex);
+    if (!host && d.pooled_bytes + c > kPoolLimit) { cudaFree(p); return; }
+    (host ? *d.pool_host : *d.pool_dev).emplace(c, p);
+    if (!host) d.pooled_bytes += c;
 }
 
 bool ensure_init()
@@ -204,7 +266,8 @@ struct jpeg_gpu_plan {
     std::vector<Group> groups;
     uint8_t* d_arena = nullptr;      size_t arena_bytes = 0;
     uint8_t* d_raw = nullptr;        // unstuffed scans, same layout as the arena
-    uint8_t* d_aux = nullptr;        // raw_bytes u64[n] + first_chunk u32[n + groups]
+    uint8_t* d_aux = nullptr;        size_t aux_bytes = 0;      // raw_bytes u64[n] + first_chunk u32[n + groups]
+    size_t images_bytes = 0;
     uint8_t* d_pixels = nullptr;     size_t pixels_bytes = 0;
     uint8_t* d_state = nullptr;      size_t state_bytes = 0;    // zeroed before every run
     uint8_t* d_results = nullptr;    size_t results_bytes = 0;  // scan_bytes[n] u64, status[n] u32
@@ -297,15 +360,17 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
     p->results_bytes = nres * 8 + nres * 4;
     if (nres == 0) return true;
 
-    JG_CUDA(cudaMalloc(&p->d_arena, std::max<size_t>(arena, 256)));
-    JG_CUDA(cudaMalloc(&p->d_raw, std::max<size_t>(arena, 256)));
-    JG_CUDA(cudaMalloc(&p->d_aux, nres * 8 + (nres + p->groups.size()) * 4 + 16));
-    if (pixels) JG_CUDA(cudaMalloc(&p->d_pixels, pixels));
-    JG_CUDA(cudaMalloc(&p->d_state, state));
-    JG_CUDA(cudaMalloc(&p->d_results, p->results_bytes));
-    JG_CUDA(cudaMemset(p->d_results, 0, p->results_bytes));
-    JG_CUDA(cudaMallocHost(&p->h_results, p->results_bytes));
-    JG_CUDA(cudaMalloc(&p->d_images, nres * sizeof(ImageDesc)));
+    p->arena_bytes = std::max<size_t>(arena, 256);
+    p->aux_bytes = nres * 8 + (nres + p->groups.size()) * 4 + 16;
+    p->images_bytes = nres * sizeof(ImageDesc);
+    if (!pool_alloc(dev, p->arena_bytes, false, (void**)&p->d_arena)) return false;
+    if (!pool_alloc(dev, p->arena_bytes, false, (void**)&p->d_raw)) return false;
+    if (!pool_alloc(dev, p->aux_bytes, false, (void**)&p->d_aux)) return false;
+    if (pixels && !pool_alloc(dev, pixels, false, (void**)&p->d_pixels)) return false;
+    if (!pool_alloc(dev, state, false, (void**)&p->d_state)) return false;
+    if (!pool_alloc(dev, p->results_bytes, false, (void**)&p->d_results)) return false;
+    if (!pool_alloc(dev, p->results_bytes, true, (void**)&p->h_results)) return false;
+    if (!pool_alloc(dev, p->images_bytes, false, (void**)&p->d_images)) return false;
     p->h_images.resize(nres);
     for (auto& g : p->groups) {
         g.d_images = p->d_images + g.result_off;
@@ -353,6 +418,7 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
     if (p->groups.empty()) return true;
     if (!plan_sync_images(p, s)) return false;
     JG_CUDA(cudaMemsetAsync(p->d_state, 0, p->state_bytes, s));
+    JG_CUDA(cudaMemsetAsync(p->d_results, 0, p->results_bytes, s));
     for (auto& g : p->groups) {
         LaunchParams P;
         P.images = g.d_images;
@@ -404,10 +470,18 @@ bool plan_results(jpeg_gpu_plan* p, cudaStream_t s)
 void plan_free(jpeg_gpu_plan* p)
 {
     if (!p) return;
-    if (p->dev_index < (int)g_devices.size()) cudaSetDevice(g_devices[p->dev_index].id);
-    cudaFree(p->d_arena); cudaFree(p->d_raw); cudaFree(p->d_aux); cudaFree(p->d_pixels); cudaFree(p->d_state); cudaFree(p->d_results);
-    cudaFree(p->d_images);
-    if (p->h_results) cudaFreeHost(p->h_results);
+    if (p->dev_index < (int)g_devices.size()) {
+        Device& dev = g_devices[p->dev_index];
+        cudaSetDevice(dev.id);
+        pool_free(dev, p->d_arena, p->arena_bytes, false);
+        pool_free(dev, p->d_raw, p->arena_bytes, false);
+        pool_free(dev, p->d_aux, p->aux_bytes, false);
+        pool_free(dev, p->d_pixels, p->pixels_bytes, false);
+        pool_free(dev, p->d_state, p->state_bytes, false);
+        pool_free(dev, p->d_results, p->results_bytes, false);
+        pool_free(dev, p->d_images, p->images_bytes, false);
+        pool_free(dev, p->h_results, p->results_bytes, true);
+    }
     for (cudaEvent_t e : p->events) cudaEventDestroy(e);
     delete p;
 }
@@ -473,6 +547,10 @@ void jpeg_gpu_shutdown(void)
         cudaSetDevice(d.id);
         cudaFree(d.d_huff);
         if (d.stream) cudaStreamDestroy(d.stream);
+        for (auto& ps : d.pipe) if (ps) cudaStreamDestroy(ps);
+        if (d.pool_dev) { for (auto& kv : *d.pool_dev) cudaFree(kv.second); delete d.pool_dev; }
+        if (d.pool_host) { for (auto& kv : *d.pool_host) cudaFreeHost(kv.second); delete d.pool_host; }
+        delete d.pool_mutex;
     }
     g_devices.clear();
 }
@@ -637,22 +715,28 @@ int jpeg_gpu_plan_fetch(jpeg_gpu_plan* p, jpeg_gpu_output* outs, int outputs_on_
 void jpeg_gpu_plan_destroy(jpeg_gpu_plan* p) { plan_free(p); }
 
 // -----------------------------------------------------------------------------------------
-static int encode_on_device(const jpeg_gpu_image* images, int n, jpeg_gpu_output* outs, int device,
-                            int outputs_on_device, cudaStream_t stream, int win_words)
+// One chunk of a batch on one stream: plan, uploads, kernels enqueued; fetched later.
+static jpeg_gpu_plan* start_chunk(const jpeg_gpu_image* images, int n, int device, cudaStream_t s, int win_words)
 {
     jpeg_gpu_plan* p = plan_create(images, n, device, win_words, false);
+    if (!p) return nullptr;
+    for (int i = 0; i < n; ++i)
+        if (p->items[i].valid && !images[i].pixels_on_device && !jpeg_gpu_plan_upload(p, i, images[i].pixels, s)) {
+            plan_free(p);
+            return nullptr;
+        }
+    if (!plan_run(p, s)) { plan_free(p); return nullptr; }
+    return p;
+}
+
+static int finish_chunk(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, jpeg_gpu_output* outs, int device,
+                        int outputs_on_device, cudaStream_t s, int win_words)
+{
     if (!p) {
         for (int i = 0; i < n; ++i) { outs[i].size = 0; outs[i].status = JPEG_GPU_ERR_CUDA; }
         return 0;
     }
-    cudaStream_t s = stream ? stream : g_devices[device].stream;
-    bool good = true;
-    for (int i = 0; i < n && good; ++i)
-        if (p->items[i].valid && !images[i].pixels_on_device) good = jpeg_gpu_plan_upload(p, i, images[i].pixels, s) != 0;
-    int ok = 0;
-    if (good && plan_run(p, s)) ok = jpeg_gpu_plan_fetch(p, outs, outputs_on_device, s);
-    else for (int i = 0; i < n; ++i) { outs[i].size = 0; outs[i].status = JPEG_GPU_ERR_CUDA; }
-
+    int ok = jpeg_gpu_plan_fetch(p, outs, outputs_on_device, s);
     // content that outgrew the default reservation: once more, alone, with the worst-case bound
     for (int i = 0; i < n; ++i) {
         if (!p->items[i].valid || outs[i].status != JPEG_GPU_ERR_CAPACITY) continue;
@@ -666,6 +750,45 @@ static int encode_on_device(const jpeg_gpu_image* images, int n, jpeg_gpu_output
         plan_free(q);
     }
     plan_free(p);
+    return ok;
+}
+
+// A batch on one device.  Large host batches are cut into chunks that travel through a small
+// ring of streams: the upload of chunk c+1 overlaps the kernels of chunk c and the download of
+// chunk c-1 (the PCIe link is the bottleneck of this path, the kernels are not).
+static int encode_on_device(const jpeg_gpu_image* images, int n, jpeg_gpu_output* outs, int device,
+                            int outputs_on_device, cudaStream_t stream, int win_words)
+{
+    Device& dev = g_devices[device];
+    if (stream) {   // caller-ordered work: everything on the caller's stream, one plan
+        jpeg_gpu_plan* p = start_chunk(images, n, device, stream, win_words);
+        return finish_chunk(p, images, n, outs, device, outputs_on_device, stream, win_words);
+    }
+    constexpr size_t kChunkPixelBytes = 192ull << 20;
+    constexpr int kRing = 4;
+    struct Chunk { int lo, hi; jpeg_gpu_plan* plan; cudaStream_t s; };
+    std::vector<Chunk> chunks;
+    for (int lo = 0; lo < n;) {
+        size_t bytes = 0;
+        int hi = lo;
+        while (hi < n && (hi == lo || bytes < kChunkPixelBytes)) {
+            bytes += (size_t)std::max(images[hi].stride, images[hi].width * images[hi].ncomp) * (size_t)std::max(images[hi].height, 0);
+            ++hi;
+        }
+        chunks.push_back({lo, hi, nullptr, dev.pipe[chunks.size() % kRing]});
+        lo = hi;
+    }
+    int ok = 0;
+    size_t started = 0;
+    for (size_t c = 0; c < chunks.size(); ++c) {
+        // keep at most kRing chunks in flight (bounds device memory), finishing them in order
+        for (; started < chunks.size() && started < c + kRing; ++started) {
+            Chunk& k = chunks[started];
+            k.plan = start_chunk(images + k.lo, k.hi - k.lo, device, k.s, win_words);
+        }
+        Chunk& k = chunks[c];
+        ok += finish_chunk(k.plan, images + k.lo, k.hi - k.lo, outs + k.lo, device, outputs_on_device, k.s, win_words);
+    }
     return ok;
 }
 
