@@ -37,6 +37,15 @@ def test_emulated_kernel_matches_oracle(label, shape, qm, q, sub, win, ctas):
         assert status[i] == 0
 
 
+def test_emulated_kernel_vector_load_paths():
+    """16-byte (4:2:0, pitch % 16 == 0), 8-byte (pitch % 8 == 0) and 4-byte pixel loads."""
+    for (w, h, nc, qm, q, sub) in [(64, 32, 3, 1, 75, 1), (40, 24, 3, 0, 3, 0), (44, 24, 3, 0, 2, 0), (32, 16, 4, 1, 90, 1), (48, 16, 1, 1, 85, 0)]:
+        batch = oracle.synth_batch(1, w, h, nc, "photo")
+        scans, sizes, status = emu_encode(batch, qm, q, sub, n_ctas=1)
+        hdr = oracle.oracle_headers(w, h, 1 if nc == 1 else 3, sub, qm, q)
+        assert hdr + scans[0] == oracle.oracle_encode(batch[0], qm, q, sub), (w, h, nc)
+
+
 def test_emulated_kernel_reports_capacity_overflow():
     batch = oracle.synth_batch(1, 64, 64, 3, "noise")
     scans, sizes, status = emu_encode(batch, 0, 3, 0, n_ctas=1, cap=4096)

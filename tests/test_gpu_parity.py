@@ -70,6 +70,62 @@ def test_sizes_and_edge_clamp(gpu, w, h, q):
         assert encode_one(gpu, img, 0, q) == oracle.oracle_encode(img, 0, q)
 
 
+def test_pitches_and_alignments(gpu):
+    """Every pixel-load path: 16/8/4-byte vector loads, the byte loader, padded rows (stride > w*ncomp)."""
+    import ctypes as C
+    L = gpu.lib()
+    for (w, h, nc, pad, shift, qm, q, sub) in [
+            (1000, 70, 3, 0, 0, 0, 2, 0),      # pitch 3000: 8-byte loads
+            (1000, 70, 3, 0, 0, 1, 75, 1),
+            (1002, 64, 3, 0, 0, 0, 3, 0),      # pitch 3006: byte loader everywhere
+            (1004, 64, 3, 0, 0, 1, 75, 1),     # pitch 3012: 4-byte loads
+            (640, 48, 3, 128, 0, 0, 3, 0),     # padded rows, 16-byte loads
+            (640, 48, 4, 64, 0, 1, 90, 1),
+            (333, 41, 3, 7, 0, 0, 1, 0),       # odd pitch
+            (640, 48, 3, 0, 4, 1, 75, 1),      # base pointer only 4-byte aligned
+            (640, 48, 1, 24, 0, 1, 85, 0),     # gray, padded
+            (640, 48, 1, 0, 1, 1, 85, 0)]:     # gray, odd base
+        img = oracle.synth_image(w, h, nc, n=w % 7)
+        stride = w * nc + pad
+        buf = np.zeros(shift + stride * h + 64, np.uint8)
+        view = buf[shift:shift + stride * h].reshape(h, stride)
+        view[:, :w * nc] = img.reshape(h, w * nc)
+        view[:, w * nc:] = 0xAB                  # padding must never be read as pixels
+        desc = gpu.Image(buf.ctypes.data + shift, w, h, nc, stride, qm, q, sub, 0)
+        cap = gpu.max_encoded_size(w, h, nc, sub)
+        out = np.empty(cap, np.uint8)
+        o = gpu.Output(out.ctypes.data, cap, 0, 0)
+        opts = gpu.BatchOpts(0, 0, None, 0)
+        assert L.jpeg_gpu_encode_batch(C.byref(desc), 1, C.byref(o), C.byref(opts)) == 1
+        assert out[:o.size].tobytes() == oracle.oracle_encode(img, qm, q, sub), (w, h, nc, pad, shift)
+
+
+def test_kernel_timing_api(gpu):
+    import torch
+    from imagecodecs_b200.synth import synth_batch
+    dev = synth_batch(8, 640, 480, 3, device="cuda"); torch.cuda.synchronize()
+    plan = gpu.Plan.for_arrays([dev[i] for i in range(8)], 1, 75, 1, device=0)
+    plan.enable_timing(True)
+    plan.run(); files = plan.fetch()
+    enc, stf = plan.kernel_times()
+    plan.close()
+    assert 0.0 < enc < 50.0 and 0.0 < stf < 50.0
+    assert files[3] == oracle.oracle_encode(dev[3].cpu().numpy(), 1, 75, 1)
+
+
+def test_large_host_batch_is_chunked(gpu):
+    """More than one pipeline chunk (> 192 MB of pixels) and more chunks than ring slots."""
+    n = 40
+    batch = oracle.synth_batch(n, 1920, 1080, 3, first=3)           # 249 MB -> 2 chunks
+    files, st = gpu.encode_batch([batch[i] for i in range(n)], 1, 75, 1, device=0)
+    assert st == [0] * n
+    for i in (0, 19, 39):
+        assert files[i] == oracle.oracle_encode(batch[i], 1, 75, 1)
+    big = oracle.synth_batch(6, 3840, 2160, 4, first=1)              # 33 MB each... six chunks of one? no: 199 MB -> 2 chunks
+    files, st = gpu.encode_batch([big[i] for i in range(6)], 0, 2, 0, device=0)
+    assert st == [0] * 6 and files[5] == oracle.oracle_encode(big[5], 0, 2, 0)
+
+
 def test_checkerboards_reach_coefficient_bounds(gpu):
     """F(0,4)/F(4,4)-style patterns hit the largest AC magnitudes."""
     yy, xx = np.mgrid[0:64, 0:64]
