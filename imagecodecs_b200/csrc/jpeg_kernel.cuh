@@ -764,7 +764,7 @@ JG_DEV void tile_back(const LaunchParams& P, Smem<LAYOUT, NC>& S, const TileCtx&
 // kernel 1: pixels -> unstuffed entropy-coded bits
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT, int NC>
-JG_KERNEL(kThreads, 3)
+JG_KERNEL(kThreads, 6)
 void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTANT QuantSet Q)
 {
     JG_DYNAMIC_SMEM(smem_raw);
@@ -830,9 +830,10 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
             // pathological tile: groups of 32 blocks (4 per warp, always fit), coded again and written
             // out right away, not pipelined.  The last group goes first, only to learn the tile's
             // last 7 bits: successors must not wait for our whole slow pass.
-            const int n_groups = (cur.nblk + 31) / 32;
+            constexpr int GB = 4 * kWarps;            // blocks per group
+            const int n_groups = (cur.nblk + GB - 1) / GB;
             {
-                const int b_lo = (n_groups - 1) * 32;
+                const int b_lo = (n_groups - 1) * GB;
                 const unsigned tg = encode_range<LAYOUT, NC>(S, b_lo, cur.nblk, 4, nullptr);
                 compact_regions<LAYOUT, NC>(S, tg);
                 if (t == 0) {
@@ -850,7 +851,7 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
             unsigned long long pos = bit_base >> 3;
             bool overflow = false;
             for (int gi = 0; gi < n_groups; ++gi) {
-                const int b_lo = gi * 32, b_hi = b_lo + 32 < cur.nblk ? b_lo + 32 : cur.nblk;
+                const int b_lo = gi * GB, b_hi = b_lo + GB < cur.nblk ? b_lo + GB : cur.nblk;
                 const unsigned tg = encode_range<LAYOUT, NC>(S, b_lo, b_hi, 4, nullptr);   // block sizes were dumped by the first attempt
                 compact_regions<LAYOUT, NC>(S, tg);
                 flush_window(P, S, cur, tg, cur.last && gi == n_groups - 1, k, hb, pos, overflow);

@@ -13,15 +13,15 @@
 
 namespace jg {
 
-constexpr int kThreads = 256;
-constexpr int kBlocksPerTile = 192;   // array bound; a tile holds mcus_per_tile(layout) * blocks-per-MCU <= 191 blocks
+constexpr int kThreads = 128;
+constexpr int kBlocksPerTile = 24 * (kThreads / 32);   // array bound; a tile holds mcus_per_tile(layout) * blocks-per-MCU blocks, 24 per warp
 constexpr int kWarps = kThreads / 32;
-constexpr int kChunkBytes = 4096;     // unstuffed bytes one stuffing step handles (16 per thread)
+constexpr int kChunkBytes = 16 * kThreads;   // unstuffed bytes one stuffing step handles (16 per thread)
 
 // MCUs per tile.  One extra "slot" per tile holds the MCU that precedes the tile (its DCs seed the
 // DC prediction), so slots = MCUs + 1 divides evenly among the CTA's lane groups.
-constexpr int mcus_per_tile(int layout) { return layout == LAYOUT_444 ? 63 : (layout == LAYOUT_420 ? 31 : 191); }
-constexpr int kWinWordsMax = 3072;   // 12 KB tile window (unstuffed bits of one tile)
+constexpr int mcus_per_tile(int layout) { return layout == LAYOUT_444 ? kThreads / 4 - 1 : (layout == LAYOUT_420 ? kThreads / 8 - 1 : 3 * kThreads / 4 - 1); }
+constexpr int kWinWordsMax = 384 * (kThreads / 32);   // tile window (unstuffed bits of one tile): 384 words per warp
 constexpr int kWinWordsMin = 64;     // must hold one worst-case block (1658 bits) + slack
 constexpr unsigned kSpinLimit = 1u << 24;
 

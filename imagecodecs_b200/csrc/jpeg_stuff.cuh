@@ -49,7 +49,7 @@ void plan_chunks_kernel(const JG_GRID_CONSTANT LaunchParams P)
     if (t == 0) P.first_chunk[P.n_images] = carry;
 }
 
-JG_KERNEL(kThreads, 4)
+JG_KERNEL(kThreads, 8)
 void stuff_kernel(const JG_GRID_CONSTANT LaunchParams P)
 {
     JG_DYNAMIC_SMEM(smem_raw);
