@@ -16,7 +16,7 @@ namespace jg {
 constexpr int kThreads = 128;
 constexpr int kBlocksPerTile = 24 * (kThreads / 32);   // array bound; a tile holds mcus_per_tile(layout) * blocks-per-MCU blocks, 24 per warp
 constexpr int kWarps = kThreads / 32;
-constexpr int kChunkBytes = 16 * kThreads;   // unstuffed bytes one stuffing step handles (16 per thread)
+constexpr int kChunkBytes = 64 * kThreads;   // unstuffed bytes one stuffing step handles (64 per thread)
 
 // MCUs per tile.  One extra "slot" per tile holds the MCU that precedes the tile (its DCs seed the
 // DC prediction), so slots = MCUs + 1 divides evenly among the CTA's lane groups.

@@ -80,15 +80,21 @@ void stuff_kernel(const JG_GRID_CONSTANT LaunchParams P)
         const unsigned nb = raw_n - off < (unsigned long long)kChunkBytes ? (unsigned)(raw_n - off) : (unsigned)kChunkBytes;
         const bool last_chunk = off + nb == raw_n;
 
-        // 16 bytes per thread (raw is 256-byte aligned, chunks are 4 KB: always a legal uint4 load)
-        const unsigned b0 = (unsigned)t * 16u;
-        uint4 v = {0u, 0u, 0u, 0u};
-        if (b0 < nb) v = *reinterpret_cast<const uint4*>(im.raw + off + b0);
-        const unsigned mine = b0 < nb ? (nb - b0 < 16u ? nb - b0 : 16u) : 0u;
-        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+        // kStuffPerThread contiguous bytes per thread, as 16-byte vectors (raw is 256-byte aligned and
+        // chunk offsets are multiples of the chunk size: always legal uint4 loads)
+        constexpr int NV = kChunkBytes / kThreads / 16;
+        const unsigned b0 = (unsigned)t * (16u * NV);
+        const unsigned mine = b0 < nb ? (nb - b0 < 16u * NV ? nb - b0 : 16u * NV) : 0u;
+        unsigned w[4 * NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            uint4 v = {0u, 0u, 0u, 0u};
+            if (b0 + 16u * q < nb) v = *reinterpret_cast<const uint4*>(im.raw + off + b0 + 16u * q);
+            w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+        }
         unsigned cnt = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 4 * NV; ++q) {
             unsigned m = v_cmpeq4(w[q], 0xffffffffu);
             const int valid = (int)mine - 4 * q;                    // bytes of this word that exist
             if (valid <= 0) m = 0; else if (valid < 4) m &= 0xffffffffu >> (8 * (4 - valid));
@@ -103,7 +109,7 @@ void stuff_kernel(const JG_GRID_CONSTANT LaunchParams P)
         {
             unsigned o = b0 + ff_ex;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < 16 * NV; ++j) {
                 if ((unsigned)j < mine) {
                     const unsigned byte = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
                     S.sbuf[o++] = (uint8_t)byte;
