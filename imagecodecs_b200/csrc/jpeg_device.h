@@ -68,6 +68,10 @@ JG_DEV void st_flag64(unsigned long long* p, unsigned long long v)
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+JG_DEV void st_flag32(unsigned* p, unsigned v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 JG_DEV unsigned ld_flag32(const unsigned* p)
 {
     unsigned v;

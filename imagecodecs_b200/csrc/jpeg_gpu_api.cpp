@@ -351,7 +351,7 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
         size_t chunks = 1;
         for (int idx : g.items) chunks += (p->items[idx].scan_cap + kChunkBytes - 1) / kChunkBytes;
         g.max_chunks = chunks;
-        state += 16 + (size_t)tiles * 16 + chunks * 8;
+        state += 16 + (size_t)tiles * 16 + chunks * 8 + (((size_t)tiles * 12 + 15) / 16) * 16;
         g.result_off = res_index;
         res_index += g.items.size();
     }
@@ -433,6 +433,7 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
         P.desc_bits = reinterpret_cast<unsigned long long*>(st + 16);
         P.desc_tail = P.desc_bits + g.n_tiles;
         P.desc_ff = P.desc_tail + g.n_tiles;
+        P.desc_dc = reinterpret_cast<unsigned*>(P.desc_ff + g.max_chunks);
         P.raw_bytes = g.d_raw_bytes;
         P.first_chunk = g.d_first_chunk;
         P.scan_bytes = g.d_scan_bytes;

@@ -59,11 +59,12 @@ struct Geo {
     static constexpr int BPM = LAYOUT == LAYOUT_444 ? 3 : (LAYOUT == LAYOUT_420 ? 6 : 1);  // blocks per MCU
     static constexpr int MCU = LAYOUT == LAYOUT_420 ? 16 : 8;                               // MCU edge in pixels
     static constexpr int M = mcus_per_tile(LAYOUT);        // MCUs per tile
-    static constexpr int SLOTS = M + 1;                    // slot 0 = the MCU preceding the tile
+    static constexpr int SLOTS = M;                        // one lane group per MCU and iteration
     static constexpr int LANES = LAYOUT == LAYOUT_420 ? 16 : 8;   // lanes that share one MCU
     static constexpr int GROUPS = kThreads / LANES;
     static constexpr int ITERS = SLOTS / GROUPS;
     static constexpr int TILES = LAYOUT == LAYOUT_420 ? 6 : 1;    // exchange tiles per lane group
+    static constexpr int NCOMP = LAYOUT == LAYOUT_GRAY ? 1 : 3;
     static_assert(SLOTS % GROUPS == 0, "slots must divide evenly among the lane groups");
     static_assert(M * BPM <= kBlocksPerTile, "tile too large");
 };
@@ -210,24 +211,22 @@ JG_DEV void row_pass_store(float (&s)[8], float* tile, int r)
 }
 
 // column u of an exchange tile: column pass, quantise, scatter to zigzag order.
-// blk < 0: the block belongs to the predecessor slot, only its DC is kept (in *pred_dc).
+// dc_out != nullptr: the block is the last of its component in the tile; its DC is published for
+// the next tile's DC prediction (the lane that computed it stores it, nobody waits for anybody).
 template <int LAYOUT, int NC>
-JG_DEV void column_pass(Smem<LAYOUT, NC>& S, const float* tile, int u, bool chroma, int blk, int* pred_dc, const LaneConst& LC)
+JG_DEV void column_pass(Smem<LAYOUT, NC>& S, const float* tile, int u, bool chroma, int blk, unsigned* dc_out, const LaneConst& LC)
 {
     float c[8];
 #pragma unroll
     for (int v = 0; v < 8; ++v) c[v] = tile[v * 9 + u];
     aan8(c);
-    if (blk >= 0) {
-        int16_t* dst = S.coef + blk * kCoefStride;
+    int16_t* dst = S.coef + blk * kCoefStride;
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-            const int k = quantise(c[v], chroma ? LC.pq_c[v] : LC.pq_l[v]);
-            const unsigned zz = ((v < 4 ? LC.zz_lo : LC.zz_hi) >> (8 * (v & 3))) & 0xffu;
-            dst[zz] = (int16_t)k;
-        }
-    } else if (u == 0 && pred_dc != nullptr) {
-        *pred_dc = quantise(c[0], chroma ? LC.pq_c[0] : LC.pq_l[0]);
+    for (int v = 0; v < 8; ++v) {
+        const int k = quantise(c[v], chroma ? LC.pq_c[v] : LC.pq_l[v]);
+        const unsigned zz = ((v < 4 ? LC.zz_lo : LC.zz_hi) >> (8 * (v & 3))) & 0xffu;
+        dst[zz] = (int16_t)k;
+        if (v == 0 && u == 0 && dc_out != nullptr) st_flag32(dc_out, 0x80000000u | ((unsigned)k & 0xffffu));
     }
 }
 
@@ -235,7 +234,7 @@ JG_DEV void column_pass(Smem<LAYOUT, NC>& S, const float* tile, int u, bool chro
 // stage 1: transform all slots of the tile
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT, int NC>
-JG_DEV void transform_tile(Smem<LAYOUT, NC>& S, const ImageDesc& im, int m0, int nM, const LaneConst& LC)
+JG_DEV void transform_tile(Smem<LAYOUT, NC>& S, const ImageDesc& im, int m0, int nM, unsigned* dc_out, const LaneConst& LC)
 {
     using G = Geo<LAYOUT>;
     const int t = JG_TID;
@@ -246,8 +245,9 @@ JG_DEV void transform_tile(Smem<LAYOUT, NC>& S, const ImageDesc& im, int m0, int
 #pragma unroll 1
     for (int it = 0; it < G::ITERS; ++it) {
         const int slot = it * G::GROUPS + grp;
-        const int m = m0 - 1 + slot;
-        const bool valid = slot == 0 ? (m0 > 0) : (slot <= nM);
+        const int m = m0 + slot;
+        const bool valid = slot < nM;
+        unsigned* dcs = (slot == nM - 1) ? dc_out : nullptr;     // the tile's last MCU publishes its DCs
         int my = 0, mx = 0;
         if (valid) { my = m / im.mcus_x; mx = m - my * im.mcus_x; }
 
@@ -263,7 +263,7 @@ JG_DEV void transform_tile(Smem<LAYOUT, NC>& S, const ImageDesc& im, int m0, int
                 row_pass_store(s, tile, u);
             }
             warp_sync();
-            if (valid) column_pass(S, tile, u, false, slot - 1, &S.pred_dc[0], LC);
+            if (valid) column_pass(S, tile, u, false, slot, dcs, LC);
             warp_sync();
         } else if (LAYOUT == LAYOUT_444) {
             float* tile = scratch + grp * kTileFloats;
@@ -285,7 +285,7 @@ JG_DEV void transform_tile(Smem<LAYOUT, NC>& S, const ImageDesc& im, int m0, int
                     row_pass_store(s, tile, u);
                 }
                 warp_sync();
-                if (valid) column_pass(S, tile, u, comp != 0, slot >= 1 ? (slot - 1) * 3 + comp : -1, &S.pred_dc[comp], LC);
+                if (valid) column_pass(S, tile, u, comp != 0, slot * 3 + comp, dcs ? dcs + comp : nullptr, LC);
                 warp_sync();
             }
         } else {
@@ -331,9 +331,9 @@ JG_DEV void transform_tile(Smem<LAYOUT, NC>& S, const ImageDesc& im, int m0, int
                 for (int k3 = 0; k3 < 3; ++k3) {
                     const int tl = (r16 >> 3) + 2 * k3;          // tiles {0,2,4} for lanes 0-7, {1,3,5} for lanes 8-15
                     const int comp = tl < 4 ? 0 : tl - 3;
-                    // of the predecessor MCU only Y11 (tile 3), Cb and Cr matter
-                    int* pd = (tl >= 3) ? &S.pred_dc[comp] : nullptr;
-                    column_pass(S, base + tl * kTileFloats, u, k3 == 2, slot >= 1 ? (slot - 1) * 6 + tl : -1, pd, LC);
+                    // the next tile predicts from Y11 (tile 3), Cb and Cr of our last MCU
+                    unsigned* pd = (dcs != nullptr && tl >= 3) ? dcs + comp : nullptr;
+                    column_pass(S, base + tl * kTileFloats, u, k3 == 2, slot * 6 + tl, pd, LC);
                 }
             }
             warp_sync();
@@ -726,11 +726,24 @@ JG_DEV void tile_front(const LaunchParams& P, Smem<LAYOUT, NC>& S, const LaneCon
     c.first = lt == 0; c.last = lt == im.n_tiles - 1; c.raw = im.raw; c.raw_cap = im.raw_cap;
     c.dbg_base = im.first_block + (unsigned long long)(m0 * G::BPM);
 
-    if (t < 4) S.pred_dc[t] = 0;          // jpeg_enc.h:1085-1087: predictors start at 0
     if (t == 0) S.slow = 0;
-    cta_sync();
-    transform_tile<LAYOUT, NC>(S, im, m0, nM, LC);
-    cta_sync();   // coefficients complete; the exchange tiles are dead, their space becomes regions + queues
+    transform_tile<LAYOUT, NC>(S, im, m0, nM, P.desc_dc + 3 * (size_t)g, LC);
+    // DC predictors of the tile's first blocks: the last DCs of the previous tile (published by the
+    // lanes that computed them, right after their column pass -- that tile started before ours, so
+    // this normally does not wait), or 0 at the start of the image (jpeg_enc.h:1085-1087)
+    if (t < G::NCOMP) {
+        int pred = 0;
+        if (!c.first) {
+            unsigned v, spins = 0;
+            while (((v = ld_flag32(P.desc_dc + 3 * (size_t)(g - 1) + t)) >> 31) == 0u) {
+                if (++spins > kSpinLimit || ld_flag32(P.error) != 0u) { S.abort = 1; gmem_atomic_or(P.error, 4u); break; }
+                backoff();
+            }
+            pred = (int)(int16_t)(v & 0xffffu);
+        }
+        S.pred_dc[t] = pred;
+    }
+    cta_sync();   // coefficients + predictors complete; the exchange tiles are dead, their space becomes regions + queues
 
     if (P.dbg_coefs) {
         for (int i = t; i < c.nblk * 64; i += kThreads)

@@ -20,7 +20,7 @@ constexpr int kChunkBytes = 64 * kThreads;   // unstuffed bytes one stuffing ste
 
 // MCUs per tile.  One extra "slot" per tile holds the MCU that precedes the tile (its DCs seed the
 // DC prediction), so slots = MCUs + 1 divides evenly among the CTA's lane groups.
-constexpr int mcus_per_tile(int layout) { return layout == LAYOUT_444 ? kThreads / 4 - 1 : (layout == LAYOUT_420 ? kThreads / 8 - 1 : 3 * kThreads / 4 - 1); }
+constexpr int mcus_per_tile(int layout) { return layout == LAYOUT_444 ? kThreads / 4 : (layout == LAYOUT_420 ? kThreads / 8 : 3 * kThreads / 4); }
 constexpr int kWinWordsMax = 384 * (kThreads / 32);   // tile window (unstuffed bits of one tile): 384 words per warp
 constexpr int kWinWordsMin = 64;     // must hold one worst-case block (1658 bits) + slack
 constexpr unsigned kSpinLimit = 1u << 24;
@@ -60,6 +60,7 @@ struct LaunchParams {
     unsigned* error;                 // OUT: non-zero if a look-back timed out
     unsigned long long* desc_bits;   // [n_tiles], zeroed: bits of the tile -> inclusive bit prefix
     unsigned long long* desc_tail;   // [n_tiles], zeroed: the tile's last 7 bits
+    unsigned* desc_dc;               // [3 * n_tiles], zeroed: valid<<31 | quantised DC of the tile's last block per component
     unsigned long long* desc_ff;     // [max_chunks], zeroed: 0xFF bytes of the chunk -> inclusive count
     unsigned long long* raw_bytes;   // [n_images] bytes of unstuffed scan (encode -> plan/stuff)
     unsigned* first_chunk;           // [n_images + 1] chunk table (plan -> stuff)

@@ -110,6 +110,7 @@ JG_DEV unsigned gmem_atomic_add(unsigned* p, unsigned v) { return __atomic_fetch
 JG_DEV void gmem_atomic_or(unsigned* p, unsigned v) { __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 JG_DEV unsigned long long ld_flag64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 JG_DEV void st_flag64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+JG_DEV void st_flag32(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 JG_DEV unsigned ld_flag32(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 JG_DEV void backoff() { sched_yield(); }
 

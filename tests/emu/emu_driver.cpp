@@ -113,7 +113,7 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
     const int n_tiles = tiles * n_images;
     const size_t max_chunks = (size_t)n_images * ((scan_cap + kChunkBytes - 1) / kChunkBytes) + 1;
     std::vector<unsigned long long> desc_bits(n_tiles, 0), desc_tail(n_tiles, 0), desc_ff(max_chunks, 0), raw_bytes(n_images, 0);
-    std::vector<unsigned> first_chunk(n_images + 1, 0);
+    std::vector<unsigned> first_chunk(n_images + 1, 0), desc_dc(3 * (size_t)n_tiles, 0);
     unsigned ticket = 0, ticket2 = 0, error = 0;
     for (int i = 0; i < n_images; ++i) { scan_bytes[i] = 0; img_status[i] = 0; }
 
@@ -122,7 +122,7 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
     P.tiles_per_image = (n_images % 2) ? tiles : 0;   // exercise both tile->image paths
     P.win_words = win_words ? win_words : kWinWordsMax;
     P.ticket = &ticket; P.ticket2 = &ticket2; P.error = &error;
-    P.desc_bits = desc_bits.data(); P.desc_tail = desc_tail.data(); P.desc_ff = desc_ff.data();
+    P.desc_bits = desc_bits.data(); P.desc_tail = desc_tail.data(); P.desc_ff = desc_ff.data(); P.desc_dc = desc_dc.data();
     P.raw_bytes = raw_bytes.data(); P.first_chunk = first_chunk.data();
     P.scan_bytes = scan_bytes; P.img_status = img_status; P.huff = &lut;
     P.dbg_coefs = dbg_coefs; P.dbg_bits = dbg_bits;
