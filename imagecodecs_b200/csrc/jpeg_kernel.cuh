@@ -231,6 +231,46 @@ JG_DEV void column_pass(Smem<LAYOUT, NC>& S, const float* tile, int u, bool chro
 }
 
 // ------------------------------------------------------------------------------------------
+// stage 1, grayscale: 8 lanes per block, 6 slots per lane group.  Gray has registers to spare,
+// so the next slot's pixels are requested while the current column pass runs.  (The colour
+// paths sit at the register cap: there the same prefetch cost more in spills than the hidden
+// latency gained -- measured -- so they load at the top of each iteration.)
+// ------------------------------------------------------------------------------------------
+template <int LAYOUT, int NC>
+JG_DEV void transform_tile_gray(Smem<LAYOUT, NC>& S, const ImageDesc& im, int m0, int nM, unsigned* dc_out, const LaneConst& LC)
+{
+    using G = Geo<LAYOUT>;
+    const int t = JG_TID, u = t & 7, grp = t >> 3;
+    float* tile = reinterpret_cast<float*>(S.r1) + grp * kTileFloats;
+    auto fetch = [&](int it, uint32_t (&w)[2]) {
+        const int slot = it * G::GROUPS + grp;
+        if (slot < nM) {
+            const int m = m0 + slot;
+            const int my = m / im.mcus_x, mx = m - my * im.mcus_x;
+            int y = my * 8 + u; if (y >= im.h) y = im.h - 1;          // replicate the last row
+            load_segment<1, 8>(im, mx * 8, y, w);
+        }
+    };
+    uint32_t w[2];
+    fetch(0, w);
+#pragma unroll 1
+    for (int it = 0; it < G::ITERS; ++it) {
+        const int slot = it * G::GROUPS + grp;
+        const bool valid = slot < nM;
+        if (valid) {
+            float s[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] = f_sub(u8_to_f(byte_of(w, i)), 128.0f);
+            row_pass_store(s, tile, u);
+        }
+        if (it + 1 < G::ITERS) fetch(it + 1, w);
+        warp_sync();
+        if (valid) column_pass(S, tile, u, false, slot, (slot == nM - 1) ? dc_out : nullptr, LC);
+        warp_sync();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // stage 1: transform all slots of the tile
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT, int NC>
@@ -727,7 +767,8 @@ JG_DEV void tile_front(const LaunchParams& P, Smem<LAYOUT, NC>& S, const LaneCon
     c.dbg_base = im.first_block + (unsigned long long)(m0 * G::BPM);
 
     if (t == 0) S.slow = 0;
-    transform_tile<LAYOUT, NC>(S, im, m0, nM, P.desc_dc + 3 * (size_t)g, LC);
+    if (LAYOUT == LAYOUT_GRAY) transform_tile_gray<LAYOUT, NC>(S, im, m0, nM, P.desc_dc + 3 * (size_t)g, LC);
+    else transform_tile<LAYOUT, NC>(S, im, m0, nM, P.desc_dc + 3 * (size_t)g, LC);
     // DC predictors of the tile's first blocks: the last DCs of the previous tile (published by the
     // lanes that computed them, right after their column pass -- that tile started before ours, so
     // this normally does not wait), or 0 at the start of the image (jpeg_enc.h:1085-1087)
