@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjpeg_gpu.so")
+LIB_PATH = os.environ.get("JPEG_GPU_LIB") or os.path.join(_HERE, "libjpeg_gpu.so")   # override: kernel-variant experiments
 
 QMODE_TJE, QMODE_IJG = 0, 1
 SUB_444, SUB_420 = 0, 1
