@@ -6,12 +6,14 @@
 // (:1160-1167).  Output bytes are identical to the reference's for its native modes.
 //
 // Work decomposition
-//   tile   = the blocks (8x8 data units) of 63 / 31 / 191 consecutive MCUs of ONE image
-//            (4:4:4 / 4:2:0 / gray) in stream order, plus one extra "slot" for the MCU that
-//            precedes the tile: it is transformed like the others but only its DC values are
-//            kept (they seed the DC prediction), so no CTA ever waits for another CTA's DCs.
-//   CTA    = 256 threads, persistent; tiles are drawn from an atomic ticket, so a tile's
-//            predecessors are always resident or finished (what makes the look-backs safe).
+//   tile   = 96 blocks (8x8 data units) = 32 / 16 / 96 consecutive MCUs of ONE image
+//            (4:4:4 / 4:2:0 / gray) in stream order.
+//   CTA    = 128 threads (4 warps, 6 CTAs per SM), persistent; tiles are drawn from an atomic
+//            ticket, so a tile's predecessors are always resident or finished (what makes the
+//            look-backs and the DC hand-over below safe).
+//   DC prediction across tiles: the lanes that compute the last DCs of a tile publish them
+//            (desc_dc) right after their column pass; the next tile reads them after its own
+//            transform.  Nothing is recomputed and no CTA waits on another CTA's entropy coding.
 //
 // Per tile:
 //   1. transform  lane groups of 8 (16 for 4:2:0) own one MCU: each lane loads ONE pixel row
@@ -26,8 +28,8 @@
 //                 category / run / Huffman lookup, warp scan of the code lengths, atomicOr of the
 //                 bits into the warp's own region.  No per-block size walk, no divergence between
 //                 sparse and dense blocks.
-//   3. publish    sum of the 8 warp bit counts = the tile's bit count, published at once.
-//   4. compact    (after the previous tile's write-out, below) the 8 regions are shifted into
+//   3. publish    sum of the 4 warp bit counts = the tile's bit count, published at once.
+//   4. compact    (after the previous tile's write-out, below) the 4 regions are shifted into
 //                 the tile window; its last 7 bits are published for the successor.
 //   5. chain      ONE LOOP ITERATION LATER: decoupled look-back over the tiles' bit counts gives
 //                 the exclusive BIT offset of the tile in its image; the predecessor's last 7
@@ -36,11 +38,11 @@
 //   6. write      the window goes to the image's UNSTUFFED scan (every byte written once, by the
 //                 tile that holds its last bit); the last tile pads with zero bits
 //                 (jpeg_enc.h:1161-1164).  0xFF00 stuffing + EOI are the second pass (jpeg_stuff.cuh).
-// HBM traffic of this kernel: every pixel read once (+1/63 for the predecessor slot), the
-// unstuffed scan written once, two 8-byte descriptors per tile.
+// HBM traffic of this kernel: every pixel read once, the unstuffed scan written once, two
+// 8-byte and three 4-byte descriptors per tile.
 //
 // A tile whose bits overflow a warp region or the window (pathological content) is redone in
-// six groups of 32 blocks; same bytes, lower speed.
+// six groups of 16 blocks; same bytes, lower speed.
 #pragma once
 #include "jpeg_device.h"
 #include "jpeg_launch.h"
