@@ -46,6 +46,16 @@ JG_DEV unsigned warp_ballot(int pred) { return __ballot_sync(0xffffffffu, pred);
 JG_DEV unsigned warp_shfl_u32(unsigned v, int lane) { return __shfl_sync(0xffffffffu, v, lane); }
 JG_DEV unsigned warp_shfl_up_u32(unsigned v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 JG_DEV void warp_sync() { __syncwarp(); }
+// inclusive prefix sum over the warp; the shuffle's own predicate replaces the lane compare (CUB idiom)
+JG_DEV unsigned warp_scan_incl_u32(unsigned v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        asm volatile("{ .reg .pred p; .reg .u32 r; shfl.sync.up.b32 r|p, %0, %1, 0, 0xffffffff; @p add.u32 %0, %0, r; }"
+                     : "+r"(v) : "r"(d));
+    }
+    return v;
+}
 JG_DEV float warp_shfl_xor_f32(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 JG_DEV unsigned long long warp_shfl_u64(unsigned long long v, int lane) { return __shfl_sync(0xffffffffu, v, lane); }
 JG_DEV unsigned long long warp_shfl_xor_u64(unsigned long long v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }

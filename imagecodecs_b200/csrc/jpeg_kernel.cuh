@@ -412,11 +412,12 @@ JG_DEV void block_kind(int blk, int& comp, int& pred_blk)
 // Symbol queue entry: value<<16 | EOB<<15 | DC<<14 | chroma<<13 | block-in-warp<<8 | zigzag position.
 // queue[-1] must be readable (one pad word).  Returns the bits emitted; sets `overflow` if they
 // did not fit region_words (the count stays right).
-template <int LAYOUT, int NC>
+template <int LAYOUT, int NC, bool DBG>
 JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint32_t* region, unsigned region_words,
                                    uint32_t* queue, uint32_t* dbg_bits, bool& overflow)
 {
     const int lane = JG_TID & 31, L = lane & 7, b4 = lane >> 3;
+    const unsigned cap_bits = region_words * 32u;
     unsigned carry = 0;
     unsigned left = 0;      // symbols queued but not yet coded (an incomplete round is carried to the next step)
 #pragma unroll 1
@@ -445,12 +446,7 @@ JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint
         }
         const unsigned eob = (valid && L == 7 && (ww[3] >> 16) == 0u) ? 1u : 0u;   // jpeg_enc.h:884-887
         const unsigned cnt = (unsigned)i_popc(m8) + eob;
-        unsigned inc = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned n = warp_shfl_up_u32(inc, d);
-            if (lane >= d) inc += n;
-        }
+        const unsigned inc = warp_scan_incl_u32(cnt);
         const unsigned N = warp_shfl_u32(inc, 31);
         uint32_t* qp = queue + left + (inc - cnt);
         const unsigned common = (comp ? 1u << 13 : 0u) | ((unsigned)(blk - first) << 8) | (unsigned)(8 * L);
@@ -484,31 +480,30 @@ JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint
             if (e & 0x8000u) idx = 0u;
             const unsigned nz = special ? 0u : run >> 4;        // one ZRL per 16 zeros (jpeg_enc.h:863-867)
             const unsigned h = S.huff[cls][idx];
-            const unsigned long long zp = S.zrl[cls][nz];       // nz ZRL codes: bits<<8 | length  (nz <= 3)
             const unsigned slen = (h & 0xffu) + cat;
-            unsigned len = slen + (unsigned)(zp & 0xffull);
-            const unsigned long long sym = ((zp >> 8) << slen) | (unsigned long long)(((h >> 8) << cat) | amplitude(v, cat));
-            if (j >= full) len = 0u;
-            if (dbg_bits != nullptr && len) gmem_atomic_add(dbg_bits + ((e >> 8) & 31u), len);
-            unsigned endb = len;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned n = warp_shfl_up_u32(endb, d);
-                if (lane >= d) endb += n;
+            unsigned len = slen;
+            unsigned long long sym = (unsigned long long)(((h >> 8) << cat) | amplitude(v, cat));
+            if (warp_ballot(nz != 0u) != 0u) {                  // some lane skipped 16+ zeros: prepend its ZRL codes
+                const unsigned long long zp = S.zrl[cls][nz];   // nz ZRL codes: bits<<8 | length  (nz <= 3)
+                sym |= (zp >> 8) << slen;
+                len += (unsigned)(zp & 0xffull);
             }
+            if (j >= full) len = 0u;
+            if (DBG) { if (len) gmem_atomic_add(dbg_bits + ((e >> 8) & 31u), len); }
+            const unsigned endb = warp_scan_incl_u32(len);
             const unsigned tot = warp_shfl_u32(endb, 31);
             if (len) {
                 const unsigned start = carry + endb - len;
-                const unsigned long long al = sym << (64u - len);
-                const unsigned hi = (unsigned)(al >> 32), lo = (unsigned)al;
-                const unsigned sh = start & 31u, wi = start >> 5;
-                if (wi + 2u < region_words) {
+                if (start + len + 64u <= cap_bits) {            // writes stay inside the region even if the tile overflows
+                    const unsigned long long al = sym << (64u - len);
+                    const unsigned hi = (unsigned)(al >> 32), lo = (unsigned)al;
+                    const unsigned sh = start & 31u, wi = start >> 5;
                     smem_atomic_or(region + wi, hi >> sh);
                     if (sh + len > 32u) {
                         smem_atomic_or(region + wi + 1, sh ? (hi << (32u - sh)) | (lo >> sh) : lo);
                         if (sh + len > 64u) smem_atomic_or(region + wi + 2, lo << (32u - sh));
                     }
-                } else overflow = true;
+                }
             }
             carry += tot;
         }
@@ -523,6 +518,7 @@ JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint
         }
         warp_sync();   // the queue is appended to by the next four blocks
     }
+    overflow = carry + 64u > cap_bits;
     return carry;
 }
 
@@ -540,8 +536,11 @@ JG_DEV unsigned encode_range(Smem<LAYOUT, NC>& S, int b_lo, int b_hi, int per_wa
     const int first = b_lo + wid * per_warp;
     const int end = first + per_warp < b_hi ? first + per_warp : b_hi;
     bool overflow = false;
-    const unsigned bits = first < end ? encode_blocks_warp<LAYOUT, NC>(S, first, end, region, kRegionWords, queue,
-                                                                       dbg_bits ? dbg_bits + first : nullptr, overflow) : 0u;
+    unsigned bits = 0;
+    if (first < end) {
+        if (dbg_bits) bits = encode_blocks_warp<LAYOUT, NC, true>(S, first, end, region, kRegionWords, queue, dbg_bits + first, overflow);
+        else bits = encode_blocks_warp<LAYOUT, NC, false>(S, first, end, region, kRegionWords, queue, nullptr, overflow);
+    }
     if (lane == 0) S.warp_bits[wid] = bits;
     if (overflow) S.slow = 1;
     cta_sync();

@@ -89,6 +89,16 @@ JG_DEV unsigned warp_shfl_up_u32(unsigned v, int d)
     return (unsigned)warp_exchange(v, lane - d >= 0 ? lane - d : lane);
 }
 JG_DEV void warp_sync() { emu::warp_barrier(); }
+JG_DEV unsigned warp_shfl_up_u32(unsigned v, int d);
+JG_DEV unsigned warp_scan_incl_u32(unsigned v)
+{
+    const int lane = emu::tls.tid & 31;
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned n = warp_shfl_up_u32(v, d);
+        if (lane >= d) v += n;
+    }
+    return v;
+}
 JG_DEV float warp_shfl_xor_f32(float v, int m)
 {
     unsigned bits; memcpy(&bits, &v, 4);
