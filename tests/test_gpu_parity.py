@@ -222,6 +222,29 @@ def test_mixed_batch_and_shard_invariance(gpu):
         assert twin[i] == oracle.oracle_encode(batch[i], 0, tq[i], 0)
 
 
+def test_random_mixed_batch(gpu):
+    """150 random images (sizes 1..200, all layouts, qualities and content kinds) in ONE call."""
+    rng = np.random.default_rng(2026)
+    imgs, qm, q, sub = [], [], [], []
+    for k in range(150):
+        w, h = int(rng.integers(1, 201)), int(rng.integers(1, 201))
+        layout = int(rng.integers(0, 3))          # 0: 4:4:4, 1: 4:2:0, 2: gray
+        nc = 1 if layout == 2 else int(rng.choice([3, 4]))
+        kind = int(rng.integers(0, 4))
+        if kind == 0: img = rng.integers(0, 256, size=(h, w, nc), dtype=np.uint8)
+        elif kind == 1: img = np.full((h, w, nc), int(rng.integers(0, 256)), np.uint8)
+        elif kind == 2: img = (rng.integers(0, 2, size=(h, w, nc)) * 255).astype(np.uint8)       # +-max: largest categories
+        else: img = oracle.synth_image(w, h, nc, n=k)
+        mode = int(rng.integers(0, 2))
+        imgs.append(np.ascontiguousarray(img)); qm.append(mode)
+        q.append(int(rng.integers(1, 4)) if mode == 0 else int(rng.integers(1, 101)))
+        sub.append(1 if layout == 1 else 0)
+    files, st = gpu.encode_batch(imgs, qm, q, sub, device=0)
+    assert st == [0] * len(imgs)
+    for k in range(len(imgs)):
+        assert files[k] == oracle.oracle_encode(imgs[k], qm[k], q[k], sub[k]), (k, imgs[k].shape, qm[k], q[k], sub[k])
+
+
 def test_mixed_layouts_in_one_call(gpu):
     imgs = [oracle.synth_image(100, 60, 3), oracle.synth_image(64, 64, 1), oracle.synth_image(33, 20, 4),
             oracle.synth_image(100, 60, 3, n=1)]
