@@ -24,7 +24,7 @@
 //                 and scatters int16 coefficients to shared memory in zigzag order.
 //   2. entropy    warp-cooperative, one pass (P5-P8 of SURVEY 8a).  A warp owns 24 consecutive
 //                 blocks; four at a time it compacts their nonzero coefficients (+ DC + EOB) into
-//                 a dense symbol queue, then codes 32 symbols per round with every lane busy:
+//                 a dense symbol queue, then codes 64 symbols per round (two per lane), every lane busy:
 //                 category / run / Huffman lookup, warp scan of the code lengths, atomicOr of the
 //                 bits into the warp's own region.  No per-block size walk, no divergence between
 //                 sparse and dense blocks.
@@ -53,7 +53,7 @@ namespace jg {
 constexpr int kTileFloats = 72;   // one 8x8 float tile with rows padded to 9 (bank-conflict free both ways)
 constexpr int kCoefStride = 72;   // int16 per block in shared memory (144 B: 16-byte aligned 8-coefficient reads)
 constexpr int kRegionWords = kWinWordsMax / kWarps;   // bits a warp may emit for its 24 blocks before the tile goes slow
-constexpr int kQueueEntries = 360;                     // 31 carried + 32 lanes x (8 coefficients + EOB) + 32 read-ahead + pad
+constexpr int kQueueEntries = 424;                     // 2 pad + 63 carried + 32 lanes x (8 coefficients + EOB) + 64 read-ahead
 constexpr int kWarpBlocks = 24;                        // blocks per warp (8 x 24 = 192)
 
 template <int LAYOUT>
@@ -408,6 +408,39 @@ JG_DEV void block_kind(int blk, int& comp, int& pred_blk)
     } else { comp = 0; pred_blk = blk - 1; }
 }
 
+// One queue entry -> its Huffman code + amplitude bits (sym, slen <= 27 bits), the number of ZRL
+// codes that precede it (nz) and its table class.  `ep` is the previous entry of the queue.
+template <int LAYOUT, int NC>
+JG_DEV void decode_symbol(const Smem<LAYOUT, NC>& S, unsigned e, unsigned ep, unsigned& sym, unsigned& slen, unsigned& nz, unsigned& cls)
+{
+    const int v = (int)e >> 16;
+    cls = (e >> 13) & 1u;
+    const unsigned cat = category(v) & 15u;                      // 0 for EOB and for a zero DC difference
+    const unsigned run = ((e & 63u) - (ep & 63u) - 1u) & 63u;    // zeros since the previous symbol of the block
+    unsigned idx = ((run & 15u) << 4) | cat;
+    if (e & 0x4000u) idx = 256u + cat;                           // DC
+    if (e & 0x8000u) idx = 0u;                                   // EOB
+    nz = (e & 0xC000u) ? 0u : run >> 4;                          // one ZRL per 16 zeros; none for DC / EOB
+    const unsigned h = S.huff[cls][idx];
+    slen = (h & 0xffu) + cat;
+    sym = ((h >> 8) << cat) | amplitude(v, cat);
+}
+
+// OR `len` (1..64) bits of `sym` into the MSB-first word array at bit `start` (nothing if they
+// would not fit the region: the tile is then redone on the slow path).
+JG_DEV void put_bits64(uint32_t* region, unsigned start, unsigned long long sym, unsigned len, unsigned cap_bits)
+{
+    if (start + len + 64u > cap_bits) return;
+    const unsigned long long al = sym << (64u - len);
+    const unsigned hi = (unsigned)(al >> 32), lo = (unsigned)al;
+    const unsigned sh = start & 31u, wi = start >> 5;
+    smem_atomic_or(region + wi, hi >> sh);
+    if (sh + len > 32u) {
+        smem_atomic_or(region + wi + 1, sh ? (hi << (32u - sh)) | (lo >> sh) : lo);
+        if (sh + len > 64u) smem_atomic_or(region + wi + 2, lo << (32u - sh));
+    }
+}
+
 // One warp codes blocks [first, end) (at most 24) into `region` (zeroed, MSB-first words).
 // Symbol queue entry: value<<16 | EOB<<15 | DC<<14 | chroma<<13 | block-in-warp<<8 | zigzag position.
 // queue[-1] must be readable (one pad word).  Returns the bits emitted; sets `overflow` if they
@@ -462,58 +495,50 @@ JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint
         if (eob) *qp = (1u << 15) | common | 7u;
         warp_sync();
 
-        // ---- 32 symbols per round, branch-free; only full rounds except at the very end ---------------
+        // ---- 64 symbols per round, two per lane, branch-free; only full rounds except at the very end ----
         const unsigned M = left + N;
-        const unsigned full = (b0 + 4 >= end) ? M : (M & ~31u);
+        const unsigned full = (b0 + 4 >= end) ? M : (M & ~63u);
 #pragma unroll 1
-        for (unsigned j0 = 0; j0 < full; j0 += 32) {
-            const unsigned j = j0 + (unsigned)lane;
-            const unsigned e = queue[j];
-            const unsigned ep = queue[(int)j - 1];
-            const int v = (int)e >> 16;
-            const unsigned cls = (e >> 13) & 1u;
-            const unsigned cat = category(v) & 15u;             // 0 for EOB and for a zero DC difference
-            const unsigned run = ((e & 63u) - (ep & 63u) - 1u) & 63u;   // zeros since the previous symbol of the block
-            const bool special = (e & 0xC000u) != 0u;           // DC or EOB: no run
-            unsigned idx = ((run & 15u) << 4) | cat;
-            if (e & 0x4000u) idx = 256u + cat;
-            if (e & 0x8000u) idx = 0u;
-            const unsigned nz = special ? 0u : run >> 4;        // one ZRL per 16 zeros (jpeg_enc.h:863-867)
-            const unsigned h = S.huff[cls][idx];
-            const unsigned slen = (h & 0xffu) + cat;
-            unsigned len = slen;
-            unsigned long long sym = (unsigned long long)(((h >> 8) << cat) | amplitude(v, cat));
-            if (warp_ballot(nz != 0u) != 0u) {                  // some lane skipped 16+ zeros: prepend its ZRL codes
-                const unsigned long long zp = S.zrl[cls][nz];   // nz ZRL codes: bits<<8 | length  (nz <= 3)
-                sym |= (zp >> 8) << slen;
-                len += (unsigned)(zp & 0xffull);
+        for (unsigned j0 = 0; j0 < full; j0 += 64) {
+            const unsigned a = j0 + 2u * (unsigned)lane;                   // this lane codes symbols a and a+1
+            const uint2 ee = *reinterpret_cast<const uint2*>(queue + a);
+            const unsigned ep = queue[(int)a - 1];
+            unsigned symA, lenA, nzA, clsA, symB, lenB, nzB, clsB;
+            decode_symbol(S, ee.x, ep, symA, lenA, nzA, clsA);
+            decode_symbol(S, ee.y, ee.x, symB, lenB, nzB, clsB);
+            if (a >= full) { lenA = 0u; symA = 0u; nzA = 0u; }
+            if (a + 1u >= full) { lenB = 0u; symB = 0u; nzB = 0u; }
+            if (DBG) {
+                if (lenA) gmem_atomic_add(dbg_bits + ((ee.x >> 8) & 31u), lenA + nzA * (S.huff[clsA][0xF0] & 0xffu));
+                if (lenB) gmem_atomic_add(dbg_bits + ((ee.y >> 8) & 31u), lenB + nzB * (S.huff[clsB][0xF0] & 0xffu));
             }
-            if (j >= full) len = 0u;
-            if (DBG) { if (len) gmem_atomic_add(dbg_bits + ((e >> 8) & 31u), len); }
-            const unsigned endb = warp_scan_incl_u32(len);
-            const unsigned tot = warp_shfl_u32(endb, 31);
-            if (len) {
-                const unsigned start = carry + endb - len;
-                if (start + len + 64u <= cap_bits) {            // writes stay inside the region even if the tile overflows
-                    const unsigned long long al = sym << (64u - len);
-                    const unsigned hi = (unsigned)(al >> 32), lo = (unsigned)al;
-                    const unsigned sh = start & 31u, wi = start >> 5;
-                    smem_atomic_or(region + wi, hi >> sh);
-                    if (sh + len > 32u) {
-                        smem_atomic_or(region + wi + 1, sh ? (hi << (32u - sh)) | (lo >> sh) : lo);
-                        if (sh + len > 64u) smem_atomic_or(region + wi + 2, lo << (32u - sh));
-                    }
-                }
+            unsigned tot;
+            if (warp_ballot((nzA | nzB) != 0u) == 0u) {
+                // common case: both codes (<= 27 bits each) travel as one string
+                const unsigned len = lenA + lenB;
+                const unsigned endb = warp_scan_incl_u32(len);
+                tot = warp_shfl_u32(endb, 31);
+                if (len) put_bits64(region, carry + endb - len, ((unsigned long long)symA << lenB) | symB, len, cap_bits);
+            } else {
+                // some lane skipped 16+ zeros: its ZRL codes (jpeg_enc.h:863-867) go in front of the symbol
+                const unsigned long long zA = S.zrl[clsA][nzA], zB = S.zrl[clsB][nzB];
+                const unsigned tA = lenA ? lenA + (unsigned)(zA & 0xffull) : 0u, tB = lenB ? lenB + (unsigned)(zB & 0xffull) : 0u;
+                const unsigned endb = warp_scan_incl_u32(tA + tB);
+                tot = warp_shfl_u32(endb, 31);
+                const unsigned start = carry + endb - (tA + tB);
+                if (tA) put_bits64(region, start, ((zA >> 8) << lenA) | symA, tA, cap_bits);
+                if (tB) put_bits64(region, start + tA, ((zB >> 8) << lenB) | symB, tB, cap_bits);
             }
             carry += tot;
         }
         // move the incomplete round to the front; queue[-1] keeps the symbol before it (for its run)
         left = M - full;
         if (left && full) {
-            const unsigned keep = queue[full + (unsigned)lane];
+            const unsigned keep0 = queue[full + (unsigned)lane], keep1 = queue[full + 32u + (unsigned)lane];
             const unsigned before = queue[full - 1u];
             warp_sync();
-            if ((unsigned)lane < left) queue[lane] = keep;
+            if ((unsigned)lane < left) queue[lane] = keep0;
+            if ((unsigned)lane + 32u < left) queue[lane + 32] = keep1;
             if (lane == 0) queue[-1] = before;
         }
         warp_sync();   // the queue is appended to by the next four blocks
@@ -530,7 +555,7 @@ JG_DEV unsigned encode_range(Smem<LAYOUT, NC>& S, int b_lo, int b_hi, int per_wa
 {
     const int t = JG_TID, lane = t & 31, wid = t >> 5;
     uint32_t* region = S.r1 + wid * kRegionWords;
-    uint32_t* queue = S.r1 + kWarps * kRegionWords + wid * kQueueEntries + 1;    // [-1] is a pad word
+    uint32_t* queue = S.r1 + kWarps * kRegionWords + wid * kQueueEntries + 2;    // 8-byte aligned; [-1] is a pad word
     for (int i = lane; i < kRegionWords; i += 32) region[i] = 0u;
     warp_sync();
     const int first = b_lo + wid * per_warp;
