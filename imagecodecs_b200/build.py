@@ -47,7 +47,18 @@ def _run(cmd):
     return r.stdout + r.stderr
 
 
-def build(force=False, verbose=False):
+def build_variant(out, defs, obj_dir):
+    """Kernel-variant experiments: build a second library with extra -D flags (tools/ab_run.sh)."""
+    global OBJ, LIB, NVCC_FLAGS
+    saved = (OBJ, LIB, NVCC_FLAGS)
+    OBJ, LIB, NVCC_FLAGS = obj_dir, out, NVCC_FLAGS + list(defs)
+    try:
+        return build(force=True, example=False)
+    finally:
+        OBJ, LIB, NVCC_FLAGS = saved
+
+
+def build(force=False, verbose=False, example=True):
     deps = _deps()
     if not force and not _stale(LIB, deps):
         return LIB
@@ -73,6 +84,8 @@ def build(force=False, verbose=False):
     with open(os.path.join(OBJ, "ptxas.log"), "w") as fh:
         for obj, log in sorted(logs):
             fh.write("== %s\n%s\n" % (os.path.basename(obj), log))
+    if not example:
+        return LIB
     # the C++ example that drives the host layer the way the reference's tests.cpp does
     exe = os.path.join(HERE, "write_jpg_like_reference")
     _run(["g++", "-std=c++17", "-O2", "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),

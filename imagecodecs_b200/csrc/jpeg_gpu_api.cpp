@@ -250,11 +250,13 @@ struct jpeg_gpu_plan {
         QuantSet quant;
         std::vector<int> items;
         int n_tiles = 0, tiles_per_image = 0;
-        size_t state_off = 0;     // offset of {ticket, ticket2, error, pad, desc_bits[], desc_tail[], desc_ff[]} in d_state
+        size_t state_off = 0;     // offset of {ticket, ticket2, error, pad, desc_bits[], desc_ff[], desc_dc[]} in d_state
         size_t max_chunks = 0;    // upper bound of stuffing chunks (from the capacities)
         unsigned long long* d_raw_bytes = nullptr;    // into d_aux
         unsigned* d_first_chunk = nullptr;
         ImageDesc* d_images = nullptr;
+        size_t sched_off = 0;     // words into d_sched (groups with images of different tile counts)
+        bool has_sched = false;
         unsigned long long* d_scan_bytes = nullptr;   // into d_results
         unsigned* d_status = nullptr;
         size_t result_off = 0;    // index of first image of the group in the results arrays
@@ -274,6 +276,8 @@ struct jpeg_gpu_plan {
     uint8_t* h_results = nullptr;                               // pinned mirror
     ImageDesc* d_images = nullptr;
     std::vector<ImageDesc> h_images;
+    uint32_t* d_sched = nullptr;     size_t sched_bytes = 0;    // ticket schedules (jpeg_tables.h build_schedule)
+    std::vector<uint32_t> h_sched;
     bool images_dirty = true;
     int16_t* dbg_coefs = nullptr;
     uint32_t* dbg_bits = nullptr;
@@ -335,7 +339,7 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
     p->arena_bytes = arena;
     p->pixels_bytes = pixels;
 
-    // device state: per group {ticket u32, error u32, pad} + desc_bits + desc_tail + desc_ff
+    // device state: per group {ticket u32, error u32, ticket2 u32, pad} + desc_bits + desc_ff + desc_dc
     size_t state = 0, res_index = 0;
     for (auto& g : p->groups) {
         int tiles = 0;
@@ -347,11 +351,19 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
         }
         g.n_tiles = tiles;
         g.tiles_per_image = uniform ? t0 : 0;
+        if (!uniform) {
+            std::vector<int> counts;
+            for (int idx : g.items) counts.push_back(p->items[idx].geo.n_tiles);
+            g.sched_off = p->h_sched.size();
+            g.has_sched = true;
+            p->h_sched.resize(g.sched_off + schedule_words((int)counts.size()));
+            build_schedule(counts.data(), (int)counts.size(), p->h_sched.data() + g.sched_off);
+        }
         g.state_off = state;
         size_t chunks = 1;
         for (int idx : g.items) chunks += (p->items[idx].scan_cap + kChunkBytes - 1) / kChunkBytes;
         g.max_chunks = chunks;
-        state += 16 + (size_t)tiles * 16 + chunks * 8 + (((size_t)tiles * 12 + 15) / 16) * 16;
+        state += 16 + (size_t)tiles * 8 + chunks * 8 + (((size_t)tiles * 12 + 15) / 16) * 16;
         g.result_off = res_index;
         res_index += g.items.size();
     }
@@ -371,6 +383,8 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
     if (!pool_alloc(dev, p->results_bytes, false, (void**)&p->d_results)) return false;
     if (!pool_alloc(dev, p->results_bytes, true, (void**)&p->h_results)) return false;
     if (!pool_alloc(dev, p->images_bytes, false, (void**)&p->d_images)) return false;
+    p->sched_bytes = p->h_sched.size() * sizeof(uint32_t);
+    if (p->sched_bytes && !pool_alloc(dev, p->sched_bytes, false, (void**)&p->d_sched)) return false;
     p->h_images.resize(nres);
     for (auto& g : p->groups) {
         g.d_images = p->d_images + g.result_off;
@@ -407,6 +421,8 @@ bool plan_sync_images(jpeg_gpu_plan* p, cudaStream_t s)
     // h_images is pageable: the copy is staged by the runtime before the call returns
     JG_CUDA(cudaMemcpyAsync(p->d_images, p->h_images.data(), p->h_images.size() * sizeof(ImageDesc),
                             cudaMemcpyHostToDevice, s));
+    if (p->sched_bytes)
+        JG_CUDA(cudaMemcpyAsync(p->d_sched, p->h_sched.data(), p->sched_bytes, cudaMemcpyHostToDevice, s));
     p->images_dirty = false;
     return true;
 }
@@ -425,14 +441,14 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
         P.n_images = (int)g.items.size();
         P.n_tiles = g.n_tiles;
         P.tiles_per_image = g.tiles_per_image;
+        P.sched = g.has_sched ? p->d_sched + g.sched_off : nullptr;
         P.win_words = p->win_words;
         uint8_t* st = p->d_state + g.state_off;
         P.ticket = reinterpret_cast<unsigned*>(st);
         P.error = reinterpret_cast<unsigned*>(st + 4);
         P.ticket2 = reinterpret_cast<unsigned*>(st + 8);
         P.desc_bits = reinterpret_cast<unsigned long long*>(st + 16);
-        P.desc_tail = P.desc_bits + g.n_tiles;
-        P.desc_ff = P.desc_tail + g.n_tiles;
+        P.desc_ff = P.desc_bits + g.n_tiles;
         P.desc_dc = reinterpret_cast<unsigned*>(P.desc_ff + g.max_chunks);
         P.raw_bytes = g.d_raw_bytes;
         P.first_chunk = g.d_first_chunk;
@@ -441,7 +457,7 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
         P.huff = dev.d_huff;
         P.dbg_coefs = p->dbg_coefs;
         P.dbg_bits = p->dbg_bits;
-        const int grid = std::min(g.n_tiles, dev.sm_count * dev.ctas_per_sm[g.spec]);
+        const int grid = std::min((g.n_tiles + kWarps - 1) / kWarps, dev.sm_count * dev.ctas_per_sm[g.spec]);   // one tile per warp at a time
         const size_t gi = (size_t)(&g - &p->groups[0]);
         if (p->timing) JG_CUDA(cudaEventRecord(p->events[3 * gi], s));
         JG_CUDA(kSpecs[g.spec].launch(grid, s, P, g.quant));
@@ -481,6 +497,7 @@ void plan_free(jpeg_gpu_plan* p)
         pool_free(dev, p->d_state, p->state_bytes, false);
         pool_free(dev, p->d_results, p->results_bytes, false);
         pool_free(dev, p->d_images, p->images_bytes, false);
+        if (p->d_sched) pool_free(dev, p->d_sched, p->sched_bytes, false);
         pool_free(dev, p->h_results, p->results_bytes, true);
     }
     for (cudaEvent_t e : p->events) cudaEventDestroy(e);

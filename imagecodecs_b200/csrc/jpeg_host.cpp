@@ -1,6 +1,8 @@
 // jpeg_host.cpp -- host-side half of the encoder: quantiser / Huffman table construction
 // and marker emission.  Everything the reference does once per image before its block
 // loop (jpeg_enc.h:962-1077, :1230-1266) lives here and stays on the CPU.
+#include <algorithm>
+#include <vector>
 #include "jpeg_tables.h"
 
 #include <string.h>
@@ -174,6 +176,35 @@ size_t emit_headers(int w, int h, int ncomp_out, int subsampling, const uint8_t 
     for (int c = 0; c < ncomp_out; ++c) { bw.u8(c + 1); bw.u8(c ? 0x11 : 0x00); }
     bw.u8(0); bw.u8(63); bw.u8(0);
     return bw.n <= cap ? bw.n : 0;
+}
+
+size_t schedule_words(int n_images) { return 1 + (size_t)(n_images + 1) + 2 * (size_t)n_images + (size_t)n_images; }
+
+size_t build_schedule(const int* tiles, int n, uint32_t* out)
+{
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tiles[a] < tiles[b]; });
+    std::vector<uint32_t> cum, lt0, first;
+    uint32_t tickets = 0;
+    int lt = 0;
+    for (int a = 0; a < n;) {
+        // images order[a..n) are active for rounds [lt, tiles[order[a]])
+        cum.push_back(tickets); lt0.push_back((uint32_t)lt); first.push_back((uint32_t)a);
+        const int until = tiles[order[a]];
+        tickets += (uint32_t)(until - lt) * (uint32_t)(n - a);
+        lt = until;
+        while (a < n && tiles[order[a]] == until) ++a;
+    }
+    const size_t D = cum.size();
+    cum.push_back(tickets);
+    size_t w = 0;
+    out[w++] = (uint32_t)D;
+    for (size_t k = 0; k <= D; ++k) out[w++] = cum[k];
+    for (size_t k = 0; k < D; ++k) out[w++] = lt0[k];
+    for (size_t k = 0; k < D; ++k) out[w++] = first[k];
+    for (int i = 0; i < n; ++i) out[w++] = (uint32_t)order[i];
+    return w;
 }
 
 }  // namespace jg

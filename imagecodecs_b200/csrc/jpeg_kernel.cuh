@@ -6,43 +6,43 @@
 // (:1160-1167).  Output bytes are identical to the reference's for its native modes.
 //
 // Work decomposition
-//   tile   = 96 blocks (8x8 data units) = 32 / 16 / 96 consecutive MCUs of ONE image
-//            (4:4:4 / 4:2:0 / gray) in stream order.
-//   CTA    = 128 threads (4 warps, 6 CTAs per SM), persistent; tiles are drawn from an atomic
-//            ticket, so a tile's predecessors are always resident or finished (what makes the
-//            look-backs and the DC hand-over below safe).
+//   tile   = 24 blocks (8x8 data units) = 8 / 4 / 24 consecutive MCUs of ONE image
+//            (4:4:4 / 4:2:0 / gray) in stream order.  A tile belongs to ONE WARP from its pixels
+//            to its bytes: after the tables are loaded no CTA barrier is executed any more, warps
+//            never wait for their siblings.
+//   CTA    = 128 threads (4 warps, 6 CTAs per SM), persistent; every warp draws its tiles from an
+//            atomic ticket, so a tile's predecessors are always resident or finished (what makes
+//            the look-back and the DC hand-over below safe).
 //   DC prediction across tiles: the lanes that compute the last DCs of a tile publish them
 //            (desc_dc) right after their column pass; the next tile reads them after its own
-//            transform.  Nothing is recomputed and no CTA waits on another CTA's entropy coding.
+//            transform.  Nothing is recomputed and nobody waits on anybody's entropy coding.
 //
-// Per tile:
+// Per tile (one warp):
 //   1. transform  lane groups of 8 (16 for 4:2:0) own one MCU: each lane loads ONE pixel row
 //                 straight from global memory (edge replication jpeg_enc.h:1106-1111 applied
 //                 on the way), converts it to Y/Cb/Cr once for all components (:1118-1120),
 //                 runs the AAN row pass (:668-709), exchanges the 8x8 through a padded
 //                 shared-memory tile, runs the column pass (:718-759), quantises (:808-816)
 //                 and scatters int16 coefficients to shared memory in zigzag order.
-//   2. entropy    warp-cooperative, one pass (P5-P8 of SURVEY 8a).  A warp owns 24 consecutive
-//                 blocks; four at a time it compacts their nonzero coefficients (+ DC + EOB) into
-//                 a dense symbol queue, then codes 64 symbols per round (two per lane), every lane busy:
-//                 category / run / Huffman lookup, warp scan of the code lengths, atomicOr of the
-//                 bits into the warp's own region.  No per-block size walk, no divergence between
-//                 sparse and dense blocks.
-//   3. publish    sum of the 4 warp bit counts = the tile's bit count, published at once.
-//   4. compact    (after the previous tile's write-out, below) the 4 regions are shifted into
-//                 the tile window; its last 7 bits are published for the successor.
-//   5. chain      ONE LOOP ITERATION LATER: decoupled look-back over the tiles' bit counts gives
-//                 the exclusive BIT offset of the tile in its image; the predecessor's last 7
-//                 bits complete the byte the two tiles share.  Because the counts were published
-//                 a whole iteration earlier the look-back practically never waits.
-//   6. write      the window goes to the image's UNSTUFFED scan (every byte written once, by the
-//                 tile that holds its last bit); the last tile pads with zero bits
-//                 (jpeg_enc.h:1161-1164).  0xFF00 stuffing + EOI are the second pass (jpeg_stuff.cuh).
-// HBM traffic of this kernel: every pixel read once, the unstuffed scan written once, two
+//   2. write the PREVIOUS tile of this warp (see 5): its offset is resolved while our own
+//                 predecessors are still coding, one whole transform after its count was published.
+//   3. entropy    warp-cooperative, one pass (P5-P8 of SURVEY 8a).  Four blocks at a time the warp
+//                 compacts the nonzero coefficients (+ DC + EOB) into a dense symbol queue, then
+//                 codes 64 symbols per round (two per lane), every lane busy: category / run /
+//                 Huffman lookup, warp scan of the code lengths, atomicOr of the bits into the
+//                 warp's region.  No per-block size walk, no divergence between sparse and dense blocks.
+//   4. publish    ONE 64-bit descriptor per tile: status | the tile's last 7 bits | its bit count.
+//   5. chain + write (one iteration later): decoupled look-back over the descriptors gives the
+//                 exclusive BIT offset of the tile in its image and, from the nearest descriptor,
+//                 the bits that complete the byte the two tiles share.  The region goes to the
+//                 image's UNSTUFFED scan (every byte written once, by the tile that holds its last
+//                 bit); the last tile pads with zero bits (jpeg_enc.h:1161-1164).
+//                 0xFF00 stuffing + EOI are the second pass (jpeg_stuff.cuh).
+// HBM traffic of this kernel: every pixel read once, the unstuffed scan written once, one
 // 8-byte and three 4-byte descriptors per tile.
 //
-// A tile whose bits overflow a warp region or the window (pathological content) is redone in
-// six groups of 16 blocks; same bytes, lower speed.
+// A tile whose bits overflow the region (pathological content) is redone in six groups of four
+// blocks; same bytes, lower speed.
 #pragma once
 #include "jpeg_device.h"
 #include "jpeg_launch.h"
@@ -52,46 +52,59 @@ namespace jg {
 
 constexpr int kTileFloats = 72;   // one 8x8 float tile with rows padded to 9 (bank-conflict free both ways)
 constexpr int kCoefStride = 72;   // int16 per block in shared memory (144 B: 16-byte aligned 8-coefficient reads)
-constexpr int kRegionWords = kWinWordsMax / kWarps;   // bits a warp may emit for its 24 blocks before the tile goes slow
 constexpr int kQueueEntries = 424;                     // 2 pad + 63 carried + 32 lanes x (8 coefficients + EOB) + 64 read-ahead
-constexpr int kWarpBlocks = 24;                        // blocks per warp (8 x 24 = 192)
+constexpr int kGroupBlocks = 4;                        // blocks per group on the slow path (always fit kWinWordsMin)
 
 template <int LAYOUT>
 struct Geo {
     static constexpr int BPM = LAYOUT == LAYOUT_444 ? 3 : (LAYOUT == LAYOUT_420 ? 6 : 1);  // blocks per MCU
     static constexpr int MCU = LAYOUT == LAYOUT_420 ? 16 : 8;                               // MCU edge in pixels
     static constexpr int M = mcus_per_tile(LAYOUT);        // MCUs per tile
-    static constexpr int SLOTS = M;                        // one lane group per MCU and iteration
     static constexpr int LANES = LAYOUT == LAYOUT_420 ? 16 : 8;   // lanes that share one MCU
-    static constexpr int GROUPS = kThreads / LANES;
-    static constexpr int ITERS = SLOTS / GROUPS;
+    static constexpr int GROUPS = 32 / LANES;                     // lane groups of the warp
+    static constexpr int ITERS = M / GROUPS;
     static constexpr int TILES = LAYOUT == LAYOUT_420 ? 6 : 1;    // exchange tiles per lane group
     static constexpr int NCOMP = LAYOUT == LAYOUT_GRAY ? 1 : 3;
-    static_assert(SLOTS % GROUPS == 0, "slots must divide evenly among the lane groups");
-    static_assert(M * BPM <= kBlocksPerTile, "tile too large");
+    static_assert(M % GROUPS == 0, "MCUs must divide evenly among the lane groups");
+    static_assert(M * BPM == kBlocksPerTile, "a full tile holds kBlocksPerTile blocks");
+};
+
+// what the pending (coded, not yet written) tile of a warp needs one iteration later
+struct Pending {
+    unsigned long long raw;       // the image's unstuffed scan
+    unsigned long long raw_cap;
+    int img_idx;
+    int first_tile_of_img;
+    unsigned T;                   // bits of the tile
+    unsigned tail;                // its last 7 bits
+    int last;                     // last tile of its image
+};
+
+// everything one warp owns
+template <int LAYOUT>
+struct WarpMem {
+    using G = Geo<LAYOUT>;
+    static constexpr int SCRATCH = G::GROUPS * G::TILES * kTileFloats;
+    static constexpr int R1_WORDS = SCRATCH > kQueueEntries ? SCRATCH : kQueueEntries;
+    alignas(16) uint32_t r1[R1_WORDS];                        // transform exchange tiles; then the symbol queue
+    alignas(16) int16_t coef[kBlocksPerTile * kCoefStride];   // quantised coefficients, zigzag order
+    alignas(16) uint32_t region[kWinWordsMax + 8];            // the tile's packed bits (MSB-first words); survives into the next iteration
+    int pred_dc[4];                                           // DCs of the MCU preceding the tile, per component
+    Pending pend[2];                                          // by iteration parity: the tile being coded / the tile to be written
+};
+
+struct CodeTables {
+    uint32_t huff[2][272];                // [class][(run<<4)|cat] AC, [class][256+cat] DC; entry = code<<8 | length
+    unsigned long long zrl[2][4];         // [class][n]: n ZRL codes back to back (<= 33 bits), bits<<8 | length
 };
 
 template <int LAYOUT, int NC>
 struct Smem {
-    using G = Geo<LAYOUT>;
-    static constexpr int SCRATCH = G::GROUPS * G::TILES * kTileFloats;
-    static constexpr int ENTROPY = kWarps * (kRegionWords + kQueueEntries);
-    static constexpr int R1_WORDS = SCRATCH > ENTROPY ? SCRATCH : ENTROPY;
-    alignas(16) uint32_t r1[R1_WORDS];                        // transform exchange tiles; then per-warp regions + symbol queues
-    alignas(16) uint32_t win[kWinWordsMax + 8];               // the tile's packed bits; survives into the next iteration
-    alignas(16) int16_t coef[kBlocksPerTile * kCoefStride];   // quantised coefficients, zigzag order
-    uint32_t huff[2][272];                // [class][(run<<4)|cat] AC, [class][256+cat] DC; entry = code<<8 | length
-    unsigned long long zrl[2][4];         // [class][n]: n ZRL codes back to back (<= 33 bits), bits<<8 | length
-    int pred_dc[4];                       // DCs of the MCU preceding the tile, per component
-    uint32_t warp_bits[kWarps];           // bits emitted by each warp
-    uint32_t warp_tmp[kWarps];
-    // tile-wide scalars (written by one thread, read after a barrier)
-    int tile;
-    int abort;
-    int slow;                             // a warp region overflowed: redo the tile in groups
+    WarpMem<LAYOUT> wm[kWarps];
+    CodeTables tab;
 };
 
-// per-lane constants: the lane's column u = tid & 7 of every coefficient matrix it finishes
+// per-lane constants: the lane's column u = lane & 7 of every coefficient matrix it finishes
 struct LaneConst {
     float pq_l[8], pq_c[8];   // reciprocal quantisers of column u: [v] = pqt[8v+u], luma / chroma
     unsigned zz_lo, zz_hi;    // zigzag positions of (v,u), v = 0..7, one byte each
@@ -215,14 +228,14 @@ JG_DEV void row_pass_store(float (&s)[8], float* tile, int r)
 // column u of an exchange tile: column pass, quantise, scatter to zigzag order.
 // dc_out != nullptr: the block is the last of its component in the tile; its DC is published for
 // the next tile's DC prediction (the lane that computed it stores it, nobody waits for anybody).
-template <int LAYOUT, int NC>
-JG_DEV void column_pass(Smem<LAYOUT, NC>& S, const float* tile, int u, bool chroma, int blk, unsigned* dc_out, const LaneConst& LC)
+template <int LAYOUT>
+JG_DEV void column_pass(WarpMem<LAYOUT>& W, const float* tile, int u, bool chroma, int blk, unsigned* dc_out, const LaneConst& LC)
 {
     float c[8];
 #pragma unroll
     for (int v = 0; v < 8; ++v) c[v] = tile[v * 9 + u];
     aan8(c);
-    int16_t* dst = S.coef + blk * kCoefStride;
+    int16_t* dst = W.coef + blk * kCoefStride;
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
         const int k = quantise(c[v], chroma ? LC.pq_c[v] : LC.pq_l[v]);
@@ -233,17 +246,17 @@ JG_DEV void column_pass(Smem<LAYOUT, NC>& S, const float* tile, int u, bool chro
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 1, grayscale: 8 lanes per block, 6 slots per lane group.  Gray has registers to spare,
+// stage 1, grayscale: 8 lanes per block, 6 blocks per lane group.  Gray has registers to spare,
 // so the next slot's pixels are requested while the current column pass runs.  (The colour
 // paths sit at the register cap: there the same prefetch cost more in spills than the hidden
 // latency gained -- measured -- so they load at the top of each iteration.)
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT, int NC>
-JG_DEV void transform_tile_gray(Smem<LAYOUT, NC>& S, const ImageDesc& im, int m0, int nM, unsigned* dc_out, const LaneConst& LC)
+JG_DEV void transform_tile_gray(WarpMem<LAYOUT>& W, const ImageDesc& im, int m0, int nM, unsigned* dc_out, const LaneConst& LC)
 {
     using G = Geo<LAYOUT>;
-    const int t = JG_TID, u = t & 7, grp = t >> 3;
-    float* tile = reinterpret_cast<float*>(S.r1) + grp * kTileFloats;
+    const int t = JG_TID & 31, u = t & 7, grp = t >> 3;
+    float* tile = reinterpret_cast<float*>(W.r1) + grp * kTileFloats;
     auto fetch = [&](int it, uint32_t (&w)[2]) {
         const int slot = it * G::GROUPS + grp;
         if (slot < nM) {
@@ -267,20 +280,20 @@ JG_DEV void transform_tile_gray(Smem<LAYOUT, NC>& S, const ImageDesc& im, int m0
         }
         if (it + 1 < G::ITERS) fetch(it + 1, w);
         warp_sync();
-        if (valid) column_pass(S, tile, u, false, slot, (slot == nM - 1) ? dc_out : nullptr, LC);
+        if (valid) column_pass(W, tile, u, false, slot, (slot == nM - 1) ? dc_out : nullptr, LC);
         warp_sync();
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 1: transform all slots of the tile
+// stage 1: transform all MCUs of the tile
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT, int NC>
-JG_DEV void transform_tile(Smem<LAYOUT, NC>& S, const ImageDesc& im, int m0, int nM, unsigned* dc_out, const LaneConst& LC)
+JG_DEV void transform_tile(WarpMem<LAYOUT>& W, const ImageDesc& im, int m0, int nM, unsigned* dc_out, const LaneConst& LC)
 {
     using G = Geo<LAYOUT>;
-    const int t = JG_TID;
-    float* scratch = reinterpret_cast<float*>(S.r1);
+    const int t = JG_TID & 31;
+    float* scratch = reinterpret_cast<float*>(W.r1);
     const int u = t & 7;
     const int grp = t / G::LANES;
 
@@ -305,7 +318,7 @@ JG_DEV void transform_tile(Smem<LAYOUT, NC>& S, const ImageDesc& im, int m0, int
                 row_pass_store(s, tile, u);
             }
             warp_sync();
-            if (valid) column_pass(S, tile, u, false, slot, dcs, LC);
+            if (valid) column_pass(W, tile, u, false, slot, dcs, LC);
             warp_sync();
         } else if (LAYOUT == LAYOUT_444) {
             float* tile = scratch + grp * kTileFloats;
@@ -327,34 +340,46 @@ JG_DEV void transform_tile(Smem<LAYOUT, NC>& S, const ImageDesc& im, int m0, int
                     row_pass_store(s, tile, u);
                 }
                 warp_sync();
-                if (valid) column_pass(S, tile, u, comp != 0, slot * 3 + comp, dcs ? dcs + comp : nullptr, LC);
+                if (valid) column_pass(W, tile, u, comp != 0, slot * 3 + comp, dcs ? dcs + comp : nullptr, LC);
                 warp_sync();
             }
         } else {
-            // 4:2:0: 16 lanes per MCU, lane r16 owns pixel row r16 (16 pixels)
+            // 4:2:0: 16 lanes per MCU, lane r16 owns pixel row r16 (16 pixels), one 8-pixel half at a time.
+            // (Keeping the halves / the column passes as real loops shrinks the hot loop to fit the
+            // instruction cache -- fetch stalls 1.3 -> 0.2 warps per issue -- but costs as many extra
+            // instructions as it saves stalls: measured equal, so the straight-line form stays.)
             const int r16 = t & 15;
             float* base = scratch + grp * (6 * kTileFloats);
-            float cbs[8], crs[8];            // horizontal pair sums (a+b) of this row
+            constexpr int HW = 8 * NC / 4;           // pixel words per half row
+            uint32_t w[2 * HW];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { cbs[i] = 0.0f; crs[i] = 0.0f; }
+            for (int i = 0; i < 2 * HW; ++i) w[i] = 0u;
             if (valid) {
                 int y = my * 16 + r16; if (y >= im.h) y = im.h - 1;
-                uint32_t w[16 * NC / 4];
                 load_segment<NC, 16>(im, mx * 16, y, w);
+            }
+            float cb0[4], cr0[4], cb1[4], cr1[4];    // horizontal pair sums (a+b) of this row: left half, right half
 #pragma unroll
-                for (int hx = 0; hx < 2; ++hx) {
-                    float R[8], Gc[8], B[8], s[8];
+            for (int i = 0; i < 4; ++i) { cb0[i] = 0.0f; cr0[i] = 0.0f; }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        rgb_of<NC>(w, 8 * hx + i, R[i], Gc[i], B[i]);
-                        s[i] = rgb_y(R[i], Gc[i], B[i]);
-                    }
-                    row_pass_store(s, base + ((r16 >> 3) * 2 + hx) * kTileFloats, r16 & 7);
+            for (int hx = 0; hx < 2; ++hx) {
+                float R[8], Gc[8], B[8], s[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        cbs[4 * hx + i] = f_add(rgb_cb(R[2 * i], Gc[2 * i], B[2 * i]), rgb_cb(R[2 * i + 1], Gc[2 * i + 1], B[2 * i + 1]));
-                        crs[4 * hx + i] = f_add(rgb_cr(R[2 * i], Gc[2 * i], B[2 * i]), rgb_cr(R[2 * i + 1], Gc[2 * i + 1], B[2 * i + 1]));
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    rgb_of<NC>(w, i, R[i], Gc[i], B[i]);
+                    s[i] = rgb_y(R[i], Gc[i], B[i]);
+                }
+                if (valid) row_pass_store(s, base + ((r16 >> 3) * 2 + hx) * kTileFloats, r16 & 7);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    cb1[i] = f_add(rgb_cb(R[2 * i], Gc[2 * i], B[2 * i]), rgb_cb(R[2 * i + 1], Gc[2 * i + 1], B[2 * i + 1]));
+                    cr1[i] = f_add(rgb_cr(R[2 * i], Gc[2 * i], B[2 * i]), rgb_cr(R[2 * i + 1], Gc[2 * i + 1], B[2 * i + 1]));
+                }
+                if (hx == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { cb0[i] = cb1[i]; cr0[i] = cr1[i]; }
+#pragma unroll
+                    for (int i = 0; i < HW; ++i) w[i] = w[HW + i];
                 }
             }
             // vertical pairs live in neighbouring lanes: the even lane finishes Cb, the odd lane Cr;
@@ -363,20 +388,22 @@ JG_DEV void transform_tile(Smem<LAYOUT, NC>& S, const ImageDesc& im, int m0, int
             float samp[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float other = warp_shfl_xor_f32(even ? crs[i] : cbs[i], 1);
-                samp[i] = even ? f_mul(f_add(cbs[i], other), 0.25f) : f_mul(f_add(other, crs[i]), 0.25f);
+                const float cbv = i < 4 ? cb0[i & 3] : cb1[i & 3], crv = i < 4 ? cr0[i & 3] : cr1[i & 3];
+                const float other = warp_shfl_xor_f32(even ? crv : cbv, 1);
+                samp[i] = even ? f_mul(f_add(cbv, other), 0.25f) : f_mul(f_add(other, crv), 0.25f);
             }
             if (valid) row_pass_store(samp, base + (4 + (r16 & 1)) * kTileFloats, r16 >> 1);
             warp_sync();
             if (valid) {
+                // lanes 0-7 finish tiles {0,2,4}, lanes 8-15 tiles {1,3,5}; the next tile predicts from
+                // Y11 (tile 3), Cb and Cr of our last MCU
+                const int h = r16 >> 3;
 #pragma unroll
-                for (int k3 = 0; k3 < 3; ++k3) {
-                    const int tl = (r16 >> 3) + 2 * k3;          // tiles {0,2,4} for lanes 0-7, {1,3,5} for lanes 8-15
-                    const int comp = tl < 4 ? 0 : tl - 3;
-                    // the next tile predicts from Y11 (tile 3), Cb and Cr of our last MCU
-                    unsigned* pd = (dcs != nullptr && tl >= 3) ? dcs + comp : nullptr;
-                    column_pass(S, base + tl * kTileFloats, u, k3 == 2, slot * 6 + tl, pd, LC);
+                for (int k3 = 0; k3 < 2; ++k3) {
+                    const int tl = h + 2 * k3;
+                    column_pass(W, base + tl * kTileFloats, u, false, slot * 6 + tl, (dcs != nullptr && tl == 3) ? dcs : nullptr, LC);
                 }
+                column_pass(W, base + (4 + h) * kTileFloats, u, true, slot * 6 + 4 + h, dcs != nullptr ? dcs + 1 + h : nullptr, LC);
             }
             warp_sync();
         }
@@ -410,8 +437,7 @@ JG_DEV void block_kind(int blk, int& comp, int& pred_blk)
 
 // One queue entry -> its Huffman code + amplitude bits (sym, slen <= 27 bits), the number of ZRL
 // codes that precede it (nz) and its table class.  `ep` is the previous entry of the queue.
-template <int LAYOUT, int NC>
-JG_DEV void decode_symbol(const Smem<LAYOUT, NC>& S, unsigned e, unsigned ep, unsigned& sym, unsigned& slen, unsigned& nz, unsigned& cls)
+JG_DEV void decode_symbol(const CodeTables& T, unsigned e, unsigned ep, unsigned& sym, unsigned& slen, unsigned& nz, unsigned& cls)
 {
     const int v = (int)e >> 16;
     cls = (e >> 13) & 1u;
@@ -421,7 +447,7 @@ JG_DEV void decode_symbol(const Smem<LAYOUT, NC>& S, unsigned e, unsigned ep, un
     if (e & 0x4000u) idx = 256u + cat;                           // DC
     if (e & 0x8000u) idx = 0u;                                   // EOB
     nz = (e & 0xC000u) ? 0u : run >> 4;                          // one ZRL per 16 zeros; none for DC / EOB
-    const unsigned h = S.huff[cls][idx];
+    const unsigned h = T.huff[cls][idx];
     slen = (h & 0xffu) + cat;
     sym = ((h >> 8) << cat) | amplitude(v, cat);
 }
@@ -441,12 +467,12 @@ JG_DEV void put_bits64(uint32_t* region, unsigned start, unsigned long long sym,
     }
 }
 
-// One warp codes blocks [first, end) (at most 24) into `region` (zeroed, MSB-first words).
+// The warp codes blocks [first, end) of its tile into `region` (zeroed, MSB-first words).
 // Symbol queue entry: value<<16 | EOB<<15 | DC<<14 | chroma<<13 | block-in-warp<<8 | zigzag position.
 // queue[-1] must be readable (one pad word).  Returns the bits emitted; sets `overflow` if they
 // did not fit region_words (the count stays right).
-template <int LAYOUT, int NC, bool DBG>
-JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint32_t* region, unsigned region_words,
+template <int LAYOUT, bool DBG>
+JG_DEV unsigned encode_blocks_warp(WarpMem<LAYOUT>& W, const CodeTables& T, int first, int end, uint32_t* region, unsigned region_words,
                                    uint32_t* queue, uint32_t* dbg_bits, bool& overflow)
 {
     const int lane = JG_TID & 31, L = lane & 7, b4 = lane >> 3;
@@ -461,7 +487,7 @@ JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint
         uint4 w = {0u, 0u, 0u, 0u};
         int comp = 0, pred_blk = -1;
         if (valid) {
-            w = *reinterpret_cast<const uint4*>(S.coef + blk * kCoefStride + 8 * L);
+            w = *reinterpret_cast<const uint4*>(W.coef + blk * kCoefStride + 8 * L);
             block_kind<LAYOUT>(blk, comp, pred_blk);
         }
         const unsigned ww[4] = {w.x, w.y, w.z, w.w};
@@ -473,7 +499,7 @@ JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint
         }
         int diff = 0;
         if (valid && L == 0) {                              // DC: always coded, as a difference (jpeg_enc.h:834-844)
-            const int pred = pred_blk >= 0 ? (int)S.coef[pred_blk * kCoefStride] : S.pred_dc[comp];
+            const int pred = pred_blk >= 0 ? (int)W.coef[pred_blk * kCoefStride] : W.pred_dc[comp];
             diff = (int)(int16_t)(ww[0] & 0xffffu) - pred;
             m8 |= 1u;
         }
@@ -504,13 +530,13 @@ JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint
             const uint2 ee = *reinterpret_cast<const uint2*>(queue + a);
             const unsigned ep = queue[(int)a - 1];
             unsigned symA, lenA, nzA, clsA, symB, lenB, nzB, clsB;
-            decode_symbol(S, ee.x, ep, symA, lenA, nzA, clsA);
-            decode_symbol(S, ee.y, ee.x, symB, lenB, nzB, clsB);
+            decode_symbol(T, ee.x, ep, symA, lenA, nzA, clsA);
+            decode_symbol(T, ee.y, ee.x, symB, lenB, nzB, clsB);
             if (a >= full) { lenA = 0u; symA = 0u; nzA = 0u; }
             if (a + 1u >= full) { lenB = 0u; symB = 0u; nzB = 0u; }
             if (DBG) {
-                if (lenA) gmem_atomic_add(dbg_bits + ((ee.x >> 8) & 31u), lenA + nzA * (S.huff[clsA][0xF0] & 0xffu));
-                if (lenB) gmem_atomic_add(dbg_bits + ((ee.y >> 8) & 31u), lenB + nzB * (S.huff[clsB][0xF0] & 0xffu));
+                if (lenA) gmem_atomic_add(dbg_bits + ((ee.x >> 8) & 31u), lenA + nzA * (T.huff[clsA][0xF0] & 0xffu));
+                if (lenB) gmem_atomic_add(dbg_bits + ((ee.y >> 8) & 31u), lenB + nzB * (T.huff[clsB][0xF0] & 0xffu));
             }
             unsigned tot;
             if (warp_ballot((nzA | nzB) != 0u) == 0u) {
@@ -521,7 +547,7 @@ JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint
                 if (len) put_bits64(region, carry + endb - len, ((unsigned long long)symA << lenB) | symB, len, cap_bits);
             } else {
                 // some lane skipped 16+ zeros: its ZRL codes (jpeg_enc.h:863-867) go in front of the symbol
-                const unsigned long long zA = S.zrl[clsA][nzA], zB = S.zrl[clsB][nzB];
+                const unsigned long long zA = T.zrl[clsA][nzA], zB = T.zrl[clsB][nzB];
                 const unsigned tA = lenA ? lenA + (unsigned)(zA & 0xffull) : 0u, tB = lenB ? lenB + (unsigned)(zB & 0xffull) : 0u;
                 const unsigned endb = warp_scan_incl_u32(tA + tB);
                 tot = warp_shfl_u32(endb, 31);
@@ -547,60 +573,11 @@ JG_DEV unsigned encode_blocks_warp(Smem<LAYOUT, NC>& S, int first, int end, uint
     return carry;
 }
 
-// Code blocks [b_lo, b_hi) of the tile, `per_warp` consecutive blocks per warp, into the warps'
-// regions.  Returns the bits of the range (CTA-uniform, after a barrier); raises S.slow if a
-// region overflowed (the bit count is right even then).
-template <int LAYOUT, int NC>
-JG_DEV unsigned encode_range(Smem<LAYOUT, NC>& S, int b_lo, int b_hi, int per_warp, uint32_t* dbg_bits)
-{
-    const int t = JG_TID, lane = t & 31, wid = t >> 5;
-    uint32_t* region = S.r1 + wid * kRegionWords;
-    uint32_t* queue = S.r1 + kWarps * kRegionWords + wid * kQueueEntries + 2;    // 8-byte aligned; [-1] is a pad word
-    for (int i = lane; i < kRegionWords; i += 32) region[i] = 0u;
-    warp_sync();
-    const int first = b_lo + wid * per_warp;
-    const int end = first + per_warp < b_hi ? first + per_warp : b_hi;
-    bool overflow = false;
-    unsigned bits = 0;
-    if (first < end) {
-        if (dbg_bits) bits = encode_blocks_warp<LAYOUT, NC, true>(S, first, end, region, kRegionWords, queue, dbg_bits + first, overflow);
-        else bits = encode_blocks_warp<LAYOUT, NC, false>(S, first, end, region, kRegionWords, queue, nullptr, overflow);
-    }
-    if (lane == 0) S.warp_bits[wid] = bits;
-    if (overflow) S.slow = 1;
-    cta_sync();
-    unsigned total = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) total += S.warp_bits[w];
-    return total;
-}
-
-// Shift the 8 warp regions (S.warp_bits[w] bits each) into the window, back to back.
-// Contains barriers; the window must not be in use.
-template <int LAYOUT, int NC>
-JG_DEV void compact_regions(Smem<LAYOUT, NC>& S, unsigned total_bits)
-{
-    const int t = JG_TID, lane = t & 31, wid = t >> 5;
-    for (int i = t; i < (int)(total_bits >> 5) + 8; i += kThreads) S.win[i] = 0u;
-    cta_sync();
-    unsigned off = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) if (w < wid) off += S.warp_bits[w];
-    const uint32_t* region = S.r1 + wid * kRegionWords;
-    const unsigned nwords = (S.warp_bits[wid] + 31u) >> 5;
-    const unsigned sh = off & 31u, d0 = off >> 5;
-    for (unsigned i = (unsigned)lane; i < nwords; i += 32) {
-        const unsigned v = region[i];
-        if (v >> sh) smem_atomic_or(S.win + d0 + i, v >> sh);
-        if (sh && (v << (32u - sh))) smem_atomic_or(S.win + d0 + i + 1, v << (32u - sh));
-    }
-    cta_sync();
-}
 
 // ------------------------------------------------------------------------------------------
-// CTA-wide helpers
+// scans and look-back
 // ------------------------------------------------------------------------------------------
-// exclusive scan over the CTA's threads; contains two barriers
+// exclusive scan over the CTA's threads; contains two barriers (second pass only)
 JG_DEV unsigned cta_scan_excl(unsigned v, uint32_t* warp_tmp, unsigned& total)
 {
     const int lane = JG_TID & 31, wid = JG_TID >> 5;
@@ -632,9 +609,11 @@ JG_DEV unsigned long long warp_sum_u64(unsigned long long v)
 }
 
 // Decoupled look-back (Merrill & Garland) executed by one full warp.  desc[i] holds
-// status[63:62] | value.  Tiles before `first` do not exist (image start): they count as
-// PREFIX 0.  Returns the exclusive prefix of tile g.  On timeout sets *timed_out (all lanes agree).
-JG_DEV unsigned long long lookback(const unsigned long long* desc, int g, int first, unsigned* err_flag, int* timed_out)
+// status[63:62] | payload[61:55] | value[54:0].  Tiles before `first` do not exist (image start):
+// they count as PREFIX 0.  Returns the exclusive prefix of tile g; *nearest (if asked for) is
+// the descriptor of tile g-1 as read.  On timeout sets *timed_out (all lanes agree).
+JG_DEV unsigned long long lookback(const unsigned long long* desc, int g, int first, unsigned* err_flag, int* timed_out,
+                                   unsigned long long* nearest = nullptr)
 {
     const int lane = JG_TID & 31;
     unsigned long long running = 0;
@@ -651,6 +630,7 @@ JG_DEV unsigned long long lookback(const unsigned long long* desc, int g, int fi
             if (warp_ballot(spins == 0xffffffffu) != 0u) { *timed_out = 1; return 0; }
             backoff();
         }
+        if (nearest != nullptr && base == g - 1) *nearest = warp_shfl_u64(w, 0);
         const unsigned pmask = warp_ballot((w >> 62) == 2u);
         const int stop = pmask ? i_ffs(pmask) - 1 : 32;   // nearest tile that already knows its prefix
         running += warp_sum_u64(lane <= stop ? (w & kCountMask) : 0ull);
@@ -675,37 +655,22 @@ JG_DEV unsigned xword(const uint32_t* L, int i, unsigned k, unsigned hb)
     return (hi << (32u - k)) | (L[i] >> k);
 }
 
-// ------------------------------------------------------------------------------------------
-// a tile's identity (CTA-uniform, lives in registers across loop iterations)
-// ------------------------------------------------------------------------------------------
-struct TileCtx {
-    int g;                   // launch-wide tile index, -1 = none
-    int img_idx;
-    int first_tile_of_img;   // launch-wide index of the image's first tile
-    int nblk;
-    unsigned T;              // bits of the tile
-    bool first, last;
-    uint8_t* raw;            // the image's unstuffed scan
-    unsigned long long raw_cap;
-    unsigned long long dbg_base;   // index of the tile's first block in the debug dumps
-};
-
-// Copy bytes [0, n_bytes) of the byte-aligned stream X = (k head bits) ++ L to dst (any
-// alignment).  Every byte is written exactly once and nothing outside the range is touched:
+// The warp copies bytes [0, n_bytes) of the byte-aligned stream X = (k head bits) ++ L to dst
+// (any alignment).  Every byte is written exactly once and nothing outside the range is touched:
 // the bytes up to the second 16-byte boundary and after the last one go out singly, the rest
 // as aligned 16-byte vectors (X words are MSB-first, memory wants them byte-swapped).
 JG_DEV void copy_stream_out(const uint32_t* L, unsigned k, unsigned hb, unsigned n_bytes, uint8_t* dst)
 {
-    const unsigned t = (unsigned)JG_TID;
+    const unsigned t = (unsigned)(JG_TID & 31);
     const unsigned d = (unsigned)((size_t)dst & 15u);
     uint8_t* A = dst - d;                         // 16-byte aligned; V = d pad bytes ++ X starts here
     const unsigned total = d + n_bytes;
     auto xbyte = [&](unsigned j) { return (xword(L, (int)(j >> 2), k, hb) >> (24u - 8u * (j & 3u))) & 0xffu; };
     // head: V bytes [d, min(total, 32))
-    if (t >= d && t < 32u && t < total) A[t] = (uint8_t)xbyte(t - d);
+    if (t >= d && t < total) A[t] = (uint8_t)xbyte(t - d);
     // body: whole vectors v >= 2 (V byte 16v is X byte 16v - d, bit 8(16v-d) - k of L: never negative here)
     const unsigned nvec = total >> 4;
-    for (unsigned v = 2u + t; v < nvec; v += kThreads) {
+    for (unsigned v = 2u + t; v < nvec; v += 32u) {
         const unsigned p = 8u * (16u * v - d) - k;      // bit position in L of the vector's first bit
         const unsigned i = p >> 5, sft = p & 31u;
         uint32_t w[5];
@@ -723,121 +688,165 @@ JG_DEV void copy_stream_out(const uint32_t* L, unsigned k, unsigned hb, unsigned
     if (tail0 + t < total) A[tail0 + t] = (uint8_t)xbyte(tail0 + t - d);
 }
 
-// Learn the tile's bit offset (look-back over desc_bits) and the predecessor's last bits.
-// EVERY warp resolves the chain for itself (same descriptors, same answer): nobody waits at a
-// barrier for one designated warp.  Warp 0 publishes the inclusive prefix.  On a timeout the
-// error flag is raised (checked CTA-uniformly at the next barrier).
-template <int LAYOUT, int NC>
-JG_DEV void chain_bits(const LaunchParams& P, Smem<LAYOUT, NC>& S, const TileCtx& c, unsigned long long& bit_base, unsigned& pred_tail)
-{
-    const int t = JG_TID;
-    unsigned long long excl = 0, ptail = 0;
-    int timed_out = 0;
-    if (!c.first) {
-        excl = lookback(P.desc_bits, c.g, c.first_tile_of_img, P.error, &timed_out);
-        if (t == 0 && !timed_out) st_flag64(P.desc_bits + c.g, kStatusPrefix | (excl + c.T));
-        unsigned spins = 0;      // the byte we share with the predecessor needs its last bits
-        while (!timed_out && ((ptail = ld_flag64(P.desc_tail + c.g - 1)) >> 62) == 0) {
-            if (++spins > kSpinLimit || ld_flag32(P.error) != 0u) timed_out = 1;
-            backoff();
-        }
-        timed_out = warp_ballot(timed_out) != 0u;
-    }
-    if (timed_out) { S.abort = 1; if ((t & 31) == 0) gmem_atomic_or(P.error, 1u); excl = 0; ptail = 0; }
-    bit_base = excl;
-    pred_tail = (unsigned)ptail & 0x7fu;
-}
-
-// Write the window (tg bits) as the next piece of the image's unstuffed scan.
-// k/hb: bits of the first byte that precede the window (carry in); updated to the carry out.
-template <int LAYOUT, int NC>
-JG_DEV void flush_window(const LaunchParams& P, Smem<LAYOUT, NC>& S, const TileCtx& c, unsigned tg, bool final_piece,
+// Write the region (tg bits) as the next piece of the image's unstuffed scan.
+// k/hb: bits of the first byte that precede the piece (carry in); updated to the carry out.
+JG_DEV void flush_region(const uint32_t* region, unsigned tg, bool final_piece, uint8_t* raw, unsigned long long raw_cap,
                          unsigned& k, unsigned& hb, unsigned long long& pos, bool& overflow)
 {
     unsigned n_bytes = (k + tg) >> 3, k_out = (k + tg) & 7u, hb_out = 0;
     if (k_out) {
         if (final_piece) { n_bytes += 1; k_out = 0; }                 // zero padding, jpeg_enc.h:1161-1164
-        else if (tg >= k_out) hb_out = peek_bits(S.win, tg - k_out, k_out);
-        else hb_out = ((hb << tg) | peek_bits(S.win, 0u, tg)) & ((1u << k_out) - 1u);
+        else if (tg >= k_out) hb_out = peek_bits(region, tg - k_out, k_out);
+        else hb_out = ((hb << tg) | peek_bits(region, 0u, tg)) & ((1u << k_out) - 1u);
     }
-    if (pos + n_bytes > c.raw_cap) overflow = true;
-    else copy_stream_out(S.win, k, hb, n_bytes, c.raw + pos);
+    if (pos + n_bytes > raw_cap) overflow = true;
+    else copy_stream_out(region, k, hb, n_bytes, raw + pos);
     pos += n_bytes;
     k = k_out; hb = hb_out;
 }
 
-JG_DEV int image_of_tile(const LaunchParams& P, int g)
+// zero words [0, n) of the region (the warp; followed by a warp barrier)
+JG_DEV void clear_region(uint32_t* region, unsigned n)
 {
-    if (P.tiles_per_image > 0) return g / P.tiles_per_image;
-    int lo = 0, hi = P.n_images - 1;
+    for (unsigned i = (unsigned)(JG_TID & 31); i < n; i += 32u) region[i] = 0u;
+    warp_sync();
+}
+
+JG_DEV unsigned tail_bits(const uint32_t* region, unsigned T) { return T >= 7u ? peek_bits(region, T - 7u, 7u) : peek_bits(region, 0u, T); }
+
+JG_DEV unsigned long long make_desc(unsigned long long status, unsigned tail, unsigned long long count)
+{
+    return status | ((unsigned long long)tail << kTailShift) | count;
+}
+
+// Draw the warp's next tile: its launch-wide index g (>= n_tiles: none left) and its image.
+// Tickets are handed out so that a tile's predecessor always holds a smaller ticket (it is then
+// resident or finished), and they walk the images ROUND-ROBIN: tile 0 of every image, tile 1 of
+// every image that has one, ...  The thousands of tiles in flight then spread over all images, each
+// image has only a handful in flight, and the look-back along an image stays within one step.
+// (In image-major order a 256 x 1080p batch is 1.7x slower: every stall of one tile sends the
+// hundreds of tiles drawn after it on long walks.)  Images of different sizes: the schedule of
+// build_schedule() tells which images are still active in which round.
+JG_DEV unsigned tile_of_ticket(const LaunchParams& P, unsigned v, unsigned& img)
+{
+    if (P.tiles_per_image > 0) {
+        const unsigned lt = v / (unsigned)P.n_images;
+        img = v - lt * (unsigned)P.n_images;
+        return img * (unsigned)P.tiles_per_image + lt;
+    }
+    const uint32_t* S = P.sched;
+    const unsigned D = ldg_u32(S);
+    const uint32_t *cum = S + 1, *lt0 = cum + D + 1, *first = lt0 + D, *order = first + D;
+    unsigned lo = 0, hi = D - 1;           // last segment whose first ticket is <= v
     while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (P.images[mid].first_tile <= g) lo = mid; else hi = mid - 1;
+        const unsigned mid = (lo + hi + 1) >> 1;
+        if (ldg_u32(cum + mid) <= v) lo = mid; else hi = mid - 1;
     }
-    return lo;
+    const unsigned rem = v - ldg_u32(cum + lo), a = ldg_u32(first + lo), c = (unsigned)P.n_images - a;
+    const unsigned r = rem / c;
+    img = ldg_u32(order + a + (rem - r * c));
+    return (unsigned)P.images[img].first_tile + ldg_u32(lt0 + lo) + r;
 }
 
-// ---- front half of a tile: transform, entropy-code into the warp regions, publish the bit count ----
-template <int LAYOUT, int NC>
-JG_DEV void tile_front(const LaunchParams& P, Smem<LAYOUT, NC>& S, const LaneConst& LC, const int g, TileCtx& c)
+JG_DEV int draw_tile(const LaunchParams& P, int& img_out)
 {
-    using G = Geo<LAYOUT>;
-    const int t = JG_TID;
-    const int img_idx = image_of_tile(P, g);
-    const ImageDesc im = P.images[img_idx];
-    const int lt = g - im.first_tile;
-    const int m0 = lt * G::M;
-    const int nM = (im.n_mcus - m0 < G::M) ? im.n_mcus - m0 : G::M;
-    c.g = g; c.img_idx = img_idx; c.first_tile_of_img = im.first_tile; c.nblk = nM * G::BPM;
-    c.first = lt == 0; c.last = lt == im.n_tiles - 1; c.raw = im.raw; c.raw_cap = im.raw_cap;
-    c.dbg_base = im.first_block + (unsigned long long)(m0 * G::BPM);
-
-    if (t == 0) S.slow = 0;
-    if (LAYOUT == LAYOUT_GRAY) transform_tile_gray<LAYOUT, NC>(S, im, m0, nM, P.desc_dc + 3 * (size_t)g, LC);
-    else transform_tile<LAYOUT, NC>(S, im, m0, nM, P.desc_dc + 3 * (size_t)g, LC);
-    // DC predictors of the tile's first blocks: the last DCs of the previous tile (published by the
-    // lanes that computed them, right after their column pass -- that tile started before ours, so
-    // this normally does not wait), or 0 at the start of the image (jpeg_enc.h:1085-1087)
-    if (t < G::NCOMP) {
-        int pred = 0;
-        if (!c.first) {
-            unsigned v, spins = 0;
-            while (((v = ld_flag32(P.desc_dc + 3 * (size_t)(g - 1) + t)) >> 31) == 0u) {
-                if (++spins > kSpinLimit || ld_flag32(P.error) != 0u) { S.abort = 1; gmem_atomic_or(P.error, 4u); break; }
-                backoff();
-            }
-            pred = (int)(int16_t)(v & 0xffffu);
-        }
-        S.pred_dc[t] = pred;
+    unsigned g = 0, img = 0;
+    if ((JG_TID & 31) == 0) {
+        g = gmem_atomic_add(P.ticket, 1u);
+        if (g < (unsigned)P.n_tiles) g = tile_of_ticket(P, g, img);
     }
-    cta_sync();   // coefficients + predictors complete; the exchange tiles are dead, their space becomes regions + queues
-
-    if (P.dbg_coefs) {
-        for (int i = t; i < c.nblk * 64; i += kThreads)
-            P.dbg_coefs[c.dbg_base * 64ull + (unsigned long long)i] = S.coef[(i >> 6) * kCoefStride + (i & 63)];
-    }
-    c.T = encode_range<LAYOUT, NC>(S, 0, c.nblk, kWarpBlocks, P.dbg_bits ? P.dbg_bits + c.dbg_base : nullptr);
-    // Publish the tile's bit count NOW: it is consumed (by us and by every successor) one
-    // loop iteration later, so the look-back practically never waits.
-    if (t == 0) st_flag64(P.desc_bits + g, (c.first ? kStatusPrefix : kStatusAgg) | (unsigned long long)c.T);
+    img_out = (int)warp_shfl_u32(img, 0);
+    return (int)warp_shfl_u32(g, 0);
 }
 
-// ---- back half of a (single-window) tile, run one iteration later: offset + write -------------
-template <int LAYOUT, int NC>
-JG_DEV void tile_back(const LaunchParams& P, Smem<LAYOUT, NC>& S, const TileCtx& c)
+// Learn a tile's bit offset and the bits that complete the byte it shares with its predecessor:
+// one look-back over the descriptors (the nearest one carries the predecessor's last 7 bits).
+// Lane 0 publishes the inclusive prefix.  Returns false on a timeout (error flag raised).
+JG_DEV bool chain_bits(const LaunchParams& P, int g, int first_tile_of_img, unsigned T, unsigned tail,
+                       unsigned long long& bit_base, unsigned& pred_tail)
 {
-    unsigned long long bit_base;
-    unsigned pred_tail;
-    chain_bits(P, S, c, bit_base, pred_tail);
+    int timed_out = 0;
+    unsigned long long nearest = 0;
+    const unsigned long long excl = lookback(P.desc_bits, g, first_tile_of_img, P.error, &timed_out, &nearest);
+    if (timed_out) {
+        if ((JG_TID & 31) == 0) gmem_atomic_or(P.error, 1u);
+        return false;
+    }
+    if ((JG_TID & 31) == 0) st_flag64(P.desc_bits + g, make_desc(kStatusPrefix, tail, excl + T));
+    bit_base = excl;
+    pred_tail = (unsigned)(nearest >> kTailShift) & 0x7fu;
+    return true;
+}
+
+// ---- back half of a tile, run one iteration after it was coded: offset + write -----------------
+template <int LAYOUT>
+JG_DEV bool tile_back(const LaunchParams& P, WarpMem<LAYOUT>& W, int g, int slot)
+{
+    const Pending pd = W.pend[slot];
+    const bool first = g == pd.first_tile_of_img;
+    unsigned long long bit_base = 0;
+    unsigned pred_tail = 0;
+    if (!first && !chain_bits(P, g, pd.first_tile_of_img, pd.T, pd.tail, bit_base, pred_tail)) return false;
     unsigned k = (unsigned)(bit_base & 7ull);          // bits of our first byte owned by the predecessor
     unsigned hb = pred_tail & ((1u << k) - 1u);
     unsigned long long pos = bit_base >> 3;
     bool overflow = false;
-    flush_window(P, S, c, c.T, c.last, k, hb, pos, overflow);
-    if (JG_TID == 0) {
-        if (c.last) P.raw_bytes[c.img_idx] = pos;
-        if (overflow) gmem_atomic_or(P.img_status + c.img_idx, 1u);
+    flush_region(W.region, pd.T, pd.last != 0, reinterpret_cast<uint8_t*>(pd.raw), pd.raw_cap, k, hb, pos, overflow);
+    if ((JG_TID & 31) == 0) {
+        if (pd.last) P.raw_bytes[pd.img_idx] = pos;
+        if (overflow) gmem_atomic_or(P.img_status + pd.img_idx, 1u);
     }
+    warp_sync();                                        // every lane has read the region
+    clear_region(W.region, (pd.T >> 5) + 2u);
+    return true;
+}
+
+// Stage-dump variant of the coder (parity tests only), kept out of line so the hot loop stays small.
+template <int LAYOUT>
+JG_DEV_NOINLINE unsigned encode_blocks_dbg(WarpMem<LAYOUT>& W, const CodeTables& T, int nblk, unsigned cap_words, uint32_t* queue,
+                                           uint32_t* dbg_bits, bool& overflow)
+{
+    return encode_blocks_warp<LAYOUT, true>(W, T, 0, nblk, W.region, cap_words, queue, dbg_bits, overflow);
+}
+
+// Pathological tile (its `bits` did not fit the region): groups of four blocks (always fit), coded
+// again and written out right away, not pipelined.  The last group goes first, only to learn the
+// tile's last 7 bits: successors must not wait for our whole slow pass.  Out of line: rare.
+// Returns false on a look-back timeout.
+template <int LAYOUT>
+JG_DEV_NOINLINE bool tile_slow(const LaunchParams& P, WarpMem<LAYOUT>& W, const CodeTables& T, uint32_t* queue, unsigned cap_words,
+                               int g, int nblk, unsigned bits, int slot)
+{
+    const int lane = JG_TID & 31;
+    const Pending pd = W.pend[slot];
+    const bool first = g == pd.first_tile_of_img;
+    const int n_groups = (nblk + kGroupBlocks - 1) / kGroupBlocks;
+    bool ovf2;
+    clear_region(W.region, cap_words + 8u);
+    const unsigned tl = encode_blocks_warp<LAYOUT, false>(W, T, (n_groups - 1) * kGroupBlocks, nblk, W.region, cap_words, queue, nullptr, ovf2);
+    const unsigned tail = tail_bits(W.region, tl);
+    if (lane == 0) st_flag64(P.desc_bits + g, make_desc(first ? kStatusPrefix : kStatusAgg, tail, bits));
+    unsigned long long bit_base = 0;
+    unsigned pred_tail = 0;
+    if (!first && !chain_bits(P, g, pd.first_tile_of_img, bits, tail, bit_base, pred_tail)) return false;
+    unsigned k = (unsigned)(bit_base & 7ull);
+    unsigned hb = pred_tail & ((1u << k) - 1u);
+    unsigned long long pos = bit_base >> 3;
+    bool cap_overflow = false;
+    for (int gi = 0; gi < n_groups; ++gi) {
+        const int b_lo = gi * kGroupBlocks, b_hi = b_lo + kGroupBlocks < nblk ? b_lo + kGroupBlocks : nblk;
+        warp_sync();
+        clear_region(W.region, cap_words + 8u);
+        const unsigned tg = encode_blocks_warp<LAYOUT, false>(W, T, b_lo, b_hi, W.region, cap_words, queue, nullptr, ovf2);
+        flush_region(W.region, tg, pd.last && gi == n_groups - 1, reinterpret_cast<uint8_t*>(pd.raw), pd.raw_cap, k, hb, pos, cap_overflow);
+    }
+    if (lane == 0) {
+        if (pd.last) P.raw_bytes[pd.img_idx] = pos;
+        if (cap_overflow) gmem_atomic_or(P.img_status + pd.img_idx, 1u);
+    }
+    warp_sync();
+    clear_region(W.region, cap_words + 8u);
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -847,19 +856,20 @@ template <int LAYOUT, int NC>
 JG_KERNEL(kThreads, 6)
 void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTANT QuantSet Q)
 {
+    using G = Geo<LAYOUT>;
     JG_DYNAMIC_SMEM(smem_raw);
     Smem<LAYOUT, NC>& S = *reinterpret_cast<Smem<LAYOUT, NC>*>(smem_raw);
-    const int t = JG_TID;
+    const int t = JG_TID, lane = t & 31;
     for (int i = t; i < 2 * 272; i += kThreads) {
         const int cls = i / 272, k = i - cls * 272;
-        S.huff[cls][k] = k < 256 ? P.huff->ac[cls][k] : P.huff->dc[cls][k - 256];
+        S.tab.huff[cls][k] = k < 256 ? P.huff->ac[cls][k] : P.huff->dc[cls][k - 256];
     }
     if (t < 8) {      // n = t & 3 ZRL codes back to back (the luma ZRL has 11 bits: up to 33 bits)
         const int cls = t >> 2, n = t & 3;
         const unsigned z = P.huff->ac[cls][0xF0];
         unsigned long long bits = 0, len = 0;
         for (int q = 0; q < n; ++q) { bits = (bits << (z & 0xffu)) | (z >> 8); len += z & 0xffu; }
-        S.zrl[cls][n] = (bits << 8) | len;
+        S.tab.zrl[cls][n] = (bits << 8) | len;
     }
     LaneConst LC;
     {
@@ -873,75 +883,96 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
             if (v < 4) LC.zz_lo |= z << (8 * v); else LC.zz_hi |= z << (8 * (v - 4));
         }
     }
-    TileCtx prev;
-    prev.g = -1;
-    for (;;) {
-        cta_sync();   // everyone is done with the previous iteration's shared state
-        if (t == 0) {
-            S.tile = (int)gmem_atomic_add(P.ticket, 1u);
-            S.abort = ld_flag32(P.error) != 0u;
-        }
-        cta_sync();
-        const int g = S.tile;
+    WarpMem<LAYOUT>& W = S.wm[t >> 5];
+    const CodeTables& T = S.tab;
+    uint32_t* const queue = W.r1 + 2;                   // 8-byte aligned; [-1] is a pad word
+    const unsigned cap_words = (unsigned)P.win_words;
+    clear_region(W.region, kWinWordsMax + 8);
+    cta_sync();       // the tables are loaded: the ONLY CTA barrier of the kernel; from here every warp is on its own
+
+    int prev_g = -1;                 // tile coded in the previous iteration, still to be written
+    for (int slot = 0;; slot ^= 1) {
+        // Tiles must START in ticket order (a tile started long before its predecessor would sit in
+        // the DC / look-back waits -- measured: drawing the ticket one iteration ahead is 30 % slower):
+        // the ticket is drawn when the warp is ready for it, not earlier.
+        int img_idx;
+        const int g = draw_tile(P, img_idx);
         const bool have = g < P.n_tiles;
-        if (S.abort) break;
-
-        // software pipeline: front of tile g, THEN the back of the tile compacted last iteration
-        TileCtx cur;
-        cur.g = -1;
-        if (have) tile_front<LAYOUT, NC>(P, S, LC, g, cur);
-        if (prev.g >= 0) {
-            tile_back<LAYOUT, NC>(P, S, prev);
-            prev.g = -1;
+        // ---- front: pixels -> coefficients (the ticket of the tile after this one is already on its way) ----
+        int nblk = 0;
+        bool first = false;
+        if (have) {
+            const ImageDesc im = P.images[img_idx];
+            const int lt = g - im.first_tile;
+            const int m0 = lt * G::M;
+            const int nM = (im.n_mcus - m0 < G::M) ? im.n_mcus - m0 : G::M;
+            nblk = nM * G::BPM;
+            first = lt == 0;
+            const bool last = lt == im.n_tiles - 1;
+            if (lane == 0) {         // what the write-out needs one iteration later; T and tail follow after the coding
+                Pending& pd = W.pend[slot];
+                pd.raw = reinterpret_cast<unsigned long long>(im.raw); pd.raw_cap = im.raw_cap;
+                pd.img_idx = img_idx; pd.first_tile_of_img = im.first_tile; pd.last = last ? 1 : 0;
+            }
+            if (LAYOUT == LAYOUT_GRAY) transform_tile_gray<LAYOUT, NC>(W, im, m0, nM, P.desc_dc + 3 * (size_t)g, LC);
+            else transform_tile<LAYOUT, NC>(W, im, m0, nM, P.desc_dc + 3 * (size_t)g, LC);
         }
-        cta_sync();   // the window is free again (tile_back has read it); S.slow / S.abort are settled
-        if (S.abort || !have) break;
-
-        const unsigned cap_bits = (unsigned)P.win_words * 32u - 64u;
-        if (!S.slow && cur.T <= cap_bits) {
-            // regions -> window; written out next iteration by tile_back()
-            compact_regions<LAYOUT, NC>(S, cur.T);
-            if (t == 0) {
-                const unsigned tail = cur.T >= 7u ? peek_bits(S.win, cur.T - 7u, 7u) : peek_bits(S.win, 0u, cur.T);
-                st_flag64(P.desc_tail + g, kStatusAgg | (unsigned long long)tail);
-            }
-            prev = cur;
-        } else {
-            // pathological tile: groups of 32 blocks (4 per warp, always fit), coded again and written
-            // out right away, not pipelined.  The last group goes first, only to learn the tile's
-            // last 7 bits: successors must not wait for our whole slow pass.
-            constexpr int GB = 4 * kWarps;            // blocks per group
-            const int n_groups = (cur.nblk + GB - 1) / GB;
-            {
-                const int b_lo = (n_groups - 1) * GB;
-                const unsigned tg = encode_range<LAYOUT, NC>(S, b_lo, cur.nblk, 4, nullptr);
-                compact_regions<LAYOUT, NC>(S, tg);
-                if (t == 0) {
-                    const unsigned tail = tg >= 7u ? peek_bits(S.win, tg - 7u, 7u) : peek_bits(S.win, 0u, tg);
-                    st_flag64(P.desc_tail + g, kStatusAgg | (unsigned long long)tail);
-                }
-            }
-            unsigned long long bit_base;
-            unsigned pred_tail;
-            chain_bits(P, S, cur, bit_base, pred_tail);
-            cta_sync();
-            if (S.abort) break;
-            unsigned k = (unsigned)(bit_base & 7ull);
-            unsigned hb = pred_tail & ((1u << k) - 1u);
-            unsigned long long pos = bit_base >> 3;
-            bool overflow = false;
-            for (int gi = 0; gi < n_groups; ++gi) {
-                const int b_lo = gi * GB, b_hi = b_lo + GB < cur.nblk ? b_lo + GB : cur.nblk;
-                const unsigned tg = encode_range<LAYOUT, NC>(S, b_lo, b_hi, 4, nullptr);   // block sizes were dumped by the first attempt
-                compact_regions<LAYOUT, NC>(S, tg);
-                flush_window(P, S, cur, tg, cur.last && gi == n_groups - 1, k, hb, pos, overflow);
-                cta_sync();   // window + regions are reused by the next group
-            }
-            if (t == 0) {
-                if (cur.last) P.raw_bytes[cur.img_idx] = pos;
-                if (overflow) gmem_atomic_or(P.img_status + cur.img_idx, 1u);
+        // DC predictors of the tile's first blocks: the last DCs of the previous tile (published by the
+        // lanes that computed them, right after their column pass -- that tile was drawn before ours), or 0
+        // at the start of the image (jpeg_enc.h:1085-1087).  Requested here, looked at after the write-out
+        // of the previous tile: the round trip to L2 costs nothing.
+        unsigned dcv = 0x80000000u;
+        const bool dc_wanted = have && !first && lane < G::NCOMP;
+        if (dc_wanted) dcv = ld_flag32(P.desc_dc + 3 * (size_t)(g - 1) + lane);
+        // ---- back of the previous tile: its count was published a whole transform ago, so were its
+        //      predecessors' -- the look-back practically never waits ----
+        if (prev_g >= 0) {
+            if (!tile_back<LAYOUT>(P, W, prev_g, slot ^ 1)) break;
+            prev_g = -1;
+        }
+        if (!have) break;
+        bool bad = false;
+        if (dc_wanted) {
+            unsigned spins = 0;
+            while ((dcv >> 31) == 0u) {
+                if (++spins > kSpinLimit || ld_flag32(P.error) != 0u) { bad = true; break; }
+                backoff();
+                dcv = ld_flag32(P.desc_dc + 3 * (size_t)(g - 1) + lane);
             }
         }
+        if (lane < G::NCOMP) W.pred_dc[lane] = (int)(int16_t)(dcv & 0xffffu);
+        if (warp_ballot(bad) != 0u) {
+            if (lane == 0) gmem_atomic_or(P.error, 4u);
+            break;
+        }
+        warp_sync();   // coefficients + predictors complete; the exchange tiles are dead, their space becomes the queue
+
+        unsigned long long dbg_base = 0;
+        if (P.dbg_coefs || P.dbg_bits) {                 // stage dumps for the parity tests
+            const int img_idx = W.pend[slot].img_idx;
+            dbg_base = P.images[img_idx].first_block + (unsigned long long)((g - P.images[img_idx].first_tile) * kBlocksPerTile);
+        }
+        if (P.dbg_coefs) {
+            for (int i = lane; i < nblk * 64; i += 32)
+                P.dbg_coefs[dbg_base * 64ull + (unsigned long long)i] = W.coef[(i >> 6) * kCoefStride + (i & 63)];
+        }
+        // ---- entropy: coefficients -> bits in the region ----
+        bool overflow = false;
+        unsigned bits;
+        if (P.dbg_bits) bits = encode_blocks_dbg<LAYOUT>(W, T, nblk, cap_words, queue, P.dbg_bits + dbg_base, overflow);
+        else bits = encode_blocks_warp<LAYOUT, false>(W, T, 0, nblk, W.region, cap_words, queue, nullptr, overflow);
+
+        if (!overflow) {
+            // Publish the tile's bit count and last bits NOW: they are consumed (by us and by every
+            // successor) one iteration later.
+            const unsigned tail = tail_bits(W.region, bits);
+            if (lane == 0) {
+                st_flag64(P.desc_bits + g, make_desc(first ? kStatusPrefix : kStatusAgg, tail, bits));
+                W.pend[slot].T = bits; W.pend[slot].tail = tail;
+            }
+            warp_sync();
+            prev_g = g;
+        } else if (!tile_slow<LAYOUT>(P, W, T, queue, cap_words, g, nblk, bits, slot)) break;
     }
 }
 

@@ -14,20 +14,20 @@
 namespace jg {
 
 constexpr int kThreads = 128;
-constexpr int kBlocksPerTile = 24 * (kThreads / 32);   // array bound; a tile holds mcus_per_tile(layout) * blocks-per-MCU blocks, 24 per warp
+constexpr int kBlocksPerTile = 24;           // blocks of a (full) tile; one warp owns a tile from pixels to bytes
 constexpr int kWarps = kThreads / 32;
 constexpr int kChunkBytes = 64 * kThreads;   // unstuffed bytes one stuffing step handles (64 per thread)
 
-// MCUs per tile.  One extra "slot" per tile holds the MCU that precedes the tile (its DCs seed the
-// DC prediction), so slots = MCUs + 1 divides evenly among the CTA's lane groups.
-constexpr int mcus_per_tile(int layout) { return layout == LAYOUT_444 ? kThreads / 4 : (layout == LAYOUT_420 ? kThreads / 8 : 3 * kThreads / 4); }
-constexpr int kWinWordsMax = 384 * (kThreads / 32);   // tile window (unstuffed bits of one tile): 384 words per warp
-constexpr int kWinWordsMin = 64;     // must hold one worst-case block (1658 bits) + slack
+// MCUs per tile: 24 blocks = 8 MCUs (4:4:4), 4 MCUs (4:2:0), 24 MCUs (gray)
+constexpr int mcus_per_tile(int layout) { return layout == LAYOUT_444 ? 8 : (layout == LAYOUT_420 ? 4 : 24); }
+constexpr int kWinWordsMax = 384;    // a warp's region (unstuffed bits of one tile): 512 bits per block before the tile goes slow
+constexpr int kWinWordsMin = 216;    // must hold four worst-case blocks (4 x 1658 bits) + slack: the slow path's group
 constexpr unsigned kSpinLimit = 1u << 24;
 
 constexpr unsigned long long kStatusAgg = 1ull << 62;
 constexpr unsigned long long kStatusPrefix = 2ull << 62;
-constexpr unsigned long long kCountMask = (1ull << 62) - 1;  // descriptors: status[63:62] | value[61:0]
+constexpr int kTailShift = 55;
+constexpr unsigned long long kCountMask = (1ull << kTailShift) - 1;  // descriptors: status[63:62] | payload[61:55] | value[54:0]
 
 struct ImageDesc {
     const uint8_t* px;               // device pixels
@@ -54,12 +54,12 @@ struct LaunchParams {
     int n_images;
     int n_tiles;
     int tiles_per_image;             // > 0 when every image of the launch has this many tiles
-    int win_words;                   // window size actually used (<= kWinWordsMax)
+    const uint32_t* sched;           // otherwise: the ticket schedule (build_schedule, jpeg_tables.h)
+    int win_words;                   // region words actually used (kWinWordsMin..kWinWordsMax)
     unsigned* ticket;                // zeroed before the launch (encode)
     unsigned* ticket2;               // zeroed before the launch (stuff)
     unsigned* error;                 // OUT: non-zero if a look-back timed out
-    unsigned long long* desc_bits;   // [n_tiles], zeroed: bits of the tile -> inclusive bit prefix
-    unsigned long long* desc_tail;   // [n_tiles], zeroed: the tile's last 7 bits
+    unsigned long long* desc_bits;   // [n_tiles], zeroed: status | the tile's last 7 bits | bits of the tile -> inclusive bit prefix
     unsigned* desc_dc;               // [3 * n_tiles], zeroed: valid<<31 | quantised DC of the tile's last block per component
     unsigned long long* desc_ff;     // [max_chunks], zeroed: 0xFF bytes of the chunk -> inclusive count
     unsigned long long* raw_bytes;   // [n_images] bytes of unstuffed scan (encode -> plan/stuff)

@@ -44,5 +44,12 @@ void build_huff_lut(HuffLut* lut);
 // header bytes up to and including SOS; ncomp_out is 3 or 1. Returns 0 if it does not fit.
 size_t emit_headers(int w, int h, int ncomp_out, int subsampling, const uint8_t qt_luma[64],
                     const uint8_t qt_chroma[64], uint8_t* out, size_t cap);
+// Ticket schedule of a launch whose images have different tile counts (see draw_tile() in
+// jpeg_kernel.cuh): tickets walk the images round-robin, tile 0 of every image, then tile 1 of
+// every image that has one, ...  `out` (n_words of it, sized schedule_words(n)) receives
+// D, cum[D+1], lt0[D], first[D], order[n]: while the round lt is in [lt0[k], lt0[k+1]) the images
+// order[first[k]..n) are active and cum[k] tickets have been handed out before lt0[k].
+size_t schedule_words(int n_images);
+size_t build_schedule(const int* tiles_per_image, int n_images, uint32_t* out);
 
 }  // namespace jg

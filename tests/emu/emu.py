@@ -33,8 +33,20 @@ def _load():
         L.emu_encode.restype = C.c_int
         L.emu_encode.argtypes = [C.c_void_p] + [C.c_int] * 10 + [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                                                 C.c_void_p, C.c_void_p]
+        L.emu_ticket_map.restype = C.c_int
+        L.emu_ticket_map.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
+
+
+def emu_ticket_map(tiles, force_schedule=False):
+    """The kernel's ticket -> (launch-wide tile, image) mapping for images with these tile counts."""
+    tiles = np.ascontiguousarray(tiles, dtype=np.int32)
+    total = int(tiles.sum())
+    g = np.zeros(total, np.uint32); img = np.zeros(total, np.uint32)
+    n = _load().emu_ticket_map(tiles.ctypes.data, len(tiles), 1 if force_schedule else 0, g.ctypes.data, img.ctypes.data)
+    assert n == total
+    return g, img
 
 
 def emu_encode(batch, qmode=0, quality=3, sub=0, win_words=0, n_ctas=2, stages=False, cap=None):

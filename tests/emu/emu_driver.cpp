@@ -112,23 +112,27 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
     }
     const int n_tiles = tiles * n_images;
     const size_t max_chunks = (size_t)n_images * ((scan_cap + kChunkBytes - 1) / kChunkBytes) + 1;
-    std::vector<unsigned long long> desc_bits(n_tiles, 0), desc_tail(n_tiles, 0), desc_ff(max_chunks, 0), raw_bytes(n_images, 0);
+    std::vector<unsigned long long> desc_bits(n_tiles, 0), desc_ff(max_chunks, 0), raw_bytes(n_images, 0);
     std::vector<unsigned> first_chunk(n_images + 1, 0), desc_dc(3 * (size_t)n_tiles, 0);
     unsigned ticket = 0, ticket2 = 0, error = 0;
     for (int i = 0; i < n_images; ++i) { scan_bytes[i] = 0; img_status[i] = 0; }
 
     LaunchParams P;
     P.images = imgs.data(); P.n_images = n_images; P.n_tiles = n_tiles;
-    P.tiles_per_image = (n_images % 2) ? tiles : 0;   // exercise both tile->image paths
-    P.win_words = win_words ? win_words : kWinWordsMax;
+    P.tiles_per_image = (n_images % 2) ? tiles : 0;   // exercise both ticket->tile paths
+    std::vector<int> counts(n_images, tiles);
+    std::vector<uint32_t> sched(schedule_words(n_images));
+    build_schedule(counts.data(), n_images, sched.data());
+    P.sched = sched.data();
+    P.win_words = win_words ? (win_words < kWinWordsMin ? kWinWordsMin : (win_words > kWinWordsMax ? kWinWordsMax : win_words)) : kWinWordsMax;
     P.ticket = &ticket; P.ticket2 = &ticket2; P.error = &error;
-    P.desc_bits = desc_bits.data(); P.desc_tail = desc_tail.data(); P.desc_ff = desc_ff.data(); P.desc_dc = desc_dc.data();
+    P.desc_bits = desc_bits.data(); P.desc_ff = desc_ff.data(); P.desc_dc = desc_dc.data();
     P.raw_bytes = raw_bytes.data(); P.first_chunk = first_chunk.data();
     P.scan_bytes = scan_bytes; P.img_status = img_status; P.huff = &lut;
     P.dbg_coefs = dbg_coefs; P.dbg_bits = dbg_bits;
 
     const int nc = ncomp;
-    launch(n_ctas > n_tiles ? n_tiles : n_ctas, smem_bytes(layout, nc), [&] {
+    launch(n_ctas > (n_tiles + kWarps - 1) / kWarps ? (n_tiles + kWarps - 1) / kWarps : n_ctas, smem_bytes(layout, nc), [&] {
         if (layout == LAYOUT_444 && nc == 3) encode_tiles_kernel<LAYOUT_444, 3>(P, Q);
         else if (layout == LAYOUT_444 && nc == 4) encode_tiles_kernel<LAYOUT_444, 4>(P, Q);
         else if (layout == LAYOUT_420 && nc == 3) encode_tiles_kernel<LAYOUT_420, 3>(P, Q);
@@ -139,5 +143,28 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
     if (!error) launch(n_ctas, sizeof(StuffSmem), [&] { stuff_kernel(P); });
     free(raw);
     return (int)error;
+}
+
+// The ticket -> tile mapping of the kernel (tile_of_ticket) for images with the given tile counts:
+// out_g / out_img receive the launch-wide tile index and the image of every ticket.
+int emu_ticket_map(const int* tiles, int n_images, int force_schedule, unsigned* out_g, unsigned* out_img)
+{
+    std::vector<ImageDesc> imgs(n_images);
+    int total = 0;
+    bool uniform = true;
+    for (int i = 0; i < n_images; ++i) {
+        imgs[i].first_tile = total; imgs[i].n_tiles = tiles[i];
+        total += tiles[i];
+        uniform = uniform && tiles[i] == tiles[0];
+    }
+    std::vector<uint32_t> sched(schedule_words(n_images));
+    build_schedule(tiles, n_images, sched.data());
+    LaunchParams P;
+    memset(&P, 0, sizeof P);
+    P.images = imgs.data(); P.n_images = n_images; P.n_tiles = total;
+    P.tiles_per_image = (uniform && !force_schedule) ? tiles[0] : 0;
+    P.sched = sched.data();
+    for (int v = 0; v < total; ++v) out_g[v] = tile_of_ticket(P, (unsigned)v, out_img[v]);
+    return total;
 }
 }

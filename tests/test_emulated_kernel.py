@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle
-from tests.emu.emu import emu_encode
+from tests.emu.emu import emu_encode, emu_ticket_map
 
 CASES = [
     # label, (n, w, h, c, kind), qmode, quality, sub, window words, CTAs
@@ -51,3 +51,22 @@ def test_emulated_kernel_reports_capacity_overflow():
     scans, sizes, status = emu_encode(batch, 0, 3, 0, n_ctas=1, cap=4096)
     want = len(oracle.oracle_encode(batch[0], 0, 3, 0)) - 655
     assert status[0] == 1 and int(sizes[0]) >= want      # flagged, nothing written past cap, a sufficient size reported
+
+
+@pytest.mark.parametrize("tiles,force", [([5, 5, 5], False), ([5, 5, 5], True), ([1], False), ([7, 1, 3, 3, 12, 1], False),
+                                         (list(np.random.default_rng(3).integers(1, 60, 150)), False)])
+def test_ticket_schedule_is_a_round_robin_bijection(tiles, force):
+    """Every tile gets exactly one ticket, a tile's predecessor in its image holds a smaller ticket
+    (what makes the look-back deadlock-free), and consecutive tickets visit different images."""
+    tiles = np.asarray(tiles)
+    g, img = emu_ticket_map(tiles, force)
+    first = np.concatenate([[0], np.cumsum(tiles)[:-1]])
+    assert sorted(g.tolist()) == list(range(int(tiles.sum())))
+    assert np.all((g >= first[img]) & (g < first[img] + tiles[img]))
+    ticket_of = np.empty(len(g), np.int64); ticket_of[g] = np.arange(len(g))
+    for i, t in enumerate(tiles):
+        tk = ticket_of[first[i]:first[i] + t]
+        assert np.all(np.diff(tk) > 0)
+        # round-robin: between two tiles of one image every other still-active image got a ticket
+        active_after = [(tiles > lt + 1).sum() for lt in range(t - 1)]
+        assert np.all(np.diff(tk) >= np.maximum(1, np.asarray(active_after, dtype=np.int64))) if t > 1 else True
