@@ -27,6 +27,15 @@ JG_DEV float f_add(float a, float b) { return __fadd_rn(a, b); }
 JG_DEV float f_sub(float a, float b) { return __fsub_rn(a, b); }
 JG_DEV float f_mul(float a, float b) { return __fmul_rn(a, b); }
 JG_DEV int f_floor_i(float a) { return __float2int_rd(a); }   // (int)floorf(a)
+// Two binary32 values per instruction (sm_100 FADD2).  Only additions are ever packed: ptxas fuses
+// a packed multiply with a following packed add into FFMA2 even when both carry .rn (checked on
+// CUDA 12.9, also with __fmul2_rn / __fadd2_rn), which would change the rounding.  x - y is
+// x + (-y) (bit-identical; the negation folds into the operand).  build.py greps the SASS for FFMA.
+typedef float2 f32x2;
+JG_DEV f32x2 f2(float x, float y) { return make_float2(x, y); }
+JG_DEV f32x2 f2_add(f32x2 a, f32x2 b) { return __fadd2_rn(a, b); }
+JG_DEV f32x2 f2_sub(f32x2 a, f32x2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+JG_DEV f32x2 f2_mul(f32x2 a, f32x2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }   // two scalar FMULs, on purpose
 JG_DEV float u8_to_f(unsigned v) { return (float)v; }          // exact
 
 // ---- integer helpers ---------------------------------------------------------------------

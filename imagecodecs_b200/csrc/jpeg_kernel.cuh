@@ -62,10 +62,11 @@ struct Geo {
     static constexpr int M = mcus_per_tile(LAYOUT);        // MCUs per tile
     static constexpr int LANES = LAYOUT == LAYOUT_420 ? 16 : 8;   // lanes that share one MCU
     static constexpr int GROUPS = 32 / LANES;                     // lane groups of the warp
-    static constexpr int ITERS = M / GROUPS;
-    static constexpr int TILES = LAYOUT == LAYOUT_420 ? 6 : 1;    // exchange tiles per lane group
+    static constexpr int PER_GROUP = LAYOUT == LAYOUT_GRAY ? 2 : 1;   // MCUs a lane group handles per iteration
+    static constexpr int ITERS = M / (GROUPS * PER_GROUP);
+    static constexpr int TILES = LAYOUT == LAYOUT_420 ? 6 : (LAYOUT == LAYOUT_444 ? 3 : 2);    // exchange tiles per lane group
     static constexpr int NCOMP = LAYOUT == LAYOUT_GRAY ? 1 : 3;
-    static_assert(M % GROUPS == 0, "MCUs must divide evenly among the lane groups");
+    static_assert(M % (GROUPS * PER_GROUP) == 0, "MCUs must divide evenly among the lane groups");
     static_assert(M * BPM == kBlocksPerTile, "a full tile holds kBlocksPerTile blocks");
 };
 
@@ -84,10 +85,10 @@ struct Pending {
 template <int LAYOUT>
 struct WarpMem {
     using G = Geo<LAYOUT>;
-    static constexpr int SCRATCH = G::GROUPS * G::TILES * kTileFloats;
+    static constexpr int SCRATCH = G::GROUPS * (G::TILES * kTileFloats + 8);
     static constexpr int R1_WORDS = SCRATCH > kQueueEntries ? SCRATCH : kQueueEntries;
     alignas(16) uint32_t r1[R1_WORDS];                        // transform exchange tiles; then the symbol queue
-    alignas(16) int16_t coef[kBlocksPerTile * kCoefStride];   // quantised coefficients, zigzag order
+    alignas(16) int16_t coef[(kBlocksPerTile + 1) * kCoefStride];   // quantised coefficients, zigzag order (+1: scratch slot)
     alignas(16) uint32_t region[kWinWordsMax + 8];            // the tile's packed bits (MSB-first words); survives into the next iteration
     int pred_dc[4];                                           // DCs of the MCU preceding the tile, per component
     Pending pend[2];                                          // by iteration parity: the tile being coded / the tile to be written
@@ -175,8 +176,6 @@ JG_DEV void rgb_of(const uint32_t* w, int i, float& r, float& g, float& b)
 
 // jpeg_enc.h:1118-1120, C's left-to-right evaluation made explicit
 JG_DEV float rgb_y(float r, float g, float b) { return f_sub(f_add(f_add(f_mul(0.299f, r), f_mul(0.587f, g)), f_mul(0.114f, b)), 128.0f); }
-JG_DEV float rgb_cb(float r, float g, float b) { return f_add(f_sub(f_mul(-0.1687f, r), f_mul(0.3313f, g)), f_mul(0.5f, b)); }
-JG_DEV float rgb_cr(float r, float g, float b) { return f_sub(f_sub(f_mul(0.5f, r), f_mul(0.4187f, g)), f_mul(0.0813f, b)); }
 
 // ------------------------------------------------------------------------------------------
 // AAN forward DCT, one 8-point pass (jpeg_enc.h:668-709 rows, :718-759 columns)
@@ -209,6 +208,37 @@ JG_DEV void aan8(float (&d)[8])
     d[7] = f_sub(z11, z4);
 }
 
+// The same pass over TWO independent 8-point vectors at once (.x and .y): the 29 additions are
+// packed (FADD2, one issue slot for two), the 5 multiplications stay scalar (jpeg_device.h says why).
+JG_DEV void aan8x2(f32x2 (&d)[8])
+{
+    const f32x2 c4 = f2(0.707106781f, 0.707106781f), c6 = f2(0.382683433f, 0.382683433f);
+    const f32x2 c2m6 = f2(0.541196100f, 0.541196100f), c2p6 = f2(1.306562965f, 1.306562965f);
+    const f32x2 t0 = f2_add(d[0], d[7]), t7 = f2_sub(d[0], d[7]);
+    const f32x2 t1 = f2_add(d[1], d[6]), t6 = f2_sub(d[1], d[6]);
+    const f32x2 t2 = f2_add(d[2], d[5]), t5 = f2_sub(d[2], d[5]);
+    const f32x2 t3 = f2_add(d[3], d[4]), t4 = f2_sub(d[3], d[4]);
+
+    const f32x2 e0 = f2_add(t0, t3), e3 = f2_sub(t0, t3);
+    const f32x2 e1 = f2_add(t1, t2), e2 = f2_sub(t1, t2);
+    d[0] = f2_add(e0, e1);
+    d[4] = f2_sub(e0, e1);
+    const f32x2 z1 = f2_mul(f2_add(e2, e3), c4);
+    d[2] = f2_add(e3, z1);
+    d[6] = f2_sub(e3, z1);
+
+    const f32x2 o0 = f2_add(t4, t5), o1 = f2_add(t5, t6), o2 = f2_add(t6, t7);
+    const f32x2 z5 = f2_mul(f2_sub(o0, o2), c6);
+    const f32x2 z2 = f2_add(f2_mul(c2m6, o0), z5);
+    const f32x2 z4 = f2_add(f2_mul(c2p6, o2), z5);
+    const f32x2 z3 = f2_mul(o1, c4);
+    const f32x2 z11 = f2_add(t7, z3), z13 = f2_sub(t7, z3);
+    d[5] = f2_add(z13, z2);
+    d[3] = f2_sub(z13, z2);
+    d[1] = f2_add(z11, z4);
+    d[7] = f2_sub(z11, z4);
+}
+
 // jpeg_enc.h:808-816: v*pqt, floorf((v + 1024) + 0.5f) - 1024, (int)
 JG_DEV int quantise(float v, float pq)
 {
@@ -224,6 +254,16 @@ JG_DEV void row_pass_store(float (&s)[8], float* tile, int r)
 #pragma unroll
     for (int i = 0; i < 8; ++i) tile[r * 9 + i] = s[i];
 }
+// two rows at once: .x into row r of tile_x, .y into row r of tile_y
+JG_DEV void row_pass_store_x2(f32x2 (&s)[8], float* tile_x, float* tile_y, int r)
+{
+    aan8x2(s);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { tile_x[r * 9 + i] = s[i].x; tile_y[r * 9 + i] = s[i].y; }
+}
+
+JG_DEV unsigned zz_at(const LaneConst& LC, int v) { return ((v < 4 ? LC.zz_lo : LC.zz_hi) >> (8 * (v & 3))) & 0xffu; }
+JG_DEV void publish_dc(unsigned* dc_out, int k) { st_flag32(dc_out, 0x80000000u | ((unsigned)k & 0xffffu)); }
 
 // column u of an exchange tile: column pass, quantise, scatter to zigzag order.
 // dc_out != nullptr: the block is the last of its component in the tile; its DC is published for
@@ -239,48 +279,85 @@ JG_DEV void column_pass(WarpMem<LAYOUT>& W, const float* tile, int u, bool chrom
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
         const int k = quantise(c[v], chroma ? LC.pq_c[v] : LC.pq_l[v]);
-        const unsigned zz = ((v < 4 ? LC.zz_lo : LC.zz_hi) >> (8 * (v & 3))) & 0xffu;
-        dst[zz] = (int16_t)k;
-        if (v == 0 && u == 0 && dc_out != nullptr) st_flag32(dc_out, 0x80000000u | ((unsigned)k & 0xffffu));
+        dst[zz_at(LC, v)] = (int16_t)k;
+        if (v == 0 && u == 0 && dc_out != nullptr) publish_dc(dc_out, k);
+    }
+}
+// the same for column u of TWO tiles that use the same quantiser table (.x -> blk_x, .y -> blk_y)
+template <int LAYOUT>
+JG_DEV void column_pass_x2(WarpMem<LAYOUT>& W, const float* tile_x, const float* tile_y, int u, bool chroma, int blk_x, int blk_y,
+                           unsigned* dc_x, unsigned* dc_y, const LaneConst& LC)
+{
+    f32x2 c[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) c[v] = f2(tile_x[v * 9 + u], tile_y[v * 9 + u]);
+    aan8x2(c);
+    int16_t* dst_x = W.coef + blk_x * kCoefStride;
+    int16_t* dst_y = W.coef + blk_y * kCoefStride;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        const float pq = chroma ? LC.pq_c[v] : LC.pq_l[v];
+        const f32x2 q = f2_add(f2_add(f2_mul(c[v], f2(pq, pq)), f2(1024.0f, 1024.0f)), f2(0.5f, 0.5f));   // jpeg_enc.h:808-813
+        const int kx = f_floor_i(q.x) - 1024, ky = f_floor_i(q.y) - 1024;
+        const unsigned zz = zz_at(LC, v);
+        dst_x[zz] = (int16_t)kx;
+        dst_y[zz] = (int16_t)ky;
+        if (v == 0 && u == 0) {
+            if (dc_x != nullptr) publish_dc(dc_x, kx);
+            if (dc_y != nullptr) publish_dc(dc_y, ky);
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 1, grayscale: 8 lanes per block, 6 blocks per lane group.  Gray has registers to spare,
-// so the next slot's pixels are requested while the current column pass runs.  (The colour
-// paths sit at the register cap: there the same prefetch cost more in spills than the hidden
-// latency gained -- measured -- so they load at the top of each iteration.)
+// stage 1, grayscale: 8 lanes per PAIR of consecutive blocks (both go through the packed passes),
+// 3 pairs per lane group.  Gray has registers to spare, so the next pair's pixels are requested
+// while the current column pass runs.  (The colour paths sit at the register cap: there the same
+// prefetch cost more in spills than the hidden latency gained -- measured -- so they load at the
+// top of each iteration.)
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT, int NC>
 JG_DEV void transform_tile_gray(WarpMem<LAYOUT>& W, const ImageDesc& im, int m0, int nM, unsigned* dc_out, const LaneConst& LC)
 {
     using G = Geo<LAYOUT>;
     const int t = JG_TID & 31, u = t & 7, grp = t >> 3;
-    float* tile = reinterpret_cast<float*>(W.r1) + grp * kTileFloats;
-    auto fetch = [&](int it, uint32_t (&w)[2]) {
-        const int slot = it * G::GROUPS + grp;
-        if (slot < nM) {
-            const int m = m0 + slot;
-            const int my = m / im.mcus_x, mx = m - my * im.mcus_x;
-            int y = my * 8 + u; if (y >= im.h) y = im.h - 1;          // replicate the last row
-            load_segment<1, 8>(im, mx * 8, y, w);
+    // group stride 2 tiles + 8 floats: the four groups start 24 banks apart, all 32 lanes hit different banks
+    float* tile_x = reinterpret_cast<float*>(W.r1) + grp * (2 * kTileFloats + 8);
+    float* tile_y = tile_x + kTileFloats;
+    auto fetch = [&](int it, uint32_t (&w)[4]) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int slot = 2 * (it * G::GROUPS + grp) + half;
+            uint32_t ww[2] = {0u, 0u};
+            if (slot < nM) {
+                const int m = m0 + slot;
+                const int my = m / im.mcus_x, mx = m - my * im.mcus_x;
+                int y = my * 8 + u; if (y >= im.h) y = im.h - 1;          // replicate the last row
+                load_segment<1, 8>(im, mx * 8, y, ww);
+            }
+            w[2 * half] = ww[0]; w[2 * half + 1] = ww[1];
         }
     };
-    uint32_t w[2];
+    uint32_t w[4];
     fetch(0, w);
 #pragma unroll 1
     for (int it = 0; it < G::ITERS; ++it) {
-        const int slot = it * G::GROUPS + grp;
-        const bool valid = slot < nM;
+        const int slot = 2 * (it * G::GROUPS + grp);
+        const bool valid = slot < nM, valid_y = slot + 1 < nM;
         if (valid) {
-            float s[8];
+            f32x2 s[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) s[i] = f_sub(u8_to_f(byte_of(w, i)), 128.0f);
-            row_pass_store(s, tile, u);
+            for (int i = 0; i < 8; ++i) s[i] = f2_sub(f2(u8_to_f(byte_of(w, i)), u8_to_f(byte_of(w, 8 + i))), f2(128.0f, 128.0f));
+            row_pass_store_x2(s, tile_x, tile_y, u);
         }
         if (it + 1 < G::ITERS) fetch(it + 1, w);
         warp_sync();
-        if (valid) column_pass(W, tile, u, false, slot, (slot == nM - 1) ? dc_out : nullptr, LC);
+        if (valid) {
+            // an absent second block computes on zeros into the coefficient slot after the tile's last block
+            // (inside the array, never read)
+            column_pass_x2(W, tile_x, tile_y, u, false, slot, valid_y ? slot + 1 : kBlocksPerTile,
+                           slot == nM - 1 ? dc_out : nullptr, slot + 1 == nM - 1 ? dc_out : nullptr, LC);
+        }
         warp_sync();
     }
 }
@@ -306,91 +383,85 @@ JG_DEV void transform_tile(WarpMem<LAYOUT>& W, const ImageDesc& im, int m0, int 
         int my = 0, mx = 0;
         if (valid) { my = m / im.mcus_x; mx = m - my * im.mcus_x; }
 
-        if (LAYOUT == LAYOUT_GRAY) {
-            float* tile = scratch + grp * kTileFloats;
-            if (valid) {
-                int y = my * 8 + u; if (y >= im.h) y = im.h - 1;          // replicate the last row
-                uint32_t w[2];
-                load_segment<1, 8>(im, mx * 8, y, w);
-                float s[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) s[i] = f_sub(u8_to_f(byte_of(w, i)), 128.0f);
-                row_pass_store(s, tile, u);
-            }
-            warp_sync();
-            if (valid) column_pass(W, tile, u, false, slot, dcs, LC);
-            warp_sync();
-        } else if (LAYOUT == LAYOUT_444) {
-            float* tile = scratch + grp * kTileFloats;
-            float R[8], Gc[8], B[8];
+        if (LAYOUT == LAYOUT_444) {
+            // 8 lanes per MCU, lane u owns pixel row u.  Y goes through the scalar passes, Cb and Cr
+            // together through the packed ones (same structure, same quantiser table).
+            float* base = scratch + grp * (3 * kTileFloats);
             if (valid) {
                 int y = my * 8 + u; if (y >= im.h) y = im.h - 1;
                 uint32_t w[8 * NC / 4];
                 load_segment<NC, 8>(im, mx * 8, y, w);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) rgb_of<NC>(w, i, R[i], Gc[i], B[i]);
-            }
-#pragma unroll
-            for (int comp = 0; comp < 3; ++comp) {
-                if (valid) {
-                    float s[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        s[i] = comp == 0 ? rgb_y(R[i], Gc[i], B[i]) : (comp == 1 ? rgb_cb(R[i], Gc[i], B[i]) : rgb_cr(R[i], Gc[i], B[i]));
-                    row_pass_store(s, tile, u);
-                }
-                warp_sync();
-                if (valid) column_pass(W, tile, u, comp != 0, slot * 3 + comp, dcs ? dcs + comp : nullptr, LC);
-                warp_sync();
-            }
-        } else {
-            // 4:2:0: 16 lanes per MCU, lane r16 owns pixel row r16 (16 pixels), one 8-pixel half at a time.
-            // (Keeping the halves / the column passes as real loops shrinks the hot loop to fit the
-            // instruction cache -- fetch stalls 1.3 -> 0.2 warps per issue -- but costs as many extra
-            // instructions as it saves stalls: measured equal, so the straight-line form stays.)
-            const int r16 = t & 15;
-            float* base = scratch + grp * (6 * kTileFloats);
-            constexpr int HW = 8 * NC / 4;           // pixel words per half row
-            uint32_t w[2 * HW];
-#pragma unroll
-            for (int i = 0; i < 2 * HW; ++i) w[i] = 0u;
-            if (valid) {
-                int y = my * 16 + r16; if (y >= im.h) y = im.h - 1;
-                load_segment<NC, 16>(im, mx * 16, y, w);
-            }
-            float cb0[4], cr0[4], cb1[4], cr1[4];    // horizontal pair sums (a+b) of this row: left half, right half
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { cb0[i] = 0.0f; cr0[i] = 0.0f; }
-#pragma unroll
-            for (int hx = 0; hx < 2; ++hx) {
-                float R[8], Gc[8], B[8], s[8];
+                float sy[8];
+                f32x2 sc[8];                 // .x = Cb, .y = Cr
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    rgb_of<NC>(w, i, R[i], Gc[i], B[i]);
-                    s[i] = rgb_y(R[i], Gc[i], B[i]);
+                    float r, g, b;
+                    rgb_of<NC>(w, i, r, g, b);
+                    sy[i] = rgb_y(r, g, b);
+                    // jpeg_enc.h:1119-1120 with x - k*y written as x + (-k)*y where the two halves differ
+                    const f32x2 p1 = f2(f_mul(-0.1687f, r), f_mul(0.5f, r));
+                    const f32x2 p2 = f2(f_mul(0.3313f, g), f_mul(0.4187f, g));
+                    const f32x2 p3 = f2(f_mul(0.5f, b), f_mul(-0.0813f, b));
+                    sc[i] = f2_add(f2_sub(p1, p2), p3);
                 }
-                if (valid) row_pass_store(s, base + ((r16 >> 3) * 2 + hx) * kTileFloats, r16 & 7);
+                row_pass_store(sy, base, u);
+                row_pass_store_x2(sc, base + kTileFloats, base + 2 * kTileFloats, u);
+            }
+            warp_sync();
+            if (valid) {
+                column_pass(W, base, u, false, slot * 3, dcs, LC);
+                column_pass_x2(W, base + kTileFloats, base + 2 * kTileFloats, u, true, slot * 3 + 1, slot * 3 + 2,
+                               dcs ? dcs + 1 : nullptr, dcs ? dcs + 2 : nullptr, LC);
+            }
+            warp_sync();
+        } else {
+            // 4:2:0: 16 lanes per MCU, lane r16 owns pixel row r16 (16 pixels).  Pixels i and i + 8 (the
+            // left and the right 8x8 luma block of the row) travel as one packed value.
+            const int r16 = t & 15;
+            float* base = scratch + grp * (6 * kTileFloats);
+            f32x2 cbs[4], crs[4];            // horizontal pair sums (a+b) of this row: .x samples 0-3, .y samples 4-7
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    cb1[i] = f_add(rgb_cb(R[2 * i], Gc[2 * i], B[2 * i]), rgb_cb(R[2 * i + 1], Gc[2 * i + 1], B[2 * i + 1]));
-                    cr1[i] = f_add(rgb_cr(R[2 * i], Gc[2 * i], B[2 * i]), rgb_cr(R[2 * i + 1], Gc[2 * i + 1], B[2 * i + 1]));
+            for (int i = 0; i < 4; ++i) { cbs[i] = f2(0.0f, 0.0f); crs[i] = f2(0.0f, 0.0f); }
+            if (valid) {
+                int y = my * 16 + r16; if (y >= im.h) y = im.h - 1;
+                uint32_t w[16 * NC / 4];
+                load_segment<NC, 16>(im, mx * 16, y, w);
+                f32x2 sy[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    f32x2 cb[2], cr[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int i = 2 * j + e;
+                        float r0, g0, b0, r1, g1, b1;
+                        rgb_of<NC>(w, i, r0, g0, b0);
+                        rgb_of<NC>(w, i + 8, r1, g1, b1);
+                        const f32x2 R = f2(r0, r1), Gc = f2(g0, g1), B = f2(b0, b1);
+                        // jpeg_enc.h:1118-1120, additions packed over the two pixels
+                        sy[i] = f2_sub(f2_add(f2_add(f2_mul(f2(0.299f, 0.299f), R), f2_mul(f2(0.587f, 0.587f), Gc)),
+                                              f2_mul(f2(0.114f, 0.114f), B)), f2(128.0f, 128.0f));
+                        cb[e] = f2_add(f2_sub(f2_mul(f2(-0.1687f, -0.1687f), R), f2_mul(f2(0.3313f, 0.3313f), Gc)),
+                                       f2_mul(f2(0.5f, 0.5f), B));
+                        cr[e] = f2_sub(f2_sub(f2_mul(f2(0.5f, 0.5f), R), f2_mul(f2(0.4187f, 0.4187f), Gc)),
+                                       f2_mul(f2(0.0813f, 0.0813f), B));
+                    }
+                    cbs[j] = f2_add(cb[0], cb[1]);
+                    crs[j] = f2_add(cr[0], cr[1]);
                 }
-                if (hx == 0) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { cb0[i] = cb1[i]; cr0[i] = cr1[i]; }
-#pragma unroll
-                    for (int i = 0; i < HW; ++i) w[i] = w[HW + i];
-                }
+                float* ty = base + ((r16 >> 3) * 2) * kTileFloats;
+                row_pass_store_x2(sy, ty, ty + kTileFloats, r16 & 7);
             }
             // vertical pairs live in neighbouring lanes: the even lane finishes Cb, the odd lane Cr;
-            // sample = ((a+b) + (c+d)) * 0.25f with (a+b) from the even row (extended mode)
+            // sample = ((a+b) + (c+d)) * 0.25f with (a+b) from the even row (extended mode);
+            // the addition commutes, so both lanes compute (mine + other)
             const bool even = (r16 & 1) == 0;
             float samp[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float cbv = i < 4 ? cb0[i & 3] : cb1[i & 3], crv = i < 4 ? cr0[i & 3] : cr1[i & 3];
-                const float other = warp_shfl_xor_f32(even ? crv : cbv, 1);
-                samp[i] = even ? f_mul(f_add(cbv, other), 0.25f) : f_mul(f_add(other, crv), 0.25f);
+            for (int i = 0; i < 4; ++i) {
+                const f32x2 mine = even ? cbs[i] : crs[i], give = even ? crs[i] : cbs[i];
+                const f32x2 other = f2(warp_shfl_xor_f32(give.x, 1), warp_shfl_xor_f32(give.y, 1));
+                const f32x2 q = f2_mul(f2_add(mine, other), f2(0.25f, 0.25f));
+                samp[i] = q.x; samp[4 + i] = q.y;
             }
             if (valid) row_pass_store(samp, base + (4 + (r16 & 1)) * kTileFloats, r16 >> 1);
             warp_sync();
@@ -398,11 +469,8 @@ JG_DEV void transform_tile(WarpMem<LAYOUT>& W, const ImageDesc& im, int m0, int 
                 // lanes 0-7 finish tiles {0,2,4}, lanes 8-15 tiles {1,3,5}; the next tile predicts from
                 // Y11 (tile 3), Cb and Cr of our last MCU
                 const int h = r16 >> 3;
-#pragma unroll
-                for (int k3 = 0; k3 < 2; ++k3) {
-                    const int tl = h + 2 * k3;
-                    column_pass(W, base + tl * kTileFloats, u, false, slot * 6 + tl, (dcs != nullptr && tl == 3) ? dcs : nullptr, LC);
-                }
+                column_pass_x2(W, base + h * kTileFloats, base + (h + 2) * kTileFloats, u, false, slot * 6 + h, slot * 6 + h + 2,
+                               nullptr, (dcs != nullptr && h == 1) ? dcs : nullptr, LC);
                 column_pass(W, base + (4 + h) * kTileFloats, u, true, slot * 6 + 4 + h, dcs != nullptr ? dcs + 1 + h : nullptr, LC);
             }
             warp_sync();

@@ -18,6 +18,7 @@
 #define JG_DYNAMIC_SMEM(name) unsigned char* name = ::jg::emu::tls.cta->smem
 
 struct uint2 { unsigned x, y; };
+struct float2 { float x, y; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
 
 namespace jg {
@@ -41,6 +42,11 @@ JG_DEV float f_add(float a, float b) { return a + b; }   // TU is built with -ff
 JG_DEV float f_sub(float a, float b) { return a - b; }
 JG_DEV float f_mul(float a, float b) { return a * b; }
 JG_DEV int f_floor_i(float a) { return (int)__builtin_floorf(a); }
+typedef float2 f32x2;
+JG_DEV f32x2 f2(float x, float y) { f32x2 r; r.x = x; r.y = y; return r; }
+JG_DEV f32x2 f2_add(f32x2 a, f32x2 b) { return f2(a.x + b.x, a.y + b.y); }
+JG_DEV f32x2 f2_sub(f32x2 a, f32x2 b) { return f2(a.x - b.x, a.y - b.y); }
+JG_DEV f32x2 f2_mul(f32x2 a, f32x2 b) { return f2(a.x * b.x, a.y * b.y); }
 JG_DEV float u8_to_f(unsigned v) { return (float)v; }
 
 JG_DEV int i_clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
