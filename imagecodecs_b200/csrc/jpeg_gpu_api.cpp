@@ -54,7 +54,7 @@ void set_error(const char* fmt, ...)
 struct Spec {
     int layout, nc;
     cudaError_t (*prepare)(int*);
-    cudaError_t (*launch)(int, cudaStream_t, const LaunchParams&, const QuantSet&);
+    cudaError_t (*launch)(int, cudaStream_t, const LaunchParams&, const QuantSet&, bool);
 };
 const Spec kSpecs[5] = {
     {LAYOUT_444, 3, prepare_0_3, launch_0_3}, {LAYOUT_444, 4, prepare_0_4, launch_0_4},
@@ -460,7 +460,7 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
         const int grid = std::min((g.n_tiles + kWarps - 1) / kWarps, dev.sm_count * dev.ctas_per_sm[g.spec]);   // one tile per warp at a time
         const size_t gi = (size_t)(&g - &p->groups[0]);
         if (p->timing) JG_CUDA(cudaEventRecord(p->events[3 * gi], s));
-        JG_CUDA(kSpecs[g.spec].launch(grid, s, P, g.quant));
+        JG_CUDA(kSpecs[g.spec].launch(grid, s, P, g.quant, P.n_images < kDeepMaxImages));
         if (p->timing) JG_CUDA(cudaEventRecord(p->events[3 * gi + 1], s));
         JG_CUDA(stuff_launch(dev.sm_count * dev.stuff_ctas_per_sm, s, P));
         if (p->timing) JG_CUDA(cudaEventRecord(p->events[3 * gi + 2], s));

@@ -54,6 +54,7 @@ constexpr int kTileFloats = 72;   // one 8x8 float tile with rows padded to 9 (b
 constexpr int kCoefStride = 72;   // int16 per block in shared memory (144 B: 16-byte aligned 8-coefficient reads)
 constexpr int kQueueEntries = 424;                     // 2 pad + 63 carried + 32 lanes x (8 coefficients + EOB) + 64 read-ahead
 constexpr int kGroupBlocks = 4;                        // blocks per group on the slow path (always fit kWinWordsMin)
+constexpr int kHalfWords = kWinWordsMax / 2;           // a tile that fits half the region leaves the other half to its successor
 
 template <int LAYOUT>
 struct Geo {
@@ -79,6 +80,7 @@ struct Pending {
     unsigned T;                   // bits of the tile
     unsigned tail;                // its last 7 bits
     int last;                     // last tile of its image
+    unsigned base;                // first word of its bits in the region (0 or kHalfWords)
 };
 
 // everything one warp owns
@@ -91,7 +93,7 @@ struct WarpMem {
     alignas(16) int16_t coef[(kBlocksPerTile + 1) * kCoefStride];   // quantised coefficients, zigzag order (+1: scratch slot)
     alignas(16) uint32_t region[kWinWordsMax + 8];            // the tile's packed bits (MSB-first words); survives into the next iteration
     int pred_dc[4];                                           // DCs of the MCU preceding the tile, per component
-    Pending pend[2];                                          // by iteration parity: the tile being coded / the tile to be written
+    Pending pend[3];                                          // iteration mod 3: the tile being coded and the (up to) two waiting to be written
 };
 
 struct CodeTables {
@@ -859,13 +861,13 @@ JG_DEV bool tile_back(const LaunchParams& P, WarpMem<LAYOUT>& W, int g, int slot
     unsigned hb = pred_tail & ((1u << k) - 1u);
     unsigned long long pos = bit_base >> 3;
     bool overflow = false;
-    flush_region(W.region, pd.T, pd.last != 0, reinterpret_cast<uint8_t*>(pd.raw), pd.raw_cap, k, hb, pos, overflow);
+    flush_region(W.region + pd.base, pd.T, pd.last != 0, reinterpret_cast<uint8_t*>(pd.raw), pd.raw_cap, k, hb, pos, overflow);
     if ((JG_TID & 31) == 0) {
         if (pd.last) P.raw_bytes[pd.img_idx] = pos;
         if (overflow) gmem_atomic_or(P.img_status + pd.img_idx, 1u);
     }
     warp_sync();                                        // every lane has read the region
-    clear_region(W.region, (pd.T >> 5) + 2u);
+    clear_region(W.region + pd.base, (pd.T >> 5) + 2u);
     return true;
 }
 
@@ -917,10 +919,30 @@ JG_DEV_NOINLINE bool tile_slow(const LaunchParams& P, WarpMem<LAYOUT>& W, const 
     return true;
 }
 
+// A tile did not fit its half of the region: write out the tile that occupies the other half (if
+// any), then code the tile again into the whole region.  Out of line: happens when the content
+// turns dense, after which the warp stops using halves for a while.  Returns false on a timeout.
+template <int LAYOUT>
+JG_DEV_NOINLINE bool tile_recode(const LaunchParams& P, WarpMem<LAYOUT>& W, const CodeTables& T, uint32_t* queue, unsigned cap_words,
+                                 int other_g, int other_slot, int nblk, unsigned& bits, bool& overflow)
+{
+    if (other_g >= 0 && !tile_back<LAYOUT>(P, W, other_g, other_slot)) return false;
+    warp_sync();
+    clear_region(W.region, cap_words + 8u);
+    bits = encode_blocks_warp<LAYOUT, false>(W, T, 0, nblk, W.region, cap_words, queue, nullptr, overflow);
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------
 // kernel 1: pixels -> unstuffed entropy-coded bits
 // ------------------------------------------------------------------------------------------
-template <int LAYOUT, int NC>
+// DEEP: tiles wait up to two iterations for their write-out (see the loop).  Chosen by the host for
+// launches with few images: there the thousands of tiles in flight belong to the same image, every
+// look-back depends on tiles drawn nanoseconds earlier, and one iteration of slack is not enough
+// (16384^2 gray: 23 % of all warp time was spent waiting in the look-back; DEEP: 1.17 -> 1.00 ms).
+// With many images in flight the round-robin ticket order already provides the slack and the
+// simpler loop is ~3 % faster.
+template <int LAYOUT, int NC, bool DEEP>
 JG_KERNEL(kThreads, 6)
 void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTANT QuantSet Q)
 {
@@ -958,15 +980,25 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
     clear_region(W.region, kWinWordsMax + 8);
     cta_sync();       // the tables are loaded: the ONLY CTA barrier of the kernel; from here every warp is on its own
 
-    int prev_g = -1;                 // tile coded in the previous iteration, still to be written
-    for (int slot = 0;; slot ^= 1) {
+    // Software pipeline: tile g is transformed and coded now, its bits wait in the region, and it is
+    // chained + written one iteration later (after the next tile's transform) -- by then its count
+    // and those of its predecessors were published long ago, so the look-back does not wait.
+    // DEEP adds a second iteration of slack, which needs room for two coded tiles: a tile that fits
+    // half the region (192 words = 256 bits per block: every BASELINE quality below ~90) is coded
+    // into the half its predecessor does not occupy.  When a tile does not fit a half the warp codes
+    // whole-region tiles for a while (`dense`), each written one iteration later.
+    int p1_g = -1, p2_g = -1;        // tiles coded one / two iterations ago that are still to be written
+    bool p1_full = false;            // p1 occupies the whole region
+    unsigned p1_base = 0;
+    unsigned dense = (DEEP && cap_words == (unsigned)kWinWordsMax && P.dbg_bits == nullptr) ? 0u : 0xffffffffu;
+    for (int slot = 0;; slot = slot == 2 ? 0 : slot + 1) {
         // Tiles must START in ticket order (a tile started long before its predecessor would sit in
         // the DC / look-back waits -- measured: drawing the ticket one iteration ahead is 30 % slower):
         // the ticket is drawn when the warp is ready for it, not earlier.
         int img_idx;
         const int g = draw_tile(P, img_idx);
         const bool have = g < P.n_tiles;
-        // ---- front: pixels -> coefficients (the ticket of the tile after this one is already on its way) ----
+        // ---- front: pixels -> coefficients ----
         int nblk = 0;
         bool first = false;
         if (have) {
@@ -977,7 +1009,7 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
             nblk = nM * G::BPM;
             first = lt == 0;
             const bool last = lt == im.n_tiles - 1;
-            if (lane == 0) {         // what the write-out needs one iteration later; T and tail follow after the coding
+            if (lane == 0) {         // what the write-out needs later; T, tail and base follow after the coding
                 Pending& pd = W.pend[slot];
                 pd.raw = reinterpret_cast<unsigned long long>(im.raw); pd.raw_cap = im.raw_cap;
                 pd.img_idx = img_idx; pd.first_tile_of_img = im.first_tile; pd.last = last ? 1 : 0;
@@ -987,16 +1019,28 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
         }
         // DC predictors of the tile's first blocks: the last DCs of the previous tile (published by the
         // lanes that computed them, right after their column pass -- that tile was drawn before ours), or 0
-        // at the start of the image (jpeg_enc.h:1085-1087).  Requested here, looked at after the write-out
-        // of the previous tile: the round trip to L2 costs nothing.
+        // at the start of the image (jpeg_enc.h:1085-1087).  Requested here, looked at after the write-outs:
+        // the round trip to L2 costs nothing.
         unsigned dcv = 0x80000000u;
         const bool dc_wanted = have && !first && lane < G::NCOMP;
         if (dc_wanted) dcv = ld_flag32(P.desc_dc + 3 * (size_t)(g - 1) + lane);
-        // ---- back of the previous tile: its count was published a whole transform ago, so were its
-        //      predecessors' -- the look-back practically never waits ----
-        if (prev_g >= 0) {
-            if (!tile_back<LAYOUT>(P, W, prev_g, slot ^ 1)) break;
-            prev_g = -1;
+        // ---- write-outs that are due: the tile coded two iterations ago; last iteration's too if the
+        //      coming tile needs the whole region (or nothing comes any more) ----
+        const int slot1 = slot == 0 ? 2 : slot - 1, slot2 = slot == 2 ? 0 : slot + 1;   // slots of p1 / p2
+        if (DEEP) {
+            const bool p1_due = p1_g >= 0 && (p1_full || dense != 0u || !have);
+            bool ok = true;
+#pragma unroll 1
+            for (int q = 0; q < 2; ++q) {                  // oldest first
+                const int fg = q == 0 ? p2_g : (p1_due ? p1_g : -1);
+                if (fg >= 0 && !tile_back<LAYOUT>(P, W, fg, q == 0 ? slot2 : slot1)) { ok = false; break; }
+            }
+            if (!ok) break;
+            p2_g = -1;
+            if (p1_due) p1_g = -1;
+        } else if (p1_g >= 0) {
+            if (!tile_back<LAYOUT>(P, W, p1_g, slot1)) break;
+            p1_g = -1;
         }
         if (!have) break;
         bool bad = false;
@@ -1017,30 +1061,49 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
 
         unsigned long long dbg_base = 0;
         if (P.dbg_coefs || P.dbg_bits) {                 // stage dumps for the parity tests
-            const int img_idx = W.pend[slot].img_idx;
-            dbg_base = P.images[img_idx].first_block + (unsigned long long)((g - P.images[img_idx].first_tile) * kBlocksPerTile);
+            const int di = W.pend[slot].img_idx;
+            dbg_base = P.images[di].first_block + (unsigned long long)((g - P.images[di].first_tile) * kBlocksPerTile);
         }
         if (P.dbg_coefs) {
             for (int i = lane; i < nblk * 64; i += 32)
                 P.dbg_coefs[dbg_base * 64ull + (unsigned long long)i] = W.coef[(i >> 6) * kCoefStride + (i & 63)];
         }
-        // ---- entropy: coefficients -> bits in the region ----
+        // ---- entropy: coefficients -> bits in the region (the half p1 does not occupy, or all of it) ----
+        const bool half = DEEP && dense == 0u;
+        const unsigned base = (half && p1_g >= 0 && p1_base == 0u) ? (unsigned)kHalfWords : 0u;
         bool overflow = false;
         unsigned bits;
         if (P.dbg_bits) bits = encode_blocks_dbg<LAYOUT>(W, T, nblk, cap_words, queue, P.dbg_bits + dbg_base, overflow);
-        else bits = encode_blocks_warp<LAYOUT, false>(W, T, 0, nblk, W.region, cap_words, queue, nullptr, overflow);
+        else bits = encode_blocks_warp<LAYOUT, false>(W, T, 0, nblk, W.region + base, half ? (unsigned)kHalfWords : cap_words, queue, nullptr, overflow);
+        bool full = !half;
+        if (DEEP && half && overflow) {
+            // the content turned dense: p1 goes out now, the tile is coded again into the whole region
+            if (!tile_recode<LAYOUT>(P, W, T, queue, cap_words, p1_g, slot1, nblk, bits, overflow)) break;
+            p1_g = -1;
+            full = true;
+            dense = 16u;
+        } else if (DEEP && !half && dense != 0xffffffffu) {
+            if (bits <= (unsigned)kHalfWords * 32u - 512u) --dense;      // 16 tiles in a row that would have fit a half: use halves again
+            else dense = 16u;
+        }
 
         if (!overflow) {
             // Publish the tile's bit count and last bits NOW: they are consumed (by us and by every
-            // successor) one iteration later.
-            const unsigned tail = tail_bits(W.region, bits);
+            // successor) at least one iteration later.
+            const unsigned cbase = full ? 0u : base;
+            const unsigned tail = tail_bits(W.region + cbase, bits);
             if (lane == 0) {
                 st_flag64(P.desc_bits + g, make_desc(first ? kStatusPrefix : kStatusAgg, tail, bits));
-                W.pend[slot].T = bits; W.pend[slot].tail = tail;
+                W.pend[slot].T = bits; W.pend[slot].tail = tail; W.pend[slot].base = cbase;
             }
             warp_sync();
-            prev_g = g;
-        } else if (!tile_slow<LAYOUT>(P, W, T, queue, cap_words, g, nblk, bits, slot)) break;
+            if (DEEP) p2_g = p1_g;   // (still waiting only if it sits in the other half)
+            p1_g = g; p1_full = full; p1_base = cbase;
+        } else {
+            // does not even fit the whole region (p1 was written out above: the region is ours)
+            if (!tile_slow<LAYOUT>(P, W, T, queue, cap_words, g, nblk, bits, slot)) break;
+            p2_g = -1; p1_g = -1;
+        }
     }
 }
 

@@ -19,16 +19,26 @@ size_t JG_FN(smem_bytes_)() { return sizeof(Smem<JG_LAYOUT, JG_NC>); }
 
 cudaError_t JG_FN(prepare_)(int* ctas_per_sm)
 {
-    auto kern = encode_tiles_kernel<JG_LAYOUT, JG_NC>;
+    auto kern = encode_tiles_kernel<JG_LAYOUT, JG_NC, false>;
+    auto kern_deep = encode_tiles_kernel<JG_LAYOUT, JG_NC, true>;
     const int smem = (int)sizeof(Smem<JG_LAYOUT, JG_NC>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kern, kThreads, smem);
+    e = cudaFuncSetAttribute(kern_deep, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    int a = 0, b = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, kern, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern_deep, kThreads, smem);
+    *ctas_per_sm = a < b ? a : b;
+    return e;
 }
 
-cudaError_t JG_FN(launch_)(int grid, cudaStream_t stream, const LaunchParams& P, const QuantSet& Q)
+// deep: the two-iteration pipeline, for launches with few images (jpeg_kernel.cuh)
+cudaError_t JG_FN(launch_)(int grid, cudaStream_t stream, const LaunchParams& P, const QuantSet& Q, bool deep)
 {
-    encode_tiles_kernel<JG_LAYOUT, JG_NC><<<grid, kThreads, sizeof(Smem<JG_LAYOUT, JG_NC>), stream>>>(P, Q);
+    if (deep) encode_tiles_kernel<JG_LAYOUT, JG_NC, true><<<grid, kThreads, sizeof(Smem<JG_LAYOUT, JG_NC>), stream>>>(P, Q);
+    else encode_tiles_kernel<JG_LAYOUT, JG_NC, false><<<grid, kThreads, sizeof(Smem<JG_LAYOUT, JG_NC>), stream>>>(P, Q);
     return cudaGetLastError();
 }
 

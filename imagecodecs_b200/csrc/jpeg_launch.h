@@ -23,6 +23,10 @@ constexpr int mcus_per_tile(int layout) { return layout == LAYOUT_444 ? 8 : (lay
 constexpr int kWinWordsMax = 384;    // a warp's region (unstuffed bits of one tile): 512 bits per block before the tile goes slow
 constexpr int kWinWordsMin = 216;    // must hold four worst-case blocks (4 x 1658 bits) + slack: the slow path's group
 constexpr unsigned kSpinLimit = 1u << 24;
+#ifndef JG_DEEP_MAX_IMAGES
+#define JG_DEEP_MAX_IMAGES 48
+#endif
+constexpr int kDeepMaxImages = JG_DEEP_MAX_IMAGES;   // launches with fewer images use the two-iteration pipeline (DEEP kernels)
 
 constexpr unsigned long long kStatusAgg = 1ull << 62;
 constexpr unsigned long long kStatusPrefix = 2ull << 62;
@@ -76,7 +80,7 @@ struct LaunchParams {
 #define JG_DECLARE_SPEC(L, N)                                                                   \
     size_t smem_bytes_##L##_##N();                                                              \
     cudaError_t prepare_##L##_##N(int* ctas_per_sm);                                            \
-    cudaError_t launch_##L##_##N(int grid, cudaStream_t stream, const LaunchParams& P, const QuantSet& Q);
+    cudaError_t launch_##L##_##N(int grid, cudaStream_t stream, const LaunchParams& P, const QuantSet& Q, bool deep);
 JG_DECLARE_SPEC(0, 3)
 JG_DECLARE_SPEC(0, 4)
 JG_DECLARE_SPEC(1, 3)

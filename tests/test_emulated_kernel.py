@@ -70,3 +70,25 @@ def test_ticket_schedule_is_a_round_robin_bijection(tiles, force):
         # round-robin: between two tiles of one image every other still-active image got a ticket
         active_after = [(tiles > lt + 1).sum() for lt in range(t - 1)]
         assert np.all(np.diff(tk) >= np.maximum(1, np.asarray(active_after, dtype=np.int64))) if t > 1 else True
+
+
+@pytest.mark.parametrize("qm,q,sub,ctas", [(1, 90, 1, 1), (1, 97, 0, 2), (0, 3, 0, 1), (1, 98, 0, 1), (1, 85, 0, 3)])
+def test_emulated_kernel_sparse_dense_transitions(qm, q, sub, ctas):
+    """Smooth / noise / smooth bands: the warps switch between half-region tiles (written two
+    iterations later), whole-region tiles and the slow path, every combination of pending tiles."""
+    w, h = 176, 240
+    photo = oracle.synth_batch(1, w, h, 3, "photo")[0]
+    noise = oracle.synth_batch(1, w, h, 3, "noise")[0]
+    img = photo.copy()
+    img[h // 3: 2 * h // 3] = noise[h // 3: 2 * h // 3]
+    img[5 * h // 6:, : w // 2] = noise[5 * h // 6:, : w // 2]
+    if qm == 1 and q == 98:
+        img = img[:, :, :1].copy()
+    nc_out = 1 if img.shape[2] == 1 else 3
+    hdr = oracle.oracle_headers(w, h, nc_out, sub, qm, q)
+    want = oracle.oracle_encode(img, qm, q, sub)
+    scans, sizes, status = emu_encode(img[None], qm, q, sub, n_ctas=ctas)          # one image: the two-iteration (DEEP) kernel
+    assert hdr + scans[0] == want and status[0] == 0
+    if ctas == 1:
+        scans, sizes, status = emu_encode(np.stack([img, img]), qm, q, sub, n_ctas=2)   # two images: the plain kernel
+        assert hdr + scans[0] == want and hdr + scans[1] == want
