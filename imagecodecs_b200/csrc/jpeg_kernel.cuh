@@ -264,6 +264,13 @@ JG_DEV void row_pass_store_x2(f32x2 (&s)[8], float* tile_x, float* tile_y, int r
     for (int i = 0; i < 8; ++i) { tile_x[r * 9 + i] = s[i].x; tile_y[r * 9 + i] = s[i].y; }
 }
 
+// MCU `slot` of a tile whose first MCU sits at (my0, mx0): one division per tile (by the caller), not one per MCU
+JG_DEV void mcu_pos(const ImageDesc& im, int my0, int mx0, int slot, int& my, int& mx)
+{
+    my = my0; mx = mx0 + slot;
+    while (mx >= im.mcus_x) { mx -= im.mcus_x; ++my; }
+}
+
 JG_DEV unsigned zz_at(const LaneConst& LC, int v) { return ((v < 4 ? LC.zz_lo : LC.zz_hi) >> (8 * (v & 3))) & 0xffu; }
 JG_DEV void publish_dc(unsigned* dc_out, int k) { st_flag32(dc_out, 0x80000000u | ((unsigned)k & 0xffffu)); }
 
@@ -319,7 +326,7 @@ JG_DEV void column_pass_x2(WarpMem<LAYOUT>& W, const float* tile_x, const float*
 // top of each iteration.)
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT, int NC>
-JG_DEV void transform_tile_gray(WarpMem<LAYOUT>& W, const ImageDesc& im, int m0, int nM, unsigned* dc_out, const LaneConst& LC)
+JG_DEV void transform_tile_gray(WarpMem<LAYOUT>& W, const ImageDesc& im, int my0, int mx0, int nM, unsigned* dc_out, const LaneConst& LC)
 {
     using G = Geo<LAYOUT>;
     const int t = JG_TID & 31, u = t & 7, grp = t >> 3;
@@ -332,8 +339,8 @@ JG_DEV void transform_tile_gray(WarpMem<LAYOUT>& W, const ImageDesc& im, int m0,
             const int slot = 2 * (it * G::GROUPS + grp) + half;
             uint32_t ww[2] = {0u, 0u};
             if (slot < nM) {
-                const int m = m0 + slot;
-                const int my = m / im.mcus_x, mx = m - my * im.mcus_x;
+                int my, mx;
+                mcu_pos(im, my0, mx0, slot, my, mx);
                 int y = my * 8 + u; if (y >= im.h) y = im.h - 1;          // replicate the last row
                 load_segment<1, 8>(im, mx * 8, y, ww);
             }
@@ -368,7 +375,7 @@ JG_DEV void transform_tile_gray(WarpMem<LAYOUT>& W, const ImageDesc& im, int m0,
 // stage 1: transform all MCUs of the tile
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT, int NC>
-JG_DEV void transform_tile(WarpMem<LAYOUT>& W, const ImageDesc& im, int m0, int nM, unsigned* dc_out, const LaneConst& LC)
+JG_DEV void transform_tile(WarpMem<LAYOUT>& W, const ImageDesc& im, int my0, int mx0, int nM, unsigned* dc_out, const LaneConst& LC)
 {
     using G = Geo<LAYOUT>;
     const int t = JG_TID & 31;
@@ -379,11 +386,10 @@ JG_DEV void transform_tile(WarpMem<LAYOUT>& W, const ImageDesc& im, int m0, int 
 #pragma unroll 1
     for (int it = 0; it < G::ITERS; ++it) {
         const int slot = it * G::GROUPS + grp;
-        const int m = m0 + slot;
         const bool valid = slot < nM;
         unsigned* dcs = (slot == nM - 1) ? dc_out : nullptr;     // the tile's last MCU publishes its DCs
         int my = 0, mx = 0;
-        if (valid) { my = m / im.mcus_x; mx = m - my * im.mcus_x; }
+        if (valid) mcu_pos(im, my0, mx0, slot, my, mx);
 
         if (LAYOUT == LAYOUT_444) {
             // 8 lanes per MCU, lane u owns pixel row u.  Y goes through the scalar passes, Cb and Cr
@@ -1014,8 +1020,9 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
                 pd.raw = reinterpret_cast<unsigned long long>(im.raw); pd.raw_cap = im.raw_cap;
                 pd.img_idx = img_idx; pd.first_tile_of_img = im.first_tile; pd.last = last ? 1 : 0;
             }
-            if (LAYOUT == LAYOUT_GRAY) transform_tile_gray<LAYOUT, NC>(W, im, m0, nM, P.desc_dc + 3 * (size_t)g, LC);
-            else transform_tile<LAYOUT, NC>(W, im, m0, nM, P.desc_dc + 3 * (size_t)g, LC);
+            const int my0 = m0 / im.mcus_x, mx0 = m0 - my0 * im.mcus_x;
+            if (LAYOUT == LAYOUT_GRAY) transform_tile_gray<LAYOUT, NC>(W, im, my0, mx0, nM, P.desc_dc + 3 * (size_t)g, LC);
+            else transform_tile<LAYOUT, NC>(W, im, my0, mx0, nM, P.desc_dc + 3 * (size_t)g, LC);
         }
         // DC predictors of the tile's first blocks: the last DCs of the previous tile (published by the
         // lanes that computed them, right after their column pass -- that tile was drawn before ours), or 0
