@@ -274,12 +274,12 @@ def run_ours(args):
         pass
     roofline = {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "kernel": "jg::encode_tiles_kernel<LAYOUT_420,3>",
+                "kernel": "jg::encode_tiles_kernel<LAYOUT_420,3,plain>",
                 "kernel_ms_per_launch": round(enc, 4), "kernel_share_of_step": round(enc / (enc + stf), 4),
                 "second_pass_ms": round(stf, 4),
                 "algorithmic_bytes_per_launch": int(algo_bytes),
                 "whole_step_frac": round(algo_bytes / (ms_step * 1e-3) / 1e9 / peak, 4),
-                "note": "a step = 1 state memset + encode kernel + plan_chunks + stuff kernel; `achieved` uses the encode kernel's own CUDA-event duration"}
+                "note": "a step = 2 memsets (state, results) + encode kernel + plan_chunks + stuff kernel; `achieved` uses the encode kernel's own CUDA-event duration"}
 
     # ---- parity spot check against the oracle (not timed) ------------------------------------
     parity = None

@@ -80,6 +80,15 @@ def build(force=False, verbose=False, example=True):
         futs = {ex.submit(_run, cmd): obj for obj, cmd in jobs if force or _stale(obj, deps)}
         for f in cf.as_completed(futs):
             logs.append((futs[f], f.result()))
+    # the reference's float math must never be contracted: no fused multiply-add of any width may
+    # appear in the encode kernels (ptxas fuses packed mul+add despite .rn -- see jpeg_device.h)
+    cuobjdump = os.path.join(os.path.dirname(_nvcc()), "cuobjdump")
+    for obj in futs.values():
+        if os.path.basename(obj).startswith("kernel_"):
+            sass = _run([cuobjdump, "-sass", obj])
+            fused = [l.strip() for l in sass.split("\n") if "FFMA" in l]
+            if fused:
+                raise RuntimeError("%s contains fused multiply-adds (output would differ from jpeg_enc.h):\n%s" % (obj, "\n".join(fused[:5])))
     _run([_nvcc(), "-shared", "-cudart", "static"] + ARCH + ["-o", LIB] + [obj for obj, _ in jobs])
     with open(os.path.join(OBJ, "ptxas.log"), "w") as fh:
         for obj, log in sorted(logs):

@@ -75,7 +75,8 @@ typedef struct jpeg_gpu_batch_opts {
     int device;            /* >=0: index into the initialised device list; -1: shard by image index */
     int outputs_on_device; /* outs[i].data are device pointers on the encoding GPU */
     void* stream;          /* optional cudaStream_t to launch on (only with device >= 0) */
-    int debug_window_words;/* 0 = default; otherwise force the per-tile window size (tests) */
+    int debug_window_words;/* 0 = default; otherwise force the words of bits a tile may hold before it goes down the
+                              slow path (tests; clamped to 216..384) */
 } jpeg_gpu_batch_opts;
 
 /* ---- lifetime ---------------------------------------------------------- */

@@ -157,16 +157,33 @@ def test_stage_parity(gpu):
 
 
 def test_window_overflow_path(gpu):
-    """Tiles whose bits exceed the shared-memory window are processed in groups: same bytes."""
+    """Tiles whose bits exceed a warp's shared-memory region are coded again in groups of four
+    blocks and written piecewise: same bytes.  (A forced region is clamped to 216..384 words.)"""
     img = oracle.synth_image(256, 256, 3, kind="noise")
     want = oracle.oracle_encode(img, 0, 3)
-    for win in (64, 100, 128, 1000):
+    for win in (64, 216, 300):
         assert encode_one(gpu, img, 0, 3, win_words=win) == want
+    # ordinary content that only overflows the smallest region: slow-path and normal tiles mixed
     img2 = oracle.synth_image(640, 480, 3)
-    assert encode_one(gpu, img2, 1, 50, 1, win_words=100) == oracle.oracle_encode(img2, 1, 50, 1)
-    # natural overflow (no forced window): 1080p noise at all-ones quantisers
+    assert encode_one(gpu, img2, 0, 3, win_words=216) == oracle.oracle_encode(img2, 0, 3)
+    assert encode_one(gpu, img2, 1, 97, 1, win_words=216) == oracle.oracle_encode(img2, 1, 97, 1)
+    # natural overflow (no forced region): 1080p noise at all-ones quantisers
     big = oracle.synth_image(1920, 1080, 3, kind="noise")
     assert sha(encode_one(gpu, big, 0, 3, capacity=12 << 20)) == "e4393984ae95a4980fed6e23e98e56d9f3877a0c48a7ef364e8afaabf35c5412"
+
+
+def test_sparse_dense_transitions_single_image(gpu):
+    """One image (the two-iteration kernel): smooth / noise / smooth bands make the warps switch between
+    half-region tiles, whole-region tiles and the slow path."""
+    w, h = 1280, 960
+    img = oracle.synth_image(w, h, 3).copy()
+    noise = oracle.synth_image(w, h, 3, kind="noise")
+    img[h // 3: 2 * h // 3] = noise[h // 3: 2 * h // 3]
+    img[5 * h // 6:, : w // 2] = noise[5 * h // 6:, : w // 2]
+    for qm, q, sub in [(1, 90, 1), (1, 97, 0), (0, 3, 0), (0, 2, 0)]:
+        assert encode_one(gpu, img, qm, q, sub, capacity=8 << 20) == oracle.oracle_encode(img, qm, q, sub), (qm, q, sub)
+    gray = img[:, :, :1].copy()
+    assert encode_one(gpu, gray, 1, 98, 0, capacity=8 << 20) == oracle.oracle_encode(gray, 1, 98, 0)
 
 
 # ---------------------------------------------------------------------------------------------
