@@ -336,6 +336,17 @@ def test_16k_rgb_native_twin(gpu):
 # ---------------------------------------------------------------------------------------------
 # error behaviour and the drop-in twins
 # ---------------------------------------------------------------------------------------------
+def test_maximum_dimensions(gpu):
+    """The reference's limits (jpeg_enc.h:958-960): 65535 pixels in either direction, one MCU row / column,
+    odd sizes (edge replication on both axes) -- against the compiled reference."""
+    for (w, h) in [(65535, 8), (8, 65535), (65535, 3), (5, 65535)]:
+        img = oracle.synth_image(w, h, 3)
+        rc, ref = oracle.ref_encode(img, 2)
+        assert rc == 1 and encode_one(gpu, img, 0, 2) == ref, (w, h)
+    img = oracle.synth_image(65535, 17, 3)
+    assert encode_one(gpu, img, 1, 75, 1) == oracle.oracle_encode(img, 1, 75, 1)
+
+
 def test_invalid_images_are_rejected_individually(gpu):
     good = oracle.synth_image(32, 32, 3)
     files, st = gpu.encode_batch([good, good, good], [0, 0, 1], [3, 7, 101], 0, device=0)
