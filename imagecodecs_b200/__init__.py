@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("JPEG_GPU_LIB") or os.path.join(_HERE, "libjpeg_gpu.so
 
 QMODE_TJE, QMODE_IJG = 0, 1
 SUB_444, SUB_420 = 0, 1
+FLAG_SWAP_RB = 1
 OK, ERR_ARG, ERR_CAPACITY, ERR_CUDA = 0, 1, 2, 3
 
 WRITE_FUNC = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int)   # jpeg_enc.h:152
@@ -23,7 +24,7 @@ WRITE_FUNC = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int)   # jpeg_enc.h:1
 class Image(C.Structure):          # jpeg_gpu_image
     _fields_ = [("pixels", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("ncomp", C.c_int),
                 ("stride", C.c_int), ("quality_mode", C.c_int), ("quality", C.c_int),
-                ("subsampling", C.c_int), ("pixels_on_device", C.c_int)]
+                ("subsampling", C.c_int), ("pixels_on_device", C.c_int), ("flags", C.c_int)]
 
 
 class Output(C.Structure):         # jpeg_gpu_output
@@ -110,8 +111,9 @@ def emit_headers(w, h, ncomp, qmode=QMODE_TJE, quality=3, sub=SUB_444):
     return buf[:n].tobytes()
 
 
-def _describe(px, qmode, quality, sub):
-    """px: numpy uint8 [h,w,c] / [h,w] (host) or anything with data_ptr()/shape (torch CUDA tensor)."""
+def _describe(px, qmode, quality, sub, flags=0, bottom_up=False):
+    """px: numpy uint8 [h,w,c] / [h,w] (host) or anything with data_ptr()/shape (torch CUDA tensor).
+    bottom_up: the array holds the rows last-to-first (BMP order); described with a negative stride."""
     on_dev = 0
     if hasattr(px, "data_ptr"):
         shape = tuple(px.shape)
@@ -125,13 +127,16 @@ def _describe(px, qmode, quality, sub):
     if len(shape) == 2:
         shape = shape + (1,)
     h, w, c = shape
-    return Image(ptr, w, h, c, 0, qmode, quality, sub, on_dev)
+    if bottom_up:
+        return Image(ptr + (h - 1) * w * c, w, h, c, -w * c, qmode, quality, sub, on_dev, flags)
+    return Image(ptr, w, h, c, 0, qmode, quality, sub, on_dev, flags)
 
 
-def encode_batch(images, qmode=QMODE_TJE, quality=3, sub=SUB_444, device=-1, capacity=None, win_words=0):
+def encode_batch(images, qmode=QMODE_TJE, quality=3, sub=SUB_444, device=-1, capacity=None, win_words=0, flags=0,
+                 bottom_up=False):
     """Encode a list of images (numpy host arrays or torch CUDA tensors, uint8 [h,w,c]).
 
-    qmode / quality / sub may be scalars or per-image sequences.  Returns (list[bytes|None], statuses).
+    qmode / quality / sub / flags may be scalars or per-image sequences.  Returns (list[bytes|None], statuses).
     """
     L = lib()
     n = len(images)
@@ -144,7 +149,7 @@ def encode_batch(images, qmode=QMODE_TJE, quality=3, sub=SUB_444, device=-1, cap
         if not hasattr(px, "data_ptr"):
             px = np.ascontiguousarray(px, dtype=np.uint8)
         keep.append(px)
-        descs[i] = _describe(px, per(qmode, i), per(quality, i), per(sub, i))
+        descs[i] = _describe(px, per(qmode, i), per(quality, i), per(sub, i), per(flags, i), bottom_up)
         cap = capacity if capacity is not None else 2048 + 6 * descs[i].width * descs[i].height + 4096
         b = np.empty(cap, np.uint8)
         bufs.append(b)

@@ -10,6 +10,13 @@
 //
 // writeJpg calls jpeg_gpu_encode_to_file exactly where codecs.cpp:853 calls
 // tje_encode_to_file; every other format of the reference is out of scope.
+//
+// flip() and swapBR() (codecs.h:78,99; codecs.cpp:162-251) do not touch the
+// pixels here.  They are remembered, and a following write("x.jpg") hands them to the encoder as
+// load-time swizzles (a negative row stride, JPEG_GPU_FLAG_SWAP_RB): the kernel reads the rows /
+// channels in the other order, no host pass over the image happens.  Anything that LOOKS at the
+// pixels (data(), write("x.bmp")) first brings the buffer into the state the reference would have
+// left it in, so the difference is not observable.
 #pragma once
 #include <stdexcept>
 #include <string>
@@ -31,16 +38,25 @@ namespace ImageCodecs
 		unsigned char* pixels_ = nullptr;
 		Type type_ = Type::UBYTE;
 
-		// codecs per filetype (only the two on the JPEG write path):
+		bool pendingFlip_ = false;    // flip() / swapBR() called an odd number of times since the pixels were last touched
+		bool pendingSwapBR_ = false;
+
+		void flip(unsigned char* pixels, const int w, const int h, const int d, const Type& type);
+		void swapBR(unsigned char* pixels, const int w, const int h, const int d, const Type& type);
+		void materialize();           // apply the pending operations to pixels_ (what the reference does at once)
+
+		// codecs per filetype (the JPEG write path and its BMP feeder):
 		void readBmp(std::string filename, unsigned char** pixels, int& w, int& h, int& d, Type& type);
+		void writeBmp(std::string filename, unsigned char* pixels, int& w, int& h, int& d, Type& type);
 		void writeJpg(std::string filename, unsigned char* pixels, int& w, int& h, int& d, Type& type);
 
 	public:
 		inline int byteSize() { return type_ == Type::FLOAT ? 4 : (type_ == Type::USHORT ? 2 : 1); }
 		inline int channels() { return d_; }
 		inline int cols() { return w_; }
-		inline unsigned char** data() { return &pixels_; }
+		inline unsigned char** data() { materialize(); return &pixels_; }
 		inline bool empty() { return h_ == 0 || w_ == 0 || d_ == 0 || pixels_ == nullptr; }
+		inline void flip() { pendingFlip_ = !pendingFlip_; }
 		// adopts the pointer (the destructor delete[]s it), like codecs.h:89-95
 		inline void load(unsigned char* pixels, int w, int h, int channels)
 		{
@@ -48,9 +64,11 @@ namespace ImageCodecs
 			w_ = w;
 			h_ = h;
 			pixels_ = pixels;
+			pendingFlip_ = pendingSwapBR_ = false;
 		}
 		void read(std::string filepath);
 		inline int rows() { return h_; }
+		inline void swapBR() { pendingSwapBR_ = !pendingSwapBR_; }
 		inline int totalBytes() { return w_ * h_ * d_ * byteSize(); }
 		inline Type type() { return type_; }
 		void write(std::string filepath);

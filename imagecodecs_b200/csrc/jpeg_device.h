@@ -43,6 +43,8 @@ JG_DEV int i_clz(unsigned v) { return __clz((int)v); }
 JG_DEV int i_ffs(unsigned v) { return __ffs((int)v); }
 JG_DEV int i_popc(unsigned v) { return __popc(v); }
 JG_DEV unsigned bswap32(unsigned v) { return __byte_perm(v, 0u, 0x0123u); }
+// byte i of the result = byte (sel >> 4i) & 7 of the 8 bytes {a: 0-3, b: 4-7}
+JG_DEV unsigned byte_perm(unsigned a, unsigned b, unsigned sel) { return __byte_perm(a, b, sel); }
 JG_DEV unsigned funnel_l(unsigned lo, unsigned hi, unsigned s) { return __funnelshift_l(lo, hi, s); }
 // per-byte compare: 0xff in every byte lane where a == b
 JG_DEV unsigned v_cmpeq4(unsigned a, unsigned b) { return __vcmpeq4(a, b); }

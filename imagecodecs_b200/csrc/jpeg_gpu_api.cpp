@@ -190,7 +190,8 @@ bool geometry_of(const jpeg_gpu_image& im, Geometry* g)
     if (im.width <= 0 || im.height <= 0 || im.width > 0xffff || im.height > 0xffff) return false;
     if (im.subsampling != JPEG_GPU_SUB_444 && im.subsampling != JPEG_GPU_SUB_420) return false;
     if (im.ncomp == 1 && im.subsampling != JPEG_GPU_SUB_444) return false;
-    if (im.stride != 0 && im.stride < im.width * im.ncomp) return false;
+    if (im.stride != 0 && std::abs(im.stride) < im.width * im.ncomp) return false;   // negative: bottom-up rows
+    if (im.flags & ~JPEG_GPU_FLAG_SWAP_RB) return false;
     g->layout = im.ncomp == 1 ? LAYOUT_GRAY : (im.subsampling == JPEG_GPU_SUB_420 ? LAYOUT_420 : LAYOUT_444);
     g->nc_in = im.ncomp;
     g->ncomp_out = im.ncomp == 1 ? 1 : 3;
@@ -220,6 +221,12 @@ size_t default_scan_bytes(const jpeg_gpu_image& im, const Geometry& g)
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// bottom-up storage (negative stride): byte offset of the top row inside the image's memory block
+size_t top_row_offset(const jpeg_gpu_image& im)
+{
+    return im.stride < 0 ? (size_t)(-(long long)im.stride) * (size_t)(im.height - 1) : 0;
+}
 
 // largest power of two <= 16 dividing both the base address and the row pitch
 int alignment_of(const void* px, int stride)
@@ -327,7 +334,7 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
         it.scan_cap = align_up(worst_case ? worst_scan_bytes(it.geo.n_blocks) : default_scan_bytes(it.img, it.geo), 256);
         it.arena_off = arena;
         arena += it.scan_cap;
-        it.pixel_bytes = (size_t)it.img.stride * it.img.height;
+        it.pixel_bytes = (size_t)std::abs(it.img.stride) * it.img.height;
         if (!it.img.pixels_on_device) {
             it.pixel_off = pixels;
             pixels += align_up(it.pixel_bytes, 256);
@@ -395,7 +402,8 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
         int tile = 0;
         for (size_t k = 0; k < g.items.size(); ++k) {
             jpeg_gpu_plan::Item& it = p->items[g.items[k]];
-            if (!it.img.pixels_on_device) it.d_pixels = p->d_pixels + it.pixel_off;
+            // `pixels` is the image's top row; with bottom-up storage that is the LAST row of the memory block
+            if (!it.img.pixels_on_device) it.d_pixels = p->d_pixels + it.pixel_off + top_row_offset(it.img);
             else it.d_pixels = it.img.pixels;
             ImageDesc& d = p->h_images[g.result_off + k];
             d.px = it.d_pixels;
@@ -407,7 +415,8 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
             d.w = it.img.width; d.h = it.img.height; d.stride = it.img.stride;
             d.mcus_x = it.geo.mcus_x; d.n_mcus = it.geo.n_mcus;
             d.first_tile = tile; d.n_tiles = it.geo.n_tiles;
-            d.align = alignment_of(d.px, d.stride);
+            d.flags = it.img.flags;
+            d.align = (d.flags & JPEG_GPU_FLAG_SWAP_RB) ? 1 : alignment_of(d.px, d.stride);   // the swizzle lives in the byte loader
             tile += it.geo.n_tiles;
         }
     }
@@ -615,7 +624,7 @@ int jpeg_gpu_plan_set_pixels(jpeg_gpu_plan* p, int i, const uint8_t* device_pixe
     it.d_pixels = device_pixels;
     ImageDesc& d = p->h_images[p->groups[it.group].result_off + it.index_in_group];
     d.px = device_pixels;
-    d.align = alignment_of(d.px, d.stride);
+    d.align = (d.flags & JPEG_GPU_FLAG_SWAP_RB) ? 1 : alignment_of(d.px, d.stride);
     p->images_dirty = true;
     return 1;
 }
@@ -627,7 +636,8 @@ int jpeg_gpu_plan_upload(jpeg_gpu_plan* p, int i, const uint8_t* host_pixels, vo
     if (it.img.pixels_on_device) { set_error("image %d was declared device-resident", i); return 0; }
     cudaStream_t s = stream ? (cudaStream_t)stream : g_devices[p->dev_index].stream;
     if (cudaSetDevice(g_devices[p->dev_index].id) != cudaSuccess) return 0;
-    cudaError_t e = cudaMemcpyAsync(p->d_pixels + it.pixel_off, host_pixels, it.pixel_bytes, cudaMemcpyHostToDevice, s);
+    // host_pixels is the top row; the memory block starts top_row_offset before it when the rows are bottom-up
+    cudaError_t e = cudaMemcpyAsync(p->d_pixels + it.pixel_off, host_pixels - top_row_offset(it.img), it.pixel_bytes, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) { set_error("pixel upload failed: %s", cudaGetErrorString(e)); return 0; }
     return 1;
 }
@@ -790,7 +800,7 @@ static int encode_on_device(const jpeg_gpu_image* images, int n, jpeg_gpu_output
         size_t bytes = 0;
         int hi = lo;
         while (hi < n && (hi == lo || bytes < kChunkPixelBytes)) {
-            bytes += (size_t)std::max(images[hi].stride, images[hi].width * images[hi].ncomp) * (size_t)std::max(images[hi].height, 0);
+            bytes += (size_t)std::max(std::abs(images[hi].stride), images[hi].width * images[hi].ncomp) * (size_t)std::max(images[hi].height, 0);
             ++hi;
         }
         chunks.push_back({lo, hi, nullptr, dev.pipe[chunks.size() % kRing]});

@@ -126,7 +126,7 @@ template <int NC, int NPX>
 JG_DEV void load_segment(const ImageDesc& im, int x0, int y, uint32_t (&w)[NPX * NC / 4])
 {
     constexpr int BYTES = NPX * NC;
-    const uint8_t* row = im.px + (size_t)y * (size_t)im.stride;
+    const uint8_t* row = im.px + (long long)y * (long long)im.stride;
     if (x0 + NPX <= im.w && im.align >= 4) {
         const uint8_t* p = row + (size_t)x0 * NC;
         // widest load the segment size and the image's alignment allow: fewer, fatter requests
@@ -147,6 +147,11 @@ JG_DEV void load_segment(const ImageDesc& im, int x0, int y, uint32_t (&w)[NPX *
             for (int i = 0; i < BYTES / 4; ++i) w[i] = ldg_u32(p + 4 * i);
         }
     } else {
+        // JPEG_GPU_FLAG_SWAP_RB: channels 0 and 2 change places.  Only this byte loader knows the flag (the
+        // host gives flagged images align = 1), as two per-channel base pointers: the vector path of everybody
+        // else stays as it is -- a 20-instruction swizzle block behind a never-taken branch there cost 3.5 %.
+        const int swz = (NC >= 3 && (im.flags & 1)) ? 2 : 0;
+        const uint8_t* base[4] = {row + swz, row, row - swz, row};
 #pragma unroll
         for (int i = 0; i < BYTES / 4; ++i) {
             uint32_t v = 0;
@@ -156,7 +161,7 @@ JG_DEV void load_segment(const ImageDesc& im, int x0, int y, uint32_t (&w)[NPX *
                 const int px = bo / NC, ch = bo - px * NC;
                 int x = x0 + px;
                 if (x >= im.w) x = im.w - 1;                     // replicate the last column
-                v |= ldg_u8(row + (size_t)x * NC + ch) << (8 * b);
+                v |= ldg_u8(base[ch] + (size_t)x * NC + ch) << (8 * b);
             }
             w[i] = v;
         }

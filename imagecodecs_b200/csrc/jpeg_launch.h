@@ -41,12 +41,13 @@ struct ImageDesc {
     unsigned long long out_cap;      // bytes available at `out`
     unsigned long long first_block;  // index of the image's first block in the debug dumps
     int w, h;
-    int stride;      // bytes per pixel row
+    int stride;      // bytes from one pixel row to the next (negative: bottom-up storage, px = top row)
     int mcus_x;      // MCUs per MCU row
     int n_mcus;
     int first_tile;  // launch-local index of the image's first tile
     int n_tiles;
     int align;       // largest power of two (<= 16) dividing both px and stride: widest legal vector load
+    int flags;       // JPEG_GPU_FLAG_* (bit 0: exchange channels 0 and 2 on load)
 };
 
 // One parameter block for the three kernels of a launch group:

@@ -43,6 +43,12 @@ extern "C" {
 #define JPEG_GPU_SUB_444 0 /* the only format the reference emits (jpeg_enc.h:1038) */
 #define JPEG_GPU_SUB_420 1 /* extended: 16x16 MCUs, Y00 Y01 Y10 Y11 Cb Cr */
 
+/* jpeg_gpu_image.flags: load-time swizzles, applied by the encode kernel while it reads the pixels
+ * (no host pass over the pixels for BGR / bottom-up sources such as BMP files) */
+#define JPEG_GPU_FLAG_SWAP_RB 1 /* channels 0 and 2 of every pixel are exchanged: the bytes produced are those of
+                                   Image::swapBR() (codecs.cpp:193-251) followed by writeJpg.  Flagged images are read
+                                   with byte loads (the transform runs ~1.5x slower); unflagged ones pay nothing */
+
 /* jpeg_gpu_output.status */
 #define JPEG_GPU_OK 0
 #define JPEG_GPU_ERR_ARG 1      /* rejected like jpeg_enc.h:954-960 / :1223-1226 would */
@@ -57,11 +63,15 @@ typedef struct jpeg_gpu_image {
     int width;             /* 1..65535 (jpeg_enc.h:958) */
     int height;            /* 1..65535 */
     int ncomp;             /* 3 = RGB, 4 = RGBA (alpha skipped), 1 = gray (extended) */
-    int stride;            /* bytes per row; 0 means width*ncomp (the reference's only layout) */
+    int stride;            /* bytes from one row to the next; 0 means width*ncomp (the reference's only layout).
+                              Negative: the rows are stored bottom-up (BMP, DIB): `pixels` still points at the
+                              image's TOP row, which then is the last one in memory -- the bytes produced are
+                              those of Image::flip() (codecs.cpp:162-191) on the bottom-up buffer + writeJpg */
     int quality_mode;      /* JPEG_GPU_QMODE_* */
     int quality;           /* 1..3 or 1..100 by mode */
     int subsampling;       /* JPEG_GPU_SUB_* */
     int pixels_on_device;  /* non-zero: `pixels` is a device pointer on the GPU that encodes this image */
+    int flags;             /* JPEG_GPU_FLAG_* */
 } jpeg_gpu_image;
 
 typedef struct jpeg_gpu_output {

@@ -1,6 +1,8 @@
 // tests/cpp/write_jpg_like_reference.cpp -- what tests.cpp:98-108 does for one file, through
 // the C++ host layer:   ./a.out in.bmp out.jpg        (read a fixture, write it as JPEG)
 //                or:    ./a.out --raw w h d in.raw out.jpg
+//                or:    ./a.out --ops <f|s|fs|sf...> in.bmp out.jpg|out.bmp   (f = img.flip(), s = img.swapBR() before the write)
+//                or:    ./a.out --ops-peek <ops> in.bmp out.jpg               (same, but data() is looked at before the write)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,6 +25,17 @@ int main(int argc, char** argv)
 			fclose(f);
 			img.load(px, w, h, d);
 			img.write(argv[6]);
+		}
+		else if (argc == 5 && (!strcmp(argv[1], "--ops") || !strcmp(argv[1], "--ops-peek")))
+		{
+			img.read(argv[3]);
+			for (const char* c = argv[2]; *c; ++c)
+			{
+				if (*c == 'f') img.flip();
+				else if (*c == 's') img.swapBR();
+			}
+			if (!strcmp(argv[1], "--ops-peek") && *img.data() == nullptr) return 3;
+			img.write(argv[4]);
 		}
 		else if (argc == 3)
 		{

@@ -53,6 +53,13 @@ JG_DEV int i_clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 JG_DEV int i_ffs(unsigned v) { return __builtin_ffs((int)v); }
 JG_DEV int i_popc(unsigned v) { return __builtin_popcount(v); }
 JG_DEV unsigned bswap32(unsigned v) { return __builtin_bswap32(v); }
+JG_DEV unsigned byte_perm(unsigned a, unsigned b, unsigned sel)
+{
+    const unsigned long long ab = ((unsigned long long)b << 32) | a;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned)((ab >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+}
 JG_DEV unsigned v_cmpne2(unsigned a, unsigned b)
 {
     return (((a ^ b) & 0xffffu) ? 0xffffu : 0u) | (((a ^ b) >> 16) ? 0xffff0000u : 0u);

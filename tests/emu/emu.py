@@ -31,7 +31,7 @@ def _load():
         build()
         L = C.CDLL(_SO)
         L.emu_encode.restype = C.c_int
-        L.emu_encode.argtypes = [C.c_void_p] + [C.c_int] * 10 + [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+        L.emu_encode.argtypes = [C.c_void_p] + [C.c_int] * 11 + [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                                                 C.c_void_p, C.c_void_p]
         L.emu_ticket_map.restype = C.c_int
         L.emu_ticket_map.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -49,7 +49,7 @@ def emu_ticket_map(tiles, force_schedule=False):
     return g, img
 
 
-def emu_encode(batch, qmode=0, quality=3, sub=0, win_words=0, n_ctas=2, stages=False, cap=None):
+def emu_encode(batch, qmode=0, quality=3, sub=0, win_words=0, n_ctas=2, stages=False, cap=None, flags=0, bottom_up=False):
     """batch: uint8 [n,h,w,c].  Returns list of scan bytes (entropy-coded segment + EOI) [, coefs, bits]."""
     batch = np.ascontiguousarray(batch, dtype=np.uint8)
     if batch.ndim == 3:
@@ -65,7 +65,7 @@ def emu_encode(batch, qmode=0, quality=3, sub=0, win_words=0, n_ctas=2, stages=F
     status = np.zeros(n, dtype=np.uint32)
     coefs = np.zeros((n * nblk, 64), dtype=np.int16) if stages else None
     bits = np.zeros(n * nblk, dtype=np.uint32) if stages else None
-    rc = _load().emu_encode(batch.ctypes.data, n, w, h, c, 0, sub, qmode, quality, win_words, n_ctas,
+    rc = _load().emu_encode(batch.ctypes.data, n, w, h, c, -w * c if bottom_up else 0, flags, sub, qmode, quality, win_words, n_ctas,
                             out.ctypes.data, cap, sizes.ctypes.data, status.ctypes.data,
                             coefs.ctypes.data if stages else None, bits.ctypes.data if stages else None)
     if rc != 0:

@@ -73,7 +73,7 @@ extern "C" {
 // Encode `n_images` images of identical geometry/quality with `n_ctas` emulated CTAs
 // running concurrently.  scan_out: [n_images][scan_cap]; scan_bytes: [n_images].
 // Returns 0 on success, otherwise the kernel's error flag / a negative setup error.
-int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int stride, int subsampling,
+int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int stride, int flags, int subsampling,
                int quality_mode, int quality, int win_words, int n_ctas,
                uint8_t* scan_out, size_t scan_cap, unsigned long long* scan_bytes, unsigned* img_status,
                int16_t* dbg_coefs, uint32_t* dbg_bits)
@@ -94,13 +94,15 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
     const int M = mcus_per_tile(layout);
     const int tiles = (n_mcus + M - 1) / M;
     if (stride == 0) stride = w * ncomp;
+    const int pitch = stride < 0 ? -stride : stride;       // negative stride: each image's rows are stored bottom-up
 
     const size_t raw_cap = (scan_cap + 255) / 256 * 256;
     uint8_t* raw = (uint8_t*)aligned_alloc(256, raw_cap * n_images);
     std::vector<ImageDesc> imgs(n_images);
     for (int i = 0; i < n_images; ++i) {
         ImageDesc& d = imgs[i];
-        d.px = pixels + (size_t)i * stride * h;
+        d.px = pixels + (size_t)i * pitch * h + (stride < 0 ? (size_t)pitch * (h - 1) : 0);
+        d.flags = flags;
         d.raw = raw + (size_t)i * raw_cap;
         d.raw_cap = scan_cap;
         d.out = scan_out + (size_t)i * scan_cap;
@@ -108,7 +110,7 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
         d.first_block = (unsigned long long)i * n_mcus * bpm;
         d.w = w; d.h = h; d.stride = stride; d.mcus_x = mcus_x; d.n_mcus = n_mcus;
         d.first_tile = i * tiles; d.n_tiles = tiles;
-        { const size_t v = (size_t)d.px | (size_t)stride | 16u; d.align = (int)(v & (~v + 1)); }
+        { const size_t v = (size_t)d.px | (size_t)stride | 16u; d.align = (flags & 1) ? 1 : (int)(v & (~v + 1)); }
     }
     const int n_tiles = tiles * n_images;
     const size_t max_chunks = (size_t)n_images * ((scan_cap + kChunkBytes - 1) / kChunkBytes) + 1;

@@ -92,3 +92,19 @@ def test_emulated_kernel_sparse_dense_transitions(qm, q, sub, ctas):
     if ctas == 1:
         scans, sizes, status = emu_encode(np.stack([img, img]), qm, q, sub, n_ctas=2)   # two images: the plain kernel
         assert hdr + scans[0] == want and hdr + scans[1] == want
+
+
+@pytest.mark.parametrize("w,h,nc,qm,q,sub", [(45, 37, 3, 0, 3, 0), (64, 32, 3, 1, 75, 1), (33, 20, 4, 0, 2, 0), (40, 24, 4, 1, 90, 1)])
+def test_emulated_kernel_load_time_swizzles(w, h, nc, qm, q, sub):
+    """SWAP_RB and bottom-up rows (negative stride) give the bytes of swapBR() / flip() + writeJpg
+    (codecs.cpp:162-251) without a host pass over the pixels -- vector and byte loaders."""
+    img = oracle.synth_batch(1, w, h, nc, "photo")[0]
+    hdr = oracle.oracle_headers(w, h, 3, sub, qm, q)
+    want = oracle.oracle_encode(img, qm, q, sub)
+    swapped = img.copy(); swapped[:, :, 0] = img[:, :, 2]; swapped[:, :, 2] = img[:, :, 0]
+    scans, _, _ = emu_encode(swapped[None], qm, q, sub, n_ctas=1, flags=1)
+    assert hdr + scans[0] == want
+    scans, _, _ = emu_encode(np.ascontiguousarray(img[::-1])[None], qm, q, sub, n_ctas=1, bottom_up=True)
+    assert hdr + scans[0] == want
+    scans, _, _ = emu_encode(np.ascontiguousarray(swapped[::-1])[None], qm, q, sub, n_ctas=1, flags=1, bottom_up=True)
+    assert hdr + scans[0] == want

@@ -9,6 +9,7 @@ import os
 import subprocess
 
 import numpy as np
+import torch
 import pytest
 
 import oracle
@@ -388,6 +389,55 @@ def test_tje_twins(gpu, tmp_path):
     assert L.jpeg_gpu_encode_to_file_at_quality(p, 9, 395, 348, 3, rgb.ctypes.data) == 0  # and leaves a 0-byte file,
     assert os.path.getsize(p) == 0                                                          # as the reference does
     assert L.jpeg_gpu_encode_to_file(b"/nonexistent-dir/x.jpg", 8, 8, 3, rgb.ctypes.data) == 0
+
+
+def _bmp_bytes(px):
+    """24-bit BMP with the reference's own row padding (w % 4), rows bottom-up; px is top-down [h,w,3]."""
+    import struct
+    h, w, _ = px.shape
+    rows = b"".join(px[y].tobytes() + b"\0" * (w % 4) for y in range(h - 1, -1, -1))
+    return b"BM" + struct.pack("<IIIIiiHHIIiiII", 54 + len(rows), 0, 54, 40, w, h, 1, 24, 0, len(rows), 0, 0, 0, 0) + rows
+
+
+def test_load_time_swizzles(gpu, fixture_pixels):
+    """B<->R exchange and bottom-up rows folded into the kernel's pixel loads give the bytes
+    the reference produces after swapBR() / flip() (codecs.cpp:162-251) -- host arrays, device arrays,
+    3 and 4 channels, vector and byte loaders, mixed flags in one launch."""
+    cases = [(fixture_pixels["cat_bgr"], 3), (oracle.synth_image(640, 360, 4), 2), (oracle.synth_image(131, 67, 3), 1)]
+    for img, q in cases:
+        swapped = img.copy(); swapped[:, :, 0] = img[:, :, 2]; swapped[:, :, 2] = img[:, :, 0]
+        rc, want = oracle.ref_encode(swapped, q)
+        rc2, want_flip = oracle.ref_encode(np.ascontiguousarray(swapped[::-1]), q)
+        assert rc == 1 and rc2 == 1
+        assert encode_one(gpu, img, 0, q, flags=gpu.FLAG_SWAP_RB) == want
+        assert encode_one(gpu, np.ascontiguousarray(swapped[::-1]), 0, q, bottom_up=True) == want
+        assert encode_one(gpu, img, 0, q, flags=gpu.FLAG_SWAP_RB, bottom_up=True) == want_flip
+        dev = torch.from_numpy(img).cuda()
+        assert encode_one(gpu, dev, 0, q, flags=gpu.FLAG_SWAP_RB, bottom_up=True) == want_flip
+    a = oracle.synth_image(320, 200, 3)
+    b = a[:, :, ::-1].copy()
+    files, st = gpu.encode_batch([a, b, a, b], 0, 2, device=0, flags=[0, gpu.FLAG_SWAP_RB, 0, gpu.FLAG_SWAP_RB])
+    assert st == [0] * 4 and files[0] == files[1] == files[2] == files[3] == oracle.ref_encode(a, 2)[1]
+    files, st = gpu.encode_batch([a], 0, 2, device=0, flags=2)                  # unknown flag bits are rejected
+    assert st == [gpu.ERR_ARG]
+
+
+def test_cpp_facade_folds_flip_and_swap_into_the_encode(gpu, fixture_pixels, tmp_path):
+    """Image::flip() / swapBR() before write(".jpg"): no host pass, same bytes as the reference's eager versions;
+    looking at data() in between (which materialises them) changes nothing."""
+    exe = os.path.join(os.path.dirname(gpu.LIB_PATH), "write_jpg_like_reference")
+    cat = fixture_pixels["cat_bgr"]
+    bmp = tmp_path / "cat.bmp"; bmp.write_bytes(_bmp_bytes(cat))
+    swapped = cat[:, :, ::-1]
+    want = {"f": np.ascontiguousarray(cat[::-1]), "s": np.ascontiguousarray(swapped), "fs": np.ascontiguousarray(swapped[::-1]),
+            "sfs": np.ascontiguousarray(cat[::-1]), "ff": cat}
+    for ops, px in want.items():
+        ref = oracle.ref_encode(px, 3)[1]
+        for mode in ("--ops", "--ops-peek"):
+            out = tmp_path / ("cat_%s_%s.jpg" % (ops, mode.strip("-")))
+            r = subprocess.run([exe, mode, ops, str(bmp), str(out)], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            assert out.read_bytes() == ref, (ops, mode)
 
 
 def test_cpp_host_layer_like_reference_tests_cpp(gpu, fixture_pixels, tmp_path):

@@ -95,3 +95,23 @@ def test_no_gpu_means_loud_failure_not_fallback():
     cb = jg.WRITE_FUNC(lambda ctx, data, size: calls.append(size))
     assert L.jpeg_gpu_encode_with_func(cb, None, 3, 16, 16, 3, img.ctypes.data) == 0
     assert calls == []
+
+
+def test_cpp_facade_bmp_round_trip_without_gpu(tmp_path):
+    """The façade's BMP feeder (codecs.cpp:255-375 semantics, incl. the reference's own row padding of w % 4):
+    read -> flip()/swapBR() -> write(".bmp") -> read back; no GPU involved."""
+    import struct, subprocess
+    import oracle
+    exe = os.path.join(os.path.dirname(jg.LIB_PATH), "write_jpg_like_reference")
+    assert os.path.exists(exe), "built by imagecodecs_b200.build"
+    px = oracle.synth_image(37, 21, 3)
+    h, w, _ = px.shape
+    rows = b"".join(px[y].tobytes() + b"\0" * (w % 4) for y in range(h - 1, -1, -1))
+    src = tmp_path / "in.bmp"
+    src.write_bytes(b"BM" + struct.pack("<IIIIiiHHIIiiII", 54 + len(rows), 0, 54, 40, w, h, 1, 24, 0, len(rows), 0, 0, 0, 0) + rows)
+    for ops, want in (("", px), ("f", px[::-1]), ("s", px[:, :, ::-1]), ("fs", px[::-1, :, ::-1])):
+        out = tmp_path / ("out_%s.bmp" % ops)
+        r = subprocess.run([exe, "--ops", ops, str(src), str(out)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        got = oracle.read_bmp(out.read_bytes())
+        assert got is not None and np.array_equal(got, want), ops
