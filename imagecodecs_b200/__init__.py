@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("JPEG_GPU_LIB") or os.path.join(_HERE, "libjpeg_gpu.so
 QMODE_TJE, QMODE_IJG = 0, 1
 SUB_444, SUB_420 = 0, 1
 FLAG_SWAP_RB = 1
+FLAG_RESTART = 2
 OK, ERR_ARG, ERR_CAPACITY, ERR_CUDA = 0, 1, 2, 3
 
 WRITE_FUNC = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int)   # jpeg_enc.h:152
@@ -44,6 +45,7 @@ SYMBOLS = {
     "jpeg_gpu_last_error": (C.c_char_p, []),
     "jpeg_gpu_max_encoded_size": (C.c_size_t, [C.c_int] * 4),
     "jpeg_gpu_emit_headers": (C.c_size_t, [C.c_int] * 6 + [C.c_void_p, C.c_size_t]),
+    "jpeg_gpu_emit_headers_for": (C.c_size_t, [C.POINTER(Image), C.c_void_p, C.c_size_t]),
     "jpeg_gpu_encode_batch": (C.c_int, [C.POINTER(Image), C.c_int, C.POINTER(Output), C.POINTER(BatchOpts)]),
     "jpeg_gpu_plan_create": (C.c_void_p, [C.POINTER(Image), C.c_int, C.c_int, C.c_int]),
     "jpeg_gpu_plan_set_pixels": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
@@ -105,9 +107,13 @@ def max_encoded_size(w, h, ncomp, sub=SUB_444):
     return int(lib().jpeg_gpu_max_encoded_size(w, h, ncomp, sub))
 
 
-def emit_headers(w, h, ncomp, qmode=QMODE_TJE, quality=3, sub=SUB_444):
+def emit_headers(w, h, ncomp, qmode=QMODE_TJE, quality=3, sub=SUB_444, flags=0):
     buf = np.empty(2048, np.uint8)
-    n = lib().jpeg_gpu_emit_headers(w, h, ncomp, qmode, quality, sub, buf.ctypes.data, buf.size)
+    if flags:
+        im = Image(None, w, h, ncomp, 0, qmode, quality, sub, 0, flags)
+        n = lib().jpeg_gpu_emit_headers_for(C.byref(im), buf.ctypes.data, buf.size)
+    else:
+        n = lib().jpeg_gpu_emit_headers(w, h, ncomp, qmode, quality, sub, buf.ctypes.data, buf.size)
     return buf[:n].tobytes()
 
 

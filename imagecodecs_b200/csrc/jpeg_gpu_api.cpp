@@ -54,7 +54,7 @@ void set_error(const char* fmt, ...)
 struct Spec {
     int layout, nc;
     cudaError_t (*prepare)(int*);
-    cudaError_t (*launch)(int, cudaStream_t, const LaunchParams&, const QuantSet&, bool);
+    cudaError_t (*launch)(int, cudaStream_t, const LaunchParams&, const QuantSet&, int);
 };
 const Spec kSpecs[5] = {
     {LAYOUT_444, 3, prepare_0_3, launch_0_3}, {LAYOUT_444, 4, prepare_0_4, launch_0_4},
@@ -191,7 +191,7 @@ bool geometry_of(const jpeg_gpu_image& im, Geometry* g)
     if (im.subsampling != JPEG_GPU_SUB_444 && im.subsampling != JPEG_GPU_SUB_420) return false;
     if (im.ncomp == 1 && im.subsampling != JPEG_GPU_SUB_444) return false;
     if (im.stride != 0 && std::abs(im.stride) < im.width * im.ncomp) return false;   // negative: bottom-up rows
-    if (im.flags & ~JPEG_GPU_FLAG_SWAP_RB) return false;
+    if (im.flags & ~(JPEG_GPU_FLAG_SWAP_RB | JPEG_GPU_FLAG_RESTART)) return false;
     g->layout = im.ncomp == 1 ? LAYOUT_GRAY : (im.subsampling == JPEG_GPU_SUB_420 ? LAYOUT_420 : LAYOUT_444);
     g->nc_in = im.ncomp;
     g->ncomp_out = im.ncomp == 1 ? 1 : 3;
@@ -262,6 +262,7 @@ struct jpeg_gpu_plan {
         unsigned long long* d_raw_bytes = nullptr;    // into d_aux
         unsigned* d_first_chunk = nullptr;
         ImageDesc* d_images = nullptr;
+        bool restart = false;     // JPEG_GPU_FLAG_RESTART images (their own kernel instantiation)
         size_t sched_off = 0;     // words into d_sched (groups with images of different tile counts)
         bool has_sched = false;
         unsigned long long* d_scan_bytes = nullptr;   // into d_results
@@ -303,7 +304,7 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
     JG_CUDA(cudaSetDevice(dev.id));
     p->worst_case = worst_case;
     p->items.resize(n);
-    std::map<std::tuple<int, int, int>, int> group_of;   // (spec, qmode, quality) -> group
+    std::map<std::tuple<int, int, int, int>, int> group_of;   // (spec, qmode, quality, restart) -> group
     size_t arena = 0, pixels = 0, blocks = 0;
     for (int i = 0; i < n; ++i) {
         jpeg_gpu_plan::Item& it = p->items[i];
@@ -314,14 +315,16 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
         ++p->n_valid;
         if (it.img.stride == 0) it.img.stride = it.img.width * it.img.ncomp;
         it.header.resize(1024);
+        const bool restart = (it.img.flags & JPEG_GPU_FLAG_RESTART) != 0;
         it.header.resize(emit_headers(it.img.width, it.img.height, it.geo.ncomp_out, it.img.subsampling, ql, qc,
-                                      it.header.data(), it.header.size()));
+                                      it.header.data(), it.header.size(), restart ? mcus_per_tile(it.geo.layout) : 0));
         const int spec = spec_index(it.geo.layout, it.geo.nc_in);
-        auto key = std::make_tuple(spec, it.img.quality_mode, it.img.quality);
+        auto key = std::make_tuple(spec, it.img.quality_mode, it.img.quality, restart ? 1 : 0);   // restart images launch on their own kernels
         auto f = group_of.find(key);
         if (f == group_of.end()) {
             jpeg_gpu_plan::Group g;
             g.spec = spec;
+            g.restart = restart;
             build_pqt(ql, g.quant.luma);
             build_pqt(qc, g.quant.chroma);
             f = group_of.emplace(key, (int)p->groups.size()).first;
@@ -331,7 +334,9 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
         it.group = f->second;
         it.index_in_group = (int)g.items.size();
         g.items.push_back(i);
-        it.scan_cap = align_up(worst_case ? worst_scan_bytes(it.geo.n_blocks) : default_scan_bytes(it.img, it.geo), 256);
+        // restart mode: + 1 pad byte and 2 marker bytes per tile
+        it.scan_cap = align_up((worst_case ? worst_scan_bytes(it.geo.n_blocks) : default_scan_bytes(it.img, it.geo)) +
+                                   (restart ? 3 * (size_t)it.geo.n_tiles : 0), 256);
         it.arena_off = arena;
         arena += it.scan_cap;
         it.pixel_bytes = (size_t)std::abs(it.img.stride) * it.img.height;
@@ -469,7 +474,8 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
         const int grid = std::min((g.n_tiles + kWarps - 1) / kWarps, dev.sm_count * dev.ctas_per_sm[g.spec]);   // one tile per warp at a time
         const size_t gi = (size_t)(&g - &p->groups[0]);
         if (p->timing) JG_CUDA(cudaEventRecord(p->events[3 * gi], s));
-        JG_CUDA(kSpecs[g.spec].launch(grid, s, P, g.quant, P.n_images < kDeepMaxImages));
+        const int mode = g.restart ? 2 : (P.n_images < kDeepMaxImages ? 1 : 0);   // kModeRestart / kModeDeep / kModePlain
+        JG_CUDA(kSpecs[g.spec].launch(grid, s, P, g.quant, mode));
         if (p->timing) JG_CUDA(cudaEventRecord(p->events[3 * gi + 1], s));
         JG_CUDA(stuff_launch(dev.sm_count * dev.stuff_ctas_per_sm, s, P));
         if (p->timing) JG_CUDA(cudaEventRecord(p->events[3 * gi + 2], s));
@@ -610,6 +616,16 @@ size_t jpeg_gpu_emit_headers(int width, int height, int ncomp, int quality_mode,
     uint8_t ql[64], qc[64];
     if (!geometry_of(im, &g) || !build_qt(quality_mode, quality, ql, qc)) return 0;
     return emit_headers(width, height, g.ncomp_out, subsampling, ql, qc, out, capacity);
+}
+
+size_t jpeg_gpu_emit_headers_for(const jpeg_gpu_image* image, uint8_t* out, size_t capacity)
+{
+    if (!image) return 0;
+    Geometry g;
+    uint8_t ql[64], qc[64];
+    if (!geometry_of(*image, &g) || !build_qt(image->quality_mode, image->quality, ql, qc)) return 0;
+    return emit_headers(image->width, image->height, g.ncomp_out, image->subsampling, ql, qc, out, capacity,
+                        (image->flags & JPEG_GPU_FLAG_RESTART) ? mcus_per_tile(g.layout) : 0);
 }
 
 jpeg_gpu_plan* jpeg_gpu_plan_create(const jpeg_gpu_image* images, int n, int device, int debug_window_words)

@@ -142,7 +142,7 @@ struct ByteWriter {
 }  // namespace
 
 size_t emit_headers(int w, int h, int ncomp_out, int subsampling, const uint8_t qt_luma[64],
-                    const uint8_t qt_chroma[64], uint8_t* out, size_t cap)
+                    const uint8_t qt_chroma[64], uint8_t* out, size_t cap, int restart_interval)
 {
     ByteWriter bw{out, cap, 0};
     const bool color = ncomp_out == 3;
@@ -171,6 +171,7 @@ size_t emit_headers(int w, int h, int ncomp_out, int subsampling, const uint8_t 
         bw.u8(((t & 1) << 4) | (t >> 1));  // class = AC?, id = chroma?
         bw.bytes(kBits[t], 16); bw.bytes(huff_vals(t), nv);
     }
+    if (restart_interval > 0) { bw.be16(0xFFDD); bw.be16(4); bw.be16((unsigned)restart_interval); }   // DRI (extended, opt-in)
     // SOS (jpeg_enc.h:1052-1077)
     bw.be16(0xFFDA); bw.be16(6 + 2 * ncomp_out); bw.u8(ncomp_out);
     for (int c = 0; c < ncomp_out; ++c) { bw.u8(c + 1); bw.u8(c ? 0x11 : 0x00); }

@@ -795,6 +795,13 @@ JG_DEV void clear_region(uint32_t* region, unsigned n)
     warp_sync();
 }
 
+// n (< 8) 1-bits at bit `pos` of the MSB-first word array (they may straddle two words); one lane
+JG_DEV void set_ones(uint32_t* region, unsigned pos, unsigned n)
+{
+    const unsigned long long m = ((1ull << n) - 1ull) << (64u - (pos & 31u) - n);
+    region[pos >> 5] |= (unsigned)(m >> 32);
+    region[(pos >> 5) + 1] |= (unsigned)m;
+}
 JG_DEV unsigned tail_bits(const uint32_t* region, unsigned T) { return T >= 7u ? peek_bits(region, T - 7u, 7u) : peek_bits(region, 0u, T); }
 
 JG_DEV unsigned long long make_desc(unsigned long long status, unsigned tail, unsigned long long count)
@@ -896,7 +903,7 @@ JG_DEV_NOINLINE unsigned encode_blocks_dbg(WarpMem<LAYOUT>& W, const CodeTables&
 // again and written out right away, not pipelined.  The last group goes first, only to learn the
 // tile's last 7 bits: successors must not wait for our whole slow pass.  Out of line: rare.
 // Returns false on a look-back timeout.
-template <int LAYOUT>
+template <int LAYOUT, bool restart>
 JG_DEV_NOINLINE bool tile_slow(const LaunchParams& P, WarpMem<LAYOUT>& W, const CodeTables& T, uint32_t* queue, unsigned cap_words,
                                int g, int nblk, unsigned bits, int slot)
 {
@@ -906,7 +913,15 @@ JG_DEV_NOINLINE bool tile_slow(const LaunchParams& P, WarpMem<LAYOUT>& W, const 
     const int n_groups = (nblk + kGroupBlocks - 1) / kGroupBlocks;
     bool ovf2;
     clear_region(W.region, cap_words + 8u);
-    const unsigned tl = encode_blocks_warp<LAYOUT, false>(W, T, (n_groups - 1) * kGroupBlocks, nblk, W.region, cap_words, queue, nullptr, ovf2);
+    unsigned tl = encode_blocks_warp<LAYOUT, false>(W, T, (n_groups - 1) * kGroupBlocks, nblk, W.region, cap_words, queue, nullptr, ovf2);
+    // restart interval: the tile ends with 1-bits up to the byte boundary (the groups are contiguous in
+    // the bit stream, so the tile's total decides the padding of its last group)
+    const unsigned pad = restart ? (0u - bits) & 7u : 0u;
+    if (pad) {
+        if (lane == 0) set_ones(W.region, tl, pad);
+        warp_sync();
+        tl += pad; bits += pad;
+    }
     const unsigned tail = tail_bits(W.region, tl);
     if (lane == 0) st_flag64(P.desc_bits + g, make_desc(first ? kStatusPrefix : kStatusAgg, tail, bits));
     unsigned long long bit_base = 0;
@@ -920,7 +935,12 @@ JG_DEV_NOINLINE bool tile_slow(const LaunchParams& P, WarpMem<LAYOUT>& W, const 
         const int b_lo = gi * kGroupBlocks, b_hi = b_lo + kGroupBlocks < nblk ? b_lo + kGroupBlocks : nblk;
         warp_sync();
         clear_region(W.region, cap_words + 8u);
-        const unsigned tg = encode_blocks_warp<LAYOUT, false>(W, T, b_lo, b_hi, W.region, cap_words, queue, nullptr, ovf2);
+        unsigned tg = encode_blocks_warp<LAYOUT, false>(W, T, b_lo, b_hi, W.region, cap_words, queue, nullptr, ovf2);
+        if (pad && gi == n_groups - 1) {
+            if (lane == 0) set_ones(W.region, tg, pad);      // (the group does not start on a byte boundary: the bits may straddle words)
+            warp_sync();
+            tg += pad;
+        }
         flush_region(W.region, tg, pd.last && gi == n_groups - 1, reinterpret_cast<uint8_t*>(pd.raw), pd.raw_cap, k, hb, pos, cap_overflow);
     }
     if (lane == 0) {
@@ -955,10 +975,17 @@ JG_DEV_NOINLINE bool tile_recode(const LaunchParams& P, WarpMem<LAYOUT>& W, cons
 // (16384^2 gray: 23 % of all warp time was spent waiting in the look-back; DEEP: 1.17 -> 1.00 ms).
 // With many images in flight the round-robin ticket order already provides the slack and the
 // simpler loop is ~3 % faster.
-template <int LAYOUT, int NC, bool DEEP>
+// MODE 2 = restart intervals (JPEG_GPU_FLAG_RESTART; one-iteration pipeline): every tile predicts its DCs
+// from 0 and ends on a byte boundary, padded with 1-bits (T.81 F.1.2.3); the markers between the tiles are
+// inserted by the stuffing pass.  Its own instantiation because even a few never-taken branches in the hot
+// loop cost 2.5 % (measured): the host groups restart images into their own launches.
+constexpr int kModePlain = 0, kModeDeep = 1, kModeRestart = 2;
+template <int LAYOUT, int NC, int MODE>
 JG_KERNEL(kThreads, 6)
 void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTANT QuantSet Q)
 {
+    constexpr bool DEEP = MODE == kModeDeep;
+    constexpr bool restart = MODE == kModeRestart;
     using G = Geo<LAYOUT>;
     JG_DYNAMIC_SMEM(smem_raw);
     Smem<LAYOUT, NC>& S = *reinterpret_cast<Smem<LAYOUT, NC>*>(smem_raw);
@@ -1036,7 +1063,7 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
         // at the start of the image (jpeg_enc.h:1085-1087).  Requested here, looked at after the write-outs:
         // the round trip to L2 costs nothing.
         unsigned dcv = 0x80000000u;
-        const bool dc_wanted = have && !first && lane < G::NCOMP;
+        const bool dc_wanted = have && !first && !restart && lane < G::NCOMP;   // a restart interval predicts from 0
         if (dc_wanted) dcv = ld_flag32(P.desc_dc + 3 * (size_t)(g - 1) + lane);
         // ---- write-outs that are due: the tile coded two iterations ago; last iteration's too if the
         //      coming tile needs the whole region (or nothing comes any more) ----
@@ -1105,7 +1132,13 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
             // Publish the tile's bit count and last bits NOW: they are consumed (by us and by every
             // successor) at least one iteration later.
             const unsigned cbase = full ? 0u : base;
-            const unsigned tail = tail_bits(W.region + cbase, bits);
+            unsigned tail = tail_bits(W.region + cbase, bits);
+            if (restart && (bits & 7u) != 0u) {      // restart interval: 1-bits up to the byte boundary (T.81 F.1.2.3)
+                const unsigned pad = 8u - (bits & 7u);
+                if (lane == 0) set_ones(W.region + cbase, bits, pad);   // read again only by the write-out, barriers later
+                tail = ((tail << pad) | ((1u << pad) - 1u)) & 0x7fu;
+                bits += pad;
+            }
             if (lane == 0) {
                 st_flag64(P.desc_bits + g, make_desc(first ? kStatusPrefix : kStatusAgg, tail, bits));
                 W.pend[slot].T = bits; W.pend[slot].tail = tail; W.pend[slot].base = cbase;
@@ -1115,7 +1148,7 @@ void encode_tiles_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CO
             p1_g = g; p1_full = full; p1_base = cbase;
         } else {
             // does not even fit the whole region (p1 was written out above: the region is ours)
-            if (!tile_slow<LAYOUT>(P, W, T, queue, cap_words, g, nblk, bits, slot)) break;
+            if (!tile_slow<LAYOUT, restart>(P, W, T, queue, cap_words, g, nblk, bits, slot)) break;
             p2_g = -1; p1_g = -1;
         }
     }

@@ -17,28 +17,36 @@ namespace jg {
 
 size_t JG_FN(smem_bytes_)() { return sizeof(Smem<JG_LAYOUT, JG_NC>); }
 
-cudaError_t JG_FN(prepare_)(int* ctas_per_sm)
+template <int MODE>
+static cudaError_t prepare_mode(int* ctas)
 {
-    auto kern = encode_tiles_kernel<JG_LAYOUT, JG_NC, false>;
-    auto kern_deep = encode_tiles_kernel<JG_LAYOUT, JG_NC, true>;
+    auto kern = encode_tiles_kernel<JG_LAYOUT, JG_NC, MODE>;
     const int smem = (int)sizeof(Smem<JG_LAYOUT, JG_NC>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kern_deep, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    int a = 0, b = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, kern, kThreads, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern_deep, kThreads, smem);
-    *ctas_per_sm = a < b ? a : b;
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kThreads, smem);
+    if (n < *ctas) *ctas = n;
     return e;
 }
 
-// deep: the two-iteration pipeline, for launches with few images (jpeg_kernel.cuh)
-cudaError_t JG_FN(launch_)(int grid, cudaStream_t stream, const LaunchParams& P, const QuantSet& Q, bool deep)
+cudaError_t JG_FN(prepare_)(int* ctas_per_sm)
 {
-    if (deep) encode_tiles_kernel<JG_LAYOUT, JG_NC, true><<<grid, kThreads, sizeof(Smem<JG_LAYOUT, JG_NC>), stream>>>(P, Q);
-    else encode_tiles_kernel<JG_LAYOUT, JG_NC, false><<<grid, kThreads, sizeof(Smem<JG_LAYOUT, JG_NC>), stream>>>(P, Q);
+    int ctas = 1 << 20;
+    cudaError_t e = prepare_mode<kModePlain>(&ctas);
+    if (e == cudaSuccess) e = prepare_mode<kModeDeep>(&ctas);
+    if (e == cudaSuccess) e = prepare_mode<kModeRestart>(&ctas);
+    *ctas_per_sm = ctas;
+    return e;
+}
+
+// mode: kModePlain / kModeDeep (launches with few images) / kModeRestart (jpeg_kernel.cuh)
+cudaError_t JG_FN(launch_)(int grid, cudaStream_t stream, const LaunchParams& P, const QuantSet& Q, int mode)
+{
+    const size_t smem = sizeof(Smem<JG_LAYOUT, JG_NC>);
+    if (mode == kModeDeep) encode_tiles_kernel<JG_LAYOUT, JG_NC, kModeDeep><<<grid, kThreads, smem, stream>>>(P, Q);
+    else if (mode == kModeRestart) encode_tiles_kernel<JG_LAYOUT, JG_NC, kModeRestart><<<grid, kThreads, smem, stream>>>(P, Q);
+    else encode_tiles_kernel<JG_LAYOUT, JG_NC, kModePlain><<<grid, kThreads, smem, stream>>>(P, Q);
     return cudaGetLastError();
 }
 

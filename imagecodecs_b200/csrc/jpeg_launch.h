@@ -30,6 +30,7 @@ constexpr int kDeepMaxImages = JG_DEEP_MAX_IMAGES;   // launches with fewer imag
 
 constexpr unsigned long long kStatusAgg = 1ull << 62;
 constexpr unsigned long long kStatusPrefix = 2ull << 62;
+constexpr int kFlagSwapRB = 1, kFlagRestart = 2;   // ImageDesc.flags == jpeg_gpu_image.flags
 constexpr int kTailShift = 55;
 constexpr unsigned long long kCountMask = (1ull << kTailShift) - 1;  // descriptors: status[63:62] | payload[61:55] | value[54:0]
 
@@ -47,7 +48,7 @@ struct ImageDesc {
     int first_tile;  // launch-local index of the image's first tile
     int n_tiles;
     int align;       // largest power of two (<= 16) dividing both px and stride: widest legal vector load
-    int flags;       // JPEG_GPU_FLAG_* (bit 0: exchange channels 0 and 2 on load)
+    int flags;       // JPEG_GPU_FLAG_* (bit 0: exchange channels 0 and 2 on load; bit 1: every tile is a restart interval)
 };
 
 // One parameter block for the three kernels of a launch group:
@@ -81,7 +82,7 @@ struct LaunchParams {
 #define JG_DECLARE_SPEC(L, N)                                                                   \
     size_t smem_bytes_##L##_##N();                                                              \
     cudaError_t prepare_##L##_##N(int* ctas_per_sm);                                            \
-    cudaError_t launch_##L##_##N(int grid, cudaStream_t stream, const LaunchParams& P, const QuantSet& Q, bool deep);
+    cudaError_t launch_##L##_##N(int grid, cudaStream_t stream, const LaunchParams& P, const QuantSet& Q, int mode);
 JG_DECLARE_SPEC(0, 3)
 JG_DECLARE_SPEC(0, 4)
 JG_DECLARE_SPEC(1, 3)

@@ -18,13 +18,36 @@
 
 namespace jg {
 
+// restart mode: a tile is at least 24 blocks x 4 bits = 12 bytes, so a chunk holds at most this many tile ends
+constexpr int kMaxMarks = kChunkBytes / 12 + 2;
+
 struct StuffSmem {
-    alignas(16) uint8_t sbuf[2 * kChunkBytes + 64];
+    alignas(16) uint8_t sbuf[2 * kChunkBytes + 2 * kMaxMarks + 64];   // every byte 0xFF + a marker per tile end
     uint32_t warp_tmp[kWarps];
+    uint32_t mark[kMaxMarks + 1];      // restart mode: raw offsets (relative to the chunk) of the tile ends inside the chunk
     int chunk;
     int abort;
+    unsigned n_marks, first_mark;      // tile ends inside the chunk / index of the first one in the image
     unsigned long long ff_base;
 };
+
+// Restart mode (JPEG_GPU_FLAG_RESTART): after pass 1 desc_bits[first_tile + j] holds the inclusive bit
+// count of tile j of the image, a multiple of 8: the raw byte offset e_j at which restart interval j
+// ends.  RST(j mod 8) goes in front of raw byte e_j for every j but the last tile.
+JG_DEV unsigned long long tile_end_byte(const LaunchParams& P, const ImageDesc& im, unsigned j)
+{
+    return (ld_flag64(P.desc_bits + im.first_tile + j) & kCountMask) >> 3;
+}
+// number of tile ends e_j (j < n) with e_j < x
+JG_DEV unsigned tile_ends_below(const LaunchParams& P, const ImageDesc& im, unsigned n, unsigned long long x)
+{
+    unsigned lo = 0, hi = n;
+    while (lo < hi) {
+        const unsigned mid = (lo + hi) >> 1;
+        if (tile_end_byte(P, im, mid) < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
 
 JG_KERNEL(kThreads, 1)
 void plan_chunks_kernel(const JG_GRID_CONSTANT LaunchParams P)
@@ -80,6 +103,20 @@ void stuff_kernel(const JG_GRID_CONSTANT LaunchParams P)
         const unsigned nb = raw_n - off < (unsigned long long)kChunkBytes ? (unsigned)(raw_n - off) : (unsigned)kChunkBytes;
         const bool last_chunk = off + nb == raw_n;
 
+        // restart mode: the tile ends e_j with off <= e_j < off + nb get a marker in front of raw byte e_j
+        const bool rst = (im.flags & kFlagRestart) != 0 && im.n_tiles > 1;
+        if (rst) {
+            const unsigned n_ends = (unsigned)im.n_tiles - 1u;          // none after the last tile
+            if (t == 0) {
+                S.first_mark = tile_ends_below(P, im, n_ends, off);
+                S.n_marks = tile_ends_below(P, im, n_ends, off + nb) - S.first_mark;
+            }
+            cta_sync();
+            for (unsigned i = (unsigned)t; i < S.n_marks; i += kThreads) S.mark[i] = (uint32_t)(tile_end_byte(P, im, S.first_mark + i) - off);
+            if (t == 0) S.mark[S.n_marks] = 0xffffffffu;
+            cta_sync();
+        }
+
         // kStuffPerThread contiguous bytes per thread, as 16-byte vectors (raw is 256-byte aligned and
         // chunk offsets are multiples of the chunk size: always legal uint4 loads)
         constexpr int NV = kChunkBytes / kThreads / 16;
@@ -100,13 +137,22 @@ void stuff_kernel(const JG_GRID_CONSTANT LaunchParams P)
             if (valid <= 0) m = 0; else if (valid < 4) m &= 0xffffffffu >> (8 * (4 - valid));
             cnt += (unsigned)i_popc(m) >> 3;
         }
-        unsigned ff_chunk;
+        unsigned mi = 0;                      // first tile end at or after my first byte
+        if (rst) {
+            unsigned lo = 0, hi = S.n_marks;
+            while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (S.mark[mid] < b0) lo = mid + 1; else hi = mid; }
+            mi = lo;
+            unsigned k = mi;
+            while (S.mark[k] < b0 + mine) ++k;                     // sentinel-terminated
+            cnt += 2u * (k - mi);                                   // two marker bytes per tile end in my range
+        }
+        unsigned ff_chunk;                    // extra bytes of the chunk: stuffed zeros (+ markers)
         const unsigned ff_ex = cta_scan_excl(cnt, S.warp_tmp, ff_chunk);
         const bool first_chunk_of_img = c == first;
         if (t == 0) st_flag64(P.desc_ff + c, (first_chunk_of_img ? kStatusPrefix : kStatusAgg) | (unsigned long long)ff_chunk);
 
         // emit (position independent) while the predecessors publish
-        {
+        if (!rst) {
             unsigned o = b0 + ff_ex;
 #pragma unroll
             for (int j = 0; j < 16 * NV; ++j) {
@@ -114,6 +160,21 @@ void stuff_kernel(const JG_GRID_CONSTANT LaunchParams P)
                     const unsigned byte = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
                     S.sbuf[o++] = (uint8_t)byte;
                     if (byte == 0xffu) S.sbuf[o++] = 0;               // jpeg_enc.h:634-638
+                }
+            }
+        } else {
+            unsigned o = b0 + ff_ex;
+#pragma unroll 4
+            for (int j = 0; j < 16 * NV; ++j) {
+                if ((unsigned)j < mine) {
+                    if (S.mark[mi] == b0 + (unsigned)j) {              // a restart interval ended in front of this byte
+                        S.sbuf[o++] = 0xff;
+                        S.sbuf[o++] = (uint8_t)(0xd0u + ((S.first_mark + mi) & 7u));
+                        ++mi;
+                    }
+                    const unsigned byte = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                    S.sbuf[o++] = (uint8_t)byte;
+                    if (byte == 0xffu) S.sbuf[o++] = 0;
                 }
             }
         }

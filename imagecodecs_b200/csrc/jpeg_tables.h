@@ -42,8 +42,9 @@ bool build_qt(int quality_mode, int quality, uint8_t qt_luma[64], uint8_t qt_chr
 void build_pqt(const uint8_t qt[64], float pqt[64]);
 void build_huff_lut(HuffLut* lut);
 // header bytes up to and including SOS; ncomp_out is 3 or 1. Returns 0 if it does not fit.
+// restart_interval > 0: a DRI segment (MCUs per restart interval) precedes SOS (extended, opt-in).
 size_t emit_headers(int w, int h, int ncomp_out, int subsampling, const uint8_t qt_luma[64],
-                    const uint8_t qt_chroma[64], uint8_t* out, size_t cap);
+                    const uint8_t qt_chroma[64], uint8_t* out, size_t cap, int restart_interval = 0);
 // Ticket schedule of a launch whose images have different tile counts (see draw_tile() in
 // jpeg_kernel.cuh): tickets walk the images round-robin, tile 0 of every image, then tile 1 of
 // every image that has one, ...  `out` (n_words of it, sized schedule_words(n)) receives

@@ -48,6 +48,12 @@ extern "C" {
 #define JPEG_GPU_FLAG_SWAP_RB 1 /* channels 0 and 2 of every pixel are exchanged: the bytes produced are those of
                                    Image::swapBR() (codecs.cpp:193-251) followed by writeJpg.  Flagged images are read
                                    with byte loads (the transform runs ~1.5x slower); unflagged ones pay nothing */
+#define JPEG_GPU_FLAG_RESTART 2 /* EXTENDED, opt-in (not in the reference encoder, so the bytes differ from
+                                   jpeg_enc.h's): restart intervals of one tile = 8 (4:4:4) / 4 (4:2:0) / 24 (gray) MCUs.
+                                   A DRI segment precedes SOS; every interval is padded to a byte boundary with 1-bits,
+                                   RSTm follows (none after the last), DC prediction restarts at 0.  The stream decodes
+                                   to exactly the pixels of the restart-free stream (checked with jpeg_dec.h) and its
+                                   intervals can be decoded in parallel.  Bytes are defined by oracle/jpeg_oracle.c */
 
 /* jpeg_gpu_output.status */
 #define JPEG_GPU_OK 0
@@ -108,6 +114,8 @@ JPEG_GPU_API size_t jpeg_gpu_max_encoded_size(int width, int height, int ncomp, 
  * (655 bytes for the native modes).  Returns bytes written, 0 if rejected/too small. */
 JPEG_GPU_API size_t jpeg_gpu_emit_headers(int width, int height, int ncomp, int quality_mode,
                                           int quality, int subsampling, uint8_t* out, size_t capacity);
+/* The same for an image with flags (JPEG_GPU_FLAG_RESTART adds the DRI segment). */
+JPEG_GPU_API size_t jpeg_gpu_emit_headers_for(const jpeg_gpu_image* image, uint8_t* out, size_t capacity);
 
 /* ---- batch encode ------------------------------------------------------ */
 

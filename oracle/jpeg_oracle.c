@@ -200,7 +200,7 @@ static void put_dht(orc_sink* s, int table, int cls, int id)      /* jpeg_enc.h:
 /* Everything before the entropy-coded segment (jpeg_enc.h:989-1077).
  * ncomp_out: 3 (YCbCr) or 1 (grayscale, extended). */
 static void put_headers(orc_sink* s, int w, int h, int ncomp_out, int sub,
-                        const uint8_t qt_luma[64], const uint8_t qt_chroma[64])
+                        const uint8_t qt_luma[64], const uint8_t qt_chroma[64], int restart)
 {
     static const char com[] = "Created by Tiny JPEG Encoder";
     put16(s, 0xffd8);
@@ -222,21 +222,27 @@ static void put_headers(orc_sink* s, int w, int h, int ncomp_out, int sub,
         put_dht(s, HT_CHROMA_DC, 0, 1);
         put_dht(s, HT_CHROMA_AC, 1, 1);
     }
+    if (restart > 0) { put16(s, 0xffdd); put16(s, 4); put16(s, restart); }   /* extended: DRI, MCUs per restart interval */
     put16(s, 0xffda); put16(s, 6 + 2 * ncomp_out); put8(s, ncomp_out);
     for (int c = 0; c < ncomp_out; ++c) { put8(s, c + 1); put8(s, c == 0 ? 0x00 : 0x11); }
     put8(s, 0); put8(s, 63); put8(s, 0);
 }
 
 /* Header only (for header-parity tests of the host emitter). */
-size_t orc_headers(int w, int h, int ncomp_out, int sub, int qmode, int quality,
-                   uint8_t* out, size_t cap)
+size_t orc_headers_ex(int w, int h, int ncomp_out, int sub, int qmode, int quality, int restart,
+                      uint8_t* out, size_t cap)
 {
     uint8_t ql[64], qc[64];
     if (!orc_build_qt(qmode, quality, ql, qc)) return 0;
     orc_sink s; memset(&s, 0, sizeof s);
     s.out = out; s.cap = cap;
-    put_headers(&s, w, h, ncomp_out, sub, ql, qc);
+    put_headers(&s, w, h, ncomp_out, sub, ql, qc, restart);
     return s.n;
+}
+size_t orc_headers(int w, int h, int ncomp_out, int sub, int qmode, int quality,
+                   uint8_t* out, size_t cap)
+{
+    return orc_headers_ex(w, h, ncomp_out, sub, qmode, quality, 0, out, cap);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -395,11 +401,34 @@ static float rgb_cr(const uint8_t* p) { float r = p[0], g = p[1], b = p[2]; retu
  *   bits_dump   uint32[nblocks]    entropy-coded bits of each block
  *   raw_dump    the scan before 0xFF00 stuffing and before padding; raw_bits = its length
  */
+/*
+ * restart > 0 (EXTENDED, not in the reference encoder; opt-in): a DRI segment announces `restart`
+ * MCUs per restart interval; after every interval but the last the entropy-coded data is padded to
+ * a byte boundary with 1-bits (ITU-T T.81 F.1.2.3), RSTm (m = interval index mod 8) follows and the
+ * DC predictors return to 0; the final interval is padded with 1-bits as well.  The decoded pixels
+ * are those of the restart-free stream (checked with the reference's own decoder, jpeg_dec.h).
+ */
+int orc_encode_ex(const uint8_t* px, int w, int h, int ncomp, ptrdiff_t stride,
+                  int qmode, int quality, int sub, int restart,
+                  uint8_t* out, size_t cap, size_t* out_size,
+                  int16_t* coef_dump, uint32_t* bits_dump,
+                  uint8_t* raw_dump, size_t raw_cap, uint64_t* raw_bits);
+
 int orc_encode(const uint8_t* px, int w, int h, int ncomp, ptrdiff_t stride,
                int qmode, int quality, int sub,
                uint8_t* out, size_t cap, size_t* out_size,
                int16_t* coef_dump, uint32_t* bits_dump,
                uint8_t* raw_dump, size_t raw_cap, uint64_t* raw_bits)
+{
+    return orc_encode_ex(px, w, h, ncomp, stride, qmode, quality, sub, 0, out, cap, out_size,
+                         coef_dump, bits_dump, raw_dump, raw_cap, raw_bits);
+}
+
+int orc_encode_ex(const uint8_t* px, int w, int h, int ncomp, ptrdiff_t stride,
+                  int qmode, int quality, int sub, int restart,
+                  uint8_t* out, size_t cap, size_t* out_size,
+                  int16_t* coef_dump, uint32_t* bits_dump,
+                  uint8_t* raw_dump, size_t raw_cap, uint64_t* raw_bits)
 {
     uint8_t qtl[64], qtc[64];
     float pql[64], pqc[64];
@@ -413,6 +442,7 @@ int orc_encode(const uint8_t* px, int w, int h, int ncomp, ptrdiff_t stride,
     if (sub != ORC_SUB_444 && sub != ORC_SUB_420) return 0;
     if (ncomp == 1 && sub != ORC_SUB_444) return 0;
     if (stride == 0) stride = (ptrdiff_t)w * ncomp;
+    if (restart < 0 || restart > 0xffff) return 0;
 
     orc_build_pqt(qtl, pql);
     orc_build_pqt(qtc, pqc);
@@ -423,12 +453,26 @@ int orc_encode(const uint8_t* px, int w, int h, int ncomp, ptrdiff_t stride,
     if (raw_dump) memset(raw_dump, 0, raw_cap);
     orc_img im = { px, w, h, ncomp, stride };
 
-    put_headers(&s, w, h, ncomp == 1 ? 1 : 3, sub, qtl, qtc);
+    put_headers(&s, w, h, ncomp == 1 ? 1 : 3, sub, qtl, qtc, restart);
 
     int pred[3] = { 0, 0, 0 };
     float blk[64];
     int du[64];
     size_t nb = 0;
+    const int mcu_px = (ncomp != 1 && sub == ORC_SUB_420) ? 16 : 8;
+    const long total_mcus = (long)((w + mcu_px - 1) / mcu_px) * ((h + mcu_px - 1) / mcu_px);
+    long mcus_done = 0;
+
+    /* end of an MCU: close the restart interval if one ends here and more MCUs follow */
+#define MCU_DONE()                                                                     \
+    do {                                                                               \
+        ++mcus_done;                                                                   \
+        if (restart > 0 && mcus_done % restart == 0 && mcus_done < total_mcus) {       \
+            if (s.fill > 0) put_bits(&s, (unsigned)(8 - s.fill), 0xffu);               \
+            put16(&s, 0xffd0 + (unsigned)((mcus_done / restart - 1) & 7));             \
+            pred[0] = pred[1] = pred[2] = 0;                                           \
+        }                                                                              \
+    } while (0)
 
 #define EMIT(comp)                                                                     \
     do {                                                                               \
@@ -450,6 +494,7 @@ int orc_encode(const uint8_t* px, int w, int h, int ncomp, ptrdiff_t stride,
                     for (int i = 0; i < 8; ++i)
                         blk[j * 8 + i] = (float)pix(&im, x0 + i, y0 + j)[0] - 128;
                 EMIT(0);
+                MCU_DONE();
             }
     } else if (sub == ORC_SUB_444) {
         /* native: jpeg_enc.h:1094-1158 */
@@ -463,6 +508,7 @@ int orc_encode(const uint8_t* px, int w, int h, int ncomp, ptrdiff_t stride,
                         }
                     EMIT(c);
                 }
+                MCU_DONE();
             }
     } else {
         /* extended: 4:2:0, 16x16 MCUs, chroma = ((a+b)+(c+d))*0.25f of float Cb/Cr */
@@ -487,16 +533,18 @@ int orc_encode(const uint8_t* px, int w, int h, int ncomp, ptrdiff_t stride,
                         }
                     EMIT(c);
                 }
+                MCU_DONE();
             }
     }
 #undef EMIT
+#undef MCU_DONE
 
     if (raw_bits) *raw_bits = s.raw_bits;
     /* jpeg_enc.h:1161-1167: pad the last byte with ZERO bits, then EOI */
     if (s.fill > 0) {
         uint8_t* keep = s.raw; uint64_t keepbits = s.raw_bits;
         s.raw = NULL;
-        put_bits(&s, (unsigned)(8 - s.fill), 0);
+        put_bits(&s, (unsigned)(8 - s.fill), restart > 0 ? 0xffu : 0u);   /* restart mode pads every interval with 1-bits */
         s.raw = keep; s.raw_bits = keepbits;
     }
     put16(&s, 0xffd9);

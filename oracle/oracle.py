@@ -36,6 +36,11 @@ def _load_orc():
                                  C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
         L.orc_num_blocks.restype = C.c_size_t
+        L.orc_encode_ex.restype = C.c_int
+        L.orc_encode_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.orc_headers_ex.restype = C.c_size_t
+        L.orc_headers_ex.argtypes = [C.c_int] * 7 + [C.c_void_p, C.c_size_t]
         L.orc_num_blocks.argtypes = [C.c_int] * 4
         L.orc_headers.restype = C.c_size_t
         L.orc_headers.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_size_t]
@@ -88,16 +93,22 @@ def worst_case_bytes(w, h, ncomp, sub=SUB_444):
     return 1024 + num_blocks(w, h, ncomp, sub) * 416 + 16
 
 
-def oracle_encode(img, qmode=QMODE_TJE, quality=3, sub=SUB_444):
-    """Encode [h,w,c] uint8 with the restatement; returns bytes or None if rejected."""
+def restart_interval(ncomp, sub):
+    """MCUs per restart interval of the GPU encoder's opt-in restart mode: one tile (24 blocks)."""
+    return 24 if ncomp == 1 else (4 if sub == SUB_420 else 8)
+
+
+def oracle_encode(img, qmode=QMODE_TJE, quality=3, sub=SUB_444, restart=0):
+    """Encode [h,w,c] uint8 with the restatement; returns bytes or None if rejected.
+    restart > 0: extended restart-interval mode (DRI + RSTn, see jpeg_oracle.c)."""
     img, w, h, nc = _geom(img)
     L = _load_orc()
     cap = 2048 + img.size * 2
     while True:
         out = np.empty(cap, dtype=np.uint8)
         n = C.c_size_t(0)
-        rc = L.orc_encode(img.ctypes.data, w, h, nc, 0, qmode, quality, sub,
-                          out.ctypes.data, cap, C.byref(n), None, None, None, 0, None)
+        rc = L.orc_encode_ex(img.ctypes.data, w, h, nc, 0, qmode, quality, sub, restart,
+                             out.ctypes.data, cap, C.byref(n), None, None, None, 0, None)
         if rc != 1:
             return None
         if n.value <= cap:
@@ -126,9 +137,9 @@ def oracle_stages(img, qmode=QMODE_TJE, quality=3, sub=SUB_444):
                 raw=raw[:(rb.value + 7) // 8].copy(), raw_bits=rb.value)
 
 
-def oracle_headers(w, h, ncomp_out=3, sub=SUB_444, qmode=QMODE_TJE, quality=3):
+def oracle_headers(w, h, ncomp_out=3, sub=SUB_444, qmode=QMODE_TJE, quality=3, restart=0):
     out = np.empty(1024, dtype=np.uint8)
-    n = _load_orc().orc_headers(w, h, ncomp_out, sub, qmode, quality, out.ctypes.data, out.size)
+    n = _load_orc().orc_headers_ex(w, h, ncomp_out, sub, qmode, quality, restart, out.ctypes.data, out.size)
     return out[:n].tobytes()
 
 

@@ -135,12 +135,20 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
 
     const int nc = ncomp;
     launch(n_ctas > (n_tiles + kWarps - 1) / kWarps ? (n_tiles + kWarps - 1) / kWarps : n_ctas, smem_bytes(layout, nc), [&] {
-        const bool deep = n_images < 2;      // the host's rule is n_images < kDeepMaxImages; here: both kernels get exercised
-        if (layout == LAYOUT_444 && nc == 3) { if (deep) encode_tiles_kernel<LAYOUT_444, 3, true>(P, Q); else encode_tiles_kernel<LAYOUT_444, 3, false>(P, Q); }
-        else if (layout == LAYOUT_444 && nc == 4) { if (deep) encode_tiles_kernel<LAYOUT_444, 4, true>(P, Q); else encode_tiles_kernel<LAYOUT_444, 4, false>(P, Q); }
-        else if (layout == LAYOUT_420 && nc == 3) { if (deep) encode_tiles_kernel<LAYOUT_420, 3, true>(P, Q); else encode_tiles_kernel<LAYOUT_420, 3, false>(P, Q); }
-        else if (layout == LAYOUT_420 && nc == 4) { if (deep) encode_tiles_kernel<LAYOUT_420, 4, true>(P, Q); else encode_tiles_kernel<LAYOUT_420, 4, false>(P, Q); }
-        else { if (deep) encode_tiles_kernel<LAYOUT_GRAY, 1, true>(P, Q); else encode_tiles_kernel<LAYOUT_GRAY, 1, false>(P, Q); }
+        // the host's rule: restart images -> kModeRestart, else n_images < kDeepMaxImages -> kModeDeep; here every mode gets exercised
+        const int mode = (flags & kFlagRestart) ? kModeRestart : (n_images < 2 ? kModeDeep : kModePlain);
+#define JG_RUN(L, N)                                                                                   \
+        do {                                                                                           \
+            if (mode == kModeDeep) encode_tiles_kernel<L, N, kModeDeep>(P, Q);                         \
+            else if (mode == kModeRestart) encode_tiles_kernel<L, N, kModeRestart>(P, Q);              \
+            else encode_tiles_kernel<L, N, kModePlain>(P, Q);                                          \
+        } while (0)
+        if (layout == LAYOUT_444 && nc == 3) JG_RUN(LAYOUT_444, 3);
+        else if (layout == LAYOUT_444 && nc == 4) JG_RUN(LAYOUT_444, 4);
+        else if (layout == LAYOUT_420 && nc == 3) JG_RUN(LAYOUT_420, 3);
+        else if (layout == LAYOUT_420 && nc == 4) JG_RUN(LAYOUT_420, 4);
+        else JG_RUN(LAYOUT_GRAY, 1);
+#undef JG_RUN
     });
     if (!error) launch(1, sizeof(StuffSmem), [&] { plan_chunks_kernel(P); });
     if (!error) launch(n_ctas, sizeof(StuffSmem), [&] { stuff_kernel(P); });

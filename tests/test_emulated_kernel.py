@@ -108,3 +108,22 @@ def test_emulated_kernel_load_time_swizzles(w, h, nc, qm, q, sub):
     assert hdr + scans[0] == want
     scans, _, _ = emu_encode(np.ascontiguousarray(swapped[::-1])[None], qm, q, sub, n_ctas=1, flags=1, bottom_up=True)
     assert hdr + scans[0] == want
+
+
+@pytest.mark.parametrize("shape,qm,q,sub,ctas", [((1, 200, 120, 3), 0, 3, 0, 2), ((2, 120, 72, 3), 1, 75, 1, 2), ((1, 200, 130, 1), 1, 85, 0, 1),
+                                                 ((1, 96, 96, 3), 0, 3, 0, 2), ((3, 64, 48, 4), 0, 2, 0, 1), ((1, 8, 8, 3), 0, 3, 0, 1)])
+def test_emulated_kernel_restart_intervals(shape, qm, q, sub, ctas):
+    """Opt-in restart mode: every tile is a restart interval -- DRI header, 1-bit padding,
+    RSTm markers inserted by the stuffing pass, DC prediction from 0.  Bytes == the oracle's restart mode,
+    and the reference's decoder reads the same pixels as from the restart-free stream."""
+    n, w, h, c = shape
+    kind = "noise" if (w, h) == (96, 96) else "photo"       # noise: slow-path tiles + many 0xFF next to markers
+    batch = oracle.synth_batch(n, w, h, c, kind)
+    ri = oracle.restart_interval(c, sub)
+    scans, sizes, status = emu_encode(batch, qm, q, sub, n_ctas=ctas, flags=2)
+    hdr = oracle.oracle_headers(w, h, 1 if c == 1 else 3, sub, qm, q, restart=ri)
+    for i in range(n):
+        want = oracle.oracle_encode(batch[i], qm, q, sub, restart=ri)
+        assert hdr + scans[i] == want and status[i] == 0
+        plain = oracle.oracle_encode(batch[i], qm, q, sub)
+        assert np.array_equal(oracle.ref_decode(want), oracle.ref_decode(plain))

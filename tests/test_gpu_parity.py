@@ -418,8 +418,40 @@ def test_load_time_swizzles(gpu, fixture_pixels):
     b = a[:, :, ::-1].copy()
     files, st = gpu.encode_batch([a, b, a, b], 0, 2, device=0, flags=[0, gpu.FLAG_SWAP_RB, 0, gpu.FLAG_SWAP_RB])
     assert st == [0] * 4 and files[0] == files[1] == files[2] == files[3] == oracle.ref_encode(a, 2)[1]
-    files, st = gpu.encode_batch([a], 0, 2, device=0, flags=2)                  # unknown flag bits are rejected
+    files, st = gpu.encode_batch([a], 0, 2, device=0, flags=4)                  # unknown flag bits are rejected
     assert st == [gpu.ERR_ARG]
+
+
+def test_restart_intervals(gpu):
+    """Opt-in restart mode: DRI + RSTm markers, one interval per tile.  Byte-identical to the
+    oracle's restart mode; the reference's decoder (jpeg_dec.h) and PIL read the same pixels as from the
+    restart-free stream; mixes with ordinary images in one launch; single images (two-iteration kernel),
+    batches, slow-path tiles (noise), device-resident pixels."""
+    from PIL import Image as PILImage
+    R = gpu.FLAG_RESTART
+    cases = [(oracle.synth_image(640, 360, 3), 0, 3, 0), (oracle.synth_image(641, 363, 3), 1, 75, 1), (oracle.synth_image(500, 300, 1), 1, 85, 0),
+             (oracle.synth_image(256, 256, 3, kind="noise"), 0, 3, 0), (oracle.synth_image(1920, 1080, 3), 1, 90, 0), (oracle.synth_image(8, 8, 3), 0, 2, 0)]
+    for img, qm, q, sub in cases:
+        nc = img.shape[2]
+        ri = oracle.restart_interval(nc, sub)
+        want = oracle.oracle_encode(img, qm, q, sub, restart=ri)
+        got = encode_one(gpu, img, qm, q, sub, flags=R, capacity=16 << 20)
+        assert got == want, (img.shape, qm, q, sub)
+        plain = encode_one(gpu, img, qm, q, sub, capacity=16 << 20)
+        assert np.array_equal(oracle.ref_decode(got), oracle.ref_decode(plain))
+        assert np.array_equal(np.asarray(PILImage.open(io.BytesIO(got))), np.asarray(PILImage.open(io.BytesIO(plain))))
+    # a launch that mixes restart and ordinary images, host + device pixels
+    a = oracle.synth_image(320, 200, 3); b = oracle.synth_image(333, 222, 3)
+    imgs = [a, b, a, b, torch.from_numpy(a).cuda()]
+    fl = [0, R, R, 0, R]
+    files, st = gpu.encode_batch(imgs, 1, 75, 1, device=0, flags=fl)
+    assert st == [0] * 5
+    for f, im, r in zip(files, [a, b, a, b, a], fl):
+        assert f == oracle.oracle_encode(im, 1, 75, 1, restart=4 if r else 0)
+    # 64 images in one launch (the plain kernel) against the oracle
+    batch = oracle.synth_batch(64, 200, 136, 3)
+    files, st = gpu.encode_batch([batch[i] for i in range(64)], 0, 2, device=0, flags=R)
+    assert all(f == oracle.oracle_encode(batch[i], 0, 2, 0, restart=8) for i, f in enumerate(files))
 
 
 def test_cpp_facade_folds_flip_and_swap_into_the_encode(gpu, fixture_pixels, tmp_path):

@@ -115,3 +115,11 @@ def test_cpp_facade_bmp_round_trip_without_gpu(tmp_path):
         assert r.returncode == 0, r.stderr
         got = oracle.read_bmp(out.read_bytes())
         assert got is not None and np.array_equal(got, want), ops
+
+
+def test_restart_headers_match_oracle():
+    """JPEG_GPU_FLAG_RESTART adds the DRI segment (one tile of MCUs per interval) in front of SOS."""
+    for (w, h, nc, qm, q, sub) in [(395, 348, 3, 0, 3, 0), (64, 64, 3, 1, 75, 1), (100, 50, 1, 1, 85, 0)]:
+        got = jg.emit_headers(w, h, nc, qm, q, sub, flags=jg.FLAG_RESTART)
+        want = oracle.oracle_headers(w, h, 1 if nc == 1 else 3, sub, qm, q, restart=oracle.restart_interval(nc, sub))
+        assert got == want and len(got) == len(jg.emit_headers(w, h, nc, qm, q, sub)) + 6
