@@ -59,6 +59,10 @@ SYMBOLS = {
     "jpeg_gpu_plan_num_blocks": (C.c_size_t, [C.c_void_p]),
     "jpeg_gpu_plan_attach_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "jpeg_gpu_plan_destroy": (None, [C.c_void_p]),
+    "jpeg_gpu_decode_info": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "jpeg_gpu_decode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "jpeg_gpu_decode_timed": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                        C.POINTER(C.c_float)]),
     "jpeg_gpu_encode_to_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "jpeg_gpu_encode_to_file_at_quality": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "jpeg_gpu_encode_with_func": (C.c_int, [WRITE_FUNC, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -169,6 +173,22 @@ def encode_batch(images, qmode=QMODE_TJE, quality=3, sub=SUB_444, device=-1, cap
     if any(s == ERR_CUDA for s in st):
         raise JpegGpuError("CUDA failure: " + last_error())
     return res, st
+
+
+def decode(jpeg, timed=False):
+    """Decode one JPEG file (bytes) on the GPU; returns uint8 [h,w,3] / [h,w] (and the kernels' device ms if timed)."""
+    L = lib()
+    buf = np.frombuffer(jpeg, dtype=np.uint8)
+    w, h, nc = C.c_int(0), C.c_int(0), C.c_int(0)
+    if not L.jpeg_gpu_decode_info(buf.ctypes.data, buf.size, C.byref(w), C.byref(h), C.byref(nc)):
+        raise JpegGpuError("decode: " + last_error())
+    out = np.empty(w.value * h.value * nc.value, np.uint8)
+    ms = C.c_float(0)
+    ok = L.jpeg_gpu_decode_timed(buf.ctypes.data, buf.size, out.ctypes.data, out.size, C.byref(w), C.byref(h), C.byref(nc), C.byref(ms))
+    if not ok:
+        raise JpegGpuError("decode: " + last_error())
+    img = out.reshape(h.value, w.value, 3) if nc.value == 3 else out.reshape(h.value, w.value)
+    return (img, ms.value) if timed else img
 
 
 class Plan:

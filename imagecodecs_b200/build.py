@@ -70,7 +70,7 @@ def build(force=False, verbose=False, example=True):
                                                    "-c", os.path.join(CSRC, "jpeg_kernel_inst.cu"), "-o", obj]))
     jobs.append((os.path.join(OBJ, "jpeg_stuff.o"), [_nvcc()] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", os.path.join(CSRC, "jpeg_stuff.cu"),
                                                                  "-o", os.path.join(OBJ, "jpeg_stuff.o")]))
-    for src in ("jpeg_gpu_api.cpp", "jpeg_host.cpp", "codecs_jpeg.cpp"):
+    for src in ("jpeg_gpu_api.cpp", "jpeg_host.cpp", "codecs_jpeg.cpp", "jpeg_decode_host.cpp", "jpeg_decode_api.cpp"):
         if not os.path.exists(os.path.join(CSRC, src)):
             continue
         obj = os.path.join(OBJ, src.replace(".cpp", ".o"))

@@ -33,6 +33,8 @@ namespace ImageCodecs
 		pendingFlip_ = pendingSwapBR_ = false;
 		if (ext == ".bmp")
 			readBmp(filepath, &pixels_, w_, h_, d_, type_);
+		else if (ext == ".jpg" || ext == ".jpeg")
+			readJpg(filepath, &pixels_, w_, h_, d_, type_);
 		else
 			throw std::invalid_argument("Cannot parse filetype");
 
@@ -125,6 +127,33 @@ namespace ImageCodecs
 		h = biHeight;
 		w = biWidth;
 		d = 3;
+	}
+
+	// codecs.cpp:821-849 with the GPU decoder where the reference calls njDecode / njGetImage; like the
+	// reference, d is 3 whatever the file holds, so only colour files are read correctly
+	void Image::readJpg(std::string filepath, unsigned char** pixels, int& w, int& h, int& d, Type&)
+	{
+		FILE* f = fopen(filepath.c_str(), "rb");
+		if (!f)
+			throw std::runtime_error("Error decoding the input file.\n");
+		fseek(f, 0, SEEK_END);
+		long size = ftell(f);
+		fseek(f, 0, SEEK_SET);
+		std::vector<unsigned char> file((size_t)std::max(size, 0L));
+		size = (long)fread(file.data(), 1, file.size(), f);
+		fclose(f);
+
+		int nc = 0;
+		if (!jpeg_gpu_decode_info(file.data(), (size_t)size, &w, &h, &nc))
+			throw std::runtime_error("Error decoding the input file.\n");
+		d = 3;
+		*pixels = new unsigned char[(size_t)w * h * 3];
+		if (!jpeg_gpu_decode(file.data(), (size_t)size, *pixels, (size_t)w * h * 3, &w, &h, &nc))
+		{
+			delete[] *pixels;
+			*pixels = nullptr;
+			throw std::runtime_error("Error decoding the input file.\n");
+		}
 	}
 
 	// 24-bit BITMAPINFOHEADER, rows bottom-up, the reference's own row padding of (w % 4) bytes and

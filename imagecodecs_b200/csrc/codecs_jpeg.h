@@ -47,6 +47,7 @@ namespace ImageCodecs
 
 		// codecs per filetype (the JPEG write path and its BMP feeder):
 		void readBmp(std::string filename, unsigned char** pixels, int& w, int& h, int& d, Type& type);
+		void readJpg(std::string filename, unsigned char** pixels, int& w, int& h, int& d, Type& type);
 		void writeBmp(std::string filename, unsigned char* pixels, int& w, int& h, int& d, Type& type);
 		void writeJpg(std::string filename, unsigned char* pixels, int& w, int& h, int& d, Type& type);
 

@@ -1,0 +1,308 @@
+// jpeg_decode.cuh -- device half of the decoder (see jpeg_decode.h).  Every stage is written as a
+// per-thread function of one work item, so that the CPU test harness (JG_EMULATE) can run the very
+// same code in plain loops; the __global__ wrappers below only hand out indices.
+//
+//   decode_interval   one restart interval: Huffman decode (njGetVLC :643-656, njDecodeBlock :658-672
+//                     without its IDCT) into quantised coefficients, natural order, int16
+//   idct_block        dequantise + njRowIDCT x 8 + njColIDCT x 8 (:350-442) -> 8x8 bytes of the plane
+//   upsample_h / _v   njUpsampleH / njUpsampleV (:736-790), one output pixel per thread
+//   to_rgb / to_gray  the tail of njConvert (:817-866)
+#pragma once
+#include "jpeg_device.h"
+
+namespace jd {
+
+struct DevComponent {
+    int ssx, ssy, bw;                 // blocks per MCU in x / y, blocks per row of the padded plane
+    int dctab, actab;                 // rows of the VLC table
+    int stride;                       // bytes per row of the padded plane
+    unsigned long long coef_off;      // first block in `coef`
+    unsigned long long plane_off;     // first byte in `planes`
+    int dq[64];                       // dequantisers in NATURAL order: dq[njZZ[k]] = qtab[k] (:666)
+};
+
+struct DevParams {
+    const uint8_t* data;              // the whole file
+    const uint32_t* interval_off;     // [n_intervals + 1]
+    int n_intervals, rstinterval, n_mcus, mbwidth, ncomp;
+    const uint16_t* vlc;              // [4][65536]
+    int16_t* coef;                    // [n_blocks][64], zeroed
+    uint8_t* planes;
+    unsigned* error;
+    DevComponent comp[3];
+};
+
+JG_DEV int zz_nat(int k)   // njZZ (jpeg_dec.h:332-337): natural index of zigzag position k
+{
+    const unsigned char t[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21,
+                                 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54,
+                                 47, 55, 62, 63};
+    return t[k];
+}
+
+// MSB-first bit reader over [p, end) with the byte rules of njShowBits (:447-482): FF 00 and FF FF
+// yield one FF, past the end the stream continues with FF bytes.
+struct BitReader {
+    const uint8_t* p;
+    const uint8_t* end;
+    unsigned long long buf;
+    int bits;
+};
+JG_DEV void refill(BitReader& r)
+{
+    while (r.bits <= 56) {
+        unsigned b = 0xFF;
+        if (r.p < r.end) {
+            b = *r.p++;
+            if (b == 0xFF && r.p < r.end) ++r.p;        // the stuffed 00 (or a fill FF): consumed, not data
+        }
+        r.buf = (r.buf << 8) | b;
+        r.bits += 8;
+    }
+}
+JG_DEV unsigned show(BitReader& r, int n)
+{
+    if (r.bits < n) refill(r);
+    return (unsigned)(r.buf >> (r.bits - n)) & ((1u << n) - 1u);
+}
+JG_DEV void skip(BitReader& r, int n) { r.bits -= n; }
+
+// njGetVLC (:643-656)
+JG_DEV int get_vlc(BitReader& r, const uint16_t* tab, unsigned* code_out, bool* bad)
+{
+    const unsigned e = tab[show(r, 16)];
+    const int len = (int)(e >> 8);
+    if (!len) { *bad = true; return 0; }
+    skip(r, len);
+    const unsigned code = e & 0xFFu;
+    *code_out = code;
+    const int nb = (int)(code & 15u);
+    if (!nb) return 0;
+    int v = (int)show(r, nb);
+    skip(r, nb);
+    if (v < (1 << (nb - 1))) v += (int)((0xFFFFFFFFu << nb) + 1u);
+    return v;
+}
+
+JG_DEV void decode_interval(const DevParams& P, int iv)
+{
+    BitReader r;
+    r.p = P.data + P.interval_off[iv];
+    r.end = P.data + (iv + 1 < P.n_intervals ? P.interval_off[iv + 1] - 2u : P.interval_off[P.n_intervals]);   // minus the RSTm marker
+    r.buf = 0; r.bits = 0;
+    int dcpred[3] = {0, 0, 0};
+    const int m0 = P.rstinterval ? iv * P.rstinterval : 0;
+    const int m1 = P.rstinterval ? (m0 + P.rstinterval < P.n_mcus ? m0 + P.rstinterval : P.n_mcus) : P.n_mcus;
+    bool bad = false;
+    int mby = m0 / P.mbwidth, mbx = m0 - mby * P.mbwidth;
+    for (int m = m0; m < m1 && !bad; ++m) {
+        for (int c = 0; c < P.ncomp && !bad; ++c) {
+            const DevComponent& K = P.comp[c];
+            const uint16_t* dct = P.vlc + (size_t)K.dctab * 65536, *act = P.vlc + (size_t)K.actab * 65536;
+            for (int sby = 0; sby < K.ssy && !bad; ++sby)
+                for (int sbx = 0; sbx < K.ssx && !bad; ++sbx) {
+                    int16_t* blk = P.coef + (K.coef_off + (unsigned long long)(mby * K.ssy + sby) * K.bw + (mbx * K.ssx + sbx)) * 64ull;
+                    unsigned code = 0;
+                    dcpred[c] += get_vlc(r, dct, &code, &bad);
+                    blk[0] = (int16_t)dcpred[c];
+                    int coef = 0;
+                    do {
+                        const int v = get_vlc(r, act, &code, &bad);
+                        if (bad || !code) break;                                  // EOB
+                        if (!(code & 0x0F) && code != 0xF0) { bad = true; break; }
+                        coef += (int)(code >> 4) + 1;
+                        if (coef > 63) { bad = true; break; }
+                        blk[zz_nat(coef)] = (int16_t)v;
+                    } while (coef < 63);
+                }
+        }
+        if (++mbx >= P.mbwidth) { mbx = 0; ++mby; }
+    }
+    if (bad) *P.error = 5u;     // NJ_SYNTAX_ERROR
+}
+
+JG_DEV unsigned char clip8(int x) { return x < 0 ? 0 : (x > 0xFF ? 0xFF : (unsigned char)x); }   // njClip (:339-341)
+
+#define JD_W1 2841
+#define JD_W2 2676
+#define JD_W3 2408
+#define JD_W5 1609
+#define JD_W6 1108
+#define JD_W7 565
+
+JG_DEV void row_idct(int* blk)   // njRowIDCT (:350-396)
+{
+    int x0, x1, x2, x3, x4, x5, x6, x7, x8;
+    if (!((x1 = blk[4] << 11) | (x2 = blk[6]) | (x3 = blk[2]) | (x4 = blk[1]) | (x5 = blk[7]) | (x6 = blk[5]) | (x7 = blk[3]))) {
+        blk[0] = blk[1] = blk[2] = blk[3] = blk[4] = blk[5] = blk[6] = blk[7] = blk[0] << 3;
+        return;
+    }
+    x0 = (blk[0] << 11) + 128;
+    x8 = JD_W7 * (x4 + x5);
+    x4 = x8 + (JD_W1 - JD_W7) * x4;
+    x5 = x8 - (JD_W1 + JD_W7) * x5;
+    x8 = JD_W3 * (x6 + x7);
+    x6 = x8 - (JD_W3 - JD_W5) * x6;
+    x7 = x8 - (JD_W3 + JD_W5) * x7;
+    x8 = x0 + x1;
+    x0 -= x1;
+    x1 = JD_W6 * (x3 + x2);
+    x2 = x1 - (JD_W2 + JD_W6) * x2;
+    x3 = x1 + (JD_W2 - JD_W6) * x3;
+    x1 = x4 + x6;
+    x4 -= x6;
+    x6 = x5 + x7;
+    x5 -= x7;
+    x7 = x8 + x3;
+    x8 -= x3;
+    x3 = x0 + x2;
+    x0 -= x2;
+    x2 = (181 * (x4 + x5) + 128) >> 8;
+    x4 = (181 * (x4 - x5) + 128) >> 8;
+    blk[0] = (x7 + x1) >> 8;
+    blk[1] = (x3 + x2) >> 8;
+    blk[2] = (x0 + x4) >> 8;
+    blk[3] = (x8 + x6) >> 8;
+    blk[4] = (x8 - x6) >> 8;
+    blk[5] = (x0 - x4) >> 8;
+    blk[6] = (x3 - x2) >> 8;
+    blk[7] = (x7 - x1) >> 8;
+}
+
+JG_DEV void col_idct(const int* blk, unsigned char* out, int stride)   // njColIDCT (:398-442)
+{
+    int x0, x1, x2, x3, x4, x5, x6, x7, x8;
+    if (!((x1 = blk[8 * 4] << 8) | (x2 = blk[8 * 6]) | (x3 = blk[8 * 2]) | (x4 = blk[8 * 1]) | (x5 = blk[8 * 7]) | (x6 = blk[8 * 5]) | (x7 = blk[8 * 3]))) {
+        x1 = clip8(((blk[0] + 32) >> 6) + 128);
+        for (x0 = 8; x0; --x0) { *out = (unsigned char)x1; out += stride; }
+        return;
+    }
+    x0 = (blk[0] << 8) + 8192;
+    x8 = JD_W7 * (x4 + x5) + 4;
+    x4 = (x8 + (JD_W1 - JD_W7) * x4) >> 3;
+    x5 = (x8 - (JD_W1 + JD_W7) * x5) >> 3;
+    x8 = JD_W3 * (x6 + x7) + 4;
+    x6 = (x8 - (JD_W3 - JD_W5) * x6) >> 3;
+    x7 = (x8 - (JD_W3 + JD_W5) * x7) >> 3;
+    x8 = x0 + x1;
+    x0 -= x1;
+    x1 = JD_W6 * (x3 + x2) + 4;
+    x2 = (x1 - (JD_W2 + JD_W6) * x2) >> 3;
+    x3 = (x1 + (JD_W2 - JD_W6) * x3) >> 3;
+    x1 = x4 + x6;
+    x4 -= x6;
+    x6 = x5 + x7;
+    x5 -= x7;
+    x7 = x8 + x3;
+    x8 -= x3;
+    x3 = x0 + x2;
+    x0 -= x2;
+    x2 = (181 * (x4 + x5) + 128) >> 8;
+    x4 = (181 * (x4 - x5) + 128) >> 8;
+    *out = clip8(((x7 + x1) >> 14) + 128); out += stride;
+    *out = clip8(((x3 + x2) >> 14) + 128); out += stride;
+    *out = clip8(((x0 + x4) >> 14) + 128); out += stride;
+    *out = clip8(((x8 + x6) >> 14) + 128); out += stride;
+    *out = clip8(((x8 - x6) >> 14) + 128); out += stride;
+    *out = clip8(((x0 - x4) >> 14) + 128); out += stride;
+    *out = clip8(((x3 - x2) >> 14) + 128); out += stride;
+    *out = clip8(((x7 - x1) >> 14) + 128);
+}
+
+// block b (raster index in its component's padded plane) of component c
+JG_DEV void idct_block(const DevParams& P, int c, unsigned long long b)
+{
+    const DevComponent& K = P.comp[c];
+    const int16_t* src = P.coef + (K.coef_off + b) * 64ull;
+    int blk[64];
+    for (int i = 0; i < 64; ++i) blk[i] = (int)src[i] * K.dq[i];
+    for (int r = 0; r < 64; r += 8) row_idct(blk + r);
+    const unsigned long long by = b / (unsigned long long)K.bw, bx = b - by * (unsigned long long)K.bw;
+    unsigned char* out = P.planes + K.plane_off + ((by * (unsigned long long)K.stride + bx) << 3);
+    for (int col = 0; col < 8; ++col) col_idct(blk + col, out + col, K.stride);
+}
+
+// ---- chroma upsampling (jpeg_dec.h:722-790) --------------------------------------------------
+#define JD_CF(x) clip8(((x) + 64) >> 7)
+
+// output pixel (y, ox) of njUpsampleH: in = plane of width w (row pitch s), out has width 2w.
+// The last three outputs read lin[-1..-3] AFTER lin += stride (:753-756): the end of the padded row.
+JG_DEV unsigned char upsample_h(const unsigned char* in, int w, int s, int y, int ox)
+{
+    const unsigned char* l = in + (size_t)y * s;
+    if (ox == 0) return JD_CF(139 * l[0] + -11 * l[1]);
+    if (ox == 1) return JD_CF(104 * l[0] + 27 * l[1] + -3 * l[2]);
+    if (ox == 2) return JD_CF(28 * l[0] + 109 * l[1] + -9 * l[2]);
+    const int W2 = w << 1;
+    if (ox >= W2 - 3) {
+        const unsigned char* t = l + s;
+        if (ox == W2 - 3) return JD_CF(28 * t[-1] + 109 * t[-2] + -9 * t[-3]);
+        if (ox == W2 - 2) return JD_CF(104 * t[-1] + 27 * t[-2] + -3 * t[-3]);
+        return JD_CF(139 * t[-1] + -11 * t[-2]);
+    }
+    if (ox & 1) { const int x = (ox - 3) >> 1; return JD_CF(-9 * l[x] + 111 * l[x + 1] + 29 * l[x + 2] + -3 * l[x + 3]); }
+    const int x = (ox - 4) >> 1;
+    return JD_CF(-3 * l[x] + 29 * l[x + 1] + 111 * l[x + 2] + -9 * l[x + 3]);
+}
+
+// output pixel (oy, x) of njUpsampleV: in = plane of height h (row pitch s), out has height 2h
+JG_DEV unsigned char upsample_v(const unsigned char* in, int h, int s, int oy, int x)
+{
+    const unsigned char* c = in + x;
+    auto r = [&](int row) { return (int)c[(size_t)row * s]; };
+    if (oy == 0) return JD_CF(139 * r(0) + -11 * r(1));
+    if (oy == 1) return JD_CF(104 * r(0) + 27 * r(1) + -3 * r(2));
+    if (oy == 2) return JD_CF(28 * r(0) + 109 * r(1) + -9 * r(2));
+    const int H2 = h << 1;
+    if (oy == H2 - 3) return JD_CF(28 * r(h - 1) + 109 * r(h - 2) + -9 * r(h - 3));
+    if (oy == H2 - 2) return JD_CF(104 * r(h - 1) + 27 * r(h - 2) + -3 * r(h - 3));
+    if (oy == H2 - 1) return JD_CF(139 * r(h - 1) + -11 * r(h - 2));
+    if (oy & 1) { const int i = (oy - 3) >> 1; return JD_CF(-9 * r(i) + 111 * r(i + 1) + 29 * r(i + 2) + -3 * r(i + 3)); }
+    const int i = (oy - 4) >> 1;
+    return JD_CF(-3 * r(i) + 29 * r(i + 1) + 111 * r(i + 2) + -9 * r(i + 3));
+}
+
+// njConvert's RGB loop (:838-852)
+JG_DEV void to_rgb(unsigned char* rgb, int yv, int cbv, int crv)
+{
+    const int y = yv << 8, cb = cbv - 128, cr = crv - 128;
+    rgb[0] = clip8((y + 359 * cr + 128) >> 8);
+    rgb[1] = clip8((y - 88 * cb - 183 * cr + 128) >> 8);
+    rgb[2] = clip8((y + 454 * cb + 128) >> 8);
+}
+
+#if !defined(JG_EMULATE)
+__global__ void decode_intervals_kernel(const __grid_constant__ DevParams P)
+{
+    const int iv = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (iv < P.n_intervals) decode_interval(P, iv);
+}
+__global__ void idct_kernel(const __grid_constant__ DevParams P, int c, unsigned long long n_blocks)
+{
+    const unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_blocks) idct_block(P, c, b);
+}
+__global__ void upsample_h_kernel(const unsigned char* in, unsigned char* out, int w, int h, int s)
+{
+    const int ox = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y;
+    if (ox < 2 * w && y < h) out[(size_t)y * (2 * w) + ox] = upsample_h(in, w, s, y, ox);
+}
+__global__ void upsample_v_kernel(const unsigned char* in, unsigned char* out, int w, int h, int s)
+{
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), oy = (int)blockIdx.y;
+    if (x < w && oy < 2 * h) out[(size_t)oy * w + x] = upsample_v(in, h, s, oy, x);
+}
+__global__ void to_rgb_kernel(const unsigned char* py, int sy, const unsigned char* pcb, int scb, const unsigned char* pcr, int scr,
+                              unsigned char* rgb, int w, int h)
+{
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y;
+    if (x < w && y < h) to_rgb(rgb + ((size_t)y * w + x) * 3, py[(size_t)y * sy + x], pcb[(size_t)y * scb + x], pcr[(size_t)y * scr + x]);
+}
+__global__ void to_gray_kernel(const unsigned char* p, int s, unsigned char* out, int w, int h)
+{
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y;
+    if (x < w && y < h) out[(size_t)y * w + x] = p[(size_t)y * s + x];
+}
+#endif
+
+}  // namespace jd

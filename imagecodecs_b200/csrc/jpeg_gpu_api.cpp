@@ -549,6 +549,16 @@ void item_result(jpeg_gpu_plan* p, int i, size_t* file_size, int* status)
 // =========================================================================================
 // C ABI
 // =========================================================================================
+// hooks for jpeg_decode_api.cpp
+namespace jg {
+int cuda_device_of(int index)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return index >= 0 && index < (int)g_devices.size() ? g_devices[index].id : 0;
+}
+void set_error_text(const char* text) { set_error("%s", text); }
+}  // namespace jg
+
 extern "C" {
 
 int jpeg_gpu_init(const int* device_ids, int n_devices)

@@ -179,6 +179,20 @@ JPEG_GPU_API int jpeg_gpu_encode_with_func(jpeg_gpu_write_func* func, void* cont
                                            const int width, const int height, const int num_components,
                                            const unsigned char* src_data);
 
+/* ---- decode: the step on the other side of the format --------------- */
+/* What Image::readJpg does with NanoJPEG (codecs.cpp:821-849: njInit, njDecode, njGetWidth / njGetHeight,
+ * njGetImage; jpeg_dec.h:880-908), on the GPU: baseline JPEG, 1 or 3 components, power-of-two sampling
+ * factors.  The pixels (RGB interleaved, or 8-bit gray) are bit-identical to NanoJPEG's, including its
+ * chroma upsampling filter.  Restart intervals (JPEG_GPU_FLAG_RESTART on the encode side) are decoded in
+ * parallel, one thread each; a stream without them is entropy-decoded by a single thread (correct, slow).
+ * Return 1 on success, 0 on failure (jpeg_gpu_last_error names the nj_result_t). */
+JPEG_GPU_API int jpeg_gpu_decode_info(const uint8_t* jpeg, size_t size, int* width, int* height, int* ncomp);
+JPEG_GPU_API int jpeg_gpu_decode(const uint8_t* jpeg, size_t size, uint8_t* pixels, size_t capacity,
+                                 int* width, int* height, int* ncomp);
+/* the same; *kernel_ms receives the device time of the kernels (CUDA events), copies excluded */
+JPEG_GPU_API int jpeg_gpu_decode_timed(const uint8_t* jpeg, size_t size, uint8_t* pixels, size_t capacity,
+                                       int* width, int* height, int* ncomp, float* kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

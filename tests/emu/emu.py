@@ -13,6 +13,9 @@ _SRC = [os.path.join(_HERE, "emu_driver.cpp"), os.path.join(_HERE, "cuda_emu.h")
         os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_kernel.cuh"),
         os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_device.h"),
         os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_tables.h"),
+        os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_decode.cuh"),
+        os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_decode.h"),
+        os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_decode_host.cpp"),
         os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_host.cpp")]
 _lib = None
 
@@ -22,7 +25,7 @@ def build():
         return
     csrc = os.path.join(_ROOT, "imagecodecs_b200", "csrc")
     subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
-                    "-I" + _HERE, "-I" + csrc, "-o", _SO, _SRC[0], _SRC[-1]], check=True)
+                    "-I" + _HERE, "-I" + csrc, "-o", _SO, _SRC[0], _SRC[-1], _SRC[-2]], check=True)
 
 
 def _load():
@@ -37,6 +40,24 @@ def _load():
         L.emu_ticket_map.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
+
+
+def emu_decode(jpeg):
+    """Decode with the product's decoder source run on the CPU (tests only). Returns uint8 [h,w,3] / [h,w] or the nj error code."""
+    L = _load()
+    L.emu_decode.restype = C.c_int
+    L.emu_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    buf = np.frombuffer(jpeg, dtype=np.uint8)
+    w, h, nc = C.c_int(0), C.c_int(0), C.c_int(0)
+    out = np.empty(1, np.uint8)
+    rc = L.emu_decode(buf.ctypes.data, buf.size, out.ctypes.data, 0, C.byref(w), C.byref(h), C.byref(nc))
+    if rc != -1:
+        return rc
+    out = np.empty(w.value * h.value * nc.value, np.uint8)
+    rc = L.emu_decode(buf.ctypes.data, buf.size, out.ctypes.data, out.size, C.byref(w), C.byref(h), C.byref(nc))
+    if rc != 0:
+        return rc
+    return out.reshape(h.value, w.value, 3) if nc.value == 3 else out.reshape(h.value, w.value)
 
 
 def emu_ticket_map(tiles, force_schedule=False):

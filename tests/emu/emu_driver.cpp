@@ -3,6 +3,8 @@
 // exposes one C function the CPU test-suite calls.  See cuda_emu.h for why this exists.
 #define JG_EMULATE 1
 #include "jpeg_stuff.cuh"
+#include "jpeg_decode.cuh"
+#include "jpeg_decode.h"
 
 #include <stdlib.h>
 
@@ -177,5 +179,60 @@ int emu_ticket_map(const int* tiles, int n_images, int force_schedule, unsigned*
     P.sched = sched.data();
     for (int v = 0; v < total; ++v) out_g[v] = tile_of_ticket(P, (unsigned)v, out_img[v]);
     return total;
+}
+
+// The decoder's per-item device functions (jpeg_decode.cuh) run in plain loops: same code as on the GPU,
+// where one thread executes one call.  Returns the nj_result_t; out receives RGB / gray pixels.
+int emu_decode(const uint8_t* jpeg, size_t size, uint8_t* out, size_t cap, int* w, int* h, int* ncomp)
+{
+    jd::Info I;
+    const int rc = jd::parse(jpeg, size, &I);
+    if (rc != jd::kOk) return rc;
+    *w = I.width; *h = I.height; *ncomp = I.ncomp;
+    if (cap < (size_t)I.width * I.height * I.ncomp) return -1;
+    std::vector<int16_t> coef(I.n_blocks * 64, 0);
+    std::vector<uint8_t> planes(I.plane_bytes + 16, 0);
+    unsigned err = 0;
+    jd::DevParams P;
+    memset(&P, 0, sizeof P);
+    P.data = jpeg; P.interval_off = I.interval_off.data(); P.n_intervals = (int)I.interval_off.size() - 1;
+    P.rstinterval = I.rstinterval; P.n_mcus = I.n_mcus; P.mbwidth = I.mbwidth; P.ncomp = I.ncomp;
+    P.vlc = I.vlc.data(); P.coef = coef.data(); P.planes = planes.data(); P.error = &err;
+    for (int c = 0; c < I.ncomp; ++c) {
+        const jd::Component& k = I.comp[c];
+        jd::DevComponent& d = P.comp[c];
+        d.ssx = k.ssx; d.ssy = k.ssy; d.bw = k.bw; d.dctab = k.dctabsel; d.actab = k.actabsel; d.stride = k.stride;
+        d.coef_off = k.coef_off; d.plane_off = k.plane_off;
+        for (int i = 0; i < 64; ++i) d.dq[jd::zz_nat(i)] = I.qtab[k.qtsel][i];
+    }
+    for (int iv = 0; iv < P.n_intervals; ++iv) jd::decode_interval(P, iv);
+    if (err) return (int)err;
+    for (int c = 0; c < I.ncomp; ++c)
+        for (unsigned long long b = 0; b < (unsigned long long)I.comp[c].bw * I.comp[c].bh; ++b) jd::idct_block(P, c, b);
+    std::vector<std::vector<uint8_t>> tmp;
+    const uint8_t* plane[3]; int pw[3], ph[3], ps[3];
+    for (int c = 0; c < I.ncomp; ++c) {
+        plane[c] = planes.data() + I.comp[c].plane_off; pw[c] = I.comp[c].width; ph[c] = I.comp[c].height; ps[c] = I.comp[c].stride;
+        while (pw[c] < I.width || ph[c] < I.height) {
+            if (pw[c] < I.width) {
+                tmp.emplace_back((size_t)pw[c] * ph[c] * 2);
+                uint8_t* o = tmp.back().data();
+                for (int y = 0; y < ph[c]; ++y) for (int ox = 0; ox < 2 * pw[c]; ++ox) o[(size_t)y * 2 * pw[c] + ox] = jd::upsample_h(plane[c], pw[c], ps[c], y, ox);
+                plane[c] = o; pw[c] <<= 1; ps[c] = pw[c];
+            }
+            if (ph[c] < I.height) {
+                tmp.emplace_back((size_t)pw[c] * ph[c] * 2);
+                uint8_t* o = tmp.back().data();
+                for (int oy = 0; oy < 2 * ph[c]; ++oy) for (int x = 0; x < pw[c]; ++x) o[(size_t)oy * pw[c] + x] = jd::upsample_v(plane[c], ph[c], ps[c], oy, x);
+                plane[c] = o; ph[c] <<= 1; ps[c] = pw[c];
+            }
+        }
+    }
+    for (int y = 0; y < I.height; ++y)
+        for (int x = 0; x < I.width; ++x) {
+            if (I.ncomp == 3) jd::to_rgb(out + ((size_t)y * I.width + x) * 3, plane[0][(size_t)y * ps[0] + x], plane[1][(size_t)y * ps[1] + x], plane[2][(size_t)y * ps[2] + x]);
+            else out[(size_t)y * I.width + x] = plane[0][(size_t)y * ps[0] + x];
+        }
+    return 0;
 }
 }

@@ -33,6 +33,9 @@ def main():
     testbmp = oracle.read_bmp(open(os.path.join(REF, "test.bmp"), "rb").read())
     testjpg = oracle.ref_decode(open(os.path.join(REF, "test.jpg"), "rb").read())
     np.savez_compressed(os.path.join(HERE, "fixture_pixels.npz"), cat_bgr=cat, testjpg=testjpg, testbmp_bgr=testbmp)
+    # the decoder's input fixture: the reference's own data/test.jpg (13 KB, 4:2:0), whose njDecode output is `testjpg` above
+    import shutil
+    shutil.copyfile(os.path.join(REF, "test.jpg"), os.path.join(HERE, "data_test.jpg"))
 
     kat = []
 

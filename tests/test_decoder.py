@@ -1,0 +1,54 @@
+"""The decoder: the product's decoder SOURCE (jpeg_decode.cuh / jpeg_decode_host.cpp) run on the
+CPU, where one loop iteration is what one GPU thread executes, against the reference's NanoJPEG (oracle/_ref)
+and the committed fixture.  Bit-exact pixels are the bar.  The GPU run of the same code is in test_gpu_parity.py."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from tests.emu.emu import emu_decode
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_reference_fixture_decodes_to_the_committed_pixels():
+    """data/test.jpg of the reference (what tests.cpp reads first) -> exactly njDecode's pixels (tests/golden/fixture_pixels.npz)."""
+    jpeg = open(os.path.join(GOLDEN, "data_test.jpg"), "rb").read()
+    want = np.load(os.path.join(GOLDEN, "fixture_pixels.npz"))["testjpg"]
+    got = emu_decode(jpeg)
+    assert isinstance(got, np.ndarray) and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("w,h,nc,qm,q,sub,rst", [(200, 120, 3, 0, 3, 0, 0), (200, 120, 3, 1, 75, 1, 0), (130, 70, 1, 1, 85, 0, 0),
+                                                 (201, 123, 3, 1, 75, 1, 4), (64, 64, 3, 0, 2, 0, 8), (17, 13, 3, 0, 1, 0, 0),
+                                                 (333, 77, 3, 1, 50, 1, 4), (96, 96, 1, 1, 90, 0, 24), (8, 8, 3, 0, 3, 0, 0)])
+def test_decodes_our_own_streams_like_the_reference_decoder(w, h, nc, qm, q, sub, rst):
+    img = oracle.synth_image(w, h, nc, kind="noise" if (w, h) == (64, 64) else "photo")
+    jpeg = oracle.oracle_encode(img, qm, q, sub, restart=rst)
+    want = oracle.ref_decode(jpeg)
+    got = emu_decode(jpeg)
+    assert want is not None and isinstance(got, np.ndarray) and np.array_equal(got, want)
+
+
+def test_decodes_other_encoders_files():
+    """Files of another encoder (PIL / libjpeg): 4:4:4, 4:2:2, 4:2:0, gray, custom Huffman tables, restart-free."""
+    from PIL import Image
+    rgb = Image.fromarray(oracle.synth_image(211, 97, 3))
+    gray = Image.fromarray(oracle.synth_image(150, 61, 1)[:, :, 0])
+    for im, kw in [(rgb, dict(subsampling=0)), (rgb, dict(subsampling=1)), (rgb, dict(subsampling=2)), (rgb, dict(subsampling=2, quality=30, optimize=True)),
+                   (gray, dict(quality=85)), (gray, dict(quality=95, optimize=True))]:
+        b = io.BytesIO(); im.save(b, "JPEG", **kw)
+        want = oracle.ref_decode(b.getvalue())
+        got = emu_decode(b.getvalue())
+        assert want is not None and isinstance(got, np.ndarray) and np.array_equal(got, want), kw
+
+
+def test_rejects_what_the_reference_rejects():
+    from PIL import Image
+    assert emu_decode(b"\x00\x01\x02\x03") == 1                                    # NJ_NO_JPEG
+    b = io.BytesIO(); Image.fromarray(oracle.synth_image(64, 48, 3)).save(b, "JPEG", progressive=True)
+    assert oracle.ref_decode(b.getvalue()) is None and emu_decode(b.getvalue()) == 2    # progressive: NJ_UNSUPPORTED
+    good = oracle.oracle_encode(oracle.synth_image(40, 40, 3), 0, 3, 0)
+    assert emu_decode(good[:300]) == 5                                             # truncated in the tables: NJ_SYNTAX_ERROR
