@@ -32,6 +32,14 @@ class Output(C.Structure):         # jpeg_gpu_output
     _fields_ = [("data", C.c_void_p), ("capacity", C.c_size_t), ("size", C.c_size_t), ("status", C.c_int)]
 
 
+class Stream(C.Structure):         # jpeg_gpu_stream
+    _fields_ = [("data", C.c_void_p), ("size", C.c_size_t)]
+
+
+class Decoded(C.Structure):        # jpeg_gpu_decoded
+    _fields_ = [("pixels", C.c_void_p), ("capacity", C.c_size_t), ("width", C.c_int), ("height", C.c_int), ("ncomp", C.c_int), ("status", C.c_int)]
+
+
 class BatchOpts(C.Structure):      # jpeg_gpu_batch_opts
     _fields_ = [("device", C.c_int), ("outputs_on_device", C.c_int), ("stream", C.c_void_p),
                 ("debug_window_words", C.c_int)]
@@ -61,6 +69,7 @@ SYMBOLS = {
     "jpeg_gpu_plan_destroy": (None, [C.c_void_p]),
     "jpeg_gpu_decode_info": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "jpeg_gpu_decode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "jpeg_gpu_decode_batch": (C.c_int, [C.POINTER(Stream), C.c_int, C.POINTER(Decoded), C.c_int, C.POINTER(C.c_float)]),
     "jpeg_gpu_decode_timed": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                         C.POINTER(C.c_float)]),
     "jpeg_gpu_encode_to_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -189,6 +198,32 @@ def decode(jpeg, timed=False):
         raise JpegGpuError("decode: " + last_error())
     img = out.reshape(h.value, w.value, 3) if nc.value == 3 else out.reshape(h.value, w.value)
     return (img, ms.value) if timed else img
+
+
+def decode_batch(files, timed=False):
+    """Decode a list of JPEG files (bytes) in one call; returns list of uint8 arrays (None where a file failed)."""
+    L = lib()
+    n = len(files)
+    bufs = [np.frombuffer(f, dtype=np.uint8) for f in files]
+    ins = (Stream * n)(*[Stream(b.ctypes.data, b.size) for b in bufs])
+    outs = (Decoded * n)()
+    pix = []
+    w, h, nc = C.c_int(0), C.c_int(0), C.c_int(0)
+    for i, b in enumerate(bufs):
+        ok = L.jpeg_gpu_decode_info(b.ctypes.data, b.size, C.byref(w), C.byref(h), C.byref(nc))
+        a = np.empty(w.value * h.value * nc.value if ok else 1, np.uint8)
+        pix.append(a)
+        outs[i] = Decoded(a.ctypes.data, a.size if ok else 0, 0, 0, 0, 0)
+    ms = C.c_float(0)
+    L.jpeg_gpu_decode_batch(ins, n, outs, 0, C.byref(ms))
+    res = []
+    for i in range(n):
+        o = outs[i]
+        if o.status != OK:
+            res.append(None)
+        else:
+            res.append(pix[i].reshape(o.height, o.width, 3) if o.ncomp == 3 else pix[i].reshape(o.height, o.width))
+    return (res, ms.value) if timed else res
 
 
 class Plan:

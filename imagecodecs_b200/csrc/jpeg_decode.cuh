@@ -12,10 +12,16 @@
 
 namespace jd {
 
+using jg::bswap32;
+using jg::ldg_u32;
+using jg::ldg_u8;
+using jg::v_cmpeq4;
+
 struct DevComponent {
     int ssx, ssy, bw;                 // blocks per MCU in x / y, blocks per row of the padded plane
     int dctab, actab;                 // rows of the VLC table
     int stride;                       // bytes per row of the padded plane
+    unsigned long long n_blocks;      // blocks of the padded plane
     unsigned long long coef_off;      // first block in `coef`
     unsigned long long plane_off;     // first byte in `planes`
     int dq[64];                       // dequantisers in NATURAL order: dq[njZZ[k]] = qtab[k] (:666)
@@ -41,7 +47,8 @@ JG_DEV int zz_nat(int k)   // njZZ (jpeg_dec.h:332-337): natural index of zigzag
 }
 
 // MSB-first bit reader over [p, end) with the byte rules of njShowBits (:447-482): FF 00 and FF FF
-// yield one FF, past the end the stream continues with FF bytes.
+// yield one FF, past the end the stream continues with FF bytes.  Four bytes per load where the
+// pointer is aligned and none of them is FF (the common case); byte by byte otherwise.
 struct BitReader {
     const uint8_t* p;
     const uint8_t* end;
@@ -51,9 +58,18 @@ struct BitReader {
 JG_DEV void refill(BitReader& r)
 {
     while (r.bits <= 56) {
+        if (r.bits <= 32 && (((size_t)r.p) & 3u) == 0 && r.p + 4 <= r.end) {
+            const unsigned w = ldg_u32(r.p);
+            if (v_cmpeq4(w, 0xffffffffu) == 0u) {
+                r.buf = (r.buf << 32) | bswap32(w);
+                r.bits += 32;
+                r.p += 4;
+                continue;
+            }
+        }
         unsigned b = 0xFF;
         if (r.p < r.end) {
-            b = *r.p++;
+            b = ldg_u8(r.p++);
             if (b == 0xFF && r.p < r.end) ++r.p;        // the stuffed 00 (or a fill FF): consumed, not data
         }
         r.buf = (r.buf << 8) | b;
@@ -67,10 +83,25 @@ JG_DEV unsigned show(BitReader& r, int n)
 }
 JG_DEV void skip(BitReader& r, int n) { r.bits -= n; }
 
-// njGetVLC (:643-656)
-JG_DEV int get_vlc(BitReader& r, const uint16_t* tab, unsigned* code_out, bool* bad)
+// First-level lookup: the kL1Bits leading bits decide every code of at most that length (all but the
+// rarest symbols); the table is the corresponding slice of the 16-bit table and lives in shared memory.
+constexpr int kL1Bits = 9;
+struct VlcTables {
+    const uint16_t* full;      // [4][65536], global memory
+    const uint16_t* l1;        // [4][1 << kL1Bits]: entry of the 16-bit table if its code length <= kL1Bits, else 0
+};
+JG_DEV uint16_t l1_entry(const uint16_t* full, int table, int i)
 {
-    const unsigned e = tab[show(r, 16)];
+    const uint16_t e = full[(size_t)table * 65536 + ((size_t)i << (16 - kL1Bits))];
+    return (e >> 8) <= kL1Bits ? e : (uint16_t)0;
+}
+
+// njGetVLC (:643-656)
+JG_DEV int get_vlc(BitReader& r, const VlcTables& T, int table, unsigned* code_out, bool* bad)
+{
+    const unsigned peek = show(r, 16);
+    unsigned e = T.l1[(table << kL1Bits) + (peek >> (16 - kL1Bits))];
+    if (!e) e = T.full[(size_t)table * 65536 + peek];
     const int len = (int)(e >> 8);
     if (!len) { *bad = true; return 0; }
     skip(r, len);
@@ -84,8 +115,9 @@ JG_DEV int get_vlc(BitReader& r, const uint16_t* tab, unsigned* code_out, bool* 
     return v;
 }
 
-JG_DEV void decode_interval(const DevParams& P, int iv)
+JG_DEV void decode_interval(const DevParams& P, const uint16_t* l1, int iv)
 {
+    VlcTables T; T.full = P.vlc; T.l1 = l1;
     BitReader r;
     r.p = P.data + P.interval_off[iv];
     r.end = P.data + (iv + 1 < P.n_intervals ? P.interval_off[iv + 1] - 2u : P.interval_off[P.n_intervals]);   // minus the RSTm marker
@@ -98,16 +130,15 @@ JG_DEV void decode_interval(const DevParams& P, int iv)
     for (int m = m0; m < m1 && !bad; ++m) {
         for (int c = 0; c < P.ncomp && !bad; ++c) {
             const DevComponent& K = P.comp[c];
-            const uint16_t* dct = P.vlc + (size_t)K.dctab * 65536, *act = P.vlc + (size_t)K.actab * 65536;
             for (int sby = 0; sby < K.ssy && !bad; ++sby)
                 for (int sbx = 0; sbx < K.ssx && !bad; ++sbx) {
                     int16_t* blk = P.coef + (K.coef_off + (unsigned long long)(mby * K.ssy + sby) * K.bw + (mbx * K.ssx + sbx)) * 64ull;
                     unsigned code = 0;
-                    dcpred[c] += get_vlc(r, dct, &code, &bad);
+                    dcpred[c] += get_vlc(r, T, K.dctab, &code, &bad);
                     blk[0] = (int16_t)dcpred[c];
                     int coef = 0;
                     do {
-                        const int v = get_vlc(r, act, &code, &bad);
+                        const int v = get_vlc(r, T, K.actab, &code, &bad);
                         if (bad || !code) break;                                  // EOB
                         if (!(code & 0x0F) && code != 0xF0) { bad = true; break; }
                         coef += (int)(code >> 4) + 1;
@@ -271,37 +302,49 @@ JG_DEV void to_rgb(unsigned char* rgb, int yv, int cbv, int crv)
     rgb[2] = clip8((y + 454 * cb + 128) >> 8);
 }
 
+// per-image work lists of the plane stages
+struct PlaneOp { const unsigned char* in; unsigned char* out; int w, h, s; };                      // one upsampling pass of one plane
+struct ColorOp { const unsigned char *py, *pcb, *pcr; int sy, scb, scr; unsigned char* out; int w, h, ncomp; };
+
 #if !defined(JG_EMULATE)
-__global__ void decode_intervals_kernel(const __grid_constant__ DevParams P)
+// Every kernel works on a BATCH: blockIdx.y (or .z) picks the image, the x dimension covers the largest
+// image's work items and the others' surplus threads leave at once.
+__global__ void decode_intervals_kernel(const DevParams* __restrict__ imgs)
 {
+    const DevParams& P = imgs[blockIdx.y];
+    __shared__ uint16_t l1[4 << kL1Bits];
+    if ((int)(blockIdx.x * blockDim.x) >= P.n_intervals) return;            // whole CTA surplus: no table needed
+    for (int i = (int)threadIdx.x; i < (4 << kL1Bits); i += (int)blockDim.x) l1[i] = l1_entry(P.vlc, i >> kL1Bits, i & ((1 << kL1Bits) - 1));
+    __syncthreads();
     const int iv = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (iv < P.n_intervals) decode_interval(P, iv);
+    if (iv < P.n_intervals) decode_interval(P, l1, iv);
 }
-__global__ void idct_kernel(const __grid_constant__ DevParams P, int c, unsigned long long n_blocks)
+__global__ void idct_kernel(const DevParams* __restrict__ imgs, int c)
 {
+    const DevParams& P = imgs[blockIdx.y];
+    if (c >= P.ncomp) return;
     const unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < n_blocks) idct_block(P, c, b);
+    if (b < P.comp[c].n_blocks) idct_block(P, c, b);
 }
-__global__ void upsample_h_kernel(const unsigned char* in, unsigned char* out, int w, int h, int s)
+__global__ void upsample_h_kernel(const PlaneOp* __restrict__ ops)
 {
+    const PlaneOp o = ops[blockIdx.z];
     const int ox = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y;
-    if (ox < 2 * w && y < h) out[(size_t)y * (2 * w) + ox] = upsample_h(in, w, s, y, ox);
+    if (ox < 2 * o.w && y < o.h) o.out[(size_t)y * (2 * o.w) + ox] = upsample_h(o.in, o.w, o.s, y, ox);
 }
-__global__ void upsample_v_kernel(const unsigned char* in, unsigned char* out, int w, int h, int s)
+__global__ void upsample_v_kernel(const PlaneOp* __restrict__ ops)
 {
+    const PlaneOp o = ops[blockIdx.z];
     const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), oy = (int)blockIdx.y;
-    if (x < w && oy < 2 * h) out[(size_t)oy * w + x] = upsample_v(in, h, s, oy, x);
+    if (x < o.w && oy < 2 * o.h) o.out[(size_t)oy * o.w + x] = upsample_v(o.in, o.h, o.s, oy, x);
 }
-__global__ void to_rgb_kernel(const unsigned char* py, int sy, const unsigned char* pcb, int scb, const unsigned char* pcr, int scr,
-                              unsigned char* rgb, int w, int h)
+__global__ void color_kernel(const ColorOp* __restrict__ ops)
 {
+    const ColorOp o = ops[blockIdx.z];
     const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y;
-    if (x < w && y < h) to_rgb(rgb + ((size_t)y * w + x) * 3, py[(size_t)y * sy + x], pcb[(size_t)y * scb + x], pcr[(size_t)y * scr + x]);
-}
-__global__ void to_gray_kernel(const unsigned char* p, int s, unsigned char* out, int w, int h)
-{
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y;
-    if (x < w && y < h) out[(size_t)y * w + x] = p[(size_t)y * s + x];
+    if (x >= o.w || y >= o.h) return;
+    if (o.ncomp == 3) to_rgb(o.out + ((size_t)y * o.w + x) * 3, o.py[(size_t)y * o.sy + x], o.pcb[(size_t)y * o.scb + x], o.pcr[(size_t)y * o.scr + x]);
+    else o.out[(size_t)y * o.w + x] = o.py[(size_t)y * o.sy + x];
 }
 #endif
 

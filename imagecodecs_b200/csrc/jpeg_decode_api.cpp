@@ -59,90 +59,194 @@ struct DeviceBuffers {     // freed in order on every exit path
         }                                                                                           \
     } while (0)
 
-int decode(const uint8_t* jpeg, size_t size, uint8_t* pixels, size_t capacity, int* width, int* height, int* ncomp, float* kernel_ms)
-{
-    if (!jpeg || !pixels) { jg::set_error_text("decode: null argument"); return 0; }
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+struct Job {                 // one image of a batch
     Info I;
-    const int rc = parse(jpeg, size, &I);
-    if (rc != kOk) { jg::set_error_text(result_text(rc)); return 0; }
-    if (width) *width = I.width;
-    if (height) *height = I.height;
-    if (ncomp) *ncomp = I.ncomp;
-    const size_t out_bytes = (size_t)I.width * I.height * I.ncomp;
-    if (capacity < out_bytes) { jg::set_error_text("decode: output buffer too small"); return 0; }
+    bool ok = false;
+    size_t data_off = 0, iv_off = 0, coef_off = 0, plane_off = 0, out_off = 0, out_bytes = 0;
+    int vlc_slot = 0;
+};
+
+// Decode n files.  outs[i].pixels are host buffers (or device buffers if pixels_on_device); kernel_ms (optional)
+// receives the device time of all kernels of the batch.  Returns the number of images decoded.
+int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int pixels_on_device, float* kernel_ms)
+{
+    if (!in || !outs || n <= 0) { jg::set_error_text("decode: null argument"); return 0; }
+    if (n > 65535) { jg::set_error_text("decode: at most 65535 images per call"); return 0; }
+    std::vector<Job> jobs((size_t)n);
+    std::vector<std::vector<uint16_t>> vlc_sets;      // distinct Huffman table sets of the batch (usually one)
+    size_t data_bytes = 0, iv_words = 0, coef_words = 0, plane_bytes = 0, out_total = 0;
+    int n_ok = 0, max_iv = 0;
+    unsigned long long max_blocks[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        Job& j = jobs[i];
+        outs[i].width = outs[i].height = outs[i].ncomp = 0;
+        const int rc = in[i].data ? parse(in[i].data, in[i].size, &j.I) : (int)kNoJpeg;
+        outs[i].status = rc == kOk ? JPEG_GPU_OK : JPEG_GPU_ERR_ARG;
+        if (rc != kOk) { jg::set_error_text(result_text(rc)); continue; }
+        outs[i].width = j.I.width; outs[i].height = j.I.height; outs[i].ncomp = j.I.ncomp;
+        j.out_bytes = (size_t)j.I.width * j.I.height * j.I.ncomp;
+        if (!outs[i].pixels || outs[i].capacity < j.out_bytes) { outs[i].status = JPEG_GPU_ERR_CAPACITY; jg::set_error_text("decode: output buffer too small"); continue; }
+        j.ok = true; ++n_ok;
+        size_t slot = 0;
+        while (slot < vlc_sets.size() && vlc_sets[slot] != j.I.vlc) ++slot;
+        if (slot == vlc_sets.size()) vlc_sets.push_back(j.I.vlc);
+        j.vlc_slot = (int)slot;
+        j.data_off = data_bytes; data_bytes += align256(j.I.scan_end + 16);
+        j.iv_off = iv_words; iv_words += j.I.interval_off.size();
+        j.coef_off = coef_words; coef_words += j.I.n_blocks * 64;
+        j.plane_off = plane_bytes; plane_bytes += align256(j.I.plane_bytes + 16);
+        j.out_off = out_total; out_total += align256(j.out_bytes);
+        max_iv = std::max(max_iv, (int)j.I.interval_off.size() - 1);
+        for (int c = 0; c < j.I.ncomp; ++c) max_blocks[c] = std::max(max_blocks[c], (unsigned long long)j.I.comp[c].bw * j.I.comp[c].bh);
+    }
+    if (n_ok == 0) return 0;
     if (jpeg_gpu_device_count() == 0 && jpeg_gpu_init(nullptr, 0) <= 0) return 0;
     JD_CUDA(cudaSetDevice(jg::cuda_device_of(0)));
 
     DeviceBuffers B;
     JD_CUDA(cudaStreamCreateWithFlags(&B.s, cudaStreamNonBlocking));
-    const int n_iv = (int)I.interval_off.size() - 1;
-    uint8_t* d_data = B.alloc<uint8_t>(I.scan_end + 16);
-    uint32_t* d_iv = B.alloc<uint32_t>(I.interval_off.size());
-    uint16_t* d_vlc = B.alloc<uint16_t>(I.vlc.size());
-    int16_t* d_coef = B.alloc<int16_t>(I.n_blocks * 64);
-    uint8_t* d_planes = B.alloc<uint8_t>(I.plane_bytes);
-    uint8_t* d_out = B.alloc<uint8_t>(out_bytes);
-    unsigned* d_err = B.alloc<unsigned>(1);
-    if (!d_data || !d_iv || !d_vlc || !d_coef || !d_planes || !d_out || !d_err) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
-    JD_CUDA(cudaMemcpyAsync(d_data, jpeg, I.scan_end, cudaMemcpyHostToDevice, B.s));
-    JD_CUDA(cudaMemcpyAsync(d_iv, I.interval_off.data(), I.interval_off.size() * 4, cudaMemcpyHostToDevice, B.s));
-    JD_CUDA(cudaMemcpyAsync(d_vlc, I.vlc.data(), I.vlc.size() * 2, cudaMemcpyHostToDevice, B.s));
-    JD_CUDA(cudaMemsetAsync(d_coef, 0, I.n_blocks * 64 * 2, B.s));
-    JD_CUDA(cudaMemsetAsync(d_err, 0, 4, B.s));
-
-    DevParams P;
-    memset(&P, 0, sizeof P);
-    P.data = d_data; P.interval_off = d_iv; P.n_intervals = n_iv; P.rstinterval = I.rstinterval; P.n_mcus = I.n_mcus;
-    P.mbwidth = I.mbwidth; P.ncomp = I.ncomp; P.vlc = d_vlc; P.coef = d_coef; P.planes = d_planes; P.error = d_err;
-    for (int c = 0; c < I.ncomp; ++c) {
-        const Component& k = I.comp[c];
-        DevComponent& d = P.comp[c];
-        d.ssx = k.ssx; d.ssy = k.ssy; d.bw = k.bw; d.dctab = k.dctabsel; d.actab = k.actabsel; d.stride = k.stride;
-        d.coef_off = k.coef_off; d.plane_off = k.plane_off;
-        static const unsigned char zz[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21,
-                                             28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54,
-                                             47, 55, 62, 63};
-        for (int i = 0; i < 64; ++i) d.dq[zz[i]] = I.qtab[k.qtsel][i];
+    uint8_t* d_data = B.alloc<uint8_t>(data_bytes);
+    uint32_t* d_iv = B.alloc<uint32_t>(iv_words);
+    uint16_t* d_vlc = B.alloc<uint16_t>(vlc_sets.size() * 4 * 65536);
+    int16_t* d_coef = B.alloc<int16_t>(coef_words);
+    uint8_t* d_planes = B.alloc<uint8_t>(plane_bytes);
+    uint8_t* d_out = pixels_on_device ? nullptr : B.alloc<uint8_t>(out_total);
+    unsigned* d_err = B.alloc<unsigned>((size_t)n);
+    DevParams* d_params = B.alloc<DevParams>((size_t)n);
+    if (!d_data || !d_iv || !d_vlc || !d_coef || !d_planes || (!pixels_on_device && !d_out) || !d_err || !d_params) {
+        jg::set_error_text(result_text(kOutOfMem)); return 0;
     }
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (kernel_ms) { JD_CUDA(cudaEventCreate(&e0)); JD_CUDA(cudaEventCreate(&e1)); JD_CUDA(cudaEventRecord(e0, B.s)); }
+    for (size_t k = 0; k < vlc_sets.size(); ++k)
+        JD_CUDA(cudaMemcpyAsync(d_vlc + k * 4 * 65536, vlc_sets[k].data(), 4 * 65536 * 2, cudaMemcpyHostToDevice, B.s));
+    JD_CUDA(cudaMemsetAsync(d_coef, 0, coef_words * 2, B.s));
+    JD_CUDA(cudaMemsetAsync(d_err, 0, (size_t)n * 4, B.s));
 
-    decode_intervals_kernel<<<(n_iv + 63) / 64, 64, 0, B.s>>>(P);
-    for (int c = 0; c < I.ncomp; ++c) {
-        const unsigned long long nb = (unsigned long long)I.comp[c].bw * I.comp[c].bh;
-        idct_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, B.s>>>(P, c, nb);
-    }
-    // njConvert (:817-836): every component is brought to the image size, H before V
-    const uint8_t* plane[3]; int pw[3], ph[3], ps[3];
-    for (int c = 0; c < I.ncomp; ++c) {
-        plane[c] = d_planes + I.comp[c].plane_off; pw[c] = I.comp[c].width; ph[c] = I.comp[c].height; ps[c] = I.comp[c].stride;
-        while (pw[c] < I.width || ph[c] < I.height) {
-            if (pw[c] < I.width) {
-                uint8_t* o = B.alloc<uint8_t>((size_t)pw[c] * ph[c] * 2);
-                if (!o) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
-                upsample_h_kernel<<<dim3((2 * pw[c] + 127) / 128, ph[c]), 128, 0, B.s>>>(plane[c], o, pw[c], ph[c], ps[c]);
-                plane[c] = o; pw[c] <<= 1; ps[c] = pw[c];
-            }
-            if (ph[c] < I.height) {
-                uint8_t* o = B.alloc<uint8_t>((size_t)pw[c] * ph[c] * 2);
-                if (!o) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
-                upsample_v_kernel<<<dim3((pw[c] + 127) / 128, 2 * ph[c]), 128, 0, B.s>>>(plane[c], o, pw[c], ph[c], ps[c]);
-                plane[c] = o; ph[c] <<= 1; ps[c] = pw[c];
-            }
+    static const unsigned char zz[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21,
+                                         28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54,
+                                         47, 55, 62, 63};
+    std::vector<DevParams> params((size_t)n);
+    std::vector<uint32_t> iv_host(iv_words);
+    // plane pipeline of njConvert (:817-836), as rounds of batch-wide passes: H before V, until the image size is reached
+    struct PlaneState { const uint8_t* p; int w, h, s; };
+    std::vector<PlaneState> st((size_t)n * 3);
+    for (int i = 0; i < n; ++i) {
+        Job& j = jobs[i];
+        DevParams& P = params[i];
+        memset(&P, 0, sizeof P);
+        if (!j.ok) continue;
+        const Info& I = j.I;
+        JD_CUDA(cudaMemcpyAsync(d_data + j.data_off, in[i].data, I.scan_end, cudaMemcpyHostToDevice, B.s));
+        std::copy(I.interval_off.begin(), I.interval_off.end(), iv_host.begin() + j.iv_off);
+        P.data = d_data + j.data_off; P.interval_off = d_iv + j.iv_off; P.n_intervals = (int)I.interval_off.size() - 1;
+        P.rstinterval = I.rstinterval; P.n_mcus = I.n_mcus; P.mbwidth = I.mbwidth; P.ncomp = I.ncomp;
+        P.vlc = d_vlc + (size_t)j.vlc_slot * 4 * 65536; P.coef = d_coef + j.coef_off; P.planes = d_planes + j.plane_off; P.error = d_err + i;
+        for (int c = 0; c < I.ncomp; ++c) {
+            const Component& k = I.comp[c];
+            DevComponent& d = P.comp[c];
+            d.ssx = k.ssx; d.ssy = k.ssy; d.bw = k.bw; d.dctab = k.dctabsel; d.actab = k.actabsel; d.stride = k.stride;
+            d.n_blocks = (unsigned long long)k.bw * k.bh; d.coef_off = k.coef_off; d.plane_off = k.plane_off;
+            for (int q = 0; q < 64; ++q) d.dq[zz[q]] = I.qtab[k.qtsel][q];
+            st[(size_t)i * 3 + c] = {P.planes + k.plane_off, k.width, k.height, k.stride};
         }
     }
-    const dim3 grid((I.width + 127) / 128, I.height);
-    if (I.ncomp == 3) to_rgb_kernel<<<grid, 128, 0, B.s>>>(plane[0], ps[0], plane[1], ps[1], plane[2], ps[2], d_out, I.width, I.height);
-    else to_gray_kernel<<<grid, 128, 0, B.s>>>(plane[0], ps[0], d_out, I.width, I.height);
+    JD_CUDA(cudaMemcpyAsync(d_iv, iv_host.data(), iv_words * 4, cudaMemcpyHostToDevice, B.s));
+    JD_CUDA(cudaMemcpyAsync(d_params, params.data(), (size_t)n * sizeof(DevParams), cudaMemcpyHostToDevice, B.s));
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (kernel_ms) { JD_CUDA(cudaEventCreate(&e0)); JD_CUDA(cudaEventCreate(&e1)); JD_CUDA(cudaEventRecord(e0, B.s)); }
+    decode_intervals_kernel<<<dim3((unsigned)((max_iv + 63) / 64), (unsigned)n), 64, 0, B.s>>>(d_params);
+    for (int c = 0; c < 3; ++c)
+        if (max_blocks[c]) idct_kernel<<<dim3((unsigned)((max_blocks[c] + 127) / 128), (unsigned)n), 128, 0, B.s>>>(d_params, c);
+    for (;;) {
+        std::vector<PlaneOp> hops, vops;
+        int hw = 0, hh = 0;
+        for (int i = 0; i < n; ++i) {
+            if (!jobs[i].ok) continue;
+            for (int c = 0; c < jobs[i].I.ncomp; ++c) {
+                PlaneState& p = st[(size_t)i * 3 + c];
+                if (p.w < jobs[i].I.width) {
+                    uint8_t* o = B.alloc<uint8_t>((size_t)p.w * p.h * 2);
+                    if (!o) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
+                    hops.push_back({p.p, o, p.w, p.h, p.s});
+                    hw = std::max(hw, 2 * p.w); hh = std::max(hh, p.h);
+                    p = {o, p.w << 1, p.h, p.w << 1};
+                }
+            }
+        }
+        if (!hops.empty()) {
+            PlaneOp* d_ops = B.alloc<PlaneOp>(hops.size());
+            if (!d_ops) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
+            JD_CUDA(cudaMemcpyAsync(d_ops, hops.data(), hops.size() * sizeof(PlaneOp), cudaMemcpyHostToDevice, B.s));
+            JD_CUDA(cudaStreamSynchronize(B.s));                  // hops is a local: the copy must have read it
+            upsample_h_kernel<<<dim3((unsigned)((hw + 127) / 128), (unsigned)hh, (unsigned)hops.size()), 128, 0, B.s>>>(d_ops);
+        }
+        int vw = 0, vh = 0;
+        for (int i = 0; i < n; ++i) {
+            if (!jobs[i].ok) continue;
+            for (int c = 0; c < jobs[i].I.ncomp; ++c) {
+                PlaneState& p = st[(size_t)i * 3 + c];
+                if (p.h < jobs[i].I.height) {
+                    uint8_t* o = B.alloc<uint8_t>((size_t)p.w * p.h * 2);
+                    if (!o) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
+                    vops.push_back({p.p, o, p.w, p.h, p.s});
+                    vw = std::max(vw, p.w); vh = std::max(vh, 2 * p.h);
+                    p = {o, p.w, p.h << 1, p.w};
+                }
+            }
+        }
+        if (!vops.empty()) {
+            PlaneOp* d_ops = B.alloc<PlaneOp>(vops.size());
+            if (!d_ops) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
+            JD_CUDA(cudaMemcpyAsync(d_ops, vops.data(), vops.size() * sizeof(PlaneOp), cudaMemcpyHostToDevice, B.s));
+            JD_CUDA(cudaStreamSynchronize(B.s));
+            upsample_v_kernel<<<dim3((unsigned)((vw + 127) / 128), (unsigned)vh, (unsigned)vops.size()), 128, 0, B.s>>>(d_ops);
+        }
+        if (hops.empty() && vops.empty()) break;
+    }
+    std::vector<ColorOp> cops;
+    int cw = 0, ch = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!jobs[i].ok) continue;
+        const Info& I = jobs[i].I;
+        const PlaneState* p = &st[(size_t)i * 3];
+        uint8_t* dst = pixels_on_device ? outs[i].pixels : d_out + jobs[i].out_off;
+        cops.push_back({p[0].p, I.ncomp == 3 ? p[1].p : nullptr, I.ncomp == 3 ? p[2].p : nullptr, p[0].s, p[1].s, p[2].s, dst, I.width, I.height, I.ncomp});
+        cw = std::max(cw, I.width); ch = std::max(ch, I.height);
+    }
+    ColorOp* d_cops = B.alloc<ColorOp>(cops.size());
+    if (!d_cops) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
+    JD_CUDA(cudaMemcpyAsync(d_cops, cops.data(), cops.size() * sizeof(ColorOp), cudaMemcpyHostToDevice, B.s));
+    color_kernel<<<dim3((unsigned)((cw + 127) / 128), (unsigned)ch, (unsigned)cops.size()), 128, 0, B.s>>>(d_cops);
     JD_CUDA(cudaGetLastError());
     if (kernel_ms) JD_CUDA(cudaEventRecord(e1, B.s));
-    unsigned err = 0;
-    JD_CUDA(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, B.s));
-    JD_CUDA(cudaMemcpyAsync(pixels, d_out, out_bytes, cudaMemcpyDeviceToHost, B.s));
+    std::vector<unsigned> errs((size_t)n, 0);
+    JD_CUDA(cudaMemcpyAsync(errs.data(), d_err, (size_t)n * 4, cudaMemcpyDeviceToHost, B.s));
+    if (!pixels_on_device)
+        for (int i = 0; i < n; ++i)
+            if (jobs[i].ok) JD_CUDA(cudaMemcpyAsync(outs[i].pixels, d_out + jobs[i].out_off, jobs[i].out_bytes, cudaMemcpyDeviceToHost, B.s));
     JD_CUDA(cudaStreamSynchronize(B.s));
     if (kernel_ms) { cudaEventElapsedTime(kernel_ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1); }
-    if (err) { jg::set_error_text(result_text((int)err)); return 0; }
-    return 1;
+    int done = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!jobs[i].ok) continue;
+        if (errs[i]) { outs[i].status = JPEG_GPU_ERR_ARG; jg::set_error_text(result_text((int)errs[i])); }
+        else ++done;
+    }
+    return done;
+}
+
+int decode(const uint8_t* jpeg, size_t size, uint8_t* pixels, size_t capacity, int* width, int* height, int* ncomp, float* kernel_ms)
+{
+    if (!jpeg || !pixels) { jg::set_error_text("decode: null argument"); return 0; }
+    jpeg_gpu_stream in = {jpeg, size};
+    jpeg_gpu_decoded out = {pixels, capacity, 0, 0, 0, 0};
+    const int ok = decode_batch(&in, 1, &out, 0, kernel_ms);
+    if (width) *width = out.width;
+    if (height) *height = out.height;
+    if (ncomp) *ncomp = out.ncomp;
+    return ok == 1 ? 1 : 0;
 }
 
 }  // namespace
@@ -164,6 +268,11 @@ int jpeg_gpu_decode_info(const uint8_t* jpeg, size_t size, int* width, int* heig
 int jpeg_gpu_decode(const uint8_t* jpeg, size_t size, uint8_t* pixels, size_t capacity, int* width, int* height, int* ncomp)
 {
     return decode(jpeg, size, pixels, capacity, width, height, ncomp, nullptr);
+}
+
+int jpeg_gpu_decode_batch(const jpeg_gpu_stream* streams, int n, jpeg_gpu_decoded* outs, int pixels_on_device, float* kernel_ms)
+{
+    return decode_batch(streams, n, outs, pixels_on_device, kernel_ms);
 }
 
 int jpeg_gpu_decode_timed(const uint8_t* jpeg, size_t size, uint8_t* pixels, size_t capacity, int* width, int* height, int* ncomp,

@@ -189,6 +189,13 @@ JPEG_GPU_API int jpeg_gpu_encode_with_func(jpeg_gpu_write_func* func, void* cont
 JPEG_GPU_API int jpeg_gpu_decode_info(const uint8_t* jpeg, size_t size, int* width, int* height, int* ncomp);
 JPEG_GPU_API int jpeg_gpu_decode(const uint8_t* jpeg, size_t size, uint8_t* pixels, size_t capacity,
                                  int* width, int* height, int* ncomp);
+/* Many files per call: every kernel runs over the whole batch (image = one grid dimension).  outs[i].pixels /
+ * capacity are the caller's buffers (device pointers if pixels_on_device); width, height, ncomp, status are filled
+ * in.  kernel_ms (optional) receives the device time of the batch's kernels.  Returns the number decoded. */
+typedef struct jpeg_gpu_stream { const uint8_t* data; size_t size; } jpeg_gpu_stream;
+typedef struct jpeg_gpu_decoded { uint8_t* pixels; size_t capacity; int width, height, ncomp, status; } jpeg_gpu_decoded;
+JPEG_GPU_API int jpeg_gpu_decode_batch(const jpeg_gpu_stream* streams, int n, jpeg_gpu_decoded* outs,
+                                       int pixels_on_device, float* kernel_ms);
 /* the same; *kernel_ms receives the device time of the kernels (CUDA events), copies excluded */
 JPEG_GPU_API int jpeg_gpu_decode_timed(const uint8_t* jpeg, size_t size, uint8_t* pixels, size_t capacity,
                                        int* width, int* height, int* ncomp, float* kernel_ms);

@@ -205,7 +205,9 @@ int emu_decode(const uint8_t* jpeg, size_t size, uint8_t* out, size_t cap, int* 
         d.coef_off = k.coef_off; d.plane_off = k.plane_off;
         for (int i = 0; i < 64; ++i) d.dq[jd::zz_nat(i)] = I.qtab[k.qtsel][i];
     }
-    for (int iv = 0; iv < P.n_intervals; ++iv) jd::decode_interval(P, iv);
+    std::vector<uint16_t> l1(4 << jd::kL1Bits);
+    for (int i = 0; i < (4 << jd::kL1Bits); ++i) l1[i] = jd::l1_entry(P.vlc, i >> jd::kL1Bits, i & ((1 << jd::kL1Bits) - 1));
+    for (int iv = 0; iv < P.n_intervals; ++iv) jd::decode_interval(P, l1.data(), iv);
     if (err) return (int)err;
     for (int c = 0; c < I.ncomp; ++c)
         for (unsigned long long b = 0; b < (unsigned long long)I.comp[c].bw * I.comp[c].bh; ++b) jd::idct_block(P, c, b);

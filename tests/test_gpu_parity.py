@@ -473,6 +473,15 @@ def test_decoder_matches_nanojpeg(gpu, fixture_pixels, golden_dir):
         assert np.array_equal(gpu.decode(b.getvalue()), oracle.ref_decode(b.getvalue())), kw
     with pytest.raises(gpu.JpegGpuError):
         gpu.decode(b"\x00\x01\x02\x03")
+    # one call, many files of different sizes / samplings / table sets, one of them broken
+    batch = [oracle.synth_image(w, h, nc) for (w, h, nc) in [(320, 200, 3), (333, 222, 3), (100, 60, 1), (64, 64, 3)]]
+    files = [encode_one(gpu, batch[0], 1, 75, 1, flags=gpu.FLAG_RESTART), encode_one(gpu, batch[1], 0, 2, 0, flags=gpu.FLAG_RESTART),
+             encode_one(gpu, batch[2], 1, 85, 0), b"not a jpeg", encode_one(gpu, batch[3], 0, 3, 0)]
+    b = io.BytesIO(); rgb.save(b, "JPEG", subsampling=2, quality=40, optimize=True); files.append(b.getvalue())
+    got = gpu.decode_batch(files)
+    for i, f in enumerate(files):
+        want = oracle.ref_decode(f)
+        assert (got[i] is None) == (want is None) and (want is None or np.array_equal(got[i], want)), i
 
 
 def test_cpp_facade_reads_jpg_and_round_trips(gpu, fixture_pixels, golden_dir, tmp_path):
