@@ -38,13 +38,11 @@ struct DevParams {
     DevComponent comp[3];
 };
 
-JG_DEV int zz_nat(int k)   // njZZ (jpeg_dec.h:332-337): natural index of zigzag position k
-{
-    const unsigned char t[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21,
-                                 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54,
-                                 47, 55, 62, 63};
-    return t[k];
-}
+// njZZ (jpeg_dec.h:332-337): natural index of zigzag position k
+JG_CONST_TABLE unsigned char kZigzagToNatural[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21,
+                                                     28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54,
+                                                     47, 55, 62, 63};
+JG_DEV int zz_nat(int k) { return kZigzagToNatural[k]; }
 
 // MSB-first bit reader over [p, end) with the byte rules of njShowBits (:447-482): FF 00 and FF FF
 // yield one FF, past the end the stream continues with FF bytes.  Four bytes per load where the
@@ -326,25 +324,54 @@ __global__ void idct_kernel(const DevParams* __restrict__ imgs, int c)
     const unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b < P.comp[c].n_blocks) idct_block(P, c, b);
 }
+// The plane stages handle FOUR neighbouring output pixels per thread and store them as one 32-bit word
+// (three for RGB) where the address allows it: a quarter of the threads and store instructions.
+__device__ __forceinline__ void store4(unsigned char* dst, const unsigned char (&v)[4], int n)
+{
+    if (n == 4 && (((size_t)dst) & 3u) == 0) *reinterpret_cast<unsigned*>(dst) = v[0] | (v[1] << 8) | (v[2] << 16) | ((unsigned)v[3] << 24);
+    else for (int i = 0; i < n; ++i) dst[i] = v[i];
+}
 __global__ void upsample_h_kernel(const PlaneOp* __restrict__ ops)
 {
     const PlaneOp o = ops[blockIdx.z];
-    const int ox = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y;
-    if (ox < 2 * o.w && y < o.h) o.out[(size_t)y * (2 * o.w) + ox] = upsample_h(o.in, o.w, o.s, y, ox);
+    const int ox = 4 * (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, W2 = 2 * o.w;
+    if (ox >= W2 || y >= o.h) return;
+    const int n = W2 - ox < 4 ? W2 - ox : 4;
+    unsigned char v[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) v[i] = upsample_h(o.in, o.w, o.s, y, ox + i);
+    store4(o.out + (size_t)y * W2 + ox, v, n);
 }
 __global__ void upsample_v_kernel(const PlaneOp* __restrict__ ops)
 {
     const PlaneOp o = ops[blockIdx.z];
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), oy = (int)blockIdx.y;
-    if (x < o.w && oy < 2 * o.h) o.out[(size_t)oy * o.w + x] = upsample_v(o.in, o.h, o.s, oy, x);
+    const int x = 4 * (int)(blockIdx.x * blockDim.x + threadIdx.x), oy = (int)blockIdx.y;
+    if (x >= o.w || oy >= 2 * o.h) return;
+    const int n = o.w - x < 4 ? o.w - x : 4;
+    unsigned char v[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) v[i] = upsample_v(o.in, o.h, o.s, oy, x + i);
+    store4(o.out + (size_t)oy * o.w + x, v, n);
 }
 __global__ void color_kernel(const ColorOp* __restrict__ ops)
 {
     const ColorOp o = ops[blockIdx.z];
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y;
+    const int x = 4 * (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y;
     if (x >= o.w || y >= o.h) return;
-    if (o.ncomp == 3) to_rgb(o.out + ((size_t)y * o.w + x) * 3, o.py[(size_t)y * o.sy + x], o.pcb[(size_t)y * o.scb + x], o.pcr[(size_t)y * o.scr + x]);
-    else o.out[(size_t)y * o.w + x] = o.py[(size_t)y * o.sy + x];
+    const int n = o.w - x < 4 ? o.w - x : 4;
+    if (o.ncomp != 3) {
+        unsigned char v[4] = {0, 0, 0, 0};
+        for (int i = 0; i < n; ++i) v[i] = o.py[(size_t)y * o.sy + x + i];
+        store4(o.out + (size_t)y * o.w + x, v, n);
+        return;
+    }
+    unsigned char rgb[12];
+    for (int i = 0; i < n; ++i) to_rgb(rgb + 3 * i, o.py[(size_t)y * o.sy + x + i], o.pcb[(size_t)y * o.scb + x + i], o.pcr[(size_t)y * o.scr + x + i]);
+    unsigned char* dst = o.out + ((size_t)y * o.w + x) * 3;
+    if (n == 4 && (((size_t)dst) & 3u) == 0) {
+        unsigned* d = reinterpret_cast<unsigned*>(dst);
+        for (int k = 0; k < 3; ++k) d[k] = rgb[4 * k] | (rgb[4 * k + 1] << 8) | (rgb[4 * k + 2] << 16) | ((unsigned)rgb[4 * k + 3] << 24);
+    } else {
+        for (int i = 0; i < 3 * n; ++i) dst[i] = rgb[i];
+    }
 }
 #endif
 

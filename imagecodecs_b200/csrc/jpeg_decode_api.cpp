@@ -73,7 +73,7 @@ struct Job {                 // one image of a batch
 int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int pixels_on_device, float* kernel_ms)
 {
     if (!in || !outs || n <= 0) { jg::set_error_text("decode: null argument"); return 0; }
-    if (n > 65535) { jg::set_error_text("decode: at most 65535 images per call"); return 0; }
+    if (n > 32767) { jg::set_error_text("decode: at most 32767 images per call"); return 0; }   // two plane ops per image in grid.z
     std::vector<Job> jobs((size_t)n);
     std::vector<std::vector<uint16_t>> vlc_sets;      // distinct Huffman table sets of the batch (usually one)
     size_t data_bytes = 0, iv_words = 0, coef_words = 0, plane_bytes = 0, out_total = 0;
@@ -154,56 +154,48 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
     JD_CUDA(cudaMemcpyAsync(d_iv, iv_host.data(), iv_words * 4, cudaMemcpyHostToDevice, B.s));
     JD_CUDA(cudaMemcpyAsync(d_params, params.data(), (size_t)n * sizeof(DevParams), cudaMemcpyHostToDevice, B.s));
 
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (kernel_ms) { JD_CUDA(cudaEventCreate(&e0)); JD_CUDA(cudaEventCreate(&e1)); JD_CUDA(cudaEventRecord(e0, B.s)); }
-    decode_intervals_kernel<<<dim3((unsigned)((max_iv + 63) / 64), (unsigned)n), 64, 0, B.s>>>(d_params);
-    for (int c = 0; c < 3; ++c)
-        if (max_blocks[c]) idct_kernel<<<dim3((unsigned)((max_blocks[c] + 127) / 128), (unsigned)n), 128, 0, B.s>>>(d_params, c);
+    // rounds of batch-wide passes; the op lists stay alive until the final synchronisation (pageable copies read them then at the latest)
+    struct Round { int dir; PlaneOp* d_ops; dim3 grid; };
+    std::vector<Round> rounds;
+    std::vector<std::vector<PlaneOp>> keep;
     for (;;) {
-        std::vector<PlaneOp> hops, vops;
-        int hw = 0, hh = 0;
-        for (int i = 0; i < n; ++i) {
-            if (!jobs[i].ok) continue;
-            for (int c = 0; c < jobs[i].I.ncomp; ++c) {
-                PlaneState& p = st[(size_t)i * 3 + c];
-                if (p.w < jobs[i].I.width) {
-                    uint8_t* o = B.alloc<uint8_t>((size_t)p.w * p.h * 2);
-                    if (!o) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
-                    hops.push_back({p.p, o, p.w, p.h, p.s});
-                    hw = std::max(hw, 2 * p.w); hh = std::max(hh, p.h);
-                    p = {o, p.w << 1, p.h, p.w << 1};
+        bool any = false;
+        for (int dir = 0; dir < 2; ++dir) {                 // 0: horizontal, 1: vertical
+            std::vector<PlaneOp> ops;
+            size_t bytes = 0;
+            int gw = 0, gh = 0;
+            for (int i = 0; i < n; ++i) {
+                if (!jobs[i].ok) continue;
+                for (int c = 0; c < jobs[i].I.ncomp; ++c) {
+                    const PlaneState& p = st[(size_t)i * 3 + c];
+                    if (dir == 0 ? p.w < jobs[i].I.width : p.h < jobs[i].I.height) bytes += align256((size_t)p.w * p.h * 2);
                 }
             }
-        }
-        if (!hops.empty()) {
-            PlaneOp* d_ops = B.alloc<PlaneOp>(hops.size());
-            if (!d_ops) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
-            JD_CUDA(cudaMemcpyAsync(d_ops, hops.data(), hops.size() * sizeof(PlaneOp), cudaMemcpyHostToDevice, B.s));
-            JD_CUDA(cudaStreamSynchronize(B.s));                  // hops is a local: the copy must have read it
-            upsample_h_kernel<<<dim3((unsigned)((hw + 127) / 128), (unsigned)hh, (unsigned)hops.size()), 128, 0, B.s>>>(d_ops);
-        }
-        int vw = 0, vh = 0;
-        for (int i = 0; i < n; ++i) {
-            if (!jobs[i].ok) continue;
-            for (int c = 0; c < jobs[i].I.ncomp; ++c) {
-                PlaneState& p = st[(size_t)i * 3 + c];
-                if (p.h < jobs[i].I.height) {
-                    uint8_t* o = B.alloc<uint8_t>((size_t)p.w * p.h * 2);
-                    if (!o) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
-                    vops.push_back({p.p, o, p.w, p.h, p.s});
-                    vw = std::max(vw, p.w); vh = std::max(vh, 2 * p.h);
-                    p = {o, p.w, p.h << 1, p.w};
+            if (!bytes) continue;
+            uint8_t* pool = B.alloc<uint8_t>(bytes);
+            if (!pool) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
+            size_t off = 0;
+            for (int i = 0; i < n; ++i) {
+                if (!jobs[i].ok) continue;
+                for (int c = 0; c < jobs[i].I.ncomp; ++c) {
+                    PlaneState& p = st[(size_t)i * 3 + c];
+                    if (!(dir == 0 ? p.w < jobs[i].I.width : p.h < jobs[i].I.height)) continue;
+                    uint8_t* o = pool + off;
+                    off += align256((size_t)p.w * p.h * 2);
+                    ops.push_back({p.p, o, p.w, p.h, p.s});
+                    if (dir == 0) { gw = std::max(gw, 2 * p.w); gh = std::max(gh, p.h); p = {o, p.w << 1, p.h, p.w << 1}; }
+                    else { gw = std::max(gw, p.w); gh = std::max(gh, 2 * p.h); p = {o, p.w, p.h << 1, p.w}; }
                 }
             }
-        }
-        if (!vops.empty()) {
-            PlaneOp* d_ops = B.alloc<PlaneOp>(vops.size());
+            PlaneOp* d_ops = B.alloc<PlaneOp>(ops.size());
             if (!d_ops) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
-            JD_CUDA(cudaMemcpyAsync(d_ops, vops.data(), vops.size() * sizeof(PlaneOp), cudaMemcpyHostToDevice, B.s));
-            JD_CUDA(cudaStreamSynchronize(B.s));
-            upsample_v_kernel<<<dim3((unsigned)((vw + 127) / 128), (unsigned)vh, (unsigned)vops.size()), 128, 0, B.s>>>(d_ops);
+            keep.push_back(std::move(ops));
+            const std::vector<PlaneOp>& kept = keep.back();
+            JD_CUDA(cudaMemcpyAsync(d_ops, kept.data(), kept.size() * sizeof(PlaneOp), cudaMemcpyHostToDevice, B.s));
+            rounds.push_back({dir, d_ops, dim3((unsigned)((gw + 511) / 512), (unsigned)gh, (unsigned)kept.size())});   // four pixels per thread
+            any = true;
         }
-        if (hops.empty() && vops.empty()) break;
+        if (!any) break;
     }
     std::vector<ColorOp> cops;
     int cw = 0, ch = 0;
@@ -218,7 +210,17 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
     ColorOp* d_cops = B.alloc<ColorOp>(cops.size());
     if (!d_cops) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
     JD_CUDA(cudaMemcpyAsync(d_cops, cops.data(), cops.size() * sizeof(ColorOp), cudaMemcpyHostToDevice, B.s));
-    color_kernel<<<dim3((unsigned)((cw + 127) / 128), (unsigned)ch, (unsigned)cops.size()), 128, 0, B.s>>>(d_cops);
+    // everything is allocated and uploaded: the kernels go out back to back (what kernel_ms measures)
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (kernel_ms) { JD_CUDA(cudaEventCreate(&e0)); JD_CUDA(cudaEventCreate(&e1)); JD_CUDA(cudaEventRecord(e0, B.s)); }
+    decode_intervals_kernel<<<dim3((unsigned)((max_iv + 63) / 64), (unsigned)n), 64, 0, B.s>>>(d_params);
+    for (int c = 0; c < 3; ++c)
+        if (max_blocks[c]) idct_kernel<<<dim3((unsigned)((max_blocks[c] + 127) / 128), (unsigned)n), 128, 0, B.s>>>(d_params, c);
+    for (const Round& r : rounds) {
+        if (r.dir == 0) upsample_h_kernel<<<r.grid, 128, 0, B.s>>>(r.d_ops);
+        else upsample_v_kernel<<<r.grid, 128, 0, B.s>>>(r.d_ops);
+    }
+    color_kernel<<<dim3((unsigned)((cw + 511) / 512), (unsigned)ch, (unsigned)cops.size()), 128, 0, B.s>>>(d_cops);
     JD_CUDA(cudaGetLastError());
     if (kernel_ms) JD_CUDA(cudaEventRecord(e1, B.s));
     std::vector<unsigned> errs((size_t)n, 0);

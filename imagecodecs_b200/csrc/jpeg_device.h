@@ -19,6 +19,7 @@
 #define JG_KERNEL(threads, min_ctas) __global__ __launch_bounds__(threads, min_ctas)
 #define JG_GRID_CONSTANT __grid_constant__
 #define JG_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define JG_CONST_TABLE static __device__ __constant__
 
 namespace jg {
 
