@@ -350,6 +350,28 @@ def run_ours(args):
                 "out_bytes_per_px": round(tsz / (BATCH * W * H), 3)}
         tplan.close()
 
+    # ---- the other direction: the same batch written with restart intervals, decoded by
+    #      jpeg_gpu_decode_batch; kernels device-timed by the library (CUDA events around its launches) ------
+    decode = None
+    if rank == 0 and not args.no_twin:
+        try:
+            rplan = jg.Plan.for_arrays(imgs, QMODE, QUALITY, SUB, device=0, flags=jg.FLAG_RESTART)
+            rplan.run(sptr); torch.cuda.synchronize()
+            rfiles = rplan.fetch(sptr); rplan.close()
+            jg.decode_batch(rfiles[:2])                               # module load, memory pool
+            t0 = time.perf_counter()
+            dec_px, dec_ms = jg.decode_batch(rfiles, timed=True)
+            dec_call = (time.perf_counter() - t0) * 1e3
+            import oracle
+            ok = all(np.array_equal(dec_px[i], oracle.ref_decode(rfiles[i])) for i in (0, BATCH - 1))
+            decode = {"workload": "the same %d images, IJG q75 4:2:0 with one restart interval per 24 blocks" % BATCH,
+                      "value": round(mp_per_step / (dec_ms * 1e-3), 1), "unit": UNIT, "kernels_ms": round(dec_ms, 3),
+                      "call_ms_host_files_to_host_pixels": round(dec_call, 1),
+                      "pixels_identical_to_reference_decoder": bool(ok)}
+            del dec_px
+        except Exception as e:
+            decode = {"error": repr(e)}
+
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample) ------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -377,6 +399,7 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": args.steps * plan_launches_per_step(),
             "native_twin": twin,
+            "decode": decode,
         }
         print(json.dumps(line))
     if world > 1:

@@ -239,9 +239,9 @@ class Plan:
             raise JpegGpuError("plan_create failed: " + last_error())
 
     @classmethod
-    def for_arrays(cls, images, qmode=QMODE_TJE, quality=3, sub=SUB_444, device=0, win_words=0):
+    def for_arrays(cls, images, qmode=QMODE_TJE, quality=3, sub=SUB_444, device=0, win_words=0, flags=0):
         per = lambda v, i: v[i] if isinstance(v, (list, tuple, np.ndarray)) else v
-        descs = [_describe(px, per(qmode, i), per(quality, i), per(sub, i)) for i, px in enumerate(images)]
+        descs = [_describe(px, per(qmode, i), per(quality, i), per(sub, i), per(flags, i)) for i, px in enumerate(images)]
         p = cls(descs, device, win_words)
         p._keep = list(images)
         return p

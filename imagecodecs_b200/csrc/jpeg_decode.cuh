@@ -115,37 +115,49 @@ JG_DEV int get_vlc(BitReader& r, const VlcTables& T, int table, unsigned* code_o
 
 JG_DEV void decode_interval(const DevParams& P, const uint16_t* l1, int iv)
 {
+    // Everything the loops need is read ONCE into locals: P lives in global memory, and after every
+    // coefficient store the compiler would otherwise have to assume it changed and load it again.
     VlcTables T; T.full = P.vlc; T.l1 = l1;
+    const int rst = P.rstinterval, n_mcus = P.n_mcus, mbwidth = P.mbwidth, ncomp = P.ncomp, n_iv = P.n_intervals;
+    int16_t* const coef = P.coef;
+    int ssx[3], ssy[3], bw[3], dctab[3], actab[3];
+    unsigned long long coff[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        ssx[c] = P.comp[c].ssx; ssy[c] = P.comp[c].ssy; bw[c] = P.comp[c].bw;
+        dctab[c] = P.comp[c].dctab; actab[c] = P.comp[c].actab; coff[c] = P.comp[c].coef_off;
+    }
     BitReader r;
     r.p = P.data + P.interval_off[iv];
-    r.end = P.data + (iv + 1 < P.n_intervals ? P.interval_off[iv + 1] - 2u : P.interval_off[P.n_intervals]);   // minus the RSTm marker
+    r.end = P.data + (iv + 1 < n_iv ? P.interval_off[iv + 1] - 2u : P.interval_off[n_iv]);   // minus the RSTm marker
     r.buf = 0; r.bits = 0;
     int dcpred[3] = {0, 0, 0};
-    const int m0 = P.rstinterval ? iv * P.rstinterval : 0;
-    const int m1 = P.rstinterval ? (m0 + P.rstinterval < P.n_mcus ? m0 + P.rstinterval : P.n_mcus) : P.n_mcus;
+    const int m0 = rst ? iv * rst : 0;
+    const int m1 = rst ? (m0 + rst < n_mcus ? m0 + rst : n_mcus) : n_mcus;
     bool bad = false;
-    int mby = m0 / P.mbwidth, mbx = m0 - mby * P.mbwidth;
+    int mby = m0 / mbwidth, mbx = m0 - mby * mbwidth;
     for (int m = m0; m < m1 && !bad; ++m) {
-        for (int c = 0; c < P.ncomp && !bad; ++c) {
-            const DevComponent& K = P.comp[c];
-            for (int sby = 0; sby < K.ssy && !bad; ++sby)
-                for (int sbx = 0; sbx < K.ssx && !bad; ++sbx) {
-                    int16_t* blk = P.coef + (K.coef_off + (unsigned long long)(mby * K.ssy + sby) * K.bw + (mbx * K.ssx + sbx)) * 64ull;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (c >= ncomp || bad) continue;
+            for (int sby = 0; sby < ssy[c] && !bad; ++sby)
+                for (int sbx = 0; sbx < ssx[c] && !bad; ++sbx) {
+                    int16_t* blk = coef + (coff[c] + (unsigned long long)(mby * ssy[c] + sby) * bw[c] + (mbx * ssx[c] + sbx)) * 64ull;
                     unsigned code = 0;
-                    dcpred[c] += get_vlc(r, T, K.dctab, &code, &bad);
+                    dcpred[c] += get_vlc(r, T, dctab[c], &code, &bad);
                     blk[0] = (int16_t)dcpred[c];
-                    int coef = 0;
+                    int k = 0;
                     do {
-                        const int v = get_vlc(r, T, K.actab, &code, &bad);
+                        const int v = get_vlc(r, T, actab[c], &code, &bad);
                         if (bad || !code) break;                                  // EOB
                         if (!(code & 0x0F) && code != 0xF0) { bad = true; break; }
-                        coef += (int)(code >> 4) + 1;
-                        if (coef > 63) { bad = true; break; }
-                        blk[zz_nat(coef)] = (int16_t)v;
-                    } while (coef < 63);
+                        k += (int)(code >> 4) + 1;
+                        if (k > 63) { bad = true; break; }
+                        blk[zz_nat(k)] = (int16_t)v;
+                    } while (k < 63);
                 }
         }
-        if (++mbx >= P.mbwidth) { mbx = 0; ++mby; }
+        if (++mbx >= mbwidth) { mbx = 0; ++mby; }
     }
     if (bad) *P.error = 5u;     // NJ_SYNTAX_ERROR
 }

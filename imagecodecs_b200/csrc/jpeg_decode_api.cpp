@@ -105,6 +105,18 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
     if (jpeg_gpu_device_count() == 0 && jpeg_gpu_init(nullptr, 0) <= 0) return 0;
     JD_CUDA(cudaSetDevice(jg::cuda_device_of(0)));
 
+    {   // keep the stream-ordered pool's memory between calls (the default hands it back at every synchronisation)
+        static int pool_ready_for = -1;
+        const int dev_id = jg::cuda_device_of(0);
+        if (pool_ready_for != dev_id) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev_id) == cudaSuccess) {
+                unsigned long long keep_all = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all);
+            }
+            pool_ready_for = dev_id;
+        }
+    }
     DeviceBuffers B;
     JD_CUDA(cudaStreamCreateWithFlags(&B.s, cudaStreamNonBlocking));
     uint8_t* d_data = B.alloc<uint8_t>(data_bytes);
