@@ -52,19 +52,28 @@ struct BitReader {
     const uint8_t* end;
     unsigned long long buf;
     int bits;
+    unsigned ahead;            // the aligned word at `pa`, requested one refill early: its latency passes behind the decoding
+    const uint8_t* pa;         // nullptr: nothing requested
 };
-JG_DEV void refill(BitReader& r)
+JG_DEV void request_ahead(BitReader& r)
 {
-    while (r.bits <= 56) {
-        if (r.bits <= 32 && (((size_t)r.p) & 3u) == 0 && r.p + 4 <= r.end) {
-            const unsigned w = ldg_u32(r.p);
-            if (v_cmpeq4(w, 0xffffffffu) == 0u) {
-                r.buf = (r.buf << 32) | bswap32(w);
-                r.bits += 32;
-                r.p += 4;
-                continue;
-            }
+    const uint8_t* a = (const uint8_t*)(((size_t)r.p + 3u) & ~(size_t)3u);      // next aligned word at or after p
+    if (a + 4 <= r.end) { r.ahead = ldg_u32(a); r.pa = a; } else r.pa = nullptr;
+}
+JG_DEV void refill(BitReader& r)       // called with fewer than 16 bits left; leaves at least 25
+{
+    if (r.pa == r.p) {                                     // p is aligned and its word is already here
+        const unsigned w = r.ahead;
+        if (v_cmpeq4(w, 0xffffffffu) == 0u) {
+            r.buf = (r.buf << 32) | bswap32(w);
+            r.bits += 32;
+            r.p += 4;
+            request_ahead(r);
+            return;
         }
+    }
+    // byte by byte: until there are enough bits AND p is aligned again (the word path needs that), or the buffer is full
+    do {
         unsigned b = 0xFF;
         if (r.p < r.end) {
             b = ldg_u8(r.p++);
@@ -72,7 +81,8 @@ JG_DEV void refill(BitReader& r)
         }
         r.buf = (r.buf << 8) | b;
         r.bits += 8;
-    }
+    } while (r.bits <= 24 || ((((size_t)r.p) & 3u) != 0 && r.bits <= 48 && r.p < r.end));
+    request_ahead(r);
 }
 JG_DEV unsigned show(BitReader& r, int n)
 {
@@ -127,21 +137,32 @@ JG_DEV void decode_interval(const DevParams& P, const uint16_t* l1, int iv)
         ssx[c] = P.comp[c].ssx; ssy[c] = P.comp[c].ssy; bw[c] = P.comp[c].bw;
         dctab[c] = P.comp[c].dctab; actab[c] = P.comp[c].actab; coff[c] = P.comp[c].coef_off;
     }
+    // Every lane of a warp walks the SAME number of blocks (a full interval) and meets the others after each
+    // one: left alone, the lanes drift apart in the data-dependent symbol loops and the warp ends up running
+    // them one after the other.  Lanes without an interval, and the image's shorter last interval, idle along.
+    const bool have = iv < n_iv;
     BitReader r;
-    r.p = P.data + P.interval_off[iv];
-    r.end = P.data + (iv + 1 < n_iv ? P.interval_off[iv + 1] - 2u : P.interval_off[n_iv]);   // minus the RSTm marker
-    r.buf = 0; r.bits = 0;
+    r.p = r.end = P.data;
+    if (have) {
+        r.p = P.data + P.interval_off[iv];
+        r.end = P.data + (iv + 1 < n_iv ? P.interval_off[iv + 1] - 2u : P.interval_off[n_iv]);   // minus the RSTm marker
+    }
+    r.buf = 0; r.bits = 0; r.ahead = 0; r.pa = nullptr;
+    request_ahead(r);
     int dcpred[3] = {0, 0, 0};
     const int m0 = rst ? iv * rst : 0;
-    const int m1 = rst ? (m0 + rst < n_mcus ? m0 + rst : n_mcus) : n_mcus;
+    const int m1 = !have ? m0 : (rst ? (m0 + rst < n_mcus ? m0 + rst : n_mcus) : n_mcus);
+    const int m_end = m0 + (rst ? rst : n_mcus);
     bool bad = false;
     int mby = m0 / mbwidth, mbx = m0 - mby * mbwidth;
-    for (int m = m0; m < m1 && !bad; ++m) {
+    for (int m = m0; m < m_end; ++m) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            if (c >= ncomp || bad) continue;
-            for (int sby = 0; sby < ssy[c] && !bad; ++sby)
-                for (int sbx = 0; sbx < ssx[c] && !bad; ++sbx) {
+            if (c >= ncomp) continue;
+            for (int sby = 0; sby < ssy[c]; ++sby)
+                for (int sbx = 0; sbx < ssx[c]; ++sbx) {
+                    JG_RECONVERGE();
+                    if (m >= m1 || bad) continue;
                     int16_t* blk = coef + (coff[c] + (unsigned long long)(mby * ssy[c] + sby) * bw[c] + (mbx * ssx[c] + sbx)) * 64ull;
                     unsigned code = 0;
                     dcpred[c] += get_vlc(r, T, dctab[c], &code, &bad);
@@ -326,8 +347,7 @@ __global__ void decode_intervals_kernel(const DevParams* __restrict__ imgs)
     if ((int)(blockIdx.x * blockDim.x) >= P.n_intervals) return;            // whole CTA surplus: no table needed
     for (int i = (int)threadIdx.x; i < (4 << kL1Bits); i += (int)blockDim.x) l1[i] = l1_entry(P.vlc, i >> kL1Bits, i & ((1 << kL1Bits) - 1));
     __syncthreads();
-    const int iv = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (iv < P.n_intervals) decode_interval(P, l1, iv);
+    decode_interval(P, l1, (int)(blockIdx.x * blockDim.x + threadIdx.x));      // every lane: the warp reconverges per block
 }
 __global__ void idct_kernel(const DevParams* __restrict__ imgs, int c)
 {
