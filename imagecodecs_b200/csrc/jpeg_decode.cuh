@@ -231,10 +231,12 @@ JG_DEV void row_idct(int* blk)   // njRowIDCT (:350-396)
     blk[7] = (x7 - x1) >> 8;
 }
 
-JG_DEV void col_idct(const int* blk, unsigned char* out, int stride)   // njColIDCT (:398-442)
+// njColIDCT (:398-442); IS = distance between the column's elements (8 in a plain block, 9 in a padded shared-memory tile)
+template <int IS>
+JG_DEV void col_idct(const int* blk, unsigned char* out, int stride)
 {
     int x0, x1, x2, x3, x4, x5, x6, x7, x8;
-    if (!((x1 = blk[8 * 4] << 8) | (x2 = blk[8 * 6]) | (x3 = blk[8 * 2]) | (x4 = blk[8 * 1]) | (x5 = blk[8 * 7]) | (x6 = blk[8 * 5]) | (x7 = blk[8 * 3]))) {
+    if (!((x1 = blk[IS * 4] << 8) | (x2 = blk[IS * 6]) | (x3 = blk[IS * 2]) | (x4 = blk[IS * 1]) | (x5 = blk[IS * 7]) | (x6 = blk[IS * 5]) | (x7 = blk[IS * 3]))) {
         x1 = clip8(((blk[0] + 32) >> 6) + 128);
         for (x0 = 8; x0; --x0) { *out = (unsigned char)x1; out += stride; }
         return;
@@ -281,7 +283,7 @@ JG_DEV void idct_block(const DevParams& P, int c, unsigned long long b)
     for (int r = 0; r < 64; r += 8) row_idct(blk + r);
     const unsigned long long by = b / (unsigned long long)K.bw, bx = b - by * (unsigned long long)K.bw;
     unsigned char* out = P.planes + K.plane_off + ((by * (unsigned long long)K.stride + bx) << 3);
-    for (int col = 0; col < 8; ++col) col_idct(blk + col, out + col, K.stride);
+    for (int col = 0; col < 8; ++col) col_idct<8>(blk + col, out + col, K.stride);
 }
 
 // ---- chroma upsampling (jpeg_dec.h:722-790) --------------------------------------------------
@@ -349,12 +351,39 @@ __global__ void decode_intervals_kernel(const DevParams* __restrict__ imgs)
     __syncthreads();
     decode_interval(P, l1, (int)(blockIdx.x * blockDim.x + threadIdx.x));      // every lane: the warp reconverges per block
 }
+// IDCT: eight threads per block.  Thread r loads row r (one 16-byte load), dequantises and runs njRowIDCT
+// in registers; the 8x8 goes through a padded shared-memory tile; thread c then runs njColIDCT on column c
+// and the eight threads write one 8-byte row segment at a time.  (idct_block above is the same arithmetic
+// with one thread per block; the CPU harness uses that one.)
+constexpr int kIdctThreads = 128;
 __global__ void idct_kernel(const DevParams* __restrict__ imgs, int c)
 {
     const DevParams& P = imgs[blockIdx.y];
     if (c >= P.ncomp) return;
-    const unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < P.comp[c].n_blocks) idct_block(P, c, b);
+    __shared__ int tile[kIdctThreads / 8][72];
+    __shared__ int dq[64];
+    const int t = (int)threadIdx.x, l = t & 7, bi = t >> 3;
+    if (t < 64) dq[t] = P.comp[c].dq[t];
+    __syncthreads();
+    const unsigned long long b = (unsigned long long)blockIdx.x * (kIdctThreads / 8) + bi;
+    const bool valid = b < P.comp[c].n_blocks;
+    if (valid) {
+        const uint4 v = *reinterpret_cast<const uint4*>(P.coef + (P.comp[c].coef_off + b) * 64ull + 8 * l);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+        int row[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) row[i] = (int)(short)((w[i >> 1] >> (16 * (i & 1))) & 0xffffu) * dq[8 * l + i];
+        row_idct(row);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tile[bi][9 * l + i] = row[i];
+    }
+    __syncwarp();
+    if (valid) {
+        const int bw = P.comp[c].bw, stride = P.comp[c].stride;
+        const unsigned long long by = b / (unsigned long long)bw, bx = b - by * (unsigned long long)bw;
+        unsigned char* out = P.planes + P.comp[c].plane_off + ((by * (unsigned long long)stride + bx) << 3);
+        col_idct<9>(&tile[bi][l], out + l, stride);
+    }
 }
 // The plane stages handle FOUR neighbouring output pixels per thread and store them as one 32-bit word
 // (three for RGB) where the address allows it: a quarter of the threads and store instructions.

@@ -227,7 +227,7 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
     if (kernel_ms) { JD_CUDA(cudaEventCreate(&e0)); JD_CUDA(cudaEventCreate(&e1)); JD_CUDA(cudaEventRecord(e0, B.s)); }
     decode_intervals_kernel<<<dim3((unsigned)((max_iv + 63) / 64), (unsigned)n), 64, 0, B.s>>>(d_params);
     for (int c = 0; c < 3; ++c)
-        if (max_blocks[c]) idct_kernel<<<dim3((unsigned)((max_blocks[c] + 127) / 128), (unsigned)n), 128, 0, B.s>>>(d_params, c);
+        if (max_blocks[c]) idct_kernel<<<dim3((unsigned)((max_blocks[c] + 15) / 16), (unsigned)n), kIdctThreads, 0, B.s>>>(d_params, c);   // 16 blocks per CTA
     for (const Round& r : rounds) {
         if (r.dir == 0) upsample_h_kernel<<<r.grid, 128, 0, B.s>>>(r.d_ops);
         else upsample_v_kernel<<<r.grid, 128, 0, B.s>>>(r.d_ops);
