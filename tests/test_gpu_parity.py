@@ -484,6 +484,21 @@ def test_decoder_matches_nanojpeg(gpu, fixture_pixels, golden_dir):
         assert (got[i] is None) == (want is None) and (want is None or np.array_equal(got[i], want)), i
 
 
+def test_encode_decode_round_trip_on_the_gpu(gpu):
+    """Both directions on the device: pixels -> restart-interval JPEG -> pixels.  The decoded images equal what the
+    reference decoder makes of the same files, and they are close to the originals (PSNR), for a batch of mixed shapes."""
+    shapes = [(640, 480, 3, 90, 0), (1000, 700, 3, 75, 1), (333, 222, 1, 85, 0), (1920, 1080, 3, 95, 0)]
+    imgs = [oracle.synth_image(w, h, nc) for (w, h, nc, q, sub) in shapes]
+    files, st = gpu.encode_batch(imgs, 1, [s[3] for s in shapes], [s[4] for s in shapes], device=0, flags=gpu.FLAG_RESTART, capacity=16 << 20)
+    assert st == [0] * len(shapes)
+    back = gpu.decode_batch(files)
+    for img, f, got, (w, h, nc, q, sub) in zip(imgs, files, back, shapes):
+        assert np.array_equal(got, oracle.ref_decode(f))
+        ref = img[:, :, 0] if nc == 1 else img
+        # (the synthetic images wrap around at 255 and carry per-channel noise: hard content, especially for 4:2:0)
+        assert psnr(ref, got) > (20.0 if sub else 30.0), (w, h, q, sub, psnr(ref, got))
+
+
 def test_cpp_facade_reads_jpg_and_round_trips(gpu, fixture_pixels, golden_dir, tmp_path):
     """tests.cpp pass 1 for the JPEG fixture, all on the GPU: Image::read("test.jpg") (decode) then write("out.jpg")
     (encode) -- the same file the reference writes for it (KAT 'testjpg')."""
