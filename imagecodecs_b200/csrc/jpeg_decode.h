@@ -38,6 +38,8 @@ struct Info {
     uint8_t qtab[4][64] = {};
     int qtused = 0, qtavail = 0;
     std::vector<uint16_t> vlc;      // [4][65536]: bits << 8 | code (nj_vlc_code_t, :291-293), tables 0,1 = DC, 2,3 = AC
+                                    // (left empty by parse(..., build_vlc = false): build_vlc_tables() makes it from `dht`)
+    std::vector<uint8_t> dht;       // the payloads of the file's DHT segments, back to back: equal bytes <=> equal tables
     size_t scan_off = 0, scan_end = 0;          // entropy-coded data [scan_off, scan_end) of the file
     std::vector<uint32_t> interval_off;         // start of every restart interval (file offsets) + one past the last
     size_t n_blocks = 0, plane_bytes = 0;
@@ -46,6 +48,8 @@ struct Info {
 
 // The marker loop of njDecode up to and including the SOS header, plus the split of the scan
 // into restart intervals.  Returns an nj_result_t.
-int parse(const uint8_t* jpeg, size_t size, Info* info);
+int parse(const uint8_t* jpeg, size_t size, Info* info, bool build_vlc = true);
+// njDecodeDHT (:573-614) over the collected DHT payloads; a batch builds each distinct table set once
+int build_vlc_tables(const std::vector<uint8_t>& dht, std::vector<uint16_t>* vlc);
 
 }  // namespace jd

@@ -75,23 +75,30 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
     if (!in || !outs || n <= 0) { jg::set_error_text("decode: null argument"); return 0; }
     if (n > 32767) { jg::set_error_text("decode: at most 32767 images per call"); return 0; }   // two plane ops per image in grid.z
     std::vector<Job> jobs((size_t)n);
-    std::vector<std::vector<uint16_t>> vlc_sets;      // distinct Huffman table sets of the batch (usually one)
+    std::vector<std::vector<uint8_t>> dht_sets;       // distinct Huffman table sets of the batch (usually one), by their DHT bytes
+    std::vector<std::vector<uint16_t>> vlc_sets;
     size_t data_bytes = 0, iv_words = 0, coef_words = 0, plane_bytes = 0, out_total = 0;
     int n_ok = 0, max_iv = 0;
     unsigned long long max_blocks[3] = {0, 0, 0};
     for (int i = 0; i < n; ++i) {
         Job& j = jobs[i];
         outs[i].width = outs[i].height = outs[i].ncomp = 0;
-        const int rc = in[i].data ? parse(in[i].data, in[i].size, &j.I) : (int)kNoJpeg;
+        int rc = in[i].data ? parse(in[i].data, in[i].size, &j.I, false) : (int)kNoJpeg;
+        size_t slot = 0;
+        if (rc == kOk) {                                      // the 65536-entry tables are built once per distinct DHT content
+            while (slot < dht_sets.size() && dht_sets[slot] != j.I.dht) ++slot;
+            if (slot == dht_sets.size()) {
+                std::vector<uint16_t> tables;
+                rc = build_vlc_tables(j.I.dht, &tables);
+                if (rc == kOk) { dht_sets.push_back(j.I.dht); vlc_sets.push_back(std::move(tables)); }
+            }
+        }
         outs[i].status = rc == kOk ? JPEG_GPU_OK : JPEG_GPU_ERR_ARG;
         if (rc != kOk) { jg::set_error_text(result_text(rc)); continue; }
         outs[i].width = j.I.width; outs[i].height = j.I.height; outs[i].ncomp = j.I.ncomp;
         j.out_bytes = (size_t)j.I.width * j.I.height * j.I.ncomp;
         if (!outs[i].pixels || outs[i].capacity < j.out_bytes) { outs[i].status = JPEG_GPU_ERR_CAPACITY; jg::set_error_text("decode: output buffer too small"); continue; }
         j.ok = true; ++n_ok;
-        size_t slot = 0;
-        while (slot < vlc_sets.size() && vlc_sets[slot] != j.I.vlc) ++slot;
-        if (slot == vlc_sets.size()) vlc_sets.push_back(j.I.vlc);
         j.vlc_slot = (int)slot;
         j.data_off = data_bytes; data_bytes += align256(j.I.scan_end + 16);
         j.iv_off = iv_words; iv_words += j.I.interval_off.size();
@@ -271,7 +278,8 @@ int jpeg_gpu_decode_info(const uint8_t* jpeg, size_t size, int* width, int* heig
 {
     if (!jpeg) return 0;
     jd::Info I;
-    const int rc = jd::parse(jpeg, size, &I);
+    int rc = jd::parse(jpeg, size, &I, false);
+    if (rc == jd::kOk) { std::vector<uint16_t> tables; rc = jd::build_vlc_tables(I.dht, &tables); }   // a file njDecode would reject is rejected here too
     if (rc != jd::kOk) { jg::set_error_text(result_text(rc)); return 0; }
     if (width) *width = I.width;
     if (height) *height = I.height;

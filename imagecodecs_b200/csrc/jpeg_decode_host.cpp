@@ -80,20 +80,19 @@ int parse_sof(Cursor& c, Info* I)      // njDecodeSOF (:520-571)
     return kOk;
 }
 
-int parse_dht(Cursor& c, Info* I)      // njDecodeDHT (:573-614)
+// njDecodeDHT (:573-614) over one segment payload [p, p + len): fills the 65536-entry tables
+int dht_payload(const uint8_t* p, size_t len, std::vector<uint16_t>* out)
 {
-    size_t len;
-    if (!segment(c, &len)) return c.error;
-    if (I->vlc.empty()) I->vlc.assign(4 * 65536, 0);
+    if (out->empty()) out->assign(4 * 65536, 0);
     while (len >= 17) {
-        int i = c.p[0];
+        int i = p[0];
         if (i & 0xEC) return kSyntaxError;
         if (i & 0x02) return kUnsupported;
         i = (i | (i >> 3)) & 3;                        // combined DC/AC + table id
         uint8_t counts[16];
-        memcpy(counts, c.p + 1, 16);
-        c.skip(17); len -= 17;
-        uint16_t* vlc = &I->vlc[(size_t)i * 65536];
+        memcpy(counts, p + 1, 16);
+        p += 17; len -= 17;
+        uint16_t* vlc = &(*out)[(size_t)i * 65536];
         int remain = 65536, spread = 65536;
         for (int codelen = 1; codelen <= 16; ++codelen) {
             spread >>= 1;
@@ -103,14 +102,25 @@ int parse_dht(Cursor& c, Info* I)      // njDecodeDHT (:573-614)
             remain -= currcnt << (16 - codelen);
             if (remain < 0) return kSyntaxError;
             for (int k = 0; k < currcnt; ++k) {
-                const uint16_t e = (uint16_t)((codelen << 8) | c.p[k]);
+                const uint16_t e = (uint16_t)((codelen << 8) | p[k]);
                 for (int j = spread; j; --j) *vlc++ = e;
             }
-            c.skip((size_t)currcnt); len -= (size_t)currcnt;
+            p += currcnt; len -= (size_t)currcnt;
         }
         while (remain--) *vlc++ = 0;
     }
     return len ? kSyntaxError : kOk;
+}
+
+// a DHT segment: remembered verbatim (length-prefixed); the tables are built from these bytes
+int parse_dht(Cursor& c, Info* I)
+{
+    size_t len;
+    if (!segment(c, &len)) return c.error;
+    I->dht.push_back((uint8_t)(len >> 8)); I->dht.push_back((uint8_t)len);
+    I->dht.insert(I->dht.end(), c.p, c.p + len);
+    c.skip(len);
+    return kOk;
 }
 
 int parse_dqt(Cursor& c, Info* I)      // njDecodeDQT (:616-631)
@@ -148,7 +158,19 @@ int parse_sos(Cursor& c, Info* I)      // header part of njDecodeScan (:674-692)
 
 }  // namespace
 
-int parse(const uint8_t* jpeg, size_t size, Info* I)
+int build_vlc_tables(const std::vector<uint8_t>& dht, std::vector<uint16_t>* vlc)
+{
+    vlc->clear();
+    for (size_t at = 0; at + 2 <= dht.size();) {
+        const size_t len = ((size_t)dht[at] << 8) | dht[at + 1];
+        const int rc = dht_payload(dht.data() + at + 2, len, vlc);
+        if (rc != kOk) return rc;
+        at += 2 + len;
+    }
+    return vlc->empty() ? (int)kSyntaxError : (int)kOk;
+}
+
+int parse(const uint8_t* jpeg, size_t size, Info* I, bool build_vlc)
 {
     size &= 0x7FFFFFFF;
     if (size < 2 || jpeg[0] != 0xFF || jpeg[1] != 0xD8) return kNoJpeg;
@@ -171,9 +193,10 @@ int parse(const uint8_t* jpeg, size_t size, Info* I)
                 c.skip(len);
                 break;
             case 0xDA:
-                if (!have_sof || I->vlc.empty()) return kSyntaxError;
+                if (!have_sof || I->dht.empty()) return kSyntaxError;
                 rc = parse_sos(c, I);
                 if (rc != kOk) return rc;
+                if (build_vlc && (rc = build_vlc_tables(I->dht, &I->vlc)) != kOk) return rc;
                 goto scan;
             case 0xFE:
                 if (!segment(c, &len)) return c.error;
