@@ -353,7 +353,7 @@ def run_ours(args):
     # ---- the other direction: the same batch written with restart intervals, decoded by
     #      jpeg_gpu_decode_batch; kernels device-timed by the library (CUDA events around its launches) ------
     decode = None
-    if rank == 0 and not args.no_twin:
+    if rank == 0 and world == 1 and not args.no_twin:
         try:
             rplan = jg.Plan.for_arrays(imgs, QMODE, QUALITY, SUB, device=0, flags=jg.FLAG_RESTART)
             rplan.run(sptr); torch.cuda.synchronize()
