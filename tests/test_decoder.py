@@ -52,3 +52,26 @@ def test_rejects_what_the_reference_rejects():
     assert oracle.ref_decode(b.getvalue()) is None and emu_decode(b.getvalue()) == 2    # progressive: NJ_UNSUPPORTED
     good = oracle.oracle_encode(oracle.synth_image(40, 40, 3), 0, 3, 0)
     assert emu_decode(good[:300]) == 5                                             # truncated in the tables: NJ_SYNTAX_ERROR
+
+
+def test_decodes_foreign_restart_streams_and_411():
+    """libjpeg (OpenCV) files with restart intervals of 1 / 7 / 16 MCUs in 4:4:4, 4:2:0, 4:2:2 and 4:1:1 (two horizontal
+    filter passes), gray with restarts, PIL 4:1:1: the parallel path on streams this encoder did not write."""
+    import cv2
+    from PIL import Image
+    img = oracle.synth_image(211, 97, 3)
+    files = []
+    for rst in (1, 7, 16):
+        for ss in (cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+                   cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411):
+            ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 85, cv2.IMWRITE_JPEG_RST_INTERVAL, rst, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, ss])
+            assert ok
+            files.append(enc.tobytes())
+    ok, enc = cv2.imencode(".jpg", img[:, :, 0].copy(), [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, 5])
+    files.append(enc.tobytes())
+    b = io.BytesIO(); Image.fromarray(img).save(b, "JPEG", subsampling="4:1:1", quality=80)
+    files.append(b.getvalue())
+    for i, f in enumerate(files):
+        want = oracle.ref_decode(f)
+        got = emu_decode(f)
+        assert want is not None and isinstance(got, np.ndarray) and np.array_equal(got, want), i

@@ -473,6 +473,12 @@ def test_decoder_matches_nanojpeg(gpu, fixture_pixels, golden_dir):
         assert np.array_equal(gpu.decode(b.getvalue()), oracle.ref_decode(b.getvalue())), kw
     with pytest.raises(gpu.JpegGpuError):
         gpu.decode(b"\x00\x01\x02\x03")
+    # libjpeg (OpenCV) restart streams, incl. 4:1:1 (two horizontal filter passes)
+    import cv2
+    src = oracle.synth_image(640, 363, 3)
+    for rst, ss in ((1, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420), (7, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411), (40, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422)):
+        ok, enc = cv2.imencode(".jpg", src, [cv2.IMWRITE_JPEG_QUALITY, 85, cv2.IMWRITE_JPEG_RST_INTERVAL, rst, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, ss])
+        assert ok and np.array_equal(gpu.decode(enc.tobytes()), oracle.ref_decode(enc.tobytes())), (rst, hex(ss))
     # one call, many files of different sizes / samplings / table sets, one of them broken
     batch = [oracle.synth_image(w, h, nc) for (w, h, nc) in [(320, 200, 3), (333, 222, 3), (100, 60, 1), (64, 64, 3)]]
     files = [encode_one(gpu, batch[0], 1, 75, 1, flags=gpu.FLAG_RESTART), encode_one(gpu, batch[1], 0, 2, 0, flags=gpu.FLAG_RESTART),
