@@ -337,7 +337,10 @@ JG_DEV void to_rgb(unsigned char* rgb, int yv, int cbv, int crv)
 
 // per-image work lists of the plane stages
 struct PlaneOp { const unsigned char* in; unsigned char* out; int w, h, s; };                      // one upsampling pass of one plane
-struct ColorOp { const unsigned char *py, *pcb, *pcr; int sy, scb, scr; unsigned char* out; int w, h, ncomp; };
+struct ColorOp {
+    const unsigned char *py, *pcb, *pcr; int sy, scb, scr; unsigned char* out; int w, h, ncomp;
+    int chroma_h;      // > 0: the chroma planes still have this many rows -- their last vertical filter pass runs inside the colour kernel
+};
 
 #if !defined(JG_EMULATE)
 // Every kernel works on a BATCH: blockIdx.y (or .z) picks the image, the x dimension covers the largest
@@ -454,13 +457,36 @@ __global__ void color_kernel(const ColorOp* __restrict__ ops)
         return;
     }
     unsigned char rgb[12];
-    const unsigned char *py = o.py + (size_t)y * o.sy + x, *pcb = o.pcb + (size_t)y * o.scb + x, *pcr = o.pcr + (size_t)y * o.scr + x;
-    if (n == 4 && ((((size_t)py) | ((size_t)pcb) | ((size_t)pcr)) & 3u) == 0) {       // a word per plane instead of four bytes
-        const unsigned wy = *reinterpret_cast<const unsigned*>(py), wb = *reinterpret_cast<const unsigned*>(pcb), wr = *reinterpret_cast<const unsigned*>(pcr);
+    const unsigned char* py = o.py + (size_t)y * o.sy + x;
+    if (o.chroma_h > 0) {
+        // 4:2:0 and friends: njUpsampleV of Cb and Cr for output row y, computed here instead of written to a plane
+        // and read back (same taps, same integer sums, same clip as upsample_v)
+        unsigned char cb[4] = {0, 0, 0, 0}, cr[4] = {0, 0, 0, 0};
+        if (n == 4 && ((((size_t)o.pcb) | ((size_t)o.pcr) | (size_t)o.scb | (size_t)o.scr) & 3u) == 0) {
+            int row[4] = {0, 0, 0, 0}, k[4] = {0, 0, 0, 0};
+            const int taps = v_taps(o.chroma_h, y, row, k);
+            int sb[4] = {0, 0, 0, 0}, sr[4] = {0, 0, 0, 0};
+            for (int j = 0; j < taps; ++j) {
+                const unsigned wb = *reinterpret_cast<const unsigned*>(o.pcb + (size_t)row[j] * o.scb + x);
+                const unsigned wr = *reinterpret_cast<const unsigned*>(o.pcr + (size_t)row[j] * o.scr + x);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) to_rgb(rgb + 3 * i, (int)((wy >> (8 * i)) & 0xffu), (int)((wb >> (8 * i)) & 0xffu), (int)((wr >> (8 * i)) & 0xffu));
+                for (int i = 0; i < 4; ++i) { sb[i] += k[j] * (int)((wb >> (8 * i)) & 0xffu); sr[i] += k[j] * (int)((wr >> (8 * i)) & 0xffu); }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { cb[i] = JD_CF(sb[i]); cr[i] = JD_CF(sr[i]); }
+        } else {
+            for (int i = 0; i < n; ++i) { cb[i] = upsample_v(o.pcb, o.chroma_h, o.scb, y, x + i); cr[i] = upsample_v(o.pcr, o.chroma_h, o.scr, y, x + i); }
+        }
+        for (int i = 0; i < n; ++i) to_rgb(rgb + 3 * i, py[i], cb[i], cr[i]);
     } else {
-        for (int i = 0; i < n; ++i) to_rgb(rgb + 3 * i, py[i], pcb[i], pcr[i]);
+        const unsigned char *pcb = o.pcb + (size_t)y * o.scb + x, *pcr = o.pcr + (size_t)y * o.scr + x;
+        if (n == 4 && ((((size_t)py) | ((size_t)pcb) | ((size_t)pcr)) & 3u) == 0) {       // a word per plane instead of four bytes
+            const unsigned wy = *reinterpret_cast<const unsigned*>(py), wb = *reinterpret_cast<const unsigned*>(pcb), wr = *reinterpret_cast<const unsigned*>(pcr);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) to_rgb(rgb + 3 * i, (int)((wy >> (8 * i)) & 0xffu), (int)((wb >> (8 * i)) & 0xffu), (int)((wr >> (8 * i)) & 0xffu));
+        } else {
+            for (int i = 0; i < n; ++i) to_rgb(rgb + 3 * i, py[i], pcb[i], pcr[i]);
+        }
     }
     unsigned char* dst = o.out + ((size_t)y * o.w + x) * 3;
     if (n == 4 && (((size_t)dst) & 3u) == 0) {

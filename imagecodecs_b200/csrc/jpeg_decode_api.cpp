@@ -174,6 +174,16 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
     JD_CUDA(cudaMemcpyAsync(d_params, params.data(), (size_t)n * sizeof(DevParams), cudaMemcpyHostToDevice, B.s));
 
     // rounds of batch-wide passes; the op lists stay alive until the final synchronisation (pageable copies read them then at the latest)
+    // 3-component images whose two chroma planes need exactly one more vertical pass at full width: that pass is fused
+    // into the colour kernel (ColorOp::chroma_h)
+    std::vector<int> fused_h((size_t)n, 0);
+    auto fuse_now = [&](int i) {
+        const Info& I = jobs[i].I;
+        if (I.ncomp != 3) return false;
+        const PlaneState &a = st[(size_t)i * 3 + 1], &b = st[(size_t)i * 3 + 2];
+        return a.w >= I.width && b.w >= I.width && a.h == b.h && a.h < I.height && 2 * a.h >= I.height && st[(size_t)i * 3].h >= I.height &&
+               st[(size_t)i * 3].w >= I.width;
+    };
     struct Round { int dir; PlaneOp* d_ops; dim3 grid; };
     std::vector<Round> rounds;
     std::vector<std::vector<PlaneOp>> keep;
@@ -183,8 +193,11 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
             std::vector<PlaneOp> ops;
             size_t bytes = 0;
             int gw = 0, gh = 0;
+            if (dir == 1)
+                for (int i = 0; i < n; ++i)
+                    if (jobs[i].ok && !fused_h[i] && fuse_now(i)) fused_h[i] = st[(size_t)i * 3 + 1].h;
             for (int i = 0; i < n; ++i) {
-                if (!jobs[i].ok) continue;
+                if (!jobs[i].ok || fused_h[i]) continue;
                 for (int c = 0; c < jobs[i].I.ncomp; ++c) {
                     const PlaneState& p = st[(size_t)i * 3 + c];
                     if (dir == 0 ? p.w < jobs[i].I.width : p.h < jobs[i].I.height) bytes += align256((size_t)p.w * p.h * 2);
@@ -195,7 +208,7 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
             if (!pool) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
             size_t off = 0;
             for (int i = 0; i < n; ++i) {
-                if (!jobs[i].ok) continue;
+                if (!jobs[i].ok || fused_h[i]) continue;
                 for (int c = 0; c < jobs[i].I.ncomp; ++c) {
                     PlaneState& p = st[(size_t)i * 3 + c];
                     if (!(dir == 0 ? p.w < jobs[i].I.width : p.h < jobs[i].I.height)) continue;
@@ -223,7 +236,8 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
         const Info& I = jobs[i].I;
         const PlaneState* p = &st[(size_t)i * 3];
         uint8_t* dst = pixels_on_device ? outs[i].pixels : d_out + jobs[i].out_off;
-        cops.push_back({p[0].p, I.ncomp == 3 ? p[1].p : nullptr, I.ncomp == 3 ? p[2].p : nullptr, p[0].s, p[1].s, p[2].s, dst, I.width, I.height, I.ncomp});
+        cops.push_back({p[0].p, I.ncomp == 3 ? p[1].p : nullptr, I.ncomp == 3 ? p[2].p : nullptr, p[0].s, p[1].s, p[2].s, dst, I.width, I.height, I.ncomp,
+                        fused_h[i]});
         cw = std::max(cw, I.width); ch = std::max(ch, I.height);
     }
     ColorOp* d_cops = B.alloc<ColorOp>(cops.size());
