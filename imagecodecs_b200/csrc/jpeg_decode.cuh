@@ -185,92 +185,66 @@ JG_DEV void decode_interval(const DevParams& P, const uint16_t* l1, int iv)
 
 JG_DEV unsigned char clip8(int x) { return x < 0 ? 0 : (x > 0xFF ? 0xFF : (unsigned char)x); }   // njClip (:339-341)
 
-#define JD_W1 2841
-#define JD_W2 2676
-#define JD_W3 2408
-#define JD_W5 1609
-#define JD_W6 1108
-#define JD_W7 565
+// ---- the 8-point inverse DCT of jpeg_dec.h:343-442 (a fixed-point Chen-Wang) ------------------------------
+// One routine for both passes; PASS 0 = row pass (input scaled by 2^11, result >> 8, stays int), PASS 1 = column
+// pass (input scaled by 2^8, the three rotations rounded and pre-shifted by 3, result >> 14, + 128, clipped).
+// The operation ORDER is the reference's: every product, sum and shift below has its twin there, so that
+// the 32-bit intermediate values (and their wrap-around on hostile input) are the same.
+constexpr int kC1 = 2841, kC2 = 2676, kC3 = 2408, kC5 = 1609, kC6 = 1108, kC7 = 565;   // 2048*sqrt(2)*cos(k*pi/16)
 
-JG_DEV void row_idct(int* blk)   // njRowIDCT (:350-396)
+template <int PASS>
+JG_DEV void idct8(int c0, int c1, int c2, int c3, int c4, int c5, int c6, int c7, int (&out)[8])
 {
-    int x0, x1, x2, x3, x4, x5, x6, x7, x8;
-    if (!((x1 = blk[4] << 11) | (x2 = blk[6]) | (x3 = blk[2]) | (x4 = blk[1]) | (x5 = blk[7]) | (x6 = blk[5]) | (x7 = blk[3]))) {
-        blk[0] = blk[1] = blk[2] = blk[3] = blk[4] = blk[5] = blk[6] = blk[7] = blk[0] << 3;
+    constexpr int kIn = PASS == 0 ? 11 : 8;             // scale of the two even inputs that are not rotated
+    constexpr int kBias = PASS == 0 ? 128 : 8192;       // rounding of the final shift, carried by the DC term
+    constexpr int kRot = PASS == 0 ? 0 : 3;             // the column pass shifts every rotation down by 3 (after + 4)
+    constexpr int kRnd = PASS == 0 ? 0 : 4;
+    // odd half: two rotations (1,7) and (5,3)
+    const int s17 = kC7 * (c1 + c7) + kRnd;
+    const int o1 = (s17 + (kC1 - kC7) * c1) >> kRot;
+    const int o7 = (s17 - (kC1 + kC7) * c7) >> kRot;
+    const int s53 = kC3 * (c5 + c3) + kRnd;
+    const int o5 = (s53 - (kC3 - kC5) * c5) >> kRot;
+    const int o3 = (s53 - (kC3 + kC5) * c3) >> kRot;
+    // even half: (0,4) butterfly and the (2,6) rotation
+    const int e0 = (c0 << kIn) + kBias, e4 = c4 << kIn;
+    const int sum04 = e0 + e4, dif04 = e0 - e4;
+    const int s26 = kC6 * (c2 + c6) + kRnd;
+    const int r6 = (s26 - (kC2 + kC6) * c6) >> kRot;
+    const int r2 = (s26 + (kC2 - kC6) * c2) >> kRot;
+    // second stage
+    const int t15 = o1 + o5, d15 = o1 - o5, t73 = o7 + o3, d73 = o7 - o3;
+    const int a = sum04 + r2, b = sum04 - r2, c = dif04 + r6, d = dif04 - r6;
+    const int m = (181 * (d15 + d73) + 128) >> 8;       // 181/256 = 1/sqrt(2)
+    const int n = (181 * (d15 - d73) + 128) >> 8;
+    out[0] = a + t15; out[1] = c + m; out[2] = d + n; out[3] = b + t73;
+    out[4] = b - t73; out[5] = d - n; out[6] = c - m; out[7] = a - t15;
+}
+
+JG_DEV void row_idct(int* blk)   // njRowIDCT (:350-396): in place, results keep 3 fraction bits
+{
+    if (!((blk[4] << 11) | blk[6] | blk[2] | blk[1] | blk[7] | blk[5] | blk[3])) {      // only DC: a flat row
+        const int v = blk[0] << 3;
+        for (int i = 0; i < 8; ++i) blk[i] = v;
         return;
     }
-    x0 = (blk[0] << 11) + 128;
-    x8 = JD_W7 * (x4 + x5);
-    x4 = x8 + (JD_W1 - JD_W7) * x4;
-    x5 = x8 - (JD_W1 + JD_W7) * x5;
-    x8 = JD_W3 * (x6 + x7);
-    x6 = x8 - (JD_W3 - JD_W5) * x6;
-    x7 = x8 - (JD_W3 + JD_W5) * x7;
-    x8 = x0 + x1;
-    x0 -= x1;
-    x1 = JD_W6 * (x3 + x2);
-    x2 = x1 - (JD_W2 + JD_W6) * x2;
-    x3 = x1 + (JD_W2 - JD_W6) * x3;
-    x1 = x4 + x6;
-    x4 -= x6;
-    x6 = x5 + x7;
-    x5 -= x7;
-    x7 = x8 + x3;
-    x8 -= x3;
-    x3 = x0 + x2;
-    x0 -= x2;
-    x2 = (181 * (x4 + x5) + 128) >> 8;
-    x4 = (181 * (x4 - x5) + 128) >> 8;
-    blk[0] = (x7 + x1) >> 8;
-    blk[1] = (x3 + x2) >> 8;
-    blk[2] = (x0 + x4) >> 8;
-    blk[3] = (x8 + x6) >> 8;
-    blk[4] = (x8 - x6) >> 8;
-    blk[5] = (x0 - x4) >> 8;
-    blk[6] = (x3 - x2) >> 8;
-    blk[7] = (x7 - x1) >> 8;
+    int o[8];
+    idct8<0>(blk[0], blk[1], blk[2], blk[3], blk[4], blk[5], blk[6], blk[7], o);
+    for (int i = 0; i < 8; ++i) blk[i] = o[i] >> 8;
 }
 
 // njColIDCT (:398-442); IS = distance between the column's elements (8 in a plain block, 9 in a padded shared-memory tile)
 template <int IS>
 JG_DEV void col_idct(const int* blk, unsigned char* out, int stride)
 {
-    int x0, x1, x2, x3, x4, x5, x6, x7, x8;
-    if (!((x1 = blk[IS * 4] << 8) | (x2 = blk[IS * 6]) | (x3 = blk[IS * 2]) | (x4 = blk[IS * 1]) | (x5 = blk[IS * 7]) | (x6 = blk[IS * 5]) | (x7 = blk[IS * 3]))) {
-        x1 = clip8(((blk[0] + 32) >> 6) + 128);
-        for (x0 = 8; x0; --x0) { *out = (unsigned char)x1; out += stride; }
+    if (!((blk[IS * 4] << 8) | blk[IS * 6] | blk[IS * 2] | blk[IS * 1] | blk[IS * 7] | blk[IS * 5] | blk[IS * 3])) {   // only DC: a flat column
+        const unsigned char v = clip8(((blk[0] + 32) >> 6) + 128);
+        for (int i = 0; i < 8; ++i) out[(size_t)i * stride] = v;
         return;
     }
-    x0 = (blk[0] << 8) + 8192;
-    x8 = JD_W7 * (x4 + x5) + 4;
-    x4 = (x8 + (JD_W1 - JD_W7) * x4) >> 3;
-    x5 = (x8 - (JD_W1 + JD_W7) * x5) >> 3;
-    x8 = JD_W3 * (x6 + x7) + 4;
-    x6 = (x8 - (JD_W3 - JD_W5) * x6) >> 3;
-    x7 = (x8 - (JD_W3 + JD_W5) * x7) >> 3;
-    x8 = x0 + x1;
-    x0 -= x1;
-    x1 = JD_W6 * (x3 + x2) + 4;
-    x2 = (x1 - (JD_W2 + JD_W6) * x2) >> 3;
-    x3 = (x1 + (JD_W2 - JD_W6) * x3) >> 3;
-    x1 = x4 + x6;
-    x4 -= x6;
-    x6 = x5 + x7;
-    x5 -= x7;
-    x7 = x8 + x3;
-    x8 -= x3;
-    x3 = x0 + x2;
-    x0 -= x2;
-    x2 = (181 * (x4 + x5) + 128) >> 8;
-    x4 = (181 * (x4 - x5) + 128) >> 8;
-    *out = clip8(((x7 + x1) >> 14) + 128); out += stride;
-    *out = clip8(((x3 + x2) >> 14) + 128); out += stride;
-    *out = clip8(((x0 + x4) >> 14) + 128); out += stride;
-    *out = clip8(((x8 + x6) >> 14) + 128); out += stride;
-    *out = clip8(((x8 - x6) >> 14) + 128); out += stride;
-    *out = clip8(((x0 - x4) >> 14) + 128); out += stride;
-    *out = clip8(((x3 - x2) >> 14) + 128); out += stride;
-    *out = clip8(((x7 - x1) >> 14) + 128);
+    int o[8];
+    idct8<1>(blk[0], blk[IS * 1], blk[IS * 2], blk[IS * 3], blk[IS * 4], blk[IS * 5], blk[IS * 6], blk[IS * 7], o);
+    for (int i = 0; i < 8; ++i) out[(size_t)i * stride] = clip8((o[i] >> 14) + 128);
 }
 
 // block b (raster index in its component's padded plane) of component c

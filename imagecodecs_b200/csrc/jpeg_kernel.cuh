@@ -199,20 +199,20 @@ JG_DEV void aan8(float (&d)[8])
     const float e1 = f_add(t1, t2), e2 = f_sub(t1, t2);
     d[0] = f_add(e0, e1);
     d[4] = f_sub(e0, e1);
-    const float z1 = f_mul(f_add(e2, e3), c4);
-    d[2] = f_add(e3, z1);
-    d[6] = f_sub(e3, z1);
+    const float half = f_mul(f_add(e2, e3), c4);
+    d[2] = f_add(e3, half);
+    d[6] = f_sub(e3, half);
 
     const float o0 = f_add(t4, t5), o1 = f_add(t5, t6), o2 = f_add(t6, t7);
-    const float z5 = f_mul(f_sub(o0, o2), c6);
-    const float z2 = f_add(f_mul(c2m6, o0), z5);
-    const float z4 = f_add(f_mul(c2p6, o2), z5);
-    const float z3 = f_mul(o1, c4);
-    const float z11 = f_add(t7, z3), z13 = f_sub(t7, z3);
-    d[5] = f_add(z13, z2);
-    d[3] = f_sub(z13, z2);
-    d[1] = f_add(z11, z4);
-    d[7] = f_sub(z11, z4);
+    const float rot = f_mul(f_sub(o0, o2), c6);
+    const float lo = f_add(f_mul(c2m6, o0), rot);
+    const float hi = f_add(f_mul(c2p6, o2), rot);
+    const float mid = f_mul(o1, c4);
+    const float sum7 = f_add(t7, mid), dif7 = f_sub(t7, mid);
+    d[5] = f_add(dif7, lo);
+    d[3] = f_sub(dif7, lo);
+    d[1] = f_add(sum7, hi);
+    d[7] = f_sub(sum7, hi);
 }
 
 // The same pass over TWO independent 8-point vectors at once (.x and .y): the 29 additions are
@@ -230,20 +230,20 @@ JG_DEV void aan8x2(f32x2 (&d)[8])
     const f32x2 e1 = f2_add(t1, t2), e2 = f2_sub(t1, t2);
     d[0] = f2_add(e0, e1);
     d[4] = f2_sub(e0, e1);
-    const f32x2 z1 = f2_mul(f2_add(e2, e3), c4);
-    d[2] = f2_add(e3, z1);
-    d[6] = f2_sub(e3, z1);
+    const f32x2 half = f2_mul(f2_add(e2, e3), c4);
+    d[2] = f2_add(e3, half);
+    d[6] = f2_sub(e3, half);
 
     const f32x2 o0 = f2_add(t4, t5), o1 = f2_add(t5, t6), o2 = f2_add(t6, t7);
-    const f32x2 z5 = f2_mul(f2_sub(o0, o2), c6);
-    const f32x2 z2 = f2_add(f2_mul(c2m6, o0), z5);
-    const f32x2 z4 = f2_add(f2_mul(c2p6, o2), z5);
-    const f32x2 z3 = f2_mul(o1, c4);
-    const f32x2 z11 = f2_add(t7, z3), z13 = f2_sub(t7, z3);
-    d[5] = f2_add(z13, z2);
-    d[3] = f2_sub(z13, z2);
-    d[1] = f2_add(z11, z4);
-    d[7] = f2_sub(z11, z4);
+    const f32x2 rot = f2_mul(f2_sub(o0, o2), c6);
+    const f32x2 lo = f2_add(f2_mul(c2m6, o0), rot);
+    const f32x2 hi = f2_add(f2_mul(c2p6, o2), rot);
+    const f32x2 mid = f2_mul(o1, c4);
+    const f32x2 sum7 = f2_add(t7, mid), dif7 = f2_sub(t7, mid);
+    d[5] = f2_add(dif7, lo);
+    d[3] = f2_sub(dif7, lo);
+    d[1] = f2_add(sum7, hi);
+    d[7] = f2_sub(sum7, hi);
 }
 
 // jpeg_enc.h:808-816: v*pqt, floorf((v + 1024) + 0.5f) - 1024, (int)
