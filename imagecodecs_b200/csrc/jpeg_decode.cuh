@@ -225,11 +225,13 @@ JG_DEV void row_idct(int* blk)   // njRowIDCT (:350-396): in place, results keep
 {
     if (!((blk[4] << 11) | blk[6] | blk[2] | blk[1] | blk[7] | blk[5] | blk[3])) {      // only DC: a flat row
         const int v = blk[0] << 3;
+#pragma unroll
         for (int i = 0; i < 8; ++i) blk[i] = v;
         return;
     }
     int o[8];
     idct8<0>(blk[0], blk[1], blk[2], blk[3], blk[4], blk[5], blk[6], blk[7], o);
+#pragma unroll
     for (int i = 0; i < 8; ++i) blk[i] = o[i] >> 8;
 }
 
@@ -239,11 +241,13 @@ JG_DEV void col_idct(const int* blk, unsigned char* out, int stride)
 {
     if (!((blk[IS * 4] << 8) | blk[IS * 6] | blk[IS * 2] | blk[IS * 1] | blk[IS * 7] | blk[IS * 5] | blk[IS * 3])) {   // only DC: a flat column
         const unsigned char v = clip8(((blk[0] + 32) >> 6) + 128);
+#pragma unroll
         for (int i = 0; i < 8; ++i) out[(size_t)i * stride] = v;
         return;
     }
     int o[8];
     idct8<1>(blk[0], blk[IS * 1], blk[IS * 2], blk[IS * 3], blk[IS * 4], blk[IS * 5], blk[IS * 6], blk[IS * 7], o);
+#pragma unroll
     for (int i = 0; i < 8; ++i) out[(size_t)i * stride] = clip8((o[i] >> 14) + 128);
 }
 
