@@ -196,7 +196,8 @@ typedef struct jpeg_gpu_stream { const uint8_t* data; size_t size; } jpeg_gpu_st
 typedef struct jpeg_gpu_decoded { uint8_t* pixels; size_t capacity; int width, height, ncomp, status; } jpeg_gpu_decoded;
 JPEG_GPU_API int jpeg_gpu_decode_batch(const jpeg_gpu_stream* streams, int n, jpeg_gpu_decoded* outs,
                                        int pixels_on_device, float* kernel_ms);
-/* the same; *kernel_ms receives the device time of the kernels (CUDA events), copies excluded */
+/* jpeg_gpu_decode; *kernel_ms receives the device time of the kernels (CUDA events), copies excluded.
+ * All decode entry points run on the first initialised GPU. */
 JPEG_GPU_API int jpeg_gpu_decode_timed(const uint8_t* jpeg, size_t size, uint8_t* pixels, size_t capacity,
                                        int* width, int* height, int* ncomp, float* kernel_ms);
 
