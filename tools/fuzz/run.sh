@@ -11,3 +11,7 @@ rm -rf in && PYTHONPATH="$ROOT" python gen.py
 g++ -std=c++17 -O1 -g -fsanitize=address -fno-omit-frame-pointer -pthread -I"$ROOT/tests/emu" -I"$ROOT/imagecodecs_b200/csrc" -o fuzz_dec \
     "$ROOT/tools/fuzz/fuzz_decoder_main.cpp" "$ROOT/tests/emu/emu_driver.cpp" "$ROOT/imagecodecs_b200/csrc/jpeg_host.cpp" "$ROOT/imagecodecs_b200/csrc/jpeg_decode_host.cpp"
 ls in/*.jpg | xargs -n 500 ./fuzz_dec
+# the encode kernel source under AddressSanitizer (18 shapes: plain / two-iteration / restart kernels, slow path, swizzles)
+g++ -std=c++17 -O1 -g -fsanitize=address -fno-omit-frame-pointer -ffp-contract=off -pthread -I"$ROOT/tests/emu" -I"$ROOT/imagecodecs_b200/csrc" -o asan_enc \
+    "$ROOT/tools/fuzz/asan_encoder_main.cpp" "$ROOT/tests/emu/emu_driver.cpp" "$ROOT/imagecodecs_b200/csrc/jpeg_host.cpp" "$ROOT/imagecodecs_b200/csrc/jpeg_decode_host.cpp"
+./asan_enc | tail -2
