@@ -4,10 +4,13 @@
 //
 //   decode_interval   one restart interval: Huffman decode (njGetVLC :643-656, njDecodeBlock :658-672
 //                     without its IDCT) into quantised coefficients, natural order, int16
+//   decode_subsequence  the same decode for a scan WITHOUT restart markers, cut into fixed-size subsequences
+//                     (speculative rounds until neighbours agree, a scan, one writing pass; see "subsequences")
 //   idct_block        dequantise + njRowIDCT x 8 + njColIDCT x 8 (:350-442) -> 8x8 bytes of the plane
 //   upsample_h / _v   njUpsampleH / njUpsampleV (:736-790), one output pixel per thread
 //   to_rgb / to_gray  the tail of njConvert (:817-866)
 #pragma once
+#include "jpeg_decode.h"
 #include "jpeg_device.h"
 
 namespace jd {
@@ -27,6 +30,10 @@ struct DevComponent {
     int dq[64];                       // dequantisers in NATURAL order: dq[njZZ[k]] = qtab[k] (:666)
 };
 
+// records of the subsequence decode (see "subsequences" below)
+struct SubState { unsigned entry_pos, entry_bs, exit_pos, exit_bs, n; int dc0, dc1, dc2; };      // bs = block-in-MCU << 8 | s
+struct SubStart { unsigned n; int dc0, dc1, dc2; };
+
 struct DevParams {
     const uint8_t* data;              // the whole file
     const uint32_t* interval_off;     // [n_intervals + 1]
@@ -36,6 +43,14 @@ struct DevParams {
     uint8_t* planes;
     unsigned* error;
     DevComponent comp[3];
+    // self-synchronising decode of a restart-free scan (n_sub == 0: not used, the interval path decodes the image)
+    int n_sub, sub_log2, bpm, sub_pad;            // subsequences, log2 of their size in bytes, blocks per MCU
+    const uint8_t* scan;                          // first byte of the entropy-coded data
+    unsigned scan_bytes, sub_pad2;
+    unsigned long long total_blocks;              // n_mcus * bpm
+    SubState* sub[2];                             // ping-pong buffers of the rounds, [n_sub] each
+    SubStart* sub_start;                          // [n_sub]
+    McuBlock blk[kMaxBlocksPerMcu];
 };
 
 // njZZ (jpeg_dec.h:332-337): natural index of zigzag position k
@@ -181,6 +196,213 @@ JG_DEV void decode_interval(const DevParams& P, const uint16_t* l1, int iv)
         if (++mbx >= mbwidth) { mbx = 0; ++mby; }
     }
     if (bad) *P.error = 5u;     // NJ_SYNTAX_ERROR
+}
+
+// ---- subsequences: parallel decode of a scan without restart markers -------------------------------------
+// (the self-synchronisation scheme of Weissenberger & Schmidt, "Accelerating JPEG decompression on GPUs", restated
+// for NanoJPEG's decode loop.)  The scan is cut every 2^sub_log2 bytes.  A decoder is in a known STATE between two
+// symbols: the position of the next bit, the block of the MCU it is in, and how far into that block's zigzag
+// sequence it is.  Thread i decodes the symbols that START inside subsequence i:
+//   round 0      from a guessed state (first bit of the subsequence, start of an MCU) -- true only for i = 0;
+//   round r > 0  again, from the state thread i-1 arrived at in round r-1, unless that is the state it already
+//                started from.  Huffman codes re-synchronise after a few symbols, the block state at the next
+//                end-of-block that both decoders see, so after a few rounds nobody has anything to redo and every
+//                recorded state is the true one (induction over i: 0 is true from the start, and i is consistent
+//                with i-1).  A wrong state that runs into an impossible code simply records "bad".
+//   scan         exclusive sums over i of the blocks completed and of the DC differences per component;
+//   write        once more from the true entry state, now storing coefficients (DC already predicted).
+// Positions are raw bit offsets into the scan, canonical: the byte that holds the next unconsumed bit (never a
+// stuffed 00) * 8 + the bit's index in it, so that two decoders at the same place hold the same number.
+constexpr unsigned kBadState = 0xFFFFu;
+// s: 0 = the block's DC symbol comes next; 1..63 = an AC symbol comes next and zigzag position s-1 was the last one filled
+
+struct SyncReader {
+    const uint8_t* p;          // next raw byte
+    const uint8_t* end;
+    unsigned long long buf;
+    int bits;
+    unsigned stuffed;          // bit j: the j-th newest byte of buf was followed by a stuffed byte
+};
+JG_DEV void sr_refill(SyncReader& r)       // called with fewer than 16 bits left; leaves at least 25
+{
+    if ((((size_t)r.p) & 3u) == 0 && r.p + 4 <= r.end) {
+        const unsigned w = ldg_u32(r.p);
+        if (v_cmpeq4(w, 0xffffffffu) == 0u) {
+            r.buf = (r.buf << 32) | bswap32(w);
+            r.bits += 32;
+            r.p += 4;
+            r.stuffed <<= 4;
+            return;
+        }
+    }
+    do {
+        unsigned b = 0xFF, st = 0;
+        if (r.p < r.end) {
+            b = ldg_u8(r.p);
+            if (b == 0xFF && r.p + 1 < r.end) st = 1;       // the stuffed 00: consumed, not data
+        }
+        r.p += 1 + st;                                      // past the end the stream continues with FF bytes (:452-456); p keeps counting
+        r.buf = (r.buf << 8) | b;
+        r.bits += 8;
+        r.stuffed = (r.stuffed << 1) | st;
+    } while (r.bits <= 24 || ((((size_t)r.p) & 3u) != 0 && r.bits <= 48 && r.p < r.end));
+}
+JG_DEV unsigned sr_show(SyncReader& r, int n)
+{
+    if (r.bits < n) sr_refill(r);
+    return (unsigned)(r.buf >> (r.bits - n)) & ((1u << n) - 1u);
+}
+JG_DEV unsigned sr_pos(const SyncReader& r, const uint8_t* base)
+{
+    const int nb = (r.bits + 7) >> 3;                                        // buffered bytes with unconsumed bits
+    const int st = jg::i_popc(r.stuffed & ((1u << nb) - 1u));                 // stuffed bytes behind them
+    return (unsigned)((r.p - base) - nb - st) * 8u + (unsigned)((8 - (r.bits & 7)) & 7);
+}
+JG_DEV void sr_start(SyncReader& r, const uint8_t* base, const uint8_t* end, unsigned pos)
+{
+    r.p = base + (pos >> 3); r.end = end; r.buf = 0; r.bits = 0; r.stuffed = 0;
+    const int off = (int)(pos & 7u);
+    if (off) { sr_refill(r); r.bits -= off; }
+}
+JG_DEV int sr_get_vlc(SyncReader& r, const VlcTables& T, int table, unsigned* code_out, bool* bad)     // njGetVLC (:643-656)
+{
+    const unsigned peek = sr_show(r, 16);
+    unsigned e = T.l1[(table << kL1Bits) + (peek >> (16 - kL1Bits))];
+    if (!e) e = T.full[(size_t)table * 65536 + peek];
+    const int len = (int)(e >> 8);
+    if (!len) { *bad = true; return 0; }
+    r.bits -= len;
+    const unsigned code = e & 0xFFu;
+    *code_out = code;
+    const int nb = (int)(code & 15u);
+    if (!nb) return 0;
+    int v = (int)sr_show(r, nb);
+    r.bits -= nb;
+    if (v < (1 << (nb - 1))) v += (int)((0xFFFFFFFFu << nb) + 1u);
+    return v;
+}
+
+// the state a subsequence is entered with when its predecessor has none to offer
+JG_DEV unsigned guessed_entry_pos(const DevParams& P, int i)
+{
+    unsigned at = (unsigned)i << P.sub_log2;
+    if (i > 0 && P.scan[at - 1] == 0xFF) ++at;           // the subsequence begins with a stuffed byte
+    return at << 3;
+}
+
+// Thread i, all symbols that start in subsequence i, from (entry_pos, entry_bs).  WRITE = false: only the state at
+// the end and the sums (a round); WRITE = true: the coefficients, `first` holding what precedes the subsequence.
+// Every lane of a warp runs the loop until the last one is done, one symbol per trip, so the lanes stay together.
+template <bool WRITE>
+JG_DEV void decode_subsequence(const DevParams& P, const uint16_t* l1, int i, bool have, unsigned entry_pos, unsigned entry_bs, SubStart first,
+                               SubState* result)
+{
+    VlcTables T; T.full = P.vlc; T.l1 = l1;
+    const uint8_t* const base = P.scan;
+    const bool last = i + 1 >= P.n_sub;
+    const unsigned limit = last ? P.scan_bytes << 3 : (unsigned)(i + 1) << (P.sub_log2 + 3);
+    const int bpm = P.bpm, mbwidth = P.mbwidth;
+    const unsigned long long total = P.total_blocks;
+    SyncReader r;
+    sr_start(r, base, P.scan + P.scan_bytes, have ? entry_pos : 0u);
+    int b = (int)(entry_bs >> 8), s = (int)(entry_bs & 0xFFu);
+    if (!have || b >= bpm) b = 0;
+    McuBlock K = P.blk[b];
+    unsigned long long g = first.n;
+    int dc0 = first.dc0, dc1 = first.dc1, dc2 = first.dc2;
+    unsigned n = 0, pos = entry_pos;
+    int mbx = 0, mby = 0;
+    int16_t* blk = nullptr;
+    if (WRITE) {
+        const unsigned long long m = g / (unsigned)bpm;
+        mby = (int)(m / (unsigned)mbwidth); mbx = (int)(m - (unsigned long long)mby * (unsigned)mbwidth);
+        blk = P.coef + (K.off + (unsigned long long)mby * K.row + (unsigned long long)mbx * K.sx) * 64ull;
+    }
+    bool bad = false;
+    for (;;) {
+        const bool go = have && !bad && (WRITE ? (g < total && (last || pos < limit)) : pos < limit);
+        if (!JG_WARP_ANY(go)) break;
+        if (!go) continue;
+        bool done = false;
+        unsigned code = 0;
+        if (s == 0) {
+            const int v = sr_get_vlc(r, T, K.dctab, &code, &bad);
+            const int d = K.comp == 0 ? (dc0 += v) : K.comp == 1 ? (dc1 += v) : (dc2 += v);
+            if (WRITE && !bad) blk[0] = (int16_t)d;
+            s = 1;
+        } else {
+            const int v = sr_get_vlc(r, T, K.actab, &code, &bad);
+            if (!bad) {
+                if (!code) done = true;                                               // EOB
+                else if (!(code & 0x0F) && code != 0xF0) bad = true;
+                else {
+                    const int k = s + (int)(code >> 4);                               // (s - 1) + run + 1
+                    if (k > 63) bad = true;
+                    else {
+                        if (WRITE) blk[zz_nat(k)] = (int16_t)v;
+                        if (k == 63) done = true; else s = k + 1;
+                    }
+                }
+            }
+        }
+        if (done) {
+            s = 0; ++n;
+            if (++b == bpm) { b = 0; if (WRITE && ++mbx == mbwidth) { mbx = 0; ++mby; } }
+            K = P.blk[b];
+            if (WRITE) { ++g; blk = P.coef + (K.off + (unsigned long long)mby * K.row + (unsigned long long)mbx * K.sx) * 64ull; }
+        }
+        pos = sr_pos(r, base);
+    }
+    if (WRITE) {
+        if (bad) *P.error = 5u;     // NJ_SYNTAX_ERROR
+    } else if (have) {
+        result->entry_pos = entry_pos; result->entry_bs = entry_bs;
+        result->exit_pos = pos; result->exit_bs = bad ? kBadState : ((unsigned)b << 8) | (unsigned)s;
+        result->n = n; result->dc0 = dc0; result->dc1 = dc1; result->dc2 = dc2;
+    }
+}
+
+// what subsequence i has to start from, given its predecessor's record
+JG_DEV void entry_of(const DevParams& P, int i, const SubState* prev, unsigned* pos, unsigned* bs)
+{
+    if (i == 0 || prev->exit_bs == kBadState) { *pos = guessed_entry_pos(P, i); *bs = 0; }
+    else { *pos = prev->exit_pos; *bs = prev->exit_bs; }
+}
+
+// One round for subsequence i: `in` = the records of the previous round (nullptr in round 0), `out` = this round's.
+// Returns whether the subsequence was decoded (again).
+JG_DEV bool sync_round(const DevParams& P, const uint16_t* l1, int i, const SubState* in, SubState* out)
+{
+    const bool have = i < P.n_sub;
+    unsigned pos = 0, bs = 0;
+    bool redo = false;
+    SubState mine = {};
+    if (have) {
+        if (!in) { pos = guessed_entry_pos(P, i); redo = true; }
+        else {
+            mine = in[i];
+            entry_of(P, i, i ? &in[i - 1] : nullptr, &pos, &bs);
+            redo = mine.entry_pos != pos || mine.entry_bs != bs;
+            if (!redo) out[i] = mine;
+        }
+    }
+    if (!JG_WARP_ANY(redo)) return false;
+    const SubStart zero = {0u, 0, 0, 0};
+    decode_subsequence<false>(P, l1, i, redo, pos, bs, zero, have ? &out[i] : nullptr);
+    return redo;
+}
+
+// the writing pass for subsequence i
+JG_DEV void write_subsequence(const DevParams& P, const uint16_t* l1, int i, const SubState* states)
+{
+    const bool have = i < P.n_sub;
+    unsigned pos = 0, bs = 0;
+    SubStart first = {0u, 0, 0, 0};
+    if (have) {
+        entry_of(P, i, i ? &states[i - 1] : nullptr, &pos, &bs);
+        first = P.sub_start[i];
+    }
+    decode_subsequence<true>(P, l1, i, have, pos, bs, first, nullptr);
 }
 
 JG_DEV unsigned char clip8(int x) { return x < 0 ? 0 : (x > 0xFF ? 0xFF : (unsigned char)x); }   // njClip (:339-341)
@@ -331,6 +553,60 @@ __global__ void decode_intervals_kernel(const DevParams* __restrict__ imgs)
     for (int i = (int)threadIdx.x; i < (4 << kL1Bits); i += (int)blockDim.x) l1[i] = l1_entry(P.vlc, i >> kL1Bits, i & ((1 << kL1Bits) - 1));
     __syncthreads();
     decode_interval(P, l1, (int)(blockIdx.x * blockDim.x + threadIdx.x));      // every lane: the warp reconverges per block
+}
+// ---- subsequence decode: blockIdx.y = image, one thread per subsequence ----
+constexpr int kSubThreads = 128;
+JG_DEV void load_l1(const DevParams& P, uint16_t* l1)
+{
+    for (int i = (int)threadIdx.x; i < (4 << kL1Bits); i += (int)blockDim.x) l1[i] = l1_entry(P.vlc, i >> kL1Bits, i & ((1 << kL1Bits) - 1));
+    __syncthreads();
+}
+// round `r` of the batch: reads sub[(r + 1) & 1] (round 0: nothing), writes sub[r & 1]; *redone counts the subsequences decoded
+__global__ void __launch_bounds__(kSubThreads) sync_round_kernel(const DevParams* __restrict__ imgs, int r, unsigned* __restrict__ redone)
+{
+    const DevParams& P = imgs[blockIdx.y];
+    __shared__ uint16_t l1[4 << kL1Bits];
+    if ((int)(blockIdx.x * blockDim.x) >= P.n_sub) return;
+    load_l1(P, l1);
+    const bool did = sync_round(P, l1, (int)(blockIdx.x * blockDim.x + threadIdx.x), r ? P.sub[(r + 1) & 1] : nullptr, P.sub[r & 1]);
+    const unsigned any = __ballot_sync(0xffffffffu, did);
+    if (any && (threadIdx.x & 31) == 0) atomicAdd(redone, (unsigned)__popc(any));
+}
+// exclusive sums of the final records (in sub[final]) per image: one CTA, a contiguous slice per thread
+__global__ void __launch_bounds__(256) sync_scan_kernel(const DevParams* __restrict__ imgs, int final)
+{
+    const DevParams& P = imgs[blockIdx.x];
+    const int n = P.n_sub, t = (int)threadIdx.x;
+    if (!n) return;
+    const SubState* S = P.sub[final];
+    const int per = (n + 255) / 256, lo = t * per < n ? t * per : n, hi = lo + per < n ? lo + per : n;
+    __shared__ SubStart part[256];
+    SubStart a = {0u, 0, 0, 0};
+    for (int j = lo; j < hi; ++j) { a.n += S[j].n; a.dc0 += S[j].dc0; a.dc1 += S[j].dc1; a.dc2 += S[j].dc2; }
+    part[t] = a;
+    __syncthreads();
+    if (t == 0) {
+        SubStart run = {0u, 0, 0, 0};
+        for (int j = 0; j < 256; ++j) {
+            const SubStart v = part[j];
+            part[j] = run;
+            run.n += v.n; run.dc0 += v.dc0; run.dc1 += v.dc1; run.dc2 += v.dc2;
+        }
+    }
+    __syncthreads();
+    a = part[t];
+    for (int j = lo; j < hi; ++j) {
+        P.sub_start[j] = a;
+        a.n += S[j].n; a.dc0 += S[j].dc0; a.dc1 += S[j].dc1; a.dc2 += S[j].dc2;
+    }
+}
+__global__ void __launch_bounds__(kSubThreads) sync_write_kernel(const DevParams* __restrict__ imgs, int final)
+{
+    const DevParams& P = imgs[blockIdx.y];
+    __shared__ uint16_t l1[4 << kL1Bits];
+    if ((int)(blockIdx.x * blockDim.x) >= P.n_sub) return;
+    load_l1(P, l1);
+    write_subsequence(P, l1, (int)(blockIdx.x * blockDim.x + threadIdx.x), P.sub[final]);
 }
 // IDCT: eight threads per block.  Thread r loads row r (one 16-byte load), dequantises and runs njRowIDCT
 // in registers; the 8x8 goes through a padded shared-memory tile; thread c then runs njColIDCT on column c

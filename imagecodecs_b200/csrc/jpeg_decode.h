@@ -6,10 +6,13 @@
 // (:817-866: chroma upsampling :736-790, YCbCr -> RGB).  Everything is integer arithmetic; the
 // decoded pixels are bit-identical to NanoJPEG's.
 //
-// Parallelism comes from restart intervals (the encoder's opt-in JPEG_GPU_FLAG_RESTART writes one
-// per 24 blocks): every interval is decoded by its own thread.  A stream without restart markers
-// is one interval = one thread for the entropy decode (correct, slow); the IDCT / upsampling /
-// colour stages are parallel either way.
+// Parallelism of the entropy decode comes from restart intervals where the file has them (the
+// encoder's opt-in JPEG_GPU_FLAG_RESTART writes one per 24 blocks): every interval is decoded by its
+// own thread.  A scan WITHOUT restart markers -- everything the reference's own encoder writes -- is
+// cut into fixed-size subsequences that are decoded speculatively and brought into agreement by the
+// self-synchronisation of Huffman codes (jpeg_decode.cuh, "subsequences"); only streams that are
+// neither (irregular marker bytes inside the scan, exotic sampling) fall back to one thread.  The
+// IDCT / upsampling / colour stages are parallel either way.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -44,7 +47,19 @@ struct Info {
     std::vector<uint32_t> interval_off;         // start of every restart interval (file offsets) + one past the last
     size_t n_blocks = 0, plane_bytes = 0;
     int n_mcus = 0;
+    bool clean_stuffing = false;    // every FF inside the scan is followed by 00 (what every encoder writes)
 };
+
+// One block of the MCU in stream order (njDecodeScan's component / sby / sbx loops, :694-704): where its
+// coefficients go and which tables decode it.
+constexpr int kMaxBlocksPerMcu = 16;
+struct McuBlock { unsigned long long off; int row, sx, comp, dctab, actab, pad; };
+// Fills map[0..return) for the file's sampling; 0 if an MCU has more than kMaxBlocksPerMcu blocks.
+int mcu_block_map(const Info& info, McuBlock* map);
+// log2 of the subsequence size (bytes) for the self-synchronising decode of this file's scan, 0 = not
+// eligible (restart intervals, irregular stuffing, tiny or huge scan, too many blocks per MCU).
+// batch_scan_bytes: entropy-coded bytes of the whole call (more data -> longer subsequences).
+int subsequence_log2(const Info& info, size_t batch_scan_bytes);
 
 // The marker loop of njDecode up to and including the SOS header, plus the split of the scan
 // into restart intervals.  Returns an nj_result_t.

@@ -64,8 +64,9 @@ size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 struct Job {                 // one image of a batch
     Info I;
     bool ok = false;
-    size_t data_off = 0, iv_off = 0, coef_off = 0, plane_off = 0, out_off = 0, out_bytes = 0;
+    size_t data_off = 0, iv_off = 0, coef_off = 0, plane_off = 0, out_off = 0, out_bytes = 0, sub_off = 0;
     int vlc_slot = 0;
+    int sub_log2 = 0, n_sub = 0;         // > 0: the scan has no restart markers and is decoded as subsequences
 };
 
 // Decode n files.  outs[i].pixels are host buffers (or device buffers if pixels_on_device); kernel_ms (optional)
@@ -105,10 +106,25 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
         j.coef_off = coef_words; coef_words += j.I.n_blocks * 64;
         j.plane_off = plane_bytes; plane_bytes += align256(j.I.plane_bytes + 16);
         j.out_off = out_total; out_total += align256(j.out_bytes);
-        max_iv = std::max(max_iv, (int)j.I.interval_off.size() - 1);
         for (int c = 0; c < j.I.ncomp; ++c) max_blocks[c] = std::max(max_blocks[c], (unsigned long long)j.I.comp[c].bw * j.I.comp[c].bh);
     }
     if (n_ok == 0) return 0;
+    // restart-free scans: subsequences (their size depends on how much entropy-coded data the whole call has)
+    size_t scan_total = 0, sub_total = 0;
+    int max_sub = 0;
+    for (const Job& j : jobs) if (j.ok) scan_total += j.I.scan_end - j.I.scan_off;
+    for (Job& j : jobs) {
+        if (!j.ok) continue;
+        j.sub_log2 = subsequence_log2(j.I, scan_total);
+        if (j.sub_log2) {
+            const size_t bytes = j.I.scan_end - j.I.scan_off;
+            j.n_sub = (int)((bytes + ((size_t)1 << j.sub_log2) - 1) >> j.sub_log2);
+            j.sub_off = sub_total; sub_total += (size_t)j.n_sub;
+            max_sub = std::max(max_sub, j.n_sub);
+        } else {
+            max_iv = std::max(max_iv, (int)j.I.interval_off.size() - 1);
+        }
+    }
     if (jpeg_gpu_device_count() == 0 && jpeg_gpu_init(nullptr, 0) <= 0) return 0;
     JD_CUDA(cudaSetDevice(jg::cuda_device_of(0)));
 
@@ -134,6 +150,11 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
     uint8_t* d_out = pixels_on_device ? nullptr : B.alloc<uint8_t>(out_total);
     unsigned* d_err = B.alloc<unsigned>((size_t)n);
     DevParams* d_params = B.alloc<DevParams>((size_t)n);
+    constexpr int kMaxRoundsPerCheck = 256;
+    SubState* d_sub = B.alloc<SubState>(2 * sub_total);
+    SubStart* d_start = B.alloc<SubStart>(sub_total);
+    unsigned* d_redone = B.alloc<unsigned>(kMaxRoundsPerCheck);
+    if (!d_sub || !d_start || !d_redone) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
     if (!d_data || !d_iv || !d_vlc || !d_coef || !d_planes || (!pixels_on_device && !d_out) || !d_err || !d_params) {
         jg::set_error_text(result_text(kOutOfMem)); return 0;
     }
@@ -168,6 +189,13 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
             d.n_blocks = (unsigned long long)k.bw * k.bh; d.coef_off = k.coef_off; d.plane_off = k.plane_off;
             for (int q = 0; q < 64; ++q) d.dq[zz[q]] = I.qtab[k.qtsel][q];
             st[(size_t)i * 3 + c] = {P.planes + k.plane_off, k.width, k.height, k.stride};
+        }
+        if (j.n_sub) {
+            P.n_intervals = 0;                        // the interval kernel passes this image by
+            P.n_sub = j.n_sub; P.sub_log2 = j.sub_log2; P.bpm = mcu_block_map(I, P.blk);
+            P.scan = P.data + I.scan_off; P.scan_bytes = (unsigned)(I.scan_end - I.scan_off);
+            P.total_blocks = (unsigned long long)I.n_mcus * P.bpm;
+            P.sub[0] = d_sub + j.sub_off; P.sub[1] = d_sub + sub_total + j.sub_off; P.sub_start = d_start + j.sub_off;
         }
     }
     JD_CUDA(cudaMemcpyAsync(d_iv, iv_host.data(), iv_words * 4, cudaMemcpyHostToDevice, B.s));
@@ -246,7 +274,25 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
     // everything is allocated and uploaded: the kernels go out back to back (what kernel_ms measures)
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (kernel_ms) { JD_CUDA(cudaEventCreate(&e0)); JD_CUDA(cudaEventCreate(&e1)); JD_CUDA(cudaEventRecord(e0, B.s)); }
-    decode_intervals_kernel<<<dim3((unsigned)((max_iv + 63) / 64), (unsigned)n), 64, 0, B.s>>>(d_params);
+    if (max_iv) decode_intervals_kernel<<<dim3((unsigned)((max_iv + 63) / 64), (unsigned)n), 64, 0, B.s>>>(d_params);
+    if (max_sub) {
+        // rounds until no subsequence is decoded again; the host looks at the count of a group's last round only
+        // (rounds after the settling one merely copy the records, so a group may overshoot)
+        const dim3 grid((unsigned)((max_sub + kSubThreads - 1) / kSubThreads), (unsigned)n);
+        int r = 0;
+        for (int group = 8;; group = std::min(2 * group, kMaxRoundsPerCheck)) {
+            JD_CUDA(cudaMemsetAsync(d_redone, 0, (size_t)group * 4, B.s));
+            for (int k = 0; k < group; ++k, ++r) sync_round_kernel<<<grid, kSubThreads, 0, B.s>>>(d_params, r, d_redone + k);
+            unsigned last = 0;
+            JD_CUDA(cudaMemcpyAsync(&last, d_redone + group - 1, 4, cudaMemcpyDeviceToHost, B.s));
+            JD_CUDA(cudaStreamSynchronize(B.s));
+            if (!last) break;
+            if (r > max_sub + 2 * kMaxRoundsPerCheck) { jg::set_error_text("decode: the subsequence rounds did not settle"); return 0; }   // every round settles at least one more
+        }
+        const int final = (r - 1) & 1;
+        sync_scan_kernel<<<(unsigned)n, 256, 0, B.s>>>(d_params, final);
+        sync_write_kernel<<<grid, kSubThreads, 0, B.s>>>(d_params, final);
+    }
     for (int c = 0; c < 3; ++c)
         if (max_blocks[c]) idct_kernel<<<dim3((unsigned)((max_blocks[c] + 15) / 16), (unsigned)n), kIdctThreads, 0, B.s>>>(d_params, c);   // 16 blocks per CTA
     for (const Round& r : rounds) {

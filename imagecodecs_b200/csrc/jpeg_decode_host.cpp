@@ -170,6 +170,30 @@ int build_vlc_tables(const std::vector<uint8_t>& dht, std::vector<uint16_t>* vlc
     return vlc->empty() ? (int)kSyntaxError : (int)kOk;
 }
 
+int mcu_block_map(const Info& I, McuBlock* map)
+{
+    int n = 0;
+    for (int c = 0; c < I.ncomp; ++c) {
+        const Component& k = I.comp[c];
+        for (int sby = 0; sby < k.ssy; ++sby)
+            for (int sbx = 0; sbx < k.ssx; ++sbx) {
+                if (n == kMaxBlocksPerMcu) return 0;
+                map[n++] = {(unsigned long long)k.coef_off + (unsigned long long)sby * k.bw + sbx, k.ssy * k.bw, k.ssx, c, k.dctabsel, k.actabsel, 0};
+            }
+    }
+    return n;
+}
+
+int subsequence_log2(const Info& I, size_t batch_scan_bytes)
+{
+    const size_t bytes = I.scan_end - I.scan_off;
+    if (I.rstinterval || !I.clean_stuffing || bytes < 512 || bytes >= ((size_t)1 << 28)) return 0;
+    McuBlock map[kMaxBlocksPerMcu];
+    if (!mcu_block_map(I, map)) return 0;
+    // enough subsequences to fill the GPU when the call is small, 128-byte ones (the size the literature settles on) when it is large
+    return batch_scan_bytes >= ((size_t)8 << 20) ? 7 : batch_scan_bytes >= ((size_t)2 << 20) ? 6 : 5;
+}
+
 int parse(const uint8_t* jpeg, size_t size, Info* I, bool build_vlc)
 {
     size &= 0x7FFFFFFF;
@@ -218,6 +242,7 @@ scan:
     size_t pos = I->scan_off;
     unsigned next_rst = 0;
     size_t end = size;
+    I->clean_stuffing = true;
     while (pos + 1 < size) {
         const uint8_t* f = (const uint8_t*)memchr(jpeg + pos, 0xFF, size - 1 - pos);
         if (!f) break;
@@ -228,6 +253,8 @@ scan:
             if (!I->rstinterval || (unsigned)(m & 7) != next_rst) return kSyntaxError;
             next_rst = (next_rst + 1) & 7;
             I->interval_off.push_back((uint32_t)(pos + 2));
+        } else if (m != 0x00) {
+            I->clean_stuffing = false;
         }
         pos += 2;
     }

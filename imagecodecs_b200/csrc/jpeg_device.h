@@ -20,6 +20,7 @@
 #define JG_GRID_CONSTANT __grid_constant__
 #define JG_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define JG_CONST_TABLE static __device__ __constant__
+#define JG_WARP_ANY(x) __any_sync(0xffffffffu, (x))   // every lane of the warp calls it
 #define JG_RECONVERGE() __syncwarp()      // all 32 lanes arrive: brings lanes that drifted apart in data-dependent loops back together
 
 namespace jg {

@@ -17,6 +17,7 @@
 #define JG_TID (::jg::emu::tls.tid)
 #define JG_DYNAMIC_SMEM(name) unsigned char* name = ::jg::emu::tls.cta->smem
 #define JG_CONST_TABLE static const
+#define JG_WARP_ANY(x) (x)
 #define JG_RECONVERGE() ((void)0)
 
 struct uint2 { unsigned x, y; };

@@ -42,22 +42,25 @@ def _load():
     return _lib
 
 
-def emu_decode(jpeg):
-    """Decode with the product's decoder source run on the CPU (tests only). Returns uint8 [h,w,3] / [h,w] or the nj error code."""
+def emu_decode(jpeg, sub_log2=-1, want_rounds=False):
+    """Decode with the product's decoder source run on the CPU (tests only). Returns uint8 [h,w,3] / [h,w] or the nj error code.
+    sub_log2: -1 = the library's own choice between restart intervals and subsequences, 0 = intervals only, n = subsequences
+    of 2**n bytes wherever the stream allows them; want_rounds: also return how many rounds the subsequence decode took."""
     L = _load()
-    L.emu_decode.restype = C.c_int
-    L.emu_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.emu_decode_sub.restype = C.c_int
+    L.emu_decode_sub.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     buf = np.frombuffer(jpeg, dtype=np.uint8)
-    w, h, nc = C.c_int(0), C.c_int(0), C.c_int(0)
+    w, h, nc, rounds = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
     out = np.empty(1, np.uint8)
-    rc = L.emu_decode(buf.ctypes.data, buf.size, out.ctypes.data, 0, C.byref(w), C.byref(h), C.byref(nc))
+    rc = L.emu_decode_sub(buf.ctypes.data, buf.size, out.ctypes.data, 0, C.byref(w), C.byref(h), C.byref(nc), sub_log2, None)
     if rc != -1:
-        return rc
+        return (rc, 0) if want_rounds else rc
     out = np.empty(w.value * h.value * nc.value, np.uint8)
-    rc = L.emu_decode(buf.ctypes.data, buf.size, out.ctypes.data, out.size, C.byref(w), C.byref(h), C.byref(nc))
+    rc = L.emu_decode_sub(buf.ctypes.data, buf.size, out.ctypes.data, out.size, C.byref(w), C.byref(h), C.byref(nc), sub_log2, C.byref(rounds))
     if rc != 0:
-        return rc
-    return out.reshape(h.value, w.value, 3) if nc.value == 3 else out.reshape(h.value, w.value)
+        return (rc, rounds.value) if want_rounds else rc
+    px = out.reshape(h.value, w.value, 3) if nc.value == 3 else out.reshape(h.value, w.value)
+    return (px, rounds.value) if want_rounds else px
 
 
 def emu_ticket_map(tiles, force_schedule=False):

@@ -183,8 +183,11 @@ int emu_ticket_map(const int* tiles, int n_images, int force_schedule, unsigned*
 
 // The decoder's per-item device functions (jpeg_decode.cuh) run in plain loops: same code as on the GPU,
 // where one thread executes one call.  Returns the nj_result_t; out receives RGB / gray pixels.
-int emu_decode(const uint8_t* jpeg, size_t size, uint8_t* out, size_t cap, int* w, int* h, int* ncomp)
+// sub_log2: -1 = the library's policy (jd::subsequence_log2), 0 = interval path, > 0 = subsequences of that size where
+// the stream allows them at all.  rounds (optional) receives the number of rounds the subsequence decode took (0: not used).
+int emu_decode_sub(const uint8_t* jpeg, size_t size, uint8_t* out, size_t cap, int* w, int* h, int* ncomp, int sub_log2, int* rounds)
 {
+    if (rounds) *rounds = 0;
     jd::Info I;
     const int rc = jd::parse(jpeg, size, &I);
     if (rc != jd::kOk) return rc;
@@ -207,7 +210,32 @@ int emu_decode(const uint8_t* jpeg, size_t size, uint8_t* out, size_t cap, int* 
     }
     std::vector<uint16_t> l1(4 << jd::kL1Bits);
     for (int i = 0; i < (4 << jd::kL1Bits); ++i) l1[i] = jd::l1_entry(P.vlc, i >> jd::kL1Bits, i & ((1 << jd::kL1Bits) - 1));
-    for (int iv = 0; iv < P.n_intervals; ++iv) jd::decode_interval(P, l1.data(), iv);
+    const size_t scan_bytes = I.scan_end - I.scan_off;
+    if (sub_log2 < 0) sub_log2 = jd::subsequence_log2(I, scan_bytes);
+    else if (sub_log2 > 0 && (I.rstinterval || !I.clean_stuffing || !jd::mcu_block_map(I, P.blk) || scan_bytes >= ((size_t)1 << 28))) sub_log2 = 0;
+    if (sub_log2 > 0) {
+        // what jpeg_decode_api.cpp launches as kernels: rounds until nobody decodes again, the scan, the writing pass
+        P.sub_log2 = sub_log2; P.n_sub = (int)((scan_bytes + ((size_t)1 << sub_log2) - 1) >> sub_log2);
+        P.bpm = jd::mcu_block_map(I, P.blk); P.scan = jpeg + I.scan_off; P.scan_bytes = (unsigned)scan_bytes;
+        P.total_blocks = (unsigned long long)I.n_mcus * P.bpm;
+        std::vector<jd::SubState> sa(P.n_sub), sb(P.n_sub);
+        std::vector<jd::SubStart> start(P.n_sub);
+        P.sub[0] = sa.data(); P.sub[1] = sb.data(); P.sub_start = start.data();
+        int r = 0;
+        for (;; ++r) {
+            int redone = 0;
+            for (int i = 0; i < P.n_sub; ++i) redone += jd::sync_round(P, l1.data(), i, r ? P.sub[(r + 1) & 1] : nullptr, P.sub[r & 1]);
+            if (!redone) break;
+            if (r > P.n_sub + 2) return -2;       // cannot happen: every round settles at least one more subsequence
+        }
+        if (rounds) *rounds = r;
+        const jd::SubState* S = P.sub[r & 1];
+        jd::SubStart run = {0u, 0, 0, 0};
+        for (int i = 0; i < P.n_sub; ++i) { start[i] = run; run.n += S[i].n; run.dc0 += S[i].dc0; run.dc1 += S[i].dc1; run.dc2 += S[i].dc2; }
+        for (int i = 0; i < P.n_sub; ++i) jd::write_subsequence(P, l1.data(), i, S);
+    } else {
+        for (int iv = 0; iv < P.n_intervals; ++iv) jd::decode_interval(P, l1.data(), iv);
+    }
     if (err) return (int)err;
     for (int c = 0; c < I.ncomp; ++c)
         for (unsigned long long b = 0; b < (unsigned long long)I.comp[c].bw * I.comp[c].bh; ++b) jd::idct_block(P, c, b);
@@ -236,5 +264,9 @@ int emu_decode(const uint8_t* jpeg, size_t size, uint8_t* out, size_t cap, int* 
             else out[(size_t)y * I.width + x] = plane[0][(size_t)y * ps[0] + x];
         }
     return 0;
+}
+int emu_decode(const uint8_t* jpeg, size_t size, uint8_t* out, size_t cap, int* w, int* h, int* ncomp)
+{
+    return emu_decode_sub(jpeg, size, out, cap, w, h, ncomp, -1, nullptr);
 }
 }

@@ -75,3 +75,73 @@ def test_decodes_foreign_restart_streams_and_411():
         want = oracle.ref_decode(f)
         got = emu_decode(f)
         assert want is not None and isinstance(got, np.ndarray) and np.array_equal(got, want), i
+
+
+# ---- restart-free scans: the subsequence (self-synchronising) decode --------------------------------------------
+
+@pytest.mark.parametrize("w,h,nc,qm,q,sub", [(200, 120, 3, 0, 3, 0), (200, 120, 3, 1, 75, 1), (130, 70, 1, 1, 85, 0), (17, 13, 3, 0, 1, 0),
+                                             (333, 77, 3, 1, 50, 1), (64, 64, 3, 0, 3, 0), (8, 8, 3, 0, 3, 0), (640, 360, 3, 1, 75, 1)])
+def test_subsequence_decode_equals_the_reference_decoder(w, h, nc, qm, q, sub):
+    """A scan without restart markers, cut into subsequences of 4 ... 128 bytes (4 bytes: shorter than one symbol can be,
+    threads that have nothing to decode, stuffed bytes on the cuts): same pixels as njDecode, whatever the size."""
+    img = oracle.synth_image(w, h, nc, kind="noise" if (w, h) == (64, 64) else "photo")
+    jpeg = oracle.oracle_encode(img, qm, q, sub)
+    want = oracle.ref_decode(jpeg)
+    assert want is not None
+    for sub_log2 in (2, 3, 5, 7):
+        got, rounds = emu_decode(jpeg, sub_log2, want_rounds=True)
+        assert isinstance(got, np.ndarray) and np.array_equal(got, want), sub_log2
+        assert rounds >= 1
+    assert np.array_equal(emu_decode(jpeg, 0), want)              # and the one-thread path still agrees
+
+
+def test_subsequence_decode_is_the_default_for_restart_free_files():
+    """The library's own policy: a restart-free scan of 512 bytes or more goes through subsequences (rounds > 0), restart
+    streams and tiny scans through the interval path (rounds == 0); the reference's data/test.jpg is such a file."""
+    jpeg = open(os.path.join(GOLDEN, "data_test.jpg"), "rb").read()
+    got, rounds = emu_decode(jpeg, want_rounds=True)
+    assert rounds > 0 and np.array_equal(got, np.load(os.path.join(GOLDEN, "fixture_pixels.npz"))["testjpg"])
+    img = oracle.synth_image(201, 123, 3)
+    assert emu_decode(oracle.oracle_encode(img, 1, 75, 1, restart=4), want_rounds=True)[1] == 0
+    assert emu_decode(oracle.oracle_encode(oracle.synth_image(8, 8, 3), 0, 3, 0), want_rounds=True)[1] == 0
+
+
+def test_subsequence_decode_of_other_encoders_files():
+    """libjpeg files: optimised Huffman tables, 4:2:2 / 4:2:0 / 4:1:1 (six blocks per MCU in another order), gray."""
+    from PIL import Image
+    rgb = Image.fromarray(oracle.synth_image(211, 97, 3))
+    gray = Image.fromarray(oracle.synth_image(150, 61, 1)[:, :, 0])
+    for im, kw in [(rgb, dict(subsampling=0, quality=95)), (rgb, dict(subsampling=1)), (rgb, dict(subsampling=2, quality=30, optimize=True)),
+                   (rgb, dict(subsampling="4:1:1", quality=80)), (gray, dict(quality=95, optimize=True))]:
+        b = io.BytesIO(); im.save(b, "JPEG", **kw)
+        want = oracle.ref_decode(b.getvalue())
+        for sub_log2 in (3, 5, -1):
+            got = emu_decode(b.getvalue(), sub_log2)
+            assert want is not None and isinstance(got, np.ndarray) and np.array_equal(got, want), (kw, sub_log2)
+
+
+def test_subsequence_decode_of_damaged_scans_agrees_with_the_one_thread_path():
+    """Truncated scans, flipped bits, marker bytes inside the scan: whatever the one-thread decode (NanoJPEG's loop) makes
+    of the file -- pixels or NJ_SYNTAX_ERROR -- the subsequence decode makes of it too."""
+    rng = np.random.default_rng(5)
+    good = bytearray(oracle.oracle_encode(oracle.synth_image(160, 96, 3), 1, 80, 1))
+    scan0 = 700
+    cases = [bytes(good[:n]) + b"\xff\xd9" for n in (len(good) // 2, len(good) - 40, scan0 + 600)]
+    for _ in range(40):
+        b = bytearray(good)
+        for _ in range(int(rng.integers(1, 4))):
+            at = int(rng.integers(scan0, len(b) - 2))
+            b[at] ^= 1 << int(rng.integers(0, 8))
+        cases.append(bytes(b))
+    seen_error = seen_pixels = 0
+    for f in cases:
+        one = emu_decode(f, 0)
+        for sub_log2 in (3, 5):
+            par = emu_decode(f, sub_log2)
+            if isinstance(one, np.ndarray):
+                assert isinstance(par, np.ndarray) and np.array_equal(par, one)
+                seen_pixels += 1
+            else:
+                assert par == one
+                seen_error += 1
+    assert seen_error and seen_pixels

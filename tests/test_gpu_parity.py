@@ -456,15 +456,13 @@ def test_restart_intervals(gpu):
 
 def test_decoder_matches_nanojpeg(gpu, fixture_pixels, golden_dir):
     """jpeg_gpu_decode == njDecode bit for bit -- the reference's own test.jpg, our streams with
-    and without restart intervals (parallel / single-thread entropy decode), another encoder's files."""
+    and without restart intervals (one thread per interval / per subsequence), another encoder's files."""
     from PIL import Image as PILImage
     jpeg = open(os.path.join(golden_dir, "data_test.jpg"), "rb").read()
     assert np.array_equal(gpu.decode(jpeg), fixture_pixels["testjpg"])
     for (w, h, nc, qm, q, sub) in [(640, 360, 3, 0, 3, 0), (641, 363, 3, 1, 75, 1), (500, 300, 1, 1, 85, 0), (1920, 1080, 3, 1, 75, 1), (17, 13, 3, 0, 1, 0)]:
         img = oracle.synth_image(w, h, nc)
         for flags in (0, gpu.FLAG_RESTART):
-            if flags == 0 and w * h > 1 << 20:
-                continue                                   # one thread for a whole 1080p scan: correct but slow, skip here
             stream = encode_one(gpu, img, qm, q, sub, flags=flags, capacity=16 << 20)
             assert np.array_equal(gpu.decode(stream), oracle.ref_decode(stream)), (w, h, nc, qm, q, sub, flags)
     rgb = PILImage.fromarray(oracle.synth_image(211, 97, 3))
@@ -484,6 +482,33 @@ def test_decoder_matches_nanojpeg(gpu, fixture_pixels, golden_dir):
     files = [encode_one(gpu, batch[0], 1, 75, 1, flags=gpu.FLAG_RESTART), encode_one(gpu, batch[1], 0, 2, 0, flags=gpu.FLAG_RESTART),
              encode_one(gpu, batch[2], 1, 85, 0), b"not a jpeg", encode_one(gpu, batch[3], 0, 3, 0)]
     b = io.BytesIO(); rgb.save(b, "JPEG", subsampling=2, quality=40, optimize=True); files.append(b.getvalue())
+    got = gpu.decode_batch(files)
+    for i, f in enumerate(files):
+        want = oracle.ref_decode(f)
+        assert (got[i] is None) == (want is None) and (want is None or np.array_equal(got[i], want)), i
+
+
+def test_decoder_subsequences_for_restart_free_scans(gpu):
+    """Scans without restart markers (all the reference's own encoder writes) are decoded as self-synchronising
+    subsequences: bit-identical to njDecode for dense 4:4:4 (slow to synchronise: three tables in rotation), 4:2:0,
+    gray, noise, libjpeg files, and for a batch that mixes them with restart streams, a tiny scan and a broken file."""
+    from PIL import Image as PILImage
+    cases = [(1920, 1080, 3, 0, 2, 0, "photo"), (1000, 700, 3, 1, 92, 1, "photo"), (2048, 1024, 1, 1, 85, 0, "photo"), (256, 256, 3, 0, 3, 0, "noise"),
+             (801, 603, 3, 1, 35, 1, "photo")]
+    files = []
+    for (w, h, nc, qm, q, sub, kind) in cases:
+        stream = encode_one(gpu, oracle.synth_image(w, h, nc, kind=kind), qm, q, sub, capacity=24 << 20)
+        assert stream == oracle.oracle_encode(oracle.synth_image(w, h, nc, kind=kind), qm, q, sub)
+        assert np.array_equal(gpu.decode(stream), oracle.ref_decode(stream)), (w, h, nc, qm, q, sub)
+        files.append(stream)
+    rgb = PILImage.fromarray(oracle.synth_image(1234, 777, 3))
+    for kw in (dict(subsampling=0, quality=90), dict(subsampling=2, quality=75, optimize=True), dict(subsampling="4:1:1", quality=80)):
+        b = io.BytesIO(); rgb.save(b, "JPEG", **kw)
+        assert np.array_equal(gpu.decode(b.getvalue()), oracle.ref_decode(b.getvalue())), kw
+        files.append(b.getvalue())
+    files.append(encode_one(gpu, oracle.synth_image(640, 360, 3), 1, 75, 1, flags=gpu.FLAG_RESTART))
+    files.append(encode_one(gpu, oracle.synth_image(8, 8, 3), 0, 3, 0))
+    files.append(files[0][:20000])                         # cut in the middle of the scan
     got = gpu.decode_batch(files)
     for i, f in enumerate(files):
         want = oracle.ref_decode(f)
