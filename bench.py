@@ -371,6 +371,24 @@ def run_ours(args):
             del dec_px
         except Exception as e:
             decode = {"error": repr(e)}
+        # the same images as ordinary files -- no restart markers, what jpeg_enc.h itself writes: subsequence decode
+        try:
+            fplan = jg.Plan.for_arrays(imgs, QMODE, QUALITY, SUB, device=0)
+            fplan.run(sptr); torch.cuda.synchronize()
+            ffiles = fplan.fetch(sptr); fplan.close()
+            jg.decode_batch(ffiles[:2])
+            t0 = time.perf_counter()
+            dec_px, dec_ms = jg.decode_batch(ffiles, timed=True)
+            dec_call = (time.perf_counter() - t0) * 1e3
+            import oracle
+            ok = all(np.array_equal(dec_px[i], oracle.ref_decode(ffiles[i])) for i in (0, BATCH - 1))
+            decode["restart_free"] = {"workload": "the same %d images as ordinary files (no restart markers): self-synchronising subsequences" % BATCH,
+                                      "value": round(mp_per_step / (dec_ms * 1e-3), 1), "unit": UNIT, "kernels_ms": round(dec_ms, 3),
+                                      "call_ms_host_files_to_host_pixels": round(dec_call, 1),
+                                      "pixels_identical_to_reference_decoder": bool(ok)}
+            del dec_px
+        except Exception as e:
+            decode["restart_free"] = {"error": repr(e)}
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample) ------------------
     cpu = None

@@ -30,8 +30,7 @@ struct DevComponent {
     int dq[64];                       // dequantisers in NATURAL order: dq[njZZ[k]] = qtab[k] (:666)
 };
 
-// records of the subsequence decode (see "subsequences" below)
-struct SubState { unsigned entry_pos, entry_bs, exit_pos, exit_bs, n; int dc0, dc1, dc2; };      // bs = block-in-MCU << 8 | s
+// per-subsequence record of the subsequence decode (see "subsequences" below): blocks completed and DC differences per component
 struct SubStart { unsigned n; int dc0, dc1, dc2; };
 
 struct DevParams {
@@ -48,8 +47,11 @@ struct DevParams {
     const uint8_t* scan;                          // first byte of the entropy-coded data
     unsigned scan_bytes, sub_pad2;
     unsigned long long total_blocks;              // n_mcus * bpm
-    SubState* sub[2];                             // ping-pong buffers of the rounds, [n_sub] each
-    SubStart* sub_start;                          // [n_sub]
+    unsigned long long* sub_exit;                 // [n_sub] state at the end of each subsequence: position << 16 | block-in-MCU << 8 | s
+    SubStart* sub_sum;                            // [n_sub] what the subsequence's last decode counted
+    SubStart* sub_start;                          // [n_sub] exclusive sums of sub_sum
+    unsigned* sub_list[2];                        // [n_sub] each: the subsequences to decode again in an even / odd round
+    unsigned* sub_cnt;                            // [3] their number, slot = round % 3
     McuBlock blk[kMaxBlocksPerMcu];
 };
 
@@ -202,19 +204,23 @@ JG_DEV void decode_interval(const DevParams& P, const uint16_t* l1, int iv)
 // (the self-synchronisation scheme of Weissenberger & Schmidt, "Accelerating JPEG decompression on GPUs", restated
 // for NanoJPEG's decode loop.)  The scan is cut every 2^sub_log2 bytes.  A decoder is in a known STATE between two
 // symbols: the position of the next bit, the block of the MCU it is in, and how far into that block's zigzag
-// sequence it is.  Thread i decodes the symbols that START inside subsequence i:
-//   round 0      from a guessed state (first bit of the subsequence, start of an MCU) -- true only for i = 0;
-//   round r > 0  again, from the state thread i-1 arrived at in round r-1, unless that is the state it already
-//                started from.  Huffman codes re-synchronise after a few symbols, the block state at the next
-//                end-of-block that both decoders see, so after a few rounds nobody has anything to redo and every
-//                recorded state is the true one (induction over i: 0 is true from the start, and i is consistent
-//                with i-1).  A wrong state that runs into an impossible code simply records "bad".
+// sequence it is.  Thread i decodes the symbols that START inside subsequence i and records the state it ends in:
+//   round 0      every subsequence from a guessed state (its first bit, start of an MCU) -- true only for i = 0;
+//   round 1      every subsequence again, from the state its predecessor recorded;
+//   round r > 1  only the subsequences whose predecessor recorded a DIFFERENT state in round r-1 than before (a work
+//                list per image, appended to by the predecessor).  Huffman codes re-synchronise after a few symbols,
+//                the block state at the next end-of-block that both decoders see, so the lists shrink geometrically.
+//                The records are updated in place by single 64-bit stores: a thread may see its predecessor's old or
+//                new state, and in the first case it is on the next list.  When a list comes out empty every record
+//                is consistent with its predecessor's, and since record 0 is true, all are (induction over i).
+//                A wrong state that runs into an impossible code records "bad"; its successor keeps its guess.
 //   scan         exclusive sums over i of the blocks completed and of the DC differences per component;
 //   write        once more from the true entry state, now storing coefficients (DC already predicted).
 // Positions are raw bit offsets into the scan, canonical: the byte that holds the next unconsumed bit (never a
 // stuffed 00) * 8 + the bit's index in it, so that two decoders at the same place hold the same number.
 constexpr unsigned kBadState = 0xFFFFu;
 // s: 0 = the block's DC symbol comes next; 1..63 = an AC symbol comes next and zigzag position s-1 was the last one filled
+JG_DEV unsigned long long pack_state(unsigned pos, unsigned bs) { return bs == kBadState ? (unsigned long long)kBadState : ((unsigned long long)pos << 16) | bs; }
 
 struct SyncReader {
     const uint8_t* p;          // next raw byte
@@ -295,7 +301,7 @@ JG_DEV unsigned guessed_entry_pos(const DevParams& P, int i)
 // Every lane of a warp runs the loop until the last one is done, one symbol per trip, so the lanes stay together.
 template <bool WRITE>
 JG_DEV void decode_subsequence(const DevParams& P, const uint16_t* l1, int i, bool have, unsigned entry_pos, unsigned entry_bs, SubStart first,
-                               SubState* result)
+                               unsigned long long* exit_state, SubStart* sums)
 {
     VlcTables T; T.full = P.vlc; T.l1 = l1;
     const uint8_t* const base = P.scan;
@@ -355,54 +361,58 @@ JG_DEV void decode_subsequence(const DevParams& P, const uint16_t* l1, int i, bo
     }
     if (WRITE) {
         if (bad) *P.error = 5u;     // NJ_SYNTAX_ERROR
-    } else if (have) {
-        result->entry_pos = entry_pos; result->entry_bs = entry_bs;
-        result->exit_pos = pos; result->exit_bs = bad ? kBadState : ((unsigned)b << 8) | (unsigned)s;
-        result->n = n; result->dc0 = dc0; result->dc1 = dc1; result->dc2 = dc2;
+    } else {
+        *exit_state = pack_state(pos, bad ? kBadState : ((unsigned)b << 8) | (unsigned)s);
+        sums->n = n; sums->dc0 = dc0; sums->dc1 = dc1; sums->dc2 = dc2;
     }
 }
 
-// what subsequence i has to start from, given its predecessor's record
-JG_DEV void entry_of(const DevParams& P, int i, const SubState* prev, unsigned* pos, unsigned* bs)
+// what subsequence i has to start from, given the state its predecessor recorded
+JG_DEV void entry_of(const DevParams& P, int i, unsigned long long prev, unsigned* pos, unsigned* bs)
 {
-    if (i == 0 || prev->exit_bs == kBadState) { *pos = guessed_entry_pos(P, i); *bs = 0; }
-    else { *pos = prev->exit_pos; *bs = prev->exit_bs; }
+    if (i == 0 || (unsigned)(prev & 0xFFFFu) == kBadState) { *pos = guessed_entry_pos(P, i); *bs = 0; }
+    else { *pos = (unsigned)(prev >> 16); *bs = (unsigned)(prev & 0xFFFFu); }
 }
 
-// One round for subsequence i: `in` = the records of the previous round (nullptr in round 0), `out` = this round's.
-// Returns whether the subsequence was decoded (again).
-JG_DEV bool sync_round(const DevParams& P, const uint16_t* l1, int i, const SubState* in, SubState* out)
+// Item t of round r for one image: decodes a subsequence, records its state and sums, and puts the successor on the
+// next round's list if the state is not the one recorded before.  Returns whether it did.  Every lane of a warp calls it.
+JG_DEV bool sync_round_item(const DevParams& P, const uint16_t* l1, int r, unsigned t, unsigned count)
 {
-    const bool have = i < P.n_sub;
+    bool have = t < count;
+    int i = 0;
+    if (have) i = r < 2 ? (int)t : (int)P.sub_list[r & 1][t];
+    if (r == 1 && i == 0) have = false;                                       // subsequence 0 was true in round 0
     unsigned pos = 0, bs = 0;
-    bool redo = false;
-    SubState mine = {};
     if (have) {
-        if (!in) { pos = guessed_entry_pos(P, i); redo = true; }
-        else {
-            mine = in[i];
-            entry_of(P, i, i ? &in[i - 1] : nullptr, &pos, &bs);
-            redo = mine.entry_pos != pos || mine.entry_bs != bs;
-            if (!redo) out[i] = mine;
-        }
+        if (r == 0) pos = guessed_entry_pos(P, i);
+        else entry_of(P, i, i ? jg::ld_flag64(&P.sub_exit[i - 1]) : 0ull, &pos, &bs);
     }
-    if (!JG_WARP_ANY(redo)) return false;
     const SubStart zero = {0u, 0, 0, 0};
-    decode_subsequence<false>(P, l1, i, redo, pos, bs, zero, have ? &out[i] : nullptr);
-    return redo;
+    unsigned long long now = 0;
+    SubStart sums = zero;
+    decode_subsequence<false>(P, l1, i, have, pos, bs, zero, &now, &sums);
+    if (!have) return false;
+    const unsigned long long before = r ? jg::ld_flag64(&P.sub_exit[i]) : ~0ull;
+    jg::st_flag64(&P.sub_exit[i], now);
+    P.sub_sum[i] = sums;
+    if (r == 0 || now == before || i + 1 >= P.n_sub) return false;
+    P.sub_list[(r + 1) & 1][jg::gmem_atomic_add(&P.sub_cnt[(r + 1) % 3], 1u)] = (unsigned)(i + 1);
+    return true;
 }
+// number of items of round r (read before any thread of the round appends: the appends go to another slot)
+JG_DEV unsigned sync_round_count(const DevParams& P, int r) { return r < 2 ? (unsigned)P.n_sub : jg::ld_flag32(&P.sub_cnt[r % 3]); }
 
 // the writing pass for subsequence i
-JG_DEV void write_subsequence(const DevParams& P, const uint16_t* l1, int i, const SubState* states)
+JG_DEV void write_subsequence(const DevParams& P, const uint16_t* l1, int i)
 {
     const bool have = i < P.n_sub;
     unsigned pos = 0, bs = 0;
     SubStart first = {0u, 0, 0, 0};
     if (have) {
-        entry_of(P, i, i ? &states[i - 1] : nullptr, &pos, &bs);
+        entry_of(P, i, i ? P.sub_exit[i - 1] : 0ull, &pos, &bs);
         first = P.sub_start[i];
     }
-    decode_subsequence<true>(P, l1, i, have, pos, bs, first, nullptr);
+    decode_subsequence<true>(P, l1, i, have, pos, bs, first, nullptr, nullptr);
 }
 
 JG_DEV unsigned char clip8(int x) { return x < 0 ? 0 : (x > 0xFF ? 0xFF : (unsigned char)x); }   // njClip (:339-341)
@@ -561,24 +571,28 @@ JG_DEV void load_l1(const DevParams& P, uint16_t* l1)
     for (int i = (int)threadIdx.x; i < (4 << kL1Bits); i += (int)blockDim.x) l1[i] = l1_entry(P.vlc, i >> kL1Bits, i & ((1 << kL1Bits) - 1));
     __syncthreads();
 }
-// round `r` of the batch: reads sub[(r + 1) & 1] (round 0: nothing), writes sub[r & 1]; *redone counts the subsequences decoded
-__global__ void __launch_bounds__(kSubThreads) sync_round_kernel(const DevParams* __restrict__ imgs, int r, unsigned* __restrict__ redone)
+// round r of the batch (see "subsequences"); *appended counts the subsequences put on the next round's lists.
+// Rounds 0 and 1 cover every subsequence, later ones their image's list: CTAs beyond its end leave at once.
+__global__ void __launch_bounds__(kSubThreads) sync_round_kernel(const DevParams* __restrict__ imgs, int r, unsigned* __restrict__ appended)
 {
     const DevParams& P = imgs[blockIdx.y];
     __shared__ uint16_t l1[4 << kL1Bits];
-    if ((int)(blockIdx.x * blockDim.x) >= P.n_sub) return;
+    if (!P.n_sub) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.sub_cnt[(r + 2) % 3] = 0u;       // the list of round r-1: read by all, appended to again in round r+1
+    const unsigned count = sync_round_count(P, r);
+    if (blockIdx.x * blockDim.x >= count) return;
     load_l1(P, l1);
-    const bool did = sync_round(P, l1, (int)(blockIdx.x * blockDim.x + threadIdx.x), r ? P.sub[(r + 1) & 1] : nullptr, P.sub[r & 1]);
+    const bool did = sync_round_item(P, l1, r, blockIdx.x * blockDim.x + threadIdx.x, count);
     const unsigned any = __ballot_sync(0xffffffffu, did);
-    if (any && (threadIdx.x & 31) == 0) atomicAdd(redone, (unsigned)__popc(any));
+    if (any && (threadIdx.x & 31) == 0) atomicAdd(appended, (unsigned)__popc(any));
 }
-// exclusive sums of the final records (in sub[final]) per image: one CTA, a contiguous slice per thread
-__global__ void __launch_bounds__(256) sync_scan_kernel(const DevParams* __restrict__ imgs, int final)
+// exclusive sums of the records per image: one CTA, a contiguous slice per thread
+__global__ void __launch_bounds__(256) sync_scan_kernel(const DevParams* __restrict__ imgs)
 {
     const DevParams& P = imgs[blockIdx.x];
     const int n = P.n_sub, t = (int)threadIdx.x;
     if (!n) return;
-    const SubState* S = P.sub[final];
+    const SubStart* S = P.sub_sum;
     const int per = (n + 255) / 256, lo = t * per < n ? t * per : n, hi = lo + per < n ? lo + per : n;
     __shared__ SubStart part[256];
     SubStart a = {0u, 0, 0, 0};
@@ -600,13 +614,13 @@ __global__ void __launch_bounds__(256) sync_scan_kernel(const DevParams* __restr
         a.n += S[j].n; a.dc0 += S[j].dc0; a.dc1 += S[j].dc1; a.dc2 += S[j].dc2;
     }
 }
-__global__ void __launch_bounds__(kSubThreads) sync_write_kernel(const DevParams* __restrict__ imgs, int final)
+__global__ void __launch_bounds__(kSubThreads) sync_write_kernel(const DevParams* __restrict__ imgs)
 {
     const DevParams& P = imgs[blockIdx.y];
     __shared__ uint16_t l1[4 << kL1Bits];
     if ((int)(blockIdx.x * blockDim.x) >= P.n_sub) return;
     load_l1(P, l1);
-    write_subsequence(P, l1, (int)(blockIdx.x * blockDim.x + threadIdx.x), P.sub[final]);
+    write_subsequence(P, l1, (int)(blockIdx.x * blockDim.x + threadIdx.x));
 }
 // IDCT: eight threads per block.  Thread r loads row r (one 16-byte load), dequantises and runs njRowIDCT
 // in registers; the 8x8 goes through a padded shared-memory tile; thread c then runs njColIDCT on column c

@@ -151,10 +151,13 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
     unsigned* d_err = B.alloc<unsigned>((size_t)n);
     DevParams* d_params = B.alloc<DevParams>((size_t)n);
     constexpr int kMaxRoundsPerCheck = 256;
-    SubState* d_sub = B.alloc<SubState>(2 * sub_total);
-    SubStart* d_start = B.alloc<SubStart>(sub_total);
-    unsigned* d_redone = B.alloc<unsigned>(kMaxRoundsPerCheck);
-    if (!d_sub || !d_start || !d_redone) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
+    unsigned long long* d_exit = B.alloc<unsigned long long>(sub_total);
+    SubStart* d_sums = B.alloc<SubStart>(2 * sub_total);                       // per subsequence: its own sums, then their exclusive sums
+    unsigned* d_lists = B.alloc<unsigned>(2 * sub_total);
+    unsigned* d_cnt = B.alloc<unsigned>(3 * (size_t)n);
+    unsigned* d_appended = B.alloc<unsigned>(kMaxRoundsPerCheck);
+    if (!d_exit || !d_sums || !d_lists || !d_cnt || !d_appended) { jg::set_error_text(result_text(kOutOfMem)); return 0; }
+    JD_CUDA(cudaMemsetAsync(d_cnt, 0, 3 * (size_t)n * 4, B.s));
     if (!d_data || !d_iv || !d_vlc || !d_coef || !d_planes || (!pixels_on_device && !d_out) || !d_err || !d_params) {
         jg::set_error_text(result_text(kOutOfMem)); return 0;
     }
@@ -195,7 +198,8 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
             P.n_sub = j.n_sub; P.sub_log2 = j.sub_log2; P.bpm = mcu_block_map(I, P.blk);
             P.scan = P.data + I.scan_off; P.scan_bytes = (unsigned)(I.scan_end - I.scan_off);
             P.total_blocks = (unsigned long long)I.n_mcus * P.bpm;
-            P.sub[0] = d_sub + j.sub_off; P.sub[1] = d_sub + sub_total + j.sub_off; P.sub_start = d_start + j.sub_off;
+            P.sub_exit = d_exit + j.sub_off; P.sub_sum = d_sums + j.sub_off; P.sub_start = d_sums + sub_total + j.sub_off;
+            P.sub_list[0] = d_lists + j.sub_off; P.sub_list[1] = d_lists + sub_total + j.sub_off; P.sub_cnt = d_cnt + 3 * (size_t)i;
         }
     }
     JD_CUDA(cudaMemcpyAsync(d_iv, iv_host.data(), iv_words * 4, cudaMemcpyHostToDevice, B.s));
@@ -276,22 +280,22 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
     if (kernel_ms) { JD_CUDA(cudaEventCreate(&e0)); JD_CUDA(cudaEventCreate(&e1)); JD_CUDA(cudaEventRecord(e0, B.s)); }
     if (max_iv) decode_intervals_kernel<<<dim3((unsigned)((max_iv + 63) / 64), (unsigned)n), 64, 0, B.s>>>(d_params);
     if (max_sub) {
-        // rounds until no subsequence is decoded again; the host looks at the count of a group's last round only
-        // (rounds after the settling one merely copy the records, so a group may overshoot)
+        // rounds until no subsequence is put on a list any more; the host looks at the count of a group's last round only
+        // (a round with empty lists costs a launch of CTAs that leave at once, so a group may overshoot)
         const dim3 grid((unsigned)((max_sub + kSubThreads - 1) / kSubThreads), (unsigned)n);
         int r = 0;
-        for (int group = 8;; group = std::min(2 * group, kMaxRoundsPerCheck)) {
-            JD_CUDA(cudaMemsetAsync(d_redone, 0, (size_t)group * 4, B.s));
-            for (int k = 0; k < group; ++k, ++r) sync_round_kernel<<<grid, kSubThreads, 0, B.s>>>(d_params, r, d_redone + k);
+        for (int check = 0;; ++check) {
+            const int group = check < 4 ? 8 : std::min(8 << (check - 3), kMaxRoundsPerCheck);     // 8 8 8 8 16 32 ... 256
+            JD_CUDA(cudaMemsetAsync(d_appended, 0, (size_t)group * 4, B.s));
+            for (int k = 0; k < group; ++k, ++r) sync_round_kernel<<<grid, kSubThreads, 0, B.s>>>(d_params, r, d_appended + k);
             unsigned last = 0;
-            JD_CUDA(cudaMemcpyAsync(&last, d_redone + group - 1, 4, cudaMemcpyDeviceToHost, B.s));
+            JD_CUDA(cudaMemcpyAsync(&last, d_appended + group - 1, 4, cudaMemcpyDeviceToHost, B.s));
             JD_CUDA(cudaStreamSynchronize(B.s));
             if (!last) break;
             if (r > max_sub + 2 * kMaxRoundsPerCheck) { jg::set_error_text("decode: the subsequence rounds did not settle"); return 0; }   // every round settles at least one more
         }
-        const int final = (r - 1) & 1;
-        sync_scan_kernel<<<(unsigned)n, 256, 0, B.s>>>(d_params, final);
-        sync_write_kernel<<<grid, kSubThreads, 0, B.s>>>(d_params, final);
+        sync_scan_kernel<<<(unsigned)n, 256, 0, B.s>>>(d_params);
+        sync_write_kernel<<<grid, kSubThreads, 0, B.s>>>(d_params);
     }
     for (int c = 0; c < 3; ++c)
         if (max_blocks[c]) idct_kernel<<<dim3((unsigned)((max_blocks[c] + 15) / 16), (unsigned)n), kIdctThreads, 0, B.s>>>(d_params, c);   // 16 blocks per CTA

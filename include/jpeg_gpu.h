@@ -183,8 +183,11 @@ JPEG_GPU_API int jpeg_gpu_encode_with_func(jpeg_gpu_write_func* func, void* cont
 /* What Image::readJpg does with NanoJPEG (codecs.cpp:821-849: njInit, njDecode, njGetWidth / njGetHeight,
  * njGetImage; jpeg_dec.h:880-908), on the GPU: baseline JPEG, 1 or 3 components, power-of-two sampling
  * factors.  The pixels (RGB interleaved, or 8-bit gray) are bit-identical to NanoJPEG's, including its
- * chroma upsampling filter.  Restart intervals (JPEG_GPU_FLAG_RESTART on the encode side) are decoded in
- * parallel, one thread each; a stream without them is entropy-decoded by a single thread (correct, slow).
+ * chroma upsampling filter.  The entropy decode is parallel either way: one thread per restart interval
+ * where the file has them (JPEG_GPU_FLAG_RESTART on the encode side), one thread per 32..128-byte subsequence
+ * of the scan where it has none (everything jpeg_enc.h writes) -- speculative decodes that are repeated until
+ * neighbouring subsequences agree (self-synchronisation of the Huffman code).  Only scans with irregular
+ * marker bytes or more than 16 blocks per MCU are left to a single thread (correct, slow).
  * Return 1 on success, 0 on failure (jpeg_gpu_last_error names the nj_result_t). */
 JPEG_GPU_API int jpeg_gpu_decode_info(const uint8_t* jpeg, size_t size, int* width, int* height, int* ncomp);
 JPEG_GPU_API int jpeg_gpu_decode(const uint8_t* jpeg, size_t size, uint8_t* pixels, size_t capacity,

@@ -42,6 +42,11 @@ def _load():
     return _lib
 
 
+def emu_set_round_order(order):
+    """Order of the emulated threads within a subsequence round: 0 alternating, 1 descending (predecessor's old state), 2 ascending."""
+    _load().emu_set_round_order(int(order))
+
+
 def emu_decode(jpeg, sub_log2=-1, want_rounds=False):
     """Decode with the product's decoder source run on the CPU (tests only). Returns uint8 [h,w,3] / [h,w] or the nj error code.
     sub_log2: -1 = the library's own choice between restart intervals and subsequences, 0 = intervals only, n = subsequences

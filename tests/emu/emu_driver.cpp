@@ -183,6 +183,12 @@ int emu_ticket_map(const int* tiles, int n_images, int force_schedule, unsigned*
 
 // The decoder's per-item device functions (jpeg_decode.cuh) run in plain loops: same code as on the GPU,
 // where one thread executes one call.  Returns the nj_result_t; out receives RGB / gray pixels.
+// Order in which the emulated threads of a subsequence round run (on the GPU: any).  0 = ascending in even rounds and
+// descending in odd ones, 1 = always descending (every thread sees its predecessor's OLD state: the slowest case),
+// 2 = always ascending (every thread sees the new one).
+static int g_round_order = 0;
+void emu_set_round_order(int o) { g_round_order = o; }
+
 // sub_log2: -1 = the library's policy (jd::subsequence_log2), 0 = interval path, > 0 = subsequences of that size where
 // the stream allows them at all.  rounds (optional) receives the number of rounds the subsequence decode took (0: not used).
 int emu_decode_sub(const uint8_t* jpeg, size_t size, uint8_t* out, size_t cap, int* w, int* h, int* ncomp, int sub_log2, int* rounds)
@@ -218,21 +224,25 @@ int emu_decode_sub(const uint8_t* jpeg, size_t size, uint8_t* out, size_t cap, i
         P.sub_log2 = sub_log2; P.n_sub = (int)((scan_bytes + ((size_t)1 << sub_log2) - 1) >> sub_log2);
         P.bpm = jd::mcu_block_map(I, P.blk); P.scan = jpeg + I.scan_off; P.scan_bytes = (unsigned)scan_bytes;
         P.total_blocks = (unsigned long long)I.n_mcus * P.bpm;
-        std::vector<jd::SubState> sa(P.n_sub), sb(P.n_sub);
-        std::vector<jd::SubStart> start(P.n_sub);
-        P.sub[0] = sa.data(); P.sub[1] = sb.data(); P.sub_start = start.data();
+        std::vector<unsigned long long> exits(P.n_sub, 0);
+        std::vector<jd::SubStart> sums(P.n_sub), start(P.n_sub);
+        std::vector<unsigned> la(P.n_sub), lb(P.n_sub);
+        unsigned cnt[3] = {0, 0, 0};
+        P.sub_exit = exits.data(); P.sub_sum = sums.data(); P.sub_start = start.data(); P.sub_list[0] = la.data(); P.sub_list[1] = lb.data(); P.sub_cnt = cnt;
         int r = 0;
         for (;; ++r) {
-            int redone = 0;
-            for (int i = 0; i < P.n_sub; ++i) redone += jd::sync_round(P, l1.data(), i, r ? P.sub[(r + 1) & 1] : nullptr, P.sub[r & 1]);
-            if (!redone) break;
+            cnt[(r + 2) % 3] = 0;
+            const unsigned count = jd::sync_round_count(P, r);
+            unsigned appended = 0;
+            const bool descending = g_round_order == 1 || (g_round_order == 0 && (r & 1));
+            for (unsigned k = 0; k < count; ++k) appended += jd::sync_round_item(P, l1.data(), r, descending ? count - 1 - k : k, count);
+            if (r >= 1 && !appended) break;
             if (r > P.n_sub + 2) return -2;       // cannot happen: every round settles at least one more subsequence
         }
-        if (rounds) *rounds = r;
-        const jd::SubState* S = P.sub[r & 1];
+        if (rounds) *rounds = r + 1;
         jd::SubStart run = {0u, 0, 0, 0};
-        for (int i = 0; i < P.n_sub; ++i) { start[i] = run; run.n += S[i].n; run.dc0 += S[i].dc0; run.dc1 += S[i].dc1; run.dc2 += S[i].dc2; }
-        for (int i = 0; i < P.n_sub; ++i) jd::write_subsequence(P, l1.data(), i, S);
+        for (int i = 0; i < P.n_sub; ++i) { start[i] = run; run.n += sums[i].n; run.dc0 += sums[i].dc0; run.dc1 += sums[i].dc1; run.dc2 += sums[i].dc2; }
+        for (int i = 0; i < P.n_sub; ++i) jd::write_subsequence(P, l1.data(), i);
     } else {
         for (int iv = 0; iv < P.n_intervals; ++iv) jd::decode_interval(P, l1.data(), iv);
     }

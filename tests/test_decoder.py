@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle
-from tests.emu.emu import emu_decode
+from tests.emu.emu import emu_decode, emu_set_round_order
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -88,10 +88,15 @@ def test_subsequence_decode_equals_the_reference_decoder(w, h, nc, qm, q, sub):
     jpeg = oracle.oracle_encode(img, qm, q, sub)
     want = oracle.ref_decode(jpeg)
     assert want is not None
-    for sub_log2 in (2, 3, 5, 7):
-        got, rounds = emu_decode(jpeg, sub_log2, want_rounds=True)
-        assert isinstance(got, np.ndarray) and np.array_equal(got, want), sub_log2
-        assert rounds >= 1
+    try:
+        for order in (0, 1, 2):                  # the threads of a round in different orders (the records are updated in place)
+            emu_set_round_order(order)
+            for sub_log2 in (2, 3, 5, 7):
+                got, rounds = emu_decode(jpeg, sub_log2, want_rounds=True)
+                assert isinstance(got, np.ndarray) and np.array_equal(got, want), (order, sub_log2)
+                assert rounds >= 2
+    finally:
+        emu_set_round_order(0)
     assert np.array_equal(emu_decode(jpeg, 0), want)              # and the one-thread path still agrees
 
 

@@ -12,3 +12,4 @@ timeout 40 python tools/decode_prof.py 16 free > gpurun_out/decode_free_plain.lo
 timeout 60 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"sync_|decode_intervals|idct_kernel|upsample|color_kernel" -c 300 --csv \
     --log-file gpurun_out/decode_free_launches.csv python tools/decode_prof.py 16 free > gpurun_out/ncu_decode_free.log 2>&1
 cat gpurun_out/decode_free_plain.log
+timeout 100 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_decode_legs.json 2> gpurun_out/bench_decode_legs.err; tail -c 1500 gpurun_out/bench_decode_legs.json
