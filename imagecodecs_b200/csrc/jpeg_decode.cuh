@@ -229,7 +229,7 @@ struct SyncReader {
     int bits;
     unsigned stuffed;          // bit j: the j-th newest byte of buf was followed by a stuffed byte
 };
-JG_DEV void sr_refill(SyncReader& r)       // called with fewer than 16 bits left; leaves at least 25
+JG_DEV void sr_refill(SyncReader& r)       // called with fewer than 32 bits left; leaves 32 ... 63
 {
     if ((((size_t)r.p) & 3u) == 0 && r.p + 4 <= r.end) {
         const unsigned w = ldg_u32(r.p);
@@ -251,12 +251,7 @@ JG_DEV void sr_refill(SyncReader& r)       // called with fewer than 16 bits lef
         r.buf = (r.buf << 8) | b;
         r.bits += 8;
         r.stuffed = (r.stuffed << 1) | st;
-    } while (r.bits <= 24 || ((((size_t)r.p) & 3u) != 0 && r.bits <= 48 && r.p < r.end));
-}
-JG_DEV unsigned sr_show(SyncReader& r, int n)
-{
-    if (r.bits < n) sr_refill(r);
-    return (unsigned)(r.buf >> (r.bits - n)) & ((1u << n) - 1u);
+    } while (r.bits < 32 || ((((size_t)r.p) & 3u) != 0 && r.bits <= 48 && r.p < r.end));
 }
 JG_DEV unsigned sr_pos(const SyncReader& r, const uint8_t* base)
 {
@@ -270,22 +265,22 @@ JG_DEV void sr_start(SyncReader& r, const uint8_t* base, const uint8_t* end, uns
     const int off = (int)(pos & 7u);
     if (off) { sr_refill(r); r.bits -= off; }
 }
-JG_DEV int sr_get_vlc(SyncReader& r, const VlcTables& T, int table, unsigned* code_out, bool* bad)     // njGetVLC (:643-656)
+// njGetVLC (:643-656) on ONE 32-bit window: a symbol is at most 16 code bits + 11 value bits, so after a top-up to 32 bits
+// the code lookup and the value bits need no second look at the buffer (and no second refill check)
+JG_DEV int sr_symbol(SyncReader& r, const VlcTables& T, int table, unsigned* code_out, bool* bad)
 {
-    const unsigned peek = sr_show(r, 16);
-    unsigned e = T.l1[(table << kL1Bits) + (peek >> (16 - kL1Bits))];
-    if (!e) e = T.full[(size_t)table * 65536 + peek];
+    if (r.bits < 32) sr_refill(r);
+    const unsigned win = jg::funnel_r((unsigned)r.buf, (unsigned)(r.buf >> 32), (unsigned)(r.bits - 32));     // the next 32 bits
+    unsigned e = T.l1[(table << kL1Bits) + (win >> (32 - kL1Bits))];
+    if (!e) e = T.full[(size_t)table * 65536 + (win >> 16)];
     const int len = (int)(e >> 8);
-    if (!len) { *bad = true; return 0; }
-    r.bits -= len;
     const unsigned code = e & 0xFFu;
-    *code_out = code;
     const int nb = (int)(code & 15u);
-    if (!nb) return 0;
-    int v = (int)sr_show(r, nb);
-    r.bits -= nb;
-    if (v < (1 << (nb - 1))) v += (int)((0xFFFFFFFFu << nb) + 1u);
-    return v;
+    *code_out = code;
+    if (!len) { *bad = true; return 0; }
+    r.bits -= len + nb;
+    const unsigned raw = ((win << len) >> 1) >> (31 - nb);                    // the nb bits behind the code; nb = 0: 0 (a shift by 32 is undefined)
+    return nb && raw < (1u << (nb - 1)) ? (int)raw + (int)((0xFFFFFFFFu << nb) + 1u) : (int)raw;
 }
 
 // the state a subsequence is entered with when its predecessor has none to offer
@@ -329,28 +324,17 @@ JG_DEV void decode_subsequence(const DevParams& P, const uint16_t* l1, int i, bo
         const bool go = have && !bad && (WRITE ? (g < total && (last || pos < limit)) : pos < limit);
         if (!JG_WARP_ANY(go)) break;
         if (!go) continue;
-        bool done = false;
+        // one path for DC and AC symbols: the table row is selected, not the code
+        const bool is_dc = s == 0;
         unsigned code = 0;
-        if (s == 0) {
-            const int v = sr_get_vlc(r, T, K.dctab, &code, &bad);
-            const int d = K.comp == 0 ? (dc0 += v) : K.comp == 1 ? (dc1 += v) : (dc2 += v);
-            if (WRITE && !bad) blk[0] = (int16_t)d;
-            s = 1;
-        } else {
-            const int v = sr_get_vlc(r, T, K.actab, &code, &bad);
-            if (!bad) {
-                if (!code) done = true;                                               // EOB
-                else if (!(code & 0x0F) && code != 0xF0) bad = true;
-                else {
-                    const int k = s + (int)(code >> 4);                               // (s - 1) + run + 1
-                    if (k > 63) bad = true;
-                    else {
-                        if (WRITE) blk[zz_nat(k)] = (int16_t)v;
-                        if (k == 63) done = true; else s = k + 1;
-                    }
-                }
-            }
-        }
+        const int v = sr_symbol(r, T, is_dc ? K.dctab : K.actab, &code, &bad);
+        const int k = s + (int)(code >> 4);                                           // AC: (s - 1) + run + 1
+        const bool eob = !is_dc && !code;
+        if (!is_dc && !eob && ((!(code & 0x0F) && code != 0xF0) || k > 63)) bad = true;
+        if (is_dc) { dc0 += K.comp == 0 ? v : 0; dc1 += K.comp == 1 ? v : 0; dc2 += K.comp == 2 ? v : 0; }
+        if (WRITE && !bad && !eob) blk[is_dc ? 0 : zz_nat(k)] = (int16_t)(is_dc ? (K.comp == 0 ? dc0 : K.comp == 1 ? dc1 : dc2) : v);
+        const bool done = !bad && (eob || (!is_dc && k == 63));
+        s = is_dc ? 1 : k + 1;
         if (done) {
             s = 0; ++n;
             if (++b == bpm) { b = 0; if (WRITE && ++mbx == mbwidth) { mbx = 0; ++mby; } }

@@ -49,6 +49,8 @@ JG_DEV unsigned bswap32(unsigned v) { return __byte_perm(v, 0u, 0x0123u); }
 // byte i of the result = byte (sel >> 4i) & 7 of the 8 bytes {a: 0-3, b: 4-7}
 JG_DEV unsigned byte_perm(unsigned a, unsigned b, unsigned sel) { return __byte_perm(a, b, sel); }
 JG_DEV unsigned funnel_l(unsigned lo, unsigned hi, unsigned s) { return __funnelshift_l(lo, hi, s); }
+// low 32 bits of (hi:lo) >> s, s in 0..31
+JG_DEV unsigned funnel_r(unsigned lo, unsigned hi, unsigned s) { return __funnelshift_r(lo, hi, s); }
 // per-byte compare: 0xff in every byte lane where a == b
 JG_DEV unsigned v_cmpeq4(unsigned a, unsigned b) { return __vcmpeq4(a, b); }
 // per-halfword compare: 0xffff in every halfword lane where a != b

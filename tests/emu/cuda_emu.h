@@ -56,6 +56,7 @@ JG_DEV int i_clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 JG_DEV int i_ffs(unsigned v) { return __builtin_ffs((int)v); }
 JG_DEV int i_popc(unsigned v) { return __builtin_popcount(v); }
 JG_DEV unsigned bswap32(unsigned v) { return __builtin_bswap32(v); }
+JG_DEV unsigned funnel_r(unsigned lo, unsigned hi, unsigned s) { return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (s & 31u)); }
 JG_DEV unsigned byte_perm(unsigned a, unsigned b, unsigned sel)
 {
     const unsigned long long ab = ((unsigned long long)b << 32) | a;
