@@ -228,16 +228,24 @@ struct SyncReader {
     unsigned long long buf;
     int bits;
     unsigned stuffed;          // bit j: the j-th newest byte of buf was followed by a stuffed byte
+    unsigned ahead;            // the aligned word at `pa`, requested one refill early: its latency passes behind the decoding
+    const uint8_t* pa;         // the next aligned word at or after p if it lies inside the scan, else nullptr
 };
+JG_DEV void sr_request(SyncReader& r)
+{
+    const uint8_t* a = (const uint8_t*)(((size_t)r.p + 3u) & ~(size_t)3u);
+    if (a + 4 <= r.end) { r.ahead = ldg_u32(a); r.pa = a; } else r.pa = nullptr;
+}
 JG_DEV void sr_refill(SyncReader& r)       // called with fewer than 32 bits left; leaves 32 ... 63
 {
-    if ((((size_t)r.p) & 3u) == 0 && r.p + 4 <= r.end) {
-        const unsigned w = ldg_u32(r.p);
+    if (r.pa == r.p) {                                      // p is aligned and its word is already here
+        const unsigned w = r.ahead;
         if (v_cmpeq4(w, 0xffffffffu) == 0u) {
             r.buf = (r.buf << 32) | bswap32(w);
             r.bits += 32;
             r.p += 4;
             r.stuffed <<= 4;
+            sr_request(r);
             return;
         }
     }
@@ -252,6 +260,7 @@ JG_DEV void sr_refill(SyncReader& r)       // called with fewer than 32 bits lef
         r.bits += 8;
         r.stuffed = (r.stuffed << 1) | st;
     } while (r.bits < 32 || ((((size_t)r.p) & 3u) != 0 && r.bits <= 48 && r.p < r.end));
+    sr_request(r);
 }
 JG_DEV unsigned sr_pos(const SyncReader& r, const uint8_t* base)
 {
@@ -261,7 +270,8 @@ JG_DEV unsigned sr_pos(const SyncReader& r, const uint8_t* base)
 }
 JG_DEV void sr_start(SyncReader& r, const uint8_t* base, const uint8_t* end, unsigned pos)
 {
-    r.p = base + (pos >> 3); r.end = end; r.buf = 0; r.bits = 0; r.stuffed = 0;
+    r.p = base + (pos >> 3); r.end = end; r.buf = 0; r.bits = 0; r.stuffed = 0; r.ahead = 0;
+    sr_request(r);
     const int off = (int)(pos & 7u);
     if (off) { sr_refill(r); r.bits -= off; }
 }
