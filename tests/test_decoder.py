@@ -150,3 +150,15 @@ def test_subsequence_decode_of_damaged_scans_agrees_with_the_one_thread_path():
                 assert par == one
                 seen_error += 1
     assert seen_error and seen_pixels
+
+
+def test_irregular_marker_bytes_in_the_scan_stay_on_the_one_thread_path():
+    """A scan in which an 0xFF is followed by something other than 00 has no canonical bit positions: such files are not cut
+    into subsequences (rounds == 0) -- they decode, or fail, exactly as before."""
+    good = bytearray(oracle.oracle_encode(oracle.synth_image(160, 96, 3), 1, 80, 1))
+    at = 700 + next(i for i in range(len(good) - 1400) if good[700 + i] != 0xFF and good[699 + i] != 0xFF and good[701 + i] != 0xFF)
+    good[at], good[at + 1] = 0xFF, 0x01
+    res, rounds = emu_decode(bytes(good), 5, want_rounds=True)
+    assert rounds == 0
+    one = emu_decode(bytes(good), 0)
+    assert (isinstance(res, np.ndarray) and np.array_equal(res, one)) or res == one
