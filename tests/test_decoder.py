@@ -162,3 +162,42 @@ def test_irregular_marker_bytes_in_the_scan_stay_on_the_one_thread_path():
     assert rounds == 0
     one = emu_decode(bytes(good), 0)
     assert (isinstance(res, np.ndarray) and np.array_equal(res, one)) or res == one
+
+
+def test_subsequence_decode_random_differential():
+    """200 random files (this encoder's oracle and libjpeg via PIL: sizes, qualities, samplings, gray, optimised tables, noise),
+    random subsequence sizes of 4 ... 128 bytes and thread orders: every one decodes to the reference decoder's pixels."""
+    from PIL import Image, ImageFile
+    ImageFile.MAXBLOCK = 1 << 24
+    rng = np.random.default_rng(20261018)
+    checked = 0
+    try:
+        for it in range(200):
+            w, h = int(rng.integers(8, 400)), int(rng.integers(8, 300))
+            kind = "noise" if rng.random() < 0.25 else "photo"
+            if rng.random() < 0.5:
+                nc = 1 if rng.random() < 0.25 else 3
+                qm = int(rng.integers(0, 2))
+                q = int(rng.integers(1, 4)) if qm == 0 else int(rng.integers(5, 101))
+                sub = 0 if (qm == 0 or nc == 1) else int(rng.integers(0, 2))
+                f = oracle.oracle_encode(oracle.synth_image(w, h, nc, n=it, kind=kind), qm, q, sub)
+            else:
+                img = oracle.synth_image(w, h, 3, n=it, kind=kind)
+                kw = dict(quality=int(rng.integers(5, 101)), optimize=bool(rng.random() < 0.5))
+                b = io.BytesIO()
+                if rng.random() < 0.2:
+                    Image.fromarray(img[:, :, 0]).save(b, "JPEG", **kw)
+                else:
+                    Image.fromarray(img).save(b, "JPEG", subsampling=[0, 1, 2, "4:1:1"][int(rng.integers(0, 4))], **kw)
+                f = b.getvalue()
+            want = oracle.ref_decode(f)
+            if want is None:
+                continue
+            emu_set_round_order(int(rng.integers(0, 3)))
+            sub_log2 = int(rng.integers(2, 8))
+            got = emu_decode(f, sub_log2)
+            assert isinstance(got, np.ndarray) and np.array_equal(got, want), (it, w, h, sub_log2)
+            checked += 1
+    finally:
+        emu_set_round_order(0)
+    assert checked > 150
