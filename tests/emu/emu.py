@@ -43,7 +43,8 @@ def _load():
 
 
 def emu_set_round_order(order):
-    """Order of the emulated threads within a subsequence round: 0 alternating, 1 descending (predecessor's old state), 2 ascending."""
+    """Order of the emulated threads within a subsequence round: 0 alternating, 1 descending (predecessor's old state), 2 ascending,
+    3 = eight racing host threads."""
     _load().emu_set_round_order(int(order))
 
 

@@ -8,7 +8,9 @@
 
 #include <stdlib.h>
 
+#include <atomic>
 #include <functional>
+#include <thread>
 #include <vector>
 
 namespace jg {
@@ -185,7 +187,8 @@ int emu_ticket_map(const int* tiles, int n_images, int force_schedule, unsigned*
 // where one thread executes one call.  Returns the nj_result_t; out receives RGB / gray pixels.
 // Order in which the emulated threads of a subsequence round run (on the GPU: any).  0 = ascending in even rounds and
 // descending in odd ones, 1 = always descending (every thread sees its predecessor's OLD state: the slowest case),
-// 2 = always ascending (every thread sees the new one).
+// 2 = always ascending (every thread sees the new one), 3 = eight host threads share a round's items and race on the
+// records like the GPU's threads do (the in-place update has to tolerate every interleaving).
 static int g_round_order = 0;
 void emu_set_round_order(int o) { g_round_order = o; }
 
@@ -235,6 +238,18 @@ int emu_decode_sub(const uint8_t* jpeg, size_t size, uint8_t* out, size_t cap, i
             const unsigned count = jd::sync_round_count(P, r);
             unsigned appended = 0;
             const bool descending = g_round_order == 1 || (g_round_order == 0 && (r & 1));
+            if (g_round_order == 3) {
+                std::atomic<unsigned> total{0};
+                std::vector<std::thread> pool;
+                for (unsigned t = 0; t < 8; ++t)
+                    pool.emplace_back([&, t] {
+                        unsigned mine = 0;
+                        for (unsigned k = t; k < count; k += 8) mine += jd::sync_round_item(P, l1.data(), r, k, count);
+                        total += mine;
+                    });
+                for (std::thread& th : pool) th.join();
+                appended = total;
+            } else
             for (unsigned k = 0; k < count; ++k) appended += jd::sync_round_item(P, l1.data(), r, descending ? count - 1 - k : k, count);
             if (r >= 1 && !appended) break;
             if (r > P.n_sub + 2) return -2;       // cannot happen: every round settles at least one more subsequence

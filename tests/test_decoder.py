@@ -89,7 +89,7 @@ def test_subsequence_decode_equals_the_reference_decoder(w, h, nc, qm, q, sub):
     want = oracle.ref_decode(jpeg)
     assert want is not None
     try:
-        for order in (0, 1, 2):                  # the threads of a round in different orders (the records are updated in place)
+        for order in (0, 1, 2, 3):               # the threads of a round in different orders / racing host threads (records are updated in place)
             emu_set_round_order(order)
             for sub_log2 in (2, 3, 5, 7):
                 got, rounds = emu_decode(jpeg, sub_log2, want_rounds=True)
@@ -193,7 +193,7 @@ def test_subsequence_decode_random_differential():
             want = oracle.ref_decode(f)
             if want is None:
                 continue
-            emu_set_round_order(int(rng.integers(0, 3)))
+            emu_set_round_order(int(rng.integers(0, 4)))
             sub_log2 = int(rng.integers(2, 8))
             got = emu_decode(f, sub_log2)
             assert isinstance(got, np.ndarray) and np.array_equal(got, want), (it, w, h, sub_log2)
