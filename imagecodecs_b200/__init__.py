@@ -62,6 +62,8 @@ SYMBOLS = {
     "jpeg_gpu_plan_launches": (C.c_int, [C.c_void_p]),
     "jpeg_gpu_plan_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "jpeg_gpu_plan_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "jpeg_gpu_plan_pass_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "jpeg_gpu_plan_is_fused": (C.c_int, [C.c_void_p]),
     "jpeg_gpu_plan_fetch": (C.c_int, [C.c_void_p, C.POINTER(Output), C.c_int, C.c_void_p]),
     "jpeg_gpu_plan_encoded_size": (C.c_size_t, [C.c_void_p, C.c_int]),
     "jpeg_gpu_plan_num_blocks": (C.c_size_t, [C.c_void_p]),
@@ -272,6 +274,17 @@ class Plan:
         if not self._L.jpeg_gpu_plan_kernel_times(self._h, C.byref(a), C.byref(b)):
             raise JpegGpuError("kernel_times unavailable")
         return a.value, b.value
+
+    def pass_times(self):
+        """(transform_ms, entropy_ms, stuff_ms) of the last run (timing enabled, run complete)."""
+        a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
+        if not self._L.jpeg_gpu_plan_pass_times(self._h, C.byref(a), C.byref(b), C.byref(c)):
+            raise JpegGpuError("pass_times unavailable")
+        return a.value, b.value, c.value
+
+    @property
+    def fused(self):
+        return bool(self._L.jpeg_gpu_plan_is_fused(self._h))
 
     def attach_debug(self, coefs_ptr, bits_ptr):
         self._L.jpeg_gpu_plan_attach_debug(self._h, coefs_ptr, bits_ptr)

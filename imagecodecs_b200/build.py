@@ -70,6 +70,8 @@ def build(force=False, verbose=False, example=True):
                                                    "-c", os.path.join(CSRC, "jpeg_kernel_inst.cu"), "-o", obj]))
     jobs.append((os.path.join(OBJ, "jpeg_stuff.o"), [_nvcc()] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", os.path.join(CSRC, "jpeg_stuff.cu"),
                                                                  "-o", os.path.join(OBJ, "jpeg_stuff.o")]))
+    jobs.append((os.path.join(OBJ, "jpeg_entropy.o"), [_nvcc()] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", os.path.join(CSRC, "jpeg_entropy.cu"),
+                                                                   "-o", os.path.join(OBJ, "jpeg_entropy.o")]))
     for src in ("jpeg_gpu_api.cpp", "jpeg_host.cpp", "codecs_jpeg.cpp", "jpeg_decode_host.cpp", "jpeg_decode_api.cpp"):
         if not os.path.exists(os.path.join(CSRC, src)):
             continue

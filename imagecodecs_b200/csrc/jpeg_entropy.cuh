@@ -1,0 +1,458 @@
+// jpeg_entropy.cuh -- pass B of the split pipeline: quantised coefficients -> the unstuffed entropy-coded bits.
+//
+// Replaces the serial half of the reference's block loop: DC / AC coding of tjei_encode_and_write_MCU
+// (jpeg_enc.h:831-888), tjei_calculate_variable_length_int (:598-610), the bit cursor of tjei_write_bits
+// (:613-643, without its 0xFF00 stuffing -- that is pass 2, jpeg_stuff.cuh) and the tail (:1160-1164).
+// Input: `du[64]` of every block as pass A (jpeg_transform.cuh) left it in HBM, zigzag order, blocks in scan
+// order.  Output: identical to pass 1 of the fused kernel (jpeg_kernel.cuh), whose chain / write-out code it shares.
+//
+// Work decomposition
+//   tile   = 32 consecutive blocks of ONE image in scan order (24 with restart intervals, so that a tile is
+//            whole MCUs), whatever the MCU shape: the DC predictor of a block is the DC of an earlier block
+//            of the same component, which is simply read (from the tile, or from HBM when it lies before it),
+//            so nothing is handed over between tiles except the bit offset.
+//   warp   owns a tile:
+//            1. stage   ONE 2-D TMA copy (cp.async.bulk.tensor, mbarrier completion) brings the tile's 32 x 128
+//                       bytes into shared memory while the warp writes out its previous tile.  The box is 72
+//                       elements wide over a tensor that is 64 wide: the out-of-bounds columns pad every block
+//                       to a 144-byte row (with 128-byte rows the 32 lanes of the map phase would all sit on the
+//                       same four banks: measured, 256 wavefronts per tile for those eight loads alone).
+//            2. map     lane l reads block l once (8 x LDS.128) and builds the 64-bit map of what the block
+//                       codes: bit 0 the DC difference, bits 1..62 the non-zero coefficients, bit 63 either the
+//                       last coefficient or -- where that is zero -- the end-of-block code.  A symbol is a set bit.
+//            3. list    a warp scan of the 32 symbol counts; every lane writes its block's symbols
+//                       (block, position, table) into ONE list for the tile, in scan order.
+//            4. code    the list is cut into 32 EQUAL pieces: lane l codes symbols [l*q, (l+1)*q) -- whatever
+//                       blocks they belong to -- serially into its own word stream: coefficient, run from the
+//                       previous list entry, category (clz), {code, length} from ONE 8-byte table load, append to
+//                       a 64-bit register accumulator, full words to shared memory.  Every lane does the same
+//                       amount of work however the symbols are spread over luma / chroma, busy / flat blocks; no
+//                       scan, no atomics, no vote inside the loop.
+//            5. merge   a warp scan of the 32 stream lengths places them; every lane shifts its words to their
+//                       final bit position in the tile's region (plain stores for words it owns alone, atomicOr
+//                       for the two it shares with its neighbours).
+//            6. publish + (one iteration later) chain + write, exactly as in jpeg_kernel.cuh.
+// A tile with more than 32768 bits or a lane stream beyond 640 bits (noise at all-ones quantisers) goes the slow way:
+// four blocks at a time (always fit), written piecewise; same bytes.
+#pragma once
+#include "jpeg_kernel.cuh"
+
+namespace jg {
+
+constexpr int kEntBlocks = 32;                              // blocks per tile at most: one per lane in the map phase
+constexpr int kEntCoefStride = 72;                          // int16 per staged block: 144-byte rows (the TMA box is 72 wide over a 64-wide tensor,
+                                                            // the out-of-bounds columns arrive as zeros) keep 32 lanes off each other's banks
+constexpr int kSubWords = 20;                               // words of a lane's private stream (640 bits)
+constexpr int kEntRegionWords = 1024;                       // a tile's merged bits on the fast path: 32768 at most
+constexpr int kListMax = 2 * kEntRegionWords;               // the symbol list (16-bit entries) lives in the region while the tile is coded
+constexpr int kSlowBlocks = 4;                              // slow path: 4 blocks at a time (<= 256 symbols, <= 8 x 59 bits per lane)
+constexpr int kEntModePlain = 0, kEntModeRestart = 2;
+constexpr unsigned kEntStageBytes = kEntBlocks * kEntCoefStride * 2;   // what one TMA box delivers (out-of-bounds rows count)
+// list entry: bits 0-5 zigzag position, 6-10 block of the tile, 11-15 the symbol's Huffman table as a multiple of 128 bytes
+constexpr unsigned kEntryBlockPos = 0x7ffu;
+constexpr unsigned kTabDc = 0u, kTabAc = 2u, kTabChroma = 1u, kTabAcChroma = 16u;   // luma DC 0, chroma DC 1, luma AC 2, chroma AC 18
+
+struct EntWarp {
+    alignas(128) int16_t coef[kEntBlocks * kEntCoefStride];  // TMA destination
+    alignas(16) uint32_t sub[kEntBlocks * kSubWords];        // word k of lane l at [k * 32 + l] (conflict-free)
+    alignas(16) uint32_t region[kEntRegionWords + 8];        // the tile's merged bits (MSB-first words); survives into the next iteration
+    uint2 mask[kEntBlocks];                                  // symbol maps of the staged blocks
+    alignas(8) unsigned long long mbar;                      // completion of the staged coefficients
+    Pending pend[2];
+};
+// Huffman tables as the symbol loop wants them: entry [(run << 4) | category] = {code, length + category}; the two DC
+// tables (16 entries, run 0) at byte 0 and 128, the two AC tables (256 entries) at byte 256 and 2304
+struct EntTables { uint2 e[32 + 512]; };
+struct EntSmem {
+    EntWarp wm[kEntWarps];
+    EntTables tab;
+};
+
+// Component class and DC predecessor of block b of an image (bpm blocks per MCU: 1 gray, 3 4:4:4, 6 4:2:0 with
+// Y00 Y01 Y10 Y11 Cb Cr): j = b mod bpm.
+JG_DEV void block_role(int bpm, int j, unsigned& cls, int& delta)
+{
+    if (bpm == 6) { cls = j >= 4 ? 1u : 0u; delta = j >= 4 ? 6 : (j == 0 ? 3 : 1); }   // Y00 follows the previous MCU's Y11
+    else { cls = (bpm == 3 && j != 0) ? 1u : 0u; delta = bpm; }
+}
+
+// 8 coefficients (one 16-byte vector) -> 8 flag bits
+JG_DEV unsigned nonzero8(uint4 v)
+{
+    const unsigned m0 = v_minu2(v.x, 0x00010001u), m1 = v_minu2(v.y, 0x00010001u);
+    const unsigned m2 = v_minu2(v.z, 0x00010001u), m3 = v_minu2(v.w, 0x00010001u);
+    const unsigned a = (m0 + 4u * m1) + 16u * (m2 + 4u * m3);     // even coefficients at bits 0,2,4,6; odd ones at 16,18,20,22
+    return (a | (a >> 15)) & 0xffu;
+}
+
+// Map phase, lane = block `slot` of the staged tile (active: slot < nblk): the block's symbol map goes to W.mask[slot], its
+// DC difference REPLACES the DC in the staged block (after every lane has read its predictor: the warp barrier inside).
+JG_DEV void map_block(EntWarp& W, int slot, int slot_j, int nblk, int jb, int bpm, int b0, int pred_outside, bool restart)
+{
+    const bool active = slot < nblk;
+    int16_t* cz = W.coef + slot * kEntCoefStride;
+    unsigned mlo = 0, mhi = 0;
+    int diff = 0;
+    if (active) {
+        const uint4* row = reinterpret_cast<const uint4*>(cz);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            mlo |= nonzero8(row[q]) << (8 * q);
+            mhi |= nonzero8(row[4 + q]) << (8 * q);
+        }
+        mlo |= 1u;                     // the DC difference is always coded (jpeg_enc.h:834-844)
+        mhi |= 0x80000000u;            // position 63: the last coefficient, or the end-of-block code where it is zero (:884-887)
+        int j = jb + slot_j; if (j >= bpm) j -= bpm;                 // slot_j = slot mod bpm
+        unsigned cls; int delta;
+        block_role(bpm, j, cls, delta);
+        const int ps = slot - delta;                                 // predecessor of the same component, tile-relative
+        int pred = 0;
+        if (ps >= 0) pred = W.coef[ps * kEntCoefStride];
+        else if (!restart && b0 + ps >= 0) pred = pred_outside;      // before the tile: fetched from HBM by the caller
+        diff = (int)cz[0] - pred;                                    // image start / restart interval: predictor 0 (jpeg_enc.h:1085-1087)
+    }
+    warp_sync();                       // every predictor has been read
+    if (active) cz[0] = (int16_t)diff;
+    fence_proxy_async();               // ... a generic store into the TMA's destination: ordered before the next tile's copy
+    uint2 m; m.x = mlo; m.y = mhi;
+    W.mask[slot] = m;
+    warp_sync();
+}
+
+// List phase: the lane appends the symbols of block `slot` (map m, class cls) at list[at...], in scan order.
+JG_DEV void list_block(uint16_t* list, unsigned at, int slot, uint2 m, unsigned cls)
+{
+    uint16_t* lp = list + at;
+    const unsigned blk = (unsigned)slot << 6;
+    const unsigned dc = blk | ((kTabDc + (cls ? kTabChroma : 0u)) << 11), ac = blk | ((kTabAc + (cls ? kTabAcChroma : 0u)) << 11);
+#pragma unroll 1
+    for (unsigned w = bit_reverse(m.x); w;) {                        // bit-reversed map: the next position is a clz
+        const unsigned p = (unsigned)i_clz(w);
+        w &= ~(0x80000000u >> p);
+        *lp++ = (uint16_t)((p ? ac : dc) | p);
+    }
+#pragma unroll 1
+    for (unsigned w = bit_reverse(m.y); w;) {
+        const unsigned p = (unsigned)i_clz(w);
+        w &= ~(0x80000000u >> p);
+        *lp++ = (uint16_t)(ac | 32u | p);
+    }
+}
+
+// Code phase: the lane codes symbols [s0, s0 + n) of the list into its private word stream (word k at shared address
+// sub + 128 * k); returns the bits.  Words beyond kSubWords pile up on the last slot (the count tells: slow path).
+// Everything inside the loop works on 32-bit shared-memory addresses.
+JG_DEV unsigned code_symbols(const EntTables& T, const int16_t* coef, const uint16_t* list, unsigned s0, unsigned n, const uint32_t* sub)
+{
+    unsigned alo = 0, ahi = 0;       // the last 64 bits appended
+    unsigned t = 0;                  // bits so far
+    unsigned wa = smem_addr(sub);    // where the next full word goes
+    const unsigned wlast = wa + (kSubWords - 1) * 128u;
+    auto put = [&](unsigned code, unsigned len) {          // len < 32
+        ahi = funnel_l(alo, ahi, len);
+        alo = (alo << len) | code;
+        const unsigned t2 = t + len;
+        if ((t ^ t2) >= 32u) {                             // a 32-bit boundary was crossed: the word that ends there is complete
+            sts_u32(wa, funnel_r(alo, ahi, t2));           // (shift count taken mod 32)
+            wa = add_min_u32(wa, 128u, wlast);
+        }
+        t = t2;
+    };
+    const unsigned tabs = smem_addr(&T.e[0]), cz = smem_addr(coef);
+    unsigned la = smem_addr(list) + 2u * s0;
+    unsigned tp = s0 ? (lds_u16(la - 2u) & kEntryBlockPos) : 0xffffu;   // block | position of the symbol before mine
+#pragma unroll 1
+    for (unsigned i = 0; i < n; ++i, la += 2u) {
+        const unsigned e = lds_u16(la);
+        const unsigned bp = e & kEntryBlockPos;
+        const int v = lds_s16(cz + 2u * bp + ((bp >> 6) << 4));    // block * 144 + position * 2
+        // zeros since the previous symbol of the block (jpeg_enc.h:856-862); the first symbol of a block is its DC (position 0)
+        unsigned run = ((bp ^ tp) < 64u) ? bp - tp - 1u : (bp & 63u);
+        tp = bp;
+        if (v == 0) run = 0u;                                  // the end-of-block code (and a zero DC difference): entry 0 of its table
+        const unsigned tb = tabs + ((e >> 11) << 7);           // table of the symbol
+        if (run >= 16u) {                                      // one ZRL per 16 zeros (:863-867)
+            const uint2 z = lds_u64(tb + 8u * 0xF0u);
+#pragma unroll 1
+            for (unsigned k = run >> 4; k; --k) put(z.x, z.y);
+            run &= 15u;
+        }
+        const unsigned lz = (unsigned)i_clz((unsigned)(v < 0 ? -v : v));   // category = 32 - lz (jpeg_enc.h:598-608)
+        const uint2 h = lds_u64(tb + 256u + (run << 7) - 8u * lz);          // entry (run << 4) | category: {code, length + category}
+        const unsigned x = funnel_lc(0u, (unsigned)(v + (v >> 31)), lz);    // amplitude bits (:601-609), left-aligned; none for category 0
+        put(funnel_rc(x, h.x, lz), h.y);                                    // (code << category) | amplitude
+    }
+    if (t & 31u) sts_u32(wa, alo << (32u - (t & 31u)));                     // the rest, left-aligned
+    return t;
+}
+
+// zero words [0, n) of a 16-byte aligned word array, 16 bytes per lane and step (may zero up to 3 words more; followed by a warp barrier)
+JG_DEV void clear_words16(uint32_t* region, unsigned n)
+{
+    const uint4 z = {0u, 0u, 0u, 0u};
+    for (unsigned i = 4u * (unsigned)(JG_TID & 31); i < n; i += 128u) *reinterpret_cast<uint4*>(region + i) = z;
+    warp_sync();
+}
+
+// The lanes' streams (lane l: nbits bits at sub[k * 32 + l], ending at bit `incl` of the tile: the inclusive scan of the
+// lengths) -> one contiguous bit string in `region` (zeroed; the caller has checked that everything fits).  A word of the region that holds bits of ONE lane only is stored, the others (at most two per
+// lane) are OR-ed in.
+JG_DEV void merge_streams(const uint32_t* sub, unsigned nbits, unsigned incl, uint32_t* region)
+{
+    const unsigned lane = (unsigned)(JG_TID & 31);
+    const unsigned o = incl - nbits, end = incl;
+    const unsigned nwords = (nbits + 31u) >> 5, s = o & 31u, d = o >> 5;
+    const unsigned kmax = warp_max_u32(nwords);
+    unsigned prev = 0;
+    for (unsigned k = 0; k <= kmax; ++k) {
+        const unsigned cur = k < nwords ? sub[k * 32u + lane] : 0u;
+        if (k <= nwords) {
+            const unsigned w = funnel_r(cur, prev, s);           // (prev:cur) >> s
+            const unsigned bit0 = (d + k) << 5;
+            if (bit0 >= o && bit0 + 32u <= end) region[d + k] = w;
+            else if (w) smem_atomic_or(region + d + k, w);
+        }
+        prev = cur;
+    }
+    warp_sync();
+}
+
+// Blocks [lo, hi) of the staged + mapped tile -> merged bits in the region (which must be zero and free: it first holds the
+// symbol list).  Lane = block lo + lane in the list phase.  Returns the bits; `fits` = symbols, streams and total all fit.
+JG_DEV unsigned code_blocks(EntWarp& W, const EntTables& T, int lo, int hi, int slot_j, int jb, int bpm, bool& fits)
+{
+    const int lane = JG_TID & 31;
+    const int slot = lo + lane;
+    const bool mine = slot < hi;
+    uint2 m; m.x = 0; m.y = 0;
+    unsigned cls = 0;
+    if (mine) {
+        m = W.mask[slot];
+        int j = jb + slot_j; if (j >= bpm) j -= bpm;     // slot_j = slot mod bpm
+        int delta;
+        block_role(bpm, j, cls, delta);
+    }
+    const unsigned cnt = (unsigned)(i_popc(m.x) + i_popc(m.y));
+    const unsigned incl = warp_scan_incl_u32(cnt);
+    const unsigned S = warp_shfl_u32(incl, 31);
+    fits = S <= (unsigned)kListMax;
+    if (!fits) return 0u;
+    uint16_t* list = reinterpret_cast<uint16_t*>(W.region);
+    if (mine) list_block(list, incl - cnt, slot, m, cls);
+    warp_sync();
+    const unsigned q = (S + 31u) >> 5;                   // symbols per lane
+    const unsigned s0 = (unsigned)lane * q < S ? (unsigned)lane * q : S;
+    const unsigned n = S - s0 < q ? S - s0 : q;
+    const unsigned nbits = code_symbols(T, W.coef, list, s0, n, W.sub + lane);
+    warp_sync();                                         // every lane is done with the list
+    clear_words16(W.region, (S + 1u) >> 1);              // (ends with a warp barrier)
+    const unsigned incl_bits = warp_scan_incl_u32(nbits);
+    const unsigned bits = warp_shfl_u32(incl_bits, 31);
+    fits = warp_ballot(nbits > (unsigned)kSubWords * 32u) == 0u && bits <= (unsigned)kEntRegionWords * 32u;
+    if (fits) merge_streams(W.sub, nbits, incl_bits, W.region);
+    return bits;
+}
+
+// Bits of every block of the mapped tile, for the stage dumps of the parity tests (lane = block; not on the product's path).
+JG_DEV_NOINLINE unsigned count_block_bits(const EntWarp& W, const EntTables& T, int slot, int nblk, int jb, int bpm)
+{
+    if (slot >= nblk) return 0u;
+    const uint2 m = W.mask[slot];
+    unsigned cls; int delta;
+    block_role(bpm, (jb + slot) % bpm, cls, delta);
+    const int16_t* cz = W.coef + slot * kEntCoefStride;
+    unsigned bits = 0;
+    int prev = -1;
+    for (int pos = 0; pos < 64; ++pos) {
+        if (!(((pos < 32 ? m.x : m.y) >> (pos & 31)) & 1u)) continue;
+        const int v = cz[pos];
+        unsigned run = (unsigned)(pos - prev - 1);
+        prev = pos;
+        if (v == 0) run = 0;
+        const uint2* tb = T.e + 16u * ((pos ? kTabAc + (cls ? kTabAcChroma : 0u) : (cls ? kTabChroma : 0u)));
+        bits += (run >> 4) * tb[0xF0].y;
+        const unsigned cat = v ? 32u - (unsigned)i_clz((unsigned)(v < 0 ? -v : v)) : 0u;
+        bits += tb[((run & 15u) << 4) | cat].y;
+    }
+    return bits;
+}
+
+JG_DEV bool ent_tile_back(const LaunchParams& P, EntWarp& W, int g, int slot)
+{
+    const Pending pd = W.pend[slot];
+    const bool first = g == pd.first_tile_of_img;
+    unsigned long long bit_base = 0;
+    unsigned pred_tail = 0;
+    if (!first && !chain_bits(P, g, pd.first_tile_of_img, pd.T, pd.tail, bit_base, pred_tail)) return false;
+    unsigned k = (unsigned)(bit_base & 7ull);          // bits of our first byte owned by the predecessor
+    unsigned hb = pred_tail & ((1u << k) - 1u);
+    unsigned long long pos = bit_base >> 3;
+    bool overflow = false;
+    flush_region(W.region, pd.T, pd.last != 0, reinterpret_cast<uint8_t*>(pd.raw), pd.raw_cap, k, hb, pos, overflow);
+    if ((JG_TID & 31) == 0) {
+        if (pd.last) P.raw_bytes[pd.img_idx] = pos;
+        if (overflow) gmem_atomic_or(P.img_status + pd.img_idx, 1u);
+    }
+    warp_sync();                                        // every lane has read the region
+    clear_words16(W.region, (pd.T >> 5) + 2u);
+    return true;
+}
+
+// A tile that does not fit the fast path: four blocks at a time, written right away.  The groups are coded once to
+// learn the tile's size and last bits (successors must not wait for the whole slow pass), then again to be written.
+// Returns false on a look-back timeout.
+template <bool restart>
+JG_DEV_NOINLINE bool ent_tile_slow(const LaunchParams& P, EntWarp& W, const EntTables& T, int g, int nblk, int jb, int bpm, int slot)
+{
+    const int lane = JG_TID & 31;
+    const Pending pd = W.pend[slot];
+    const bool first = g == pd.first_tile_of_img;
+    bool fits;
+    unsigned bits = 0, tail = 0;
+    for (int lo = 0; lo < nblk; lo += kSlowBlocks) {
+        warp_sync();
+        clear_region(W.region, kEntRegionWords + 8);
+        const unsigned tg = code_blocks(W, T, lo, lo + kSlowBlocks < nblk ? lo + kSlowBlocks : nblk, (lo + lane) % bpm, jb, bpm, fits);
+        bits += tg;
+        // running last-7-bits of the tile (a group may hold fewer than 7)
+        tail = tg >= 7u ? tail_bits(W.region, tg) : (((tail << tg) | peek_bits(W.region, 0u, tg)) & 0x7fu);
+    }
+    const unsigned pad = restart ? (0u - bits) & 7u : 0u;       // restart interval: 1-bits up to the byte boundary
+    if (pad) { tail = ((tail << pad) | ((1u << pad) - 1u)) & 0x7fu; bits += pad; }
+    if (lane == 0) st_flag64(P.desc_bits + g, make_desc(first ? kStatusPrefix : kStatusAgg, tail, bits));
+    unsigned long long bit_base = 0;
+    unsigned pred_tail = 0;
+    if (!first && !chain_bits(P, g, pd.first_tile_of_img, bits, tail, bit_base, pred_tail)) return false;
+    unsigned k = (unsigned)(bit_base & 7ull);
+    unsigned hb = pred_tail & ((1u << k) - 1u);
+    unsigned long long pos = bit_base >> 3;
+    bool cap_overflow = false;
+    for (int lo = 0; lo < nblk; lo += kSlowBlocks) {
+        const int hi = lo + kSlowBlocks < nblk ? lo + kSlowBlocks : nblk;
+        warp_sync();
+        clear_region(W.region, kEntRegionWords + 8);
+        unsigned tg = code_blocks(W, T, lo, hi, (lo + lane) % bpm, jb, bpm, fits);
+        if (pad && hi == nblk) {
+            if (lane == 0) set_ones(W.region, tg, pad);
+            warp_sync();
+            tg += pad;
+        }
+        flush_region(W.region, tg, pd.last && hi == nblk, reinterpret_cast<uint8_t*>(pd.raw), pd.raw_cap, k, hb, pos, cap_overflow);
+    }
+    if (lane == 0) {
+        if (pd.last) P.raw_bytes[pd.img_idx] = pos;
+        if (cap_overflow) gmem_atomic_or(P.img_status + pd.img_idx, 1u);
+    }
+    warp_sync();
+    clear_region(W.region, kEntRegionWords + 8);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel B: coefficients -> unstuffed entropy-coded bits (raw), bits chained over the tiles of an image
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+JG_KERNEL(kEntThreads, 3)
+void entropy_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTANT CoefMap cmap)
+{
+    constexpr bool restart = MODE == kEntModeRestart;
+    JG_DYNAMIC_SMEM(smem_raw);
+    EntSmem& S = *reinterpret_cast<EntSmem*>(smem_raw);
+    const int t = JG_TID, lane = t & 31;
+    for (int i = t; i < 32 + 512; i += kEntThreads) {
+        const int cls = i < 32 ? i >> 4 : (i - 32) >> 8, k = i < 32 ? i & 15 : (i - 32) & 255;
+        const unsigned h = i < 32 ? P.huff->dc[cls][k] : P.huff->ac[cls][k];      // code << 8 | length
+        uint2 e;
+        e.x = h >> 8;
+        e.y = (h & 0xffu) + (unsigned)(k & 15);
+        S.tab.e[i] = e;
+    }
+    EntWarp& W = S.wm[t >> 5];
+    const EntTables& T = S.tab;
+    if (lane == 0) mbar_init(&W.mbar, 1u);
+    clear_region(W.region, kEntRegionWords + 8);
+    mbar_fence_init();
+    cta_sync();       // tables + barriers are set up: the only CTA barrier; from here every warp is on its own
+
+    const int bpm = P.bpm, bpt = P.blocks_per_tile;
+    const int lane_j = lane % bpm;
+    unsigned phase = 0;
+    int p1_g = -1;                    // the tile coded one iteration ago, still to be written
+    for (int slot = 0;; slot ^= 1) {
+        int img_idx;
+        const int g = draw_tile(P, img_idx);
+        const bool have = g < P.n_tiles;
+        int nblk = 0, b0 = 0, jb = 0, pred_outside = 0;
+        bool first = false;
+        if (have) {
+            const ImageDesc im = P.images[img_idx];
+            const int lt = g - im.first_tile;
+            const int n_blocks = im.n_mcus * bpm;
+            b0 = lt * bpt;
+            nblk = n_blocks - b0 < bpt ? n_blocks - b0 : bpt;
+            first = lt == 0;
+            jb = b0 % bpm;
+            // ---- stage: one TMA box (32 blocks from row first_block + b0 of the coefficient plane; rows past the
+            //      plane's end arrive as zeros and are never looked at).  The previous tile's coefficients were
+            //      overwritten by generic stores (DC differences): order them before the async-proxy write. ----
+            if (lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&W.mbar, kEntStageBytes);
+                tma_load_2d(W.coef, &cmap, 0, (int)(im.first_block + (unsigned long long)b0), &W.mbar);
+            }
+            // DC predecessor that lies before the tile (not with restart intervals: they predict from 0)
+            if (!restart && lane < nblk) {
+                int j = jb + lane_j; if (j >= bpm) j -= bpm;
+                unsigned cls; int delta;
+                block_role(bpm, j, cls, delta);
+                const int ps = lane - delta;
+                if (ps < 0 && b0 + ps >= 0)
+                    pred_outside = (int)ldg_s16(P.coefs + (im.first_block + (unsigned long long)(b0 + ps)) * 64ull);
+            }
+            if (lane == 0) {         // what the write-out needs later; T and tail follow after the coding
+                Pending& pd = W.pend[slot];
+                pd.raw = reinterpret_cast<unsigned long long>(im.raw); pd.raw_cap = im.raw_cap;
+                pd.img_idx = img_idx; pd.first_tile_of_img = im.first_tile; pd.last = (lt == im.n_tiles - 1) ? 1 : 0;
+                pd.base = 0;
+            }
+        }
+        // ---- the previous tile goes out while the copy is in flight ----
+        if (p1_g >= 0) {
+            if (!ent_tile_back(P, W, p1_g, slot ^ 1)) break;
+            p1_g = -1;
+        }
+        if (!have) break;
+        mbar_wait(&W.mbar, phase);
+        phase ^= 1u;
+
+        // ---- map (lane = block), then list + code (lane = an equal share of the tile's symbols) ----
+        map_block(W, lane, lane_j, nblk, jb, bpm, b0, pred_outside, restart);
+        if (P.dbg_bits) {
+            const unsigned nb = count_block_bits(W, T, lane, nblk, jb, bpm);
+            if (lane < nblk) P.dbg_bits[P.images[img_idx].first_block + (unsigned long long)(b0 + lane)] = nb;
+        }
+        bool fits;
+        unsigned bits = code_blocks(W, T, 0, nblk, lane_j, jb, bpm, fits);
+        if (fits) {
+            // Publish the tile's bit count and last bits NOW: they are consumed (by us and by every successor)
+            // one iteration later.
+            unsigned tail = tail_bits(W.region, bits);
+            if (restart && (bits & 7u) != 0u) {      // restart interval: 1-bits up to the byte boundary (T.81 F.1.2.3)
+                const unsigned pad = 8u - (bits & 7u);
+                if (lane == 0) set_ones(W.region, bits, pad);
+                tail = ((tail << pad) | ((1u << pad) - 1u)) & 0x7fu;
+                bits += pad;
+            }
+            if (lane == 0) {
+                st_flag64(P.desc_bits + g, make_desc(first ? kStatusPrefix : kStatusAgg, tail, bits));
+                W.pend[slot].T = bits; W.pend[slot].tail = tail;
+            }
+            warp_sync();
+            p1_g = g;
+        } else {
+            if (!ent_tile_slow<restart>(P, W, T, g, nblk, jb, bpm, slot)) break;
+        }
+    }
+}
+
+}  // namespace jg

@@ -8,8 +8,10 @@
 // There is no CPU encode path in this library: if CUDA is unusable every entry point fails.
 #include "jpeg_gpu.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -55,11 +57,30 @@ struct Spec {
     int layout, nc;
     cudaError_t (*prepare)(int*);
     cudaError_t (*launch)(int, cudaStream_t, const LaunchParams&, const QuantSet&, int);
+    cudaError_t (*transform_prepare)();
+    cudaError_t (*transform_launch)(cudaStream_t, const TransformParams&, const QuantSet&);
 };
 const Spec kSpecs[5] = {
-    {LAYOUT_444, 3, prepare_0_3, launch_0_3}, {LAYOUT_444, 4, prepare_0_4, launch_0_4},
-    {LAYOUT_420, 3, prepare_1_3, launch_1_3}, {LAYOUT_420, 4, prepare_1_4, launch_1_4},
-    {LAYOUT_GRAY, 1, prepare_2_1, launch_2_1}};
+    {LAYOUT_444, 3, prepare_0_3, launch_0_3, transform_prepare_0_3, transform_launch_0_3},
+    {LAYOUT_444, 4, prepare_0_4, launch_0_4, transform_prepare_0_4, transform_launch_0_4},
+    {LAYOUT_420, 3, prepare_1_3, launch_1_3, transform_prepare_1_3, transform_launch_1_3},
+    {LAYOUT_420, 4, prepare_1_4, launch_1_4, transform_prepare_1_4, transform_launch_1_4},
+    {LAYOUT_GRAY, 1, prepare_2_1, launch_2_1, transform_prepare_2_1, transform_launch_2_1}};
+
+// Which pipeline new plans use.  Split (default): transform kernel -> coefficient plane in HBM -> entropy kernel
+// (jpeg_transform.cuh, jpeg_entropy.cuh).  Fused: the single pass-1 kernel of round 1 (jpeg_kernel.cuh), kept for the
+// A/B numbers in DESIGN.md; selected with JPEG_GPU_PIPELINE=fused in the environment.  Same bytes either way.
+bool use_fused_pipeline()
+{
+    const char* e = getenv("JPEG_GPU_PIPELINE");
+    return e && strcmp(e, "fused") == 0;
+}
+
+// cuTensorMapEncodeTiled comes from the driver (the library links the static runtime only)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
 
 int spec_index(int layout, int nc)
 {
@@ -74,6 +95,7 @@ struct Device {
     int sm_count = 0;
     int ctas_per_sm[5] = {0, 0, 0, 0, 0};
     int stuff_ctas_per_sm = 0;
+    int entropy_ctas_per_sm = 0;
     HuffLut* d_huff = nullptr;
     cudaStream_t stream = nullptr;   // used when the caller gives none
     cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};   // chunk pipeline of jpeg_gpu_encode_batch
@@ -101,6 +123,16 @@ bool init_device(Device& d, int id)
     for (int i = 0; i < 5; ++i) {
         JG_CUDA(kSpecs[i].prepare(&d.ctas_per_sm[i]));
         if (d.ctas_per_sm[i] < 1) { set_error("kernel spec %d does not fit an SM", i); return false; }
+    }
+    for (int i = 0; i < 5; ++i) JG_CUDA(kSpecs[i].transform_prepare());
+    JG_CUDA(entropy_prepare(&d.entropy_ctas_per_sm));
+    if (d.entropy_ctas_per_sm < 1) { set_error("entropy kernel does not fit an SM"); return false; }
+    if (!g_encode_tiled) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        JG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("the driver has no cuTensorMapEncodeTiled"); return false; }
+        g_encode_tiled = (EncodeTiledFn)fn;
     }
     JG_CUDA(stuff_prepare(&d.stuff_ctas_per_sm));
     if (d.stuff_ctas_per_sm < 1) { set_error("stuffing kernel does not fit an SM"); return false; }
@@ -182,6 +214,14 @@ struct Geometry {
     int layout, nc_in, ncomp_out, mcu, bpm, mcus_x, mcus_y, n_mcus, n_tiles;
     size_t n_blocks;
 };
+
+// tiles of pass 1: 24 blocks = whole MCUs (fused kernel; split pipeline with restart intervals) or 32 blocks (split)
+int tiles_of(const Geometry& g, bool fused, bool restart)
+{
+    if (fused) { const int M = mcus_per_tile(g.layout); return (g.n_mcus + M - 1) / M; }
+    const size_t bpt = restart ? kEntTileBlocksRestart : kEntTileBlocks;
+    return (int)((g.n_blocks + bpt - 1) / bpt);
+}
 
 bool geometry_of(const jpeg_gpu_image& im, Geometry* g)
 {
@@ -268,7 +308,15 @@ struct jpeg_gpu_plan {
         unsigned long long* d_scan_bytes = nullptr;   // into d_results
         unsigned* d_status = nullptr;
         size_t result_off = 0;    // index of first image of the group in the results arrays
+        int n_items = 0, items_per_image = 0;     // pass A work items (split pipeline)
+        size_t item_off = 0;      // words into d_sched: first_item[n + 1] when the images differ
+        bool has_items = false;
     };
+    bool fused = false;           // pipeline of this plan (use_fused_pipeline() at creation)
+    int16_t* d_coefs = nullptr;      size_t coefs_bytes = 0;    // split pipeline: the coefficient plane between pass A and pass B
+    CoefMap cmap;                    // its TMA descriptor
+    cudaStream_t run_stream = nullptr;   // stream of the last run / upload: results are fetched on it, the plan's memory is released after it
+    bool ran = false;
     int dev_index = 0;
     int win_words = kWinWordsMax;
     bool worst_case = false;
@@ -293,7 +341,7 @@ struct jpeg_gpu_plan {
     int n_valid = 0;
     bool fetched_results = false;
     bool timing = false;
-    std::vector<cudaEvent_t> events;   // per group: before encode, after encode, after stuff
+    std::vector<cudaEvent_t> events;   // per group: before pass A, after pass A, after pass B (fused: same as after A), after stuff
 };
 
 namespace {
@@ -303,6 +351,7 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
     Device& dev = g_devices[p->dev_index];
     JG_CUDA(cudaSetDevice(dev.id));
     p->worst_case = worst_case;
+    p->fused = use_fused_pipeline();
     p->items.resize(n);
     std::map<std::tuple<int, int, int, int>, int> group_of;   // (spec, qmode, quality, restart) -> group
     size_t arena = 0, pixels = 0, blocks = 0;
@@ -311,6 +360,7 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
         it.img = images[i];
         uint8_t ql[64], qc[64];
         if (!geometry_of(it.img, &it.geo) || !build_qt(it.img.quality_mode, it.img.quality, ql, qc)) continue;
+        it.geo.n_tiles = tiles_of(it.geo, p->fused, (it.img.flags & JPEG_GPU_FLAG_RESTART) != 0);
         it.valid = true;
         ++p->n_valid;
         if (it.img.stride == 0) it.img.stride = it.img.width * it.img.ncomp;
@@ -371,6 +421,27 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
             p->h_sched.resize(g.sched_off + schedule_words((int)counts.size()));
             build_schedule(counts.data(), (int)counts.size(), p->h_sched.data() + g.sched_off);
         }
+        if (!p->fused) {
+            // pass A: one warp per item of transform_item_mcus(layout) MCUs
+            const int im = transform_item_mcus(kSpecs[g.spec].layout);
+            int items = 0;
+            bool same = true;
+            const int i0 = (p->items[g.items[0]].geo.n_mcus + im - 1) / im;
+            for (int idx : g.items) {
+                const int k = (p->items[idx].geo.n_mcus + im - 1) / im;
+                items += k;
+                same = same && k == i0;
+            }
+            g.n_items = items;
+            g.items_per_image = same ? i0 : 0;
+            if (!same) {
+                g.item_off = p->h_sched.size();
+                g.has_items = true;
+                uint32_t run = 0;
+                for (int idx : g.items) { p->h_sched.push_back(run); run += (uint32_t)((p->items[idx].geo.n_mcus + im - 1) / im); }
+                p->h_sched.push_back(run);
+            }
+        }
         g.state_off = state;
         size_t chunks = 1;
         for (int idx : g.items) chunks += (p->items[idx].scan_cap + kChunkBytes - 1) / kChunkBytes;
@@ -395,6 +466,22 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
     if (!pool_alloc(dev, p->results_bytes, false, (void**)&p->d_results)) return false;
     if (!pool_alloc(dev, p->results_bytes, true, (void**)&p->h_results)) return false;
     if (!pool_alloc(dev, p->images_bytes, false, (void**)&p->d_images)) return false;
+    if (!p->fused) {
+        p->coefs_bytes = std::max<size_t>(p->n_blocks, 1) * 128;
+        if (!pool_alloc(dev, p->coefs_bytes, false, (void**)&p->d_coefs)) return false;
+        // 2-D tensor {64 int16, blocks}; the box is 72 x 32 (one pass-B tile): its 8 out-of-bounds columns arrive as zeros
+        // and pad every block to a 144-byte row in shared memory (jpeg_entropy.cuh)
+        CUtensorMap tm;
+        const cuuint64_t dims[2] = {64, (cuuint64_t)std::max<size_t>(p->n_blocks, 1)};
+        const cuuint64_t strides[1] = {128};
+        const cuuint32_t box[2] = {72, 32}, estr[2] = {1, 1};
+        const CUresult r = g_encode_tiled(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, p->d_coefs, dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return false; }
+        static_assert(sizeof(CoefMap) == sizeof(CUtensorMap), "CoefMap carries a CUtensorMap");
+        memcpy(&p->cmap, &tm, sizeof tm);
+    }
     p->sched_bytes = p->h_sched.size() * sizeof(uint32_t);
     if (p->sched_bytes && !pool_alloc(dev, p->sched_bytes, false, (void**)&p->d_sched)) return false;
     p->h_images.resize(nres);
@@ -446,11 +533,14 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
     Device& dev = g_devices[p->dev_index];
     JG_CUDA(cudaSetDevice(dev.id));
     if (p->groups.empty()) return true;
+    p->run_stream = s;
+    p->ran = true;
     if (!plan_sync_images(p, s)) return false;
     JG_CUDA(cudaMemsetAsync(p->d_state, 0, p->state_bytes, s));
     JG_CUDA(cudaMemsetAsync(p->d_results, 0, p->results_bytes, s));
     for (auto& g : p->groups) {
         LaunchParams P;
+        memset(&P, 0, sizeof P);
         P.images = g.d_images;
         P.n_images = (int)g.items.size();
         P.n_tiles = g.n_tiles;
@@ -471,23 +561,48 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
         P.huff = dev.d_huff;
         P.dbg_coefs = p->dbg_coefs;
         P.dbg_bits = p->dbg_bits;
-        const int grid = std::min((g.n_tiles + kWarps - 1) / kWarps, dev.sm_count * dev.ctas_per_sm[g.spec]);   // one tile per warp at a time
         const size_t gi = (size_t)(&g - &p->groups[0]);
-        if (p->timing) JG_CUDA(cudaEventRecord(p->events[3 * gi], s));
-        const int mode = g.restart ? 2 : (P.n_images < kDeepMaxImages ? 1 : 0);   // kModeRestart / kModeDeep / kModePlain
-        JG_CUDA(kSpecs[g.spec].launch(grid, s, P, g.quant, mode));
-        if (p->timing) JG_CUDA(cudaEventRecord(p->events[3 * gi + 1], s));
+        if (p->timing) JG_CUDA(cudaEventRecord(p->events[4 * gi], s));
+        if (p->fused) {
+            const int grid = std::min((g.n_tiles + kWarps - 1) / kWarps, dev.sm_count * dev.ctas_per_sm[g.spec]);   // one tile per warp at a time
+            const int mode = g.restart ? 2 : (P.n_images < kDeepMaxImages ? 1 : 0);   // kModeRestart / kModeDeep / kModePlain
+            JG_CUDA(kSpecs[g.spec].launch(grid, s, P, g.quant, mode));
+            if (p->timing) JG_CUDA(cudaEventRecord(p->events[4 * gi + 1], s));
+        } else {
+            // pass A: pixels -> coefficient plane; pass B: coefficient plane -> unstuffed bits
+            TransformParams TP;
+            TP.images = g.d_images;
+            TP.n_images = P.n_images;
+            TP.n_items = g.n_items;
+            TP.items_per_image = g.items_per_image;
+            TP.first_item = g.has_items ? p->d_sched + g.item_off : nullptr;
+            TP.coefs = p->d_coefs;
+            JG_CUDA(kSpecs[g.spec].transform_launch(s, TP, g.quant));
+            if (p->timing) JG_CUDA(cudaEventRecord(p->events[4 * gi + 1], s));
+            P.coefs = p->d_coefs;
+            P.bpm = kSpecs[g.spec].layout == LAYOUT_444 ? 3 : (kSpecs[g.spec].layout == LAYOUT_420 ? 6 : 1);
+            P.blocks_per_tile = g.restart ? kEntTileBlocksRestart : kEntTileBlocks;
+            P.dbg_coefs = nullptr;
+            const int grid = std::min((g.n_tiles + kEntWarps - 1) / kEntWarps, dev.sm_count * dev.entropy_ctas_per_sm);
+            JG_CUDA(entropy_launch(grid, s, P, p->cmap, g.restart ? 2 : 0));
+        }
+        if (p->timing) JG_CUDA(cudaEventRecord(p->events[4 * gi + 2], s));
         JG_CUDA(stuff_launch(dev.sm_count * dev.stuff_ctas_per_sm, s, P));
-        if (p->timing) JG_CUDA(cudaEventRecord(p->events[3 * gi + 2], s));
+        if (p->timing) JG_CUDA(cudaEventRecord(p->events[4 * gi + 3], s));
     }
+    // stage dump of the split pipeline: the coefficient plane IS the dump
+    if (!p->fused && p->dbg_coefs)
+        JG_CUDA(cudaMemcpyAsync(p->dbg_coefs, p->d_coefs, p->n_blocks * 128, cudaMemcpyDeviceToDevice, s));
     p->fetched_results = false;
     return true;
 }
 
-// bring scan sizes / status / error flags to the host (synchronises `s`)
-bool plan_results(jpeg_gpu_plan* p, cudaStream_t s)
+// Bring scan sizes / status / error flags to the host.  The copies are ordered behind the kernels: they go to the
+// stream of the last run (whatever stream the caller passes for the output copies), which is then synchronised.
+bool plan_results(jpeg_gpu_plan* p, cudaStream_t caller)
 {
     if (p->fetched_results || p->groups.empty()) return true;
+    cudaStream_t s = p->ran ? p->run_stream : caller;
     JG_CUDA(cudaMemcpyAsync(p->h_results, p->d_results, p->results_bytes, cudaMemcpyDeviceToHost, s));
     std::vector<unsigned> errs(p->groups.size());
     for (size_t k = 0; k < p->groups.size(); ++k)
@@ -505,6 +620,10 @@ void plan_free(jpeg_gpu_plan* p)
     if (p->dev_index < (int)g_devices.size()) {
         Device& dev = g_devices[p->dev_index];
         cudaSetDevice(dev.id);
+        // The pool hands these blocks to the next plan at once (no cudaFree, so nothing waits for the device):
+        // kernels or copies of this plan that are still in flight must finish first.
+        if (p->ran) cudaStreamSynchronize(p->run_stream);
+        if (p->d_coefs) pool_free(dev, p->d_coefs, p->coefs_bytes, false);
         pool_free(dev, p->d_arena, p->arena_bytes, false);
         pool_free(dev, p->d_raw, p->arena_bytes, false);
         pool_free(dev, p->d_aux, p->aux_bytes, false);
@@ -525,6 +644,7 @@ jpeg_gpu_plan* plan_create(const jpeg_gpu_image* images, int n, int device, int 
     if (n < 0 || (n > 0 && !images)) { set_error("bad image list"); return nullptr; }
     if (device < 0 || device >= (int)g_devices.size()) { set_error("device index %d out of range", device); return nullptr; }
     jpeg_gpu_plan* p = new jpeg_gpu_plan();
+    memset(&p->cmap, 0, sizeof p->cmap);
     p->dev_index = device;
     if (win_words) p->win_words = std::max(kWinWordsMin, std::min(kWinWordsMax, win_words));
     if (!plan_build(p, images, n, worst_case)) { plan_free(p); return nullptr; }
@@ -660,27 +780,29 @@ int jpeg_gpu_plan_upload(jpeg_gpu_plan* p, int i, const uint8_t* host_pixels, vo
     if (!p || i < 0 || i >= (int)p->items.size() || !p->items[i].valid) return 0;
     jpeg_gpu_plan::Item& it = p->items[i];
     if (it.img.pixels_on_device) { set_error("image %d was declared device-resident", i); return 0; }
+    if (p->dev_index >= (int)g_devices.size()) { set_error("library shut down"); return 0; }
     cudaStream_t s = stream ? (cudaStream_t)stream : g_devices[p->dev_index].stream;
     if (cudaSetDevice(g_devices[p->dev_index].id) != cudaSuccess) return 0;
     // host_pixels is the top row; the memory block starts top_row_offset before it when the rows are bottom-up
     cudaError_t e = cudaMemcpyAsync(p->d_pixels + it.pixel_off, host_pixels - top_row_offset(it.img), it.pixel_bytes, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) { set_error("pixel upload failed: %s", cudaGetErrorString(e)); return 0; }
+    if (!p->ran) { p->run_stream = s; p->ran = true; }     // plan_free waits for it
     return 1;
 }
 
 int jpeg_gpu_plan_run(jpeg_gpu_plan* p, void* stream)
 {
-    if (!p) return 0;
+    if (!p || p->dev_index >= (int)g_devices.size()) { set_error("no plan / library shut down"); return 0; }
     cudaStream_t s = stream ? (cudaStream_t)stream : g_devices[p->dev_index].stream;
     return plan_run(p, s) ? 1 : 0;
 }
 
 int jpeg_gpu_plan_enable_timing(jpeg_gpu_plan* p, int enable)
 {
-    if (!p) return 0;
+    if (!p || g_devices.empty()) return 0;
     if (enable && p->events.empty()) {
         if (cudaSetDevice(g_devices[p->dev_index].id) != cudaSuccess) return 0;
-        p->events.resize(3 * p->groups.size());
+        p->events.resize(4 * p->groups.size());
         for (auto& e : p->events)
             if (cudaEventCreate(&e) != cudaSuccess) { set_error("cudaEventCreate failed"); return 0; }
     }
@@ -688,23 +810,37 @@ int jpeg_gpu_plan_enable_timing(jpeg_gpu_plan* p, int enable)
     return 1;
 }
 
-int jpeg_gpu_plan_kernel_times(jpeg_gpu_plan* p, float* encode_ms, float* stuff_ms)
+int jpeg_gpu_plan_pass_times(jpeg_gpu_plan* p, float* transform_ms, float* entropy_ms, float* stuff_ms)
 {
     if (!p || !p->timing || p->events.empty()) return 0;
-    float enc = 0.f, stf = 0.f;
+    float ta = 0.f, tb = 0.f, tc = 0.f;
     for (size_t gi = 0; gi < p->groups.size(); ++gi) {
-        float a = 0.f, b = 0.f;
-        if (cudaEventSynchronize(p->events[3 * gi + 2]) != cudaSuccess) return 0;
-        if (cudaEventElapsedTime(&a, p->events[3 * gi], p->events[3 * gi + 1]) != cudaSuccess) return 0;
-        if (cudaEventElapsedTime(&b, p->events[3 * gi + 1], p->events[3 * gi + 2]) != cudaSuccess) return 0;
-        enc += a; stf += b;
+        float a = 0.f, b = 0.f, c = 0.f;
+        if (cudaEventSynchronize(p->events[4 * gi + 3]) != cudaSuccess) return 0;
+        if (cudaEventElapsedTime(&a, p->events[4 * gi], p->events[4 * gi + 1]) != cudaSuccess) return 0;
+        if (cudaEventElapsedTime(&b, p->events[4 * gi + 1], p->events[4 * gi + 2]) != cudaSuccess) return 0;
+        if (cudaEventElapsedTime(&c, p->events[4 * gi + 2], p->events[4 * gi + 3]) != cudaSuccess) return 0;
+        ta += a; tb += b; tc += c;
     }
-    if (encode_ms) *encode_ms = enc;
-    if (stuff_ms) *stuff_ms = stf;
+    if (transform_ms) *transform_ms = ta;
+    if (entropy_ms) *entropy_ms = tb;
+    if (stuff_ms) *stuff_ms = tc;
     return 1;
 }
 
-int jpeg_gpu_plan_launches(const jpeg_gpu_plan* p) { return p ? 3 * (int)p->groups.size() : 0; }   // encode + plan + stuff
+int jpeg_gpu_plan_kernel_times(jpeg_gpu_plan* p, float* encode_ms, float* stuff_ms)
+{
+    float a = 0.f, b = 0.f, c = 0.f;
+    if (!jpeg_gpu_plan_pass_times(p, &a, &b, &c)) return 0;
+    if (encode_ms) *encode_ms = a + b;
+    if (stuff_ms) *stuff_ms = c;
+    return 1;
+}
+
+int jpeg_gpu_plan_is_fused(const jpeg_gpu_plan* p) { return p && p->fused ? 1 : 0; }
+
+// fused: encode + plan_chunks + stuff; split: transform + entropy + plan_chunks + stuff
+int jpeg_gpu_plan_launches(const jpeg_gpu_plan* p) { return p ? (p->fused ? 3 : 4) * (int)p->groups.size() : 0; }
 
 size_t jpeg_gpu_plan_num_blocks(const jpeg_gpu_plan* p) { return p ? p->n_blocks : 0; }
 
@@ -718,7 +854,7 @@ int jpeg_gpu_plan_attach_debug(jpeg_gpu_plan* p, int16_t* dev_coefs, uint32_t* d
 
 size_t jpeg_gpu_plan_encoded_size(jpeg_gpu_plan* p, int i)
 {
-    if (!p || i < 0 || i >= (int)p->items.size()) return 0;
+    if (!p || i < 0 || i >= (int)p->items.size() || p->dev_index >= (int)g_devices.size()) return 0;
     if (!plan_results(p, g_devices[p->dev_index].stream)) return 0;
     size_t sz; int st;
     item_result(p, i, &sz, &st);
@@ -727,7 +863,7 @@ size_t jpeg_gpu_plan_encoded_size(jpeg_gpu_plan* p, int i)
 
 int jpeg_gpu_plan_fetch(jpeg_gpu_plan* p, jpeg_gpu_output* outs, int outputs_on_device, void* stream)
 {
-    if (!p || !outs) return 0;
+    if (!p || !outs || p->dev_index >= (int)g_devices.size()) return 0;
     cudaStream_t s = stream ? (cudaStream_t)stream : g_devices[p->dev_index].stream;
     if (cudaSetDevice(g_devices[p->dev_index].id) != cudaSuccess) return 0;
     if (!plan_results(p, s)) {
@@ -854,6 +990,11 @@ int jpeg_gpu_encode_batch(const jpeg_gpu_image* images, int n, jpeg_gpu_output* 
         return 0;
     }
     const int device = opts ? opts->device : -1;
+    if (device >= (int)g_devices.size()) {
+        set_error("device index %d out of range (%d initialised)", device, (int)g_devices.size());
+        for (int i = 0; i < n; ++i) { outs[i].size = 0; outs[i].status = JPEG_GPU_ERR_ARG; }
+        return 0;
+    }
     const int on_dev = opts ? opts->outputs_on_device : 0;
     const int win = opts ? opts->debug_window_words : 0;
     if (device >= 0)

@@ -705,16 +705,21 @@ JG_DEV unsigned long long lookback(const unsigned long long* desc, int g, int fi
         const int idx = base - lane;
         const bool in_range = idx >= first;
         unsigned long long w = kStatusPrefix;  // virtual tile before the image: PREFIX 0
-        unsigned spins = 0;
+        unsigned spins = 0, pmask;
         for (;;) {
             if (in_range) w = ld_flag64(desc + idx);
-            if (warp_ballot(in_range && (w >> 62) == 0) == 0u) break;
-            if (++spins > kSpinLimit || ld_flag32(err_flag) != 0u) spins = 0xffffffffu;
+            // what is needed: every descriptor from g-1 back to the NEAREST one that knows its prefix; older ones may lag
+            pmask = warp_ballot((w >> 62) == 2u);
+            const unsigned waiting = warp_ballot(in_range && (w >> 62) == 0);
+            if ((waiting & (pmask ? (pmask & (0u - pmask)) - 1u : 0xffffffffu)) == 0u) break;
+            // the error flag is ONE address for every spinning warp of the launch: looked at every 16th round only
+            // (a hot line in L2 makes every round of every spinning warp slower, which makes more warps spin)
+            ++spins;
+            if (spins > kSpinLimit || ((spins & 15u) == 0u && ld_flag32(err_flag) != 0u)) spins = 0xffffffffu;
             if (warp_ballot(spins == 0xffffffffu) != 0u) { *timed_out = 1; return 0; }
             backoff();
         }
         if (nearest != nullptr && base == g - 1) *nearest = warp_shfl_u64(w, 0);
-        const unsigned pmask = warp_ballot((w >> 62) == 2u);
         const int stop = pmask ? i_ffs(pmask) - 1 : 32;   // nearest tile that already knows its prefix
         running += warp_sum_u64(lane <= stop ? (w & kCountMask) : 0ull);
         if (pmask) return running;

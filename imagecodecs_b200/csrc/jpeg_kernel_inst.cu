@@ -3,6 +3,7 @@
 // so the specialisations build in parallel.  Always with --fmad=false: the float math of
 // jpeg_kernel.cuh additionally uses __fadd_rn/__fmul_rn so that no flag can re-fuse it.
 #include "jpeg_kernel.cuh"
+#include "jpeg_transform.cuh"
 #include "jpeg_launch.h"
 
 #ifndef JG_LAYOUT
@@ -47,6 +48,19 @@ cudaError_t JG_FN(launch_)(int grid, cudaStream_t stream, const LaunchParams& P,
     if (mode == kModeDeep) encode_tiles_kernel<JG_LAYOUT, JG_NC, kModeDeep><<<grid, kThreads, smem, stream>>>(P, Q);
     else if (mode == kModeRestart) encode_tiles_kernel<JG_LAYOUT, JG_NC, kModeRestart><<<grid, kThreads, smem, stream>>>(P, Q);
     else encode_tiles_kernel<JG_LAYOUT, JG_NC, kModePlain><<<grid, kThreads, smem, stream>>>(P, Q);
+    return cudaGetLastError();
+}
+
+// ---- pass A of the split pipeline ----
+cudaError_t JG_FN(transform_prepare_)()
+{
+    return cudaFuncSetAttribute(transform_kernel<JG_LAYOUT, JG_NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TSmem<JG_LAYOUT>));
+}
+
+cudaError_t JG_FN(transform_launch_)(cudaStream_t stream, const TransformParams& P, const QuantSet& Q)
+{
+    const int grid = (P.n_items + kWarps - 1) / kWarps;
+    if (grid > 0) transform_kernel<JG_LAYOUT, JG_NC><<<grid, kThreads, sizeof(TSmem<JG_LAYOUT>), stream>>>(P, Q);
     return cudaGetLastError();
 }
 

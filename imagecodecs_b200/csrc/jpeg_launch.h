@@ -75,20 +75,47 @@ struct LaunchParams {
     const HuffLut* huff;
     int16_t* dbg_coefs;              // optional [blocks*64], zigzag order
     uint32_t* dbg_bits;              // optional [blocks]
+    // split pipeline (jpeg_transform.cuh -> jpeg_entropy.cuh): the coefficient plane between pass A and pass B
+    const int16_t* coefs;            // [blocks of the plan][64] int16, zigzag order; an image starts at ImageDesc.first_block
+    int bpm;                         // blocks per MCU of the launch: 1 gray, 3 4:4:4, 6 4:2:0
+    int blocks_per_tile;             // pass B tile: 32 blocks (24 = whole MCUs with restart intervals)
 };
+
+// pass B (jpeg_entropy.cuh): tiles, CTA shape, and the TMA descriptor of the coefficient plane
+constexpr int kEntTileBlocks = 32, kEntTileBlocksRestart = 24;
+constexpr int kEntThreads = 192, kEntWarps = kEntThreads / 32;      // 6 warps: three CTAs of ~75 KB per SM
+// A CUtensorMap (cuTensorMapEncodeTiled, filled in by the host: 2-D, int16, {64, blocks} with a {72, 32} box), passed
+// by value as a __grid_constant__ kernel parameter.  Under the CPU emulation: q[0] = base pointer, q[1] = rows.
+struct alignas(64) CoefMap { unsigned long long q[16]; };
+
+// pass A of the split pipeline (jpeg_transform.cuh): one warp per item = transform_item_mcus(layout) consecutive MCUs of one image
+struct TransformParams {
+    const ImageDesc* images;
+    int n_images;
+    int n_items;                 // work items of the launch
+    int items_per_image;         // > 0 when every image of the launch has this many items
+    const uint32_t* first_item;  // otherwise [n_images + 1]: first item of every image
+    int16_t* coefs;              // [blocks of the plan][64], zigzag order
+};
+constexpr int transform_item_mcus(int layout) { return layout == LAYOUT_444 ? 32 : (layout == LAYOUT_420 ? 16 : 64); }
 
 #if !defined(JG_EMULATE)
 // one set per (layout, channels) specialisation; see jpeg_kernel_inst.cu
 #define JG_DECLARE_SPEC(L, N)                                                                   \
     size_t smem_bytes_##L##_##N();                                                              \
     cudaError_t prepare_##L##_##N(int* ctas_per_sm);                                            \
-    cudaError_t launch_##L##_##N(int grid, cudaStream_t stream, const LaunchParams& P, const QuantSet& Q, int mode);
+    cudaError_t launch_##L##_##N(int grid, cudaStream_t stream, const LaunchParams& P, const QuantSet& Q, int mode);      \
+    cudaError_t transform_prepare_##L##_##N();                                                                            \
+    cudaError_t transform_launch_##L##_##N(cudaStream_t stream, const struct TransformParams& P, const QuantSet& Q);
 JG_DECLARE_SPEC(0, 3)
 JG_DECLARE_SPEC(0, 4)
 JG_DECLARE_SPEC(1, 3)
 JG_DECLARE_SPEC(1, 4)
 JG_DECLARE_SPEC(2, 1)
 #undef JG_DECLARE_SPEC
+// layout-independent pass B of the split pipeline (jpeg_entropy.cu); mode 0 plain, 2 restart intervals
+cudaError_t entropy_prepare(int* ctas_per_sm);
+cudaError_t entropy_launch(int grid, cudaStream_t stream, const LaunchParams& P, const CoefMap& cmap, int mode);
 // layout-independent second pass (jpeg_stuff.cu)
 size_t stuff_smem_bytes();
 cudaError_t stuff_prepare(int* ctas_per_sm);

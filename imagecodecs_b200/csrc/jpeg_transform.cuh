@@ -1,0 +1,368 @@
+// jpeg_transform.cuh -- pass A of the split pipeline: pixels -> quantised coefficients in HBM.
+//
+// Replaces, for every 8x8 block of the batch, the reference's block gather + edge replication
+// (jpeg_enc.h:1094-1112), RGB -> YCbCr (:1114-1124), tjei_fdct (:656-763) and the quantiser of
+// tjei_encode_and_write_MCU (:799-817): the result is `du[64]` of that function, as int16 in ZIGZAG
+// order, 128 bytes per block, blocks in the order the scan codes them (MCU after MCU, inside an MCU
+// Y.. Cb Cr, :1128-1154).  The entropy pass (jpeg_entropy.cuh) reads nothing else.
+//
+// Why its own kernel: no chain, no tickets, no queue -- a warp's whole state is one MCU row of floats,
+// the hot loop is ~6 KB of straight-line FADD2/FMUL, and the arithmetic is issued two values at a time
+// wherever two identically shaped computations exist:
+//   4:4:4  8 lanes own TWO MCUs (m and m+4 of the warp's eight); lane u holds pixel row u of both, so
+//          Y, Cb and Cr of the pair go through the packed passes together (the fused kernel could
+//          pack only Cb with Cr).
+//   4:2:0  16 lanes own one MCU; the left and the right luma block of a row travel packed.
+//   gray   8 lanes own two consecutive blocks.
+// The 8x8 transposition between the row and the column pass goes through shared memory as float2
+// (STS.64 / LDS.64: both members of a pair in one access), rows padded to 9 -- conflict-free both ways.
+// Multiplications stay scalar (ptxas fuses FMUL2 into a following FADD2, see jpeg_device.h).
+// Coefficients are scattered to zigzag order in shared memory (16-bit stores) and leave as 16-byte
+// vectors: 128 contiguous bytes per block, 3 KB per warp iteration.
+#pragma once
+#include "jpeg_kernel.cuh"
+
+namespace jg {
+
+template <int LAYOUT>
+struct TGeo {
+    static constexpr int BPM = LAYOUT == LAYOUT_444 ? 3 : (LAYOUT == LAYOUT_420 ? 6 : 1);
+    static constexpr int ITER_MCUS = LAYOUT == LAYOUT_420 ? 2 : 8;          // MCUs one warp iteration transforms
+    static constexpr int ITERS = LAYOUT == LAYOUT_444 ? 4 : 8;              // iterations per item
+    static constexpr int ITEM_MCUS = ITER_MCUS * ITERS;                     // 32 / 16 / 64
+    static constexpr int ITER_BLOCKS = ITER_MCUS * BPM;                     // 24 / 12 / 8
+    // exchange space of one lane group, in floats: 4:4:4 three pair tiles, 4:2:0 two pair tiles + two single tiles, gray one pair tile
+    static constexpr int GROUP_FLOATS = LAYOUT == LAYOUT_444 ? 3 * 2 * kTileFloats : (LAYOUT == LAYOUT_420 ? 6 * kTileFloats : 2 * kTileFloats);
+    static constexpr int GROUPS = LAYOUT == LAYOUT_420 ? 2 : 4;
+};
+static_assert(TGeo<LAYOUT_444>::ITEM_MCUS == transform_item_mcus(LAYOUT_444) && TGeo<LAYOUT_420>::ITEM_MCUS == transform_item_mcus(LAYOUT_420) &&
+              TGeo<LAYOUT_GRAY>::ITEM_MCUS == transform_item_mcus(LAYOUT_GRAY), "host and kernel agree on the item size");
+
+template <int LAYOUT>
+struct TWarp {
+    using G = TGeo<LAYOUT>;
+    alignas(16) float xch[G::GROUPS * G::GROUP_FLOATS];                 // row pass -> column pass
+    alignas(16) int16_t stage[G::ITER_BLOCKS * kCoefStride];             // zigzag scatter -> 16-byte vectors
+};
+template <int LAYOUT>
+struct TSmem { TWarp<LAYOUT> wm[kWarps]; };
+
+struct TLane {
+    float pq_l[8], pq_c[8];      // reciprocal quantisers of column u = lane & 7: [v] = pqt[8v+u]
+    int zz[8];                   // zigzag position of (v, u)
+};
+
+// (v*pq + 1024) + 0.5, floor, - 1024 (jpeg_enc.h:808-816) for a pair; the results are the LOW 16 BITS of kx / ky.
+// b = (t + 1024) + 0.5 as the reference rounds it; then ONE more packed add, rounded toward minus infinity, of
+// 1.5 * 2^23 - 1024: the sum lies in [2^23, 2^24) where the ulp is 1, so it equals 1.5 * 2^23 + floor(b) - 1024 exactly
+// and, 1.5 * 2^23 being 0x4B400000, the low 16 bits of its bit pattern are floor(b) - 1024 in two's complement.
+// No F2I, no integer subtraction: the XU pipe (16 lanes per clock) stays out of the quantiser.
+constexpr float kFloorMagic = 12582912.0f - 1024.0f;
+JG_DEV void quantise2(f32x2 c, float pq, unsigned& kx, unsigned& ky)
+{
+    const f32x2 b = f2_add(f2_add(f2_mul(c, f2(pq, pq)), f2(1024.0f, 1024.0f)), f2(0.5f, 0.5f));
+    const f32x2 r = f2_add_rd(b, f2(kFloorMagic, kFloorMagic));
+    kx = f_bits(r.x);
+    ky = f_bits(r.y);
+}
+JG_DEV unsigned quantise1(float c, float pq)
+{
+    return f_bits(f_add_rd(f_add(f_add(f_mul(c, pq), 1024.0f), 0.5f), kFloorMagic));
+}
+// Channels of pixel i of a loaded row segment as 2^23 + value (see u8_biased): one PRMT each
+template <int NC>
+JG_DEV void rgb_biased(const uint32_t* w, int i, float& r, float& g, float& b)
+{
+    if (NC == 4) { r = u8_biased(w[i], 0); g = u8_biased(w[i], 1); b = u8_biased(w[i], 2); }
+    else {
+        r = u8_biased(w[(3 * i) >> 2], (3 * i) & 3);
+        g = u8_biased(w[(3 * i + 1) >> 2], (3 * i + 1) & 3);
+        b = u8_biased(w[(3 * i + 2) >> 2], (3 * i + 2) & 3);
+    }
+}
+#ifndef JG_U8_VIA_PRMT
+#define JG_U8_VIA_PRMT 1      // 0: I2F.U8 (XU pipe) -- kept for the A/B in DESIGN.md
+#endif
+// R, G, B of pixel i of two row segments, as pairs
+template <int NC>
+JG_DEV void rgb_pair(const uint32_t* wa, const uint32_t* wb, int ia, int ib, f32x2& R, f32x2& G, f32x2& B)
+{
+    float r0, g0, b0, r1, g1, b1;
+#if JG_U8_VIA_PRMT
+    rgb_biased<NC>(wa, ia, r0, g0, b0);
+    rgb_biased<NC>(wb, ib, r1, g1, b1);
+    const f32x2 bias = f2(kU8Bias, kU8Bias);
+    R = f2_sub(f2(r0, r1), bias); G = f2_sub(f2(g0, g1), bias); B = f2_sub(f2(b0, b1), bias);
+#else
+    rgb_of<NC>(wa, ia, r0, g0, b0);
+    rgb_of<NC>(wb, ib, r1, g1, b1);
+    R = f2(r0, r1); G = f2(g0, g1); B = f2(b0, b1);
+#endif
+}
+
+// copy `nblk` staged blocks (kCoefStride apart) to global memory, 16 bytes per lane and step
+template <int MAXBLK>
+JG_DEV void stage_to_global(const int16_t* stage, int16_t* gout, int nblk)
+{
+    const int t = JG_TID & 31;
+#pragma unroll
+    for (int q = 0; q < (MAXBLK * 8 + 31) / 32; ++q) {
+        const int c = q * 32 + t, blk = c >> 3, part = c & 7;
+        if (blk < nblk) {
+            const uint4 v = *reinterpret_cast<const uint4*>(stage + blk * kCoefStride + part * 8);
+            *reinterpret_cast<uint4*>(gout + blk * 64 + part * 8) = v;
+        }
+    }
+}
+
+// ---- 4:4:4: eight MCUs per iteration, lane group g owns MCUs g and g + 4 -----------------------------------------
+template <int NC>
+JG_DEV void transform_iter_444(TWarp<LAYOUT_444>& W, const ImageDesc& im, int my0, int mx0, int nM, int16_t* gout, const TLane& LC)
+{
+    const int t = JG_TID & 31, u = t & 7, g = t >> 3;
+    f32x2* xt = reinterpret_cast<f32x2*>(W.xch) + g * (3 * kTileFloats);
+    const bool vA = g < nM, vB = g + 4 < nM;
+    uint32_t wA[8 * NC / 4], wB[8 * NC / 4];
+#pragma unroll
+    for (int i = 0; i < 8 * NC / 4; ++i) { wA[i] = 0u; wB[i] = 0u; }
+    if (vA) {
+        int my, mx;
+        mcu_pos(im, my0, mx0, g, my, mx);
+        int y = my * 8 + u; if (y >= im.h) y = im.h - 1;               // replicate the last row (jpeg_enc.h:1106-1111)
+        load_segment<NC, 8>(im, mx * 8, y, wA);
+    }
+    if (vB) {
+        int my, mx;
+        mcu_pos(im, my0, mx0, g + 4, my, mx);
+        int y = my * 8 + u; if (y >= im.h) y = im.h - 1;
+        load_segment<NC, 8>(im, mx * 8, y, wB);
+    }
+    f32x2 sy[8], sb[8], sr[8];       // .x = MCU A, .y = MCU B
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        f32x2 R, Gc, B;
+        rgb_pair<NC>(wA, wB, i, i, R, Gc, B);
+        // jpeg_enc.h:1118-1120, additions packed over the two MCUs
+        sy[i] = f2_sub(f2_add(f2_add(f2_mul(f2(0.299f, 0.299f), R), f2_mul(f2(0.587f, 0.587f), Gc)), f2_mul(f2(0.114f, 0.114f), B)),
+                       f2(128.0f, 128.0f));
+        sb[i] = f2_add(f2_sub(f2_mul(f2(-0.1687f, -0.1687f), R), f2_mul(f2(0.3313f, 0.3313f), Gc)), f2_mul(f2(0.5f, 0.5f), B));
+        sr[i] = f2_sub(f2_sub(f2_mul(f2(0.5f, 0.5f), R), f2_mul(f2(0.4187f, 0.4187f), Gc)), f2_mul(f2(0.0813f, 0.0813f), B));
+    }
+    aan8x2(sy);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xt[u * 9 + i] = sy[i];
+    aan8x2(sb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xt[kTileFloats + u * 9 + i] = sb[i];
+    aan8x2(sr);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xt[2 * kTileFloats + u * 9 + i] = sr[i];
+    warp_sync();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        f32x2 col[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) col[v] = xt[c * kTileFloats + v * 9 + u];
+        aan8x2(col);
+        int16_t* dA = W.stage + (g * 3 + c) * kCoefStride;
+        int16_t* dB = W.stage + ((g + 4) * 3 + c) * kCoefStride;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            unsigned ka, kb;
+            quantise2(col[v], c ? LC.pq_c[v] : LC.pq_l[v], ka, kb);
+            dA[LC.zz[v]] = (int16_t)ka;
+            dB[LC.zz[v]] = (int16_t)kb;     // (an absent MCU B computes on zeros into its own staging slot, never copied out)
+        }
+    }
+    warp_sync();
+    stage_to_global<24>(W.stage, gout, nM * 3);
+}
+
+// ---- 4:2:0: two MCUs per iteration, 16 lanes per MCU, lane r16 owns pixel row r16 ---------------------------------
+template <int NC>
+JG_DEV void transform_iter_420(TWarp<LAYOUT_420>& W, const ImageDesc& im, int my0, int mx0, int nM, int16_t* gout, const TLane& LC)
+{
+    const int t = JG_TID & 31, u = t & 7, grp = t >> 4, r16 = t & 15, h = r16 >> 3;
+    float* base = W.xch + grp * (6 * kTileFloats);
+    f32x2* ypair = reinterpret_cast<f32x2*>(base);           // pair tile 0: (Y00, Y01), pair tile 1: (Y10, Y11)
+    float* ctile = base + 4 * kTileFloats;                   // Cb tile, Cr tile
+    const bool valid = grp < nM;
+    f32x2 cbs[4], crs[4];            // horizontal pair sums (a+b) of this row: .x samples 0-3, .y samples 4-7
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { cbs[i] = f2(0.0f, 0.0f); crs[i] = f2(0.0f, 0.0f); }
+    if (valid) {
+        int my, mx;
+        mcu_pos(im, my0, mx0, grp, my, mx);
+        int y = my * 16 + r16; if (y >= im.h) y = im.h - 1;
+        uint32_t w[16 * NC / 4];
+        load_segment<NC, 16>(im, mx * 16, y, w);
+        f32x2 sy[8];                 // .x = pixel i (left luma block), .y = pixel i + 8 (right luma block)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            f32x2 cb[2], cr[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int i = 2 * j + e;
+                f32x2 R, Gc, B;
+                rgb_pair<NC>(w, w, i, i + 8, R, Gc, B);
+                sy[i] = f2_sub(f2_add(f2_add(f2_mul(f2(0.299f, 0.299f), R), f2_mul(f2(0.587f, 0.587f), Gc)),
+                                      f2_mul(f2(0.114f, 0.114f), B)), f2(128.0f, 128.0f));
+                cb[e] = f2_add(f2_sub(f2_mul(f2(-0.1687f, -0.1687f), R), f2_mul(f2(0.3313f, 0.3313f), Gc)),
+                               f2_mul(f2(0.5f, 0.5f), B));
+                cr[e] = f2_sub(f2_sub(f2_mul(f2(0.5f, 0.5f), R), f2_mul(f2(0.4187f, 0.4187f), Gc)),
+                               f2_mul(f2(0.0813f, 0.0813f), B));
+            }
+            cbs[j] = f2_add(cb[0], cb[1]);
+            crs[j] = f2_add(cr[0], cr[1]);
+        }
+        aan8x2(sy);
+        f32x2* ty = ypair + h * kTileFloats + (r16 & 7) * 9;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ty[i] = sy[i];
+    }
+    // vertical pairs live in neighbouring lanes: the even lane finishes Cb, the odd lane Cr;
+    // sample = ((a+b) + (c+d)) * 0.25f with (a+b) from the even row (extended mode); the addition commutes
+    const bool even = (r16 & 1) == 0;
+    float samp[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const f32x2 mine = even ? cbs[i] : crs[i], give = even ? crs[i] : cbs[i];
+        const f32x2 other = f2(warp_shfl_xor_f32(give.x, 1), warp_shfl_xor_f32(give.y, 1));
+        const f32x2 q = f2_mul(f2_add(mine, other), f2(0.25f, 0.25f));
+        samp[i] = q.x; samp[4 + i] = q.y;
+    }
+    if (valid) row_pass_store(samp, ctile + (r16 & 1) * kTileFloats, r16 >> 1);
+    warp_sync();
+    if (valid) {
+        // lanes 0-7 finish (Y00, Y01) and Cb, lanes 8-15 (Y10, Y11) and Cr
+        f32x2 col[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) col[v] = ypair[h * kTileFloats + v * 9 + u];
+        aan8x2(col);
+        int16_t* dL = W.stage + (grp * 6 + 2 * h) * kCoefStride;
+        int16_t* dR = dL + kCoefStride;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            unsigned kl, kr;
+            quantise2(col[v], LC.pq_l[v], kl, kr);
+            dL[LC.zz[v]] = (int16_t)kl;
+            dR[LC.zz[v]] = (int16_t)kr;
+        }
+        float c[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) c[v] = ctile[h * kTileFloats + v * 9 + u];
+        aan8(c);
+        int16_t* dC = W.stage + (grp * 6 + 4 + h) * kCoefStride;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) dC[LC.zz[v]] = (int16_t)quantise1(c[v], LC.pq_c[v]);
+    }
+    warp_sync();
+    stage_to_global<12>(W.stage, gout, nM * 6);
+}
+
+// ---- gray: eight blocks per iteration, lane group g owns blocks 2g and 2g + 1 ------------------------------------
+JG_DEV void transform_iter_gray(TWarp<LAYOUT_GRAY>& W, const ImageDesc& im, int my0, int mx0, int nM, int16_t* gout, const TLane& LC)
+{
+    const int t = JG_TID & 31, u = t & 7, g = t >> 3;
+    f32x2* xt = reinterpret_cast<f32x2*>(W.xch) + g * kTileFloats;
+    const bool vA = 2 * g < nM, vB = 2 * g + 1 < nM;
+    uint32_t wA[2] = {0u, 0u}, wB[2] = {0u, 0u};
+    if (vA) {
+        int my, mx;
+        mcu_pos(im, my0, mx0, 2 * g, my, mx);
+        int y = my * 8 + u; if (y >= im.h) y = im.h - 1;
+        load_segment<1, 8>(im, mx * 8, y, wA);
+    }
+    if (vB) {
+        int my, mx;
+        mcu_pos(im, my0, mx0, 2 * g + 1, my, mx);
+        int y = my * 8 + u; if (y >= im.h) y = im.h - 1;
+        load_segment<1, 8>(im, mx * 8, y, wB);
+    }
+    f32x2 s[8];
+#pragma unroll
+#if JG_U8_VIA_PRMT
+    for (int i = 0; i < 8; ++i)
+        s[i] = f2_sub(f2_sub(f2(u8_biased(wA[i >> 2], i & 3), u8_biased(wB[i >> 2], i & 3)), f2(kU8Bias, kU8Bias)), f2(128.0f, 128.0f));
+#else
+    for (int i = 0; i < 8; ++i) s[i] = f2_sub(f2(u8_to_f(byte_of(wA, i)), u8_to_f(byte_of(wB, i))), f2(128.0f, 128.0f));
+#endif
+    aan8x2(s);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xt[u * 9 + i] = s[i];
+    warp_sync();
+    f32x2 col[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) col[v] = xt[v * 9 + u];
+    aan8x2(col);
+    int16_t* dA = W.stage + (2 * g) * kCoefStride;
+    int16_t* dB = dA + kCoefStride;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        unsigned ka, kb;
+        quantise2(col[v], LC.pq_l[v], ka, kb);
+        dA[LC.zz[v]] = (int16_t)ka;
+        dB[LC.zz[v]] = (int16_t)kb;
+    }
+    warp_sync();
+    stage_to_global<8>(W.stage, gout, nM);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel A: one warp per item (ITEM_MCUS consecutive MCUs of one image)
+// ------------------------------------------------------------------------------------------
+#ifndef JG_TR_MINB
+#define JG_TR_MINB 5          // resident CTAs per SM the register allocation aims at (variant builds: tools/build_variants.py)
+#endif
+template <int LAYOUT, int NC>
+JG_KERNEL(kThreads, JG_TR_MINB)
+void transform_kernel(const JG_GRID_CONSTANT TransformParams P, const JG_GRID_CONSTANT QuantSet Q)
+{
+    using G = TGeo<LAYOUT>;
+    JG_DYNAMIC_SMEM(smem_raw);
+    TSmem<LAYOUT>& S = *reinterpret_cast<TSmem<LAYOUT>*>(smem_raw);
+    const int t = JG_TID;
+    const unsigned item = (unsigned)JG_CTA_ID * (unsigned)kWarps + (unsigned)(t >> 5);
+    if (item >= (unsigned)P.n_items) return;             // whole warps leave; no CTA barrier in this kernel
+    TLane LC;
+    {
+        const int u = t & 7;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            LC.pq_l[v] = Q.luma[8 * v + u];
+            LC.pq_c[v] = Q.chroma[8 * v + u];
+            LC.zz[v] = zz_of(8 * v + u);
+        }
+    }
+    unsigned img, local;
+    if (P.items_per_image > 0) {
+        img = item / (unsigned)P.items_per_image;
+        local = item - img * (unsigned)P.items_per_image;
+    } else {
+        unsigned lo = 0, hi = (unsigned)P.n_images - 1u;       // last image whose first item is <= item
+        while (lo < hi) {
+            const unsigned mid = (lo + hi + 1u) >> 1;
+            if (ldg_u32(P.first_item + mid) <= item) lo = mid; else hi = mid - 1u;
+        }
+        img = lo;
+        local = item - ldg_u32(P.first_item + lo);
+    }
+    const ImageDesc im = P.images[img];
+    TWarp<LAYOUT>& W = S.wm[t >> 5];
+    const int m_begin = (int)local * G::ITEM_MCUS;
+    const int m_end = (im.n_mcus - m_begin < G::ITEM_MCUS) ? im.n_mcus : m_begin + G::ITEM_MCUS;
+    int16_t* gout = P.coefs + (im.first_block + (unsigned long long)m_begin * G::BPM) * 64ull;
+    int my0 = m_begin / im.mcus_x, mx0 = m_begin - my0 * im.mcus_x;
+#pragma unroll 1
+    for (int m0 = m_begin; m0 < m_end; m0 += G::ITER_MCUS) {
+        const int nM = m_end - m0 < G::ITER_MCUS ? m_end - m0 : G::ITER_MCUS;
+        if (LAYOUT == LAYOUT_444) transform_iter_444<NC>(reinterpret_cast<TWarp<LAYOUT_444>&>(W), im, my0, mx0, nM, gout, LC);
+        else if (LAYOUT == LAYOUT_420) transform_iter_420<NC>(reinterpret_cast<TWarp<LAYOUT_420>&>(W), im, my0, mx0, nM, gout, LC);
+        else transform_iter_gray(reinterpret_cast<TWarp<LAYOUT_GRAY>&>(W), im, my0, mx0, nM, gout, LC);
+        gout += G::ITER_BLOCKS * 64;
+        mx0 += G::ITER_MCUS;
+        while (mx0 >= im.mcus_x) { mx0 -= im.mcus_x; ++my0; }
+    }
+}
+
+}  // namespace jg

@@ -145,6 +145,11 @@ JPEG_GPU_API int jpeg_gpu_plan_run(jpeg_gpu_plan* plan, void* stream);
  * plan+stuff kernels (pass 2) of the LAST run, in milliseconds.  Returns 0 if unavailable. */
 JPEG_GPU_API int jpeg_gpu_plan_enable_timing(jpeg_gpu_plan* plan, int enable);
 JPEG_GPU_API int jpeg_gpu_plan_kernel_times(jpeg_gpu_plan* plan, float* encode_ms, float* stuff_ms);
+/* The same per pass of the split pipeline: pass A (pixels -> coefficients, jpeg_transform.cuh), pass B (coefficients ->
+ * unstuffed bits, jpeg_entropy.cuh), pass 2 (plan + stuff).  With the fused round-1 kernel (JPEG_GPU_PIPELINE=fused in
+ * the environment when the plan is created; same bytes) entropy_ms is 0 and transform_ms is the fused kernel. */
+JPEG_GPU_API int jpeg_gpu_plan_pass_times(jpeg_gpu_plan* plan, float* transform_ms, float* entropy_ms, float* stuff_ms);
+JPEG_GPU_API int jpeg_gpu_plan_is_fused(const jpeg_gpu_plan* plan);
 /* Number of kernel launches one jpeg_gpu_plan_run enqueues. */
 JPEG_GPU_API int jpeg_gpu_plan_launches(const jpeg_gpu_plan* plan);
 /* Wait for `stream`, then deliver headers + scans into outs[] (host or device buffers). */

@@ -11,6 +11,9 @@ _SO = os.path.join(_HERE, "libjpeg_emu.so")
 _SRC = [os.path.join(_HERE, "emu_driver.cpp"), os.path.join(_HERE, "cuda_emu.h"),
         os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_stuff.cuh"),
         os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_kernel.cuh"),
+        os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_transform.cuh"),
+        os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_entropy.cuh"),
+        os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_launch.h"),
         os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_device.h"),
         os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_tables.h"),
         os.path.join(_ROOT, "imagecodecs_b200", "csrc", "jpeg_decode.cuh"),
@@ -36,6 +39,8 @@ def _load():
         L.emu_encode.restype = C.c_int
         L.emu_encode.argtypes = [C.c_void_p] + [C.c_int] * 11 + [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                                                 C.c_void_p, C.c_void_p]
+        L.emu_encode_split.restype = C.c_int
+        L.emu_encode_split.argtypes = L.emu_encode.argtypes
         L.emu_ticket_map.restype = C.c_int
         L.emu_ticket_map.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
@@ -79,8 +84,9 @@ def emu_ticket_map(tiles, force_schedule=False):
     return g, img
 
 
-def emu_encode(batch, qmode=0, quality=3, sub=0, win_words=0, n_ctas=2, stages=False, cap=None, flags=0, bottom_up=False):
-    """batch: uint8 [n,h,w,c].  Returns list of scan bytes (entropy-coded segment + EOI) [, coefs, bits]."""
+def emu_encode(batch, qmode=0, quality=3, sub=0, win_words=0, n_ctas=2, stages=False, cap=None, flags=0, bottom_up=False, split=True):
+    """batch: uint8 [n,h,w,c].  Returns list of scan bytes (entropy-coded segment + EOI) [, coefs, bits].
+    split: the split pipeline (transform -> entropy -> stuff, what the library runs) or the fused r01 kernel."""
     batch = np.ascontiguousarray(batch, dtype=np.uint8)
     if batch.ndim == 3:
         batch = batch[None]
@@ -95,7 +101,8 @@ def emu_encode(batch, qmode=0, quality=3, sub=0, win_words=0, n_ctas=2, stages=F
     status = np.zeros(n, dtype=np.uint32)
     coefs = np.zeros((n * nblk, 64), dtype=np.int16) if stages else None
     bits = np.zeros(n * nblk, dtype=np.uint32) if stages else None
-    rc = _load().emu_encode(batch.ctypes.data, n, w, h, c, -w * c if bottom_up else 0, flags, sub, qmode, quality, win_words, n_ctas,
+    fn = _load().emu_encode_split if split else _load().emu_encode
+    rc = fn(batch.ctypes.data, n, w, h, c, -w * c if bottom_up else 0, flags, sub, qmode, quality, win_words, n_ctas,
                             out.ctypes.data, cap, sizes.ctypes.data, status.ctypes.data,
                             coefs.ctypes.data if stages else None, bits.ctypes.data if stages else None)
     if rc != 0:

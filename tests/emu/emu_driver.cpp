@@ -3,6 +3,8 @@
 // exposes one C function the CPU test-suite calls.  See cuda_emu.h for why this exists.
 #define JG_EMULATE 1
 #include "jpeg_stuff.cuh"
+#include "jpeg_transform.cuh"
+#include "jpeg_entropy.cuh"
 #include "jpeg_decode.cuh"
 #include "jpeg_decode.h"
 
@@ -39,7 +41,7 @@ void* thread_main(void* p)
 }
 
 // "launch" n_ctas CTAs of kThreads threads that all run concurrently
-void launch(int n_ctas, size_t smem_bytes, const std::function<void()>& body)
+void launch(int n_ctas, size_t smem_bytes, const std::function<void()>& body, int kThreads = jg::kThreads, int first_cta = 0)
 {
     std::vector<emu::Cta> ctas(n_ctas);
     std::vector<ThreadArg> args((size_t)n_ctas * kThreads);
@@ -50,6 +52,7 @@ void launch(int n_ctas, size_t smem_bytes, const std::function<void()>& body)
     for (int c = 0; c < n_ctas; ++c) {
         emu::Cta& cta = ctas[c];
         cta.nthreads = kThreads;
+        cta.id = first_cta + c;
         cta.smem = (unsigned char*)aligned_alloc(64, (smem_bytes + 63) / 64 * 64);
         pthread_barrier_init(&cta.bar, nullptr, kThreads);
         for (int wv = 0; wv < kThreads / 32; ++wv) pthread_barrier_init(&cta.wbar[wv], nullptr, 32);
@@ -154,6 +157,113 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
         else JG_RUN(LAYOUT_GRAY, 1);
 #undef JG_RUN
     });
+    if (!error) launch(1, sizeof(StuffSmem), [&] { plan_chunks_kernel(P); });
+    if (!error) launch(n_ctas, sizeof(StuffSmem), [&] { stuff_kernel(P); });
+    free(raw);
+    return (int)error;
+}
+
+// The same through the split pipeline: transform_kernel (pass A) -> entropy_kernel (pass B) -> plan_chunks / stuff.
+// n_ctas bounds how many CTAs of pass B and of the stuffing pass run concurrently; pass A runs its grid in waves.
+// dbg_coefs (optional) receives the coefficient plane, dbg_bits the bits of every block.
+int emu_encode_split(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int stride, int flags, int subsampling,
+                     int quality_mode, int quality, int win_words, int n_ctas,
+                     uint8_t* scan_out, size_t scan_cap, unsigned long long* scan_bytes, unsigned* img_status,
+                     int16_t* dbg_coefs, uint32_t* dbg_bits)
+{
+    (void)win_words;
+    const int layout = ncomp == 1 ? LAYOUT_GRAY : (subsampling ? LAYOUT_420 : LAYOUT_444);
+    uint8_t ql[64], qc[64];
+    if (!build_qt(quality_mode, quality, ql, qc)) return -1;
+    QuantSet Q;
+    build_pqt(ql, Q.luma);
+    build_pqt(qc, Q.chroma);
+    HuffLut lut;
+    build_huff_lut(&lut);
+
+    const int mcu = layout == LAYOUT_420 ? 16 : 8;
+    const int bpm = layout == LAYOUT_444 ? 3 : (layout == LAYOUT_420 ? 6 : 1);
+    const int mcus_x = (w + mcu - 1) / mcu, mcus_y = (h + mcu - 1) / mcu;
+    const int n_mcus = mcus_x * mcus_y;
+    const bool restart = (flags & kFlagRestart) != 0;
+    const int bpt = restart ? kEntTileBlocksRestart : kEntTileBlocks;
+    const int n_blocks = n_mcus * bpm;
+    const int tiles = (n_blocks + bpt - 1) / bpt;
+    const int item_mcus = transform_item_mcus(layout);
+    const int items = (n_mcus + item_mcus - 1) / item_mcus;
+    if (stride == 0) stride = w * ncomp;
+    const int pitch = stride < 0 ? -stride : stride;
+
+    const size_t raw_cap = (scan_cap + 255) / 256 * 256;
+    uint8_t* raw = (uint8_t*)aligned_alloc(256, raw_cap * n_images);
+    std::vector<int16_t> coefs((size_t)n_images * n_blocks * 64 + 64, (int16_t)0x5555);
+    std::vector<ImageDesc> imgs(n_images);
+    for (int i = 0; i < n_images; ++i) {
+        ImageDesc& d = imgs[i];
+        d.px = pixels + (size_t)i * pitch * h + (stride < 0 ? (size_t)pitch * (h - 1) : 0);
+        d.flags = flags;
+        d.raw = raw + (size_t)i * raw_cap;
+        d.raw_cap = scan_cap;
+        d.out = scan_out + (size_t)i * scan_cap;
+        d.out_cap = scan_cap;
+        d.first_block = (unsigned long long)i * n_blocks;
+        d.w = w; d.h = h; d.stride = stride; d.mcus_x = mcus_x; d.n_mcus = n_mcus;
+        d.first_tile = i * tiles; d.n_tiles = tiles;
+        { const size_t v = (size_t)d.px | (size_t)stride | 16u; d.align = (flags & 1) ? 1 : (int)(v & (~v + 1)); }
+    }
+    const int n_tiles = tiles * n_images;
+    const size_t max_chunks = (size_t)n_images * ((scan_cap + kChunkBytes - 1) / kChunkBytes) + 1;
+    std::vector<unsigned long long> desc_bits(n_tiles, 0), desc_ff(max_chunks, 0), raw_bytes(n_images, 0);
+    std::vector<unsigned> first_chunk(n_images + 1, 0);
+    unsigned ticket = 0, ticket2 = 0, error = 0;
+    for (int i = 0; i < n_images; ++i) { scan_bytes[i] = 0; img_status[i] = 0; }
+
+    // ---- pass A ----
+    std::vector<uint32_t> first_item(n_images + 1);
+    for (int i = 0; i <= n_images; ++i) first_item[i] = (uint32_t)(i * items);
+    TransformParams TP;
+    TP.images = imgs.data(); TP.n_images = n_images; TP.n_items = items * n_images;
+    TP.items_per_image = (n_images % 2) ? items : 0;     // exercise both item -> image paths
+    TP.first_item = first_item.data();
+    TP.coefs = coefs.data();
+    const int gridA = (TP.n_items + kWarps - 1) / kWarps;
+    const size_t smemA = layout == LAYOUT_444 ? sizeof(TSmem<LAYOUT_444>) : (layout == LAYOUT_420 ? sizeof(TSmem<LAYOUT_420>) : sizeof(TSmem<LAYOUT_GRAY>));
+    for (int c0 = 0; c0 < gridA; c0 += 16) {
+        launch(gridA - c0 < 16 ? gridA - c0 : 16, smemA, [&] {
+            if (layout == LAYOUT_444 && ncomp == 3) transform_kernel<LAYOUT_444, 3>(TP, Q);
+            else if (layout == LAYOUT_444) transform_kernel<LAYOUT_444, 4>(TP, Q);
+            else if (layout == LAYOUT_420 && ncomp == 3) transform_kernel<LAYOUT_420, 3>(TP, Q);
+            else if (layout == LAYOUT_420) transform_kernel<LAYOUT_420, 4>(TP, Q);
+            else transform_kernel<LAYOUT_GRAY, 1>(TP, Q);
+        }, kThreads, c0);
+    }
+    if (dbg_coefs) memcpy(dbg_coefs, coefs.data(), (size_t)n_images * n_blocks * 64 * sizeof(int16_t));
+
+    // ---- pass B ----
+    LaunchParams P;
+    memset(&P, 0, sizeof P);
+    P.images = imgs.data(); P.n_images = n_images; P.n_tiles = n_tiles;
+    P.tiles_per_image = (n_images % 2) ? tiles : 0;
+    std::vector<int> counts(n_images, tiles);
+    std::vector<uint32_t> sched(schedule_words(n_images));
+    build_schedule(counts.data(), n_images, sched.data());
+    P.sched = sched.data();
+    P.win_words = kWinWordsMax;
+    P.ticket = &ticket; P.ticket2 = &ticket2; P.error = &error;
+    P.desc_bits = desc_bits.data(); P.desc_ff = desc_ff.data(); P.desc_dc = nullptr;
+    P.raw_bytes = raw_bytes.data(); P.first_chunk = first_chunk.data();
+    P.scan_bytes = scan_bytes; P.img_status = img_status; P.huff = &lut;
+    P.dbg_coefs = nullptr; P.dbg_bits = dbg_bits;
+    P.coefs = coefs.data(); P.bpm = bpm; P.blocks_per_tile = bpt;
+    CoefMap cmap;
+    memset(&cmap, 0, sizeof cmap);
+    cmap.q[0] = (unsigned long long)(size_t)coefs.data();
+    cmap.q[1] = (unsigned long long)n_images * n_blocks;
+    const int gridB = n_ctas > (n_tiles + kEntWarps - 1) / kEntWarps ? (n_tiles + kEntWarps - 1) / kEntWarps : n_ctas;
+    launch(gridB, sizeof(EntSmem), [&] {
+        if (restart) entropy_kernel<kEntModeRestart>(P, cmap);
+        else entropy_kernel<kEntModePlain>(P, cmap);
+    }, kEntThreads);
     if (!error) launch(1, sizeof(StuffSmem), [&] { plan_chunks_kernel(P); });
     if (!error) launch(n_ctas, sizeof(StuffSmem), [&] { stuff_kernel(P); });
     free(raw);

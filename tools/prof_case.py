@@ -31,7 +31,7 @@ e1.record(stream); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
 mp = sum(int(im.shape[0]) * a.w for im in imgs) / 1e6
 sz = sum(plan.encoded_size(i) for i in range(a.n))
-plan.enable_timing(True); plan.run(sp); torch.cuda.synchronize(); enc_ms, stuff_ms = plan.kernel_times(); plan.enable_timing(False)
-print("%dx%dx%d n=%d qmode=%d q=%d sub=%d %s%s: %.3f ms/step (encode %.3f + stuff %.3f)  %.1f GP/s  out %.3f B/px  roofline %.4f" % (
-    a.w, a.h, a.nc, a.n, a.qmode, a.q, a.sub, a.kind, (" mixed" if a.mixed else "") + (" restart" if a.restart else ""), ms, enc_ms, stuff_ms, mp / ms, sz / (mp * 1e6),
+plan.enable_timing(True); plan.run(sp); torch.cuda.synchronize(); ta, tb, tc = plan.pass_times(); plan.enable_timing(False)
+print("%s %dx%dx%d n=%d qmode=%d q=%d sub=%d %s%s: %.3f ms/step (transform %.3f + entropy %.3f + stuff %.3f)  %.1f GP/s  out %.3f B/px  roofline %.4f" % (
+    "fused" if plan.fused else "split", a.w, a.h, a.nc, a.n, a.qmode, a.q, a.sub, a.kind, (" mixed" if a.mixed else "") + (" restart" if a.restart else ""), ms, ta, tb, tc, mp / ms, sz / (mp * 1e6),
     (mp * 1e6 * a.nc + sz) / (ms * 1e-3) / 6550.1e9))
