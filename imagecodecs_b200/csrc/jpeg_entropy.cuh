@@ -44,7 +44,6 @@ constexpr int kEntCoefStride = 72;                          // int16 per staged 
                                                             // the out-of-bounds columns arrive as zeros) keep 32 lanes off each other's banks
 constexpr int kSubWords = 20;                               // words of a lane's private stream (640 bits)
 constexpr int kEntRegionWords = 1024;                       // a tile's merged bits on the fast path: 32768 at most
-constexpr int kListMax = 2 * kEntRegionWords;               // the symbol list (16-bit entries) lives in the region while the tile is coded
 constexpr int kSlowBlocks = 4;                              // slow path: 4 blocks at a time (<= 256 symbols, <= 8 x 59 bits per lane)
 constexpr int kEntModePlain = 0, kEntModeRestart = 2;
 constexpr unsigned kEntStageBytes = kEntBlocks * kEntCoefStride * 2;   // what one TMA box delivers (out-of-bounds rows count)
@@ -217,9 +216,11 @@ JG_DEV void merge_streams(const uint32_t* sub, unsigned nbits, unsigned incl, ui
     warp_sync();
 }
 
-// Blocks [lo, hi) of the staged + mapped tile -> merged bits in the region (which must be zero and free: it first holds the
-// symbol list).  Lane = block lo + lane in the list phase.  Returns the bits; `fits` = symbols, streams and total all fit.
-JG_DEV unsigned code_blocks(EntWarp& W, const EntTables& T, int lo, int hi, int slot_j, int jb, int bpm, bool& fits)
+// Blocks [lo, hi) of the staged + mapped tile -> their bits appended at bit `bit_base` of the region (zero from there on).
+// The symbol list of the blocks lives at word `list_off` of the region while they are coded (zeroed again before the
+// merge).  Lane = block lo + lane in the list phase.  Returns the bits of the blocks; `fits` = streams and total fit.
+JG_DEV unsigned code_blocks(EntWarp& W, const EntTables& T, int lo, int hi, int slot_j, int jb, int bpm, unsigned list_off,
+                            unsigned bit_base, bool& fits)
 {
     const int lane = JG_TID & 31;
     const int slot = lo + lane;
@@ -235,9 +236,7 @@ JG_DEV unsigned code_blocks(EntWarp& W, const EntTables& T, int lo, int hi, int 
     const unsigned cnt = (unsigned)(i_popc(m.x) + i_popc(m.y));
     const unsigned incl = warp_scan_incl_u32(cnt);
     const unsigned S = warp_shfl_u32(incl, 31);
-    fits = S <= (unsigned)kListMax;
-    if (!fits) return 0u;
-    uint16_t* list = reinterpret_cast<uint16_t*>(W.region);
+    uint16_t* list = reinterpret_cast<uint16_t*>(W.region + list_off);
     if (mine) list_block(list, incl - cnt, slot, m, cls);
     warp_sync();
     const unsigned q = (S + 31u) >> 5;                   // symbols per lane
@@ -245,11 +244,32 @@ JG_DEV unsigned code_blocks(EntWarp& W, const EntTables& T, int lo, int hi, int 
     const unsigned n = S - s0 < q ? S - s0 : q;
     const unsigned nbits = code_symbols(T, W.coef, list, s0, n, W.sub + lane);
     warp_sync();                                         // every lane is done with the list
-    clear_words16(W.region, (S + 1u) >> 1);              // (ends with a warp barrier)
+    clear_words16(W.region + list_off, (S + 1u) >> 1);   // (ends with a warp barrier)
     const unsigned incl_bits = warp_scan_incl_u32(nbits);
     const unsigned bits = warp_shfl_u32(incl_bits, 31);
-    fits = warp_ballot(nbits > (unsigned)kSubWords * 32u) == 0u && bits <= (unsigned)kEntRegionWords * 32u;
-    if (fits) merge_streams(W.sub, nbits, incl_bits, W.region);
+    fits = warp_ballot(nbits > (unsigned)kSubWords * 32u) == 0u && bit_base + bits <= (unsigned)kEntRegionWords * 32u;
+    if (fits) merge_streams(W.sub, nbits, bit_base + incl_bits, W.region);
+    return bits;
+}
+
+// The whole staged + mapped tile on the fast path.  A tile with many symbols is coded in two halves (16 blocks each):
+// every lane then holds half as many bits (its stream takes 640), and the second half's list sits in the upper half of
+// the region, above the first half's merged bits.
+JG_DEV unsigned code_tile(EntWarp& W, const EntTables& T, int nblk, int lane_j, int jb, int bpm, bool& fits)
+{
+    const int lane = JG_TID & 31;
+    unsigned cnt = 0;
+    if (lane < nblk) { const uint2 m = W.mask[lane]; cnt = (unsigned)(i_popc(m.x) + i_popc(m.y)); }
+    const unsigned S = warp_shfl_u32(warp_scan_incl_u32(cnt), 31);
+    if (S <= 3u * (unsigned)kEntRegionWords / 2u || nblk <= 16) {      // up to 48 symbols per lane in one go
+        const unsigned bits = code_blocks(W, T, 0, nblk, lane_j, jb, bpm, 0u, 0u, fits);
+        if (fits || nblk <= 16 || bits > (unsigned)kEntRegionWords * 32u) return bits;
+        // a lane's stream overflowed: once more, in halves
+    }
+    unsigned bits = code_blocks(W, T, 0, 16, lane_j, jb, bpm, 0u, 0u, fits);
+    if (!fits || bits > (unsigned)kEntRegionWords * 16u) { fits = false; return bits; }
+    int j2 = lane_j + 16 % bpm; if (j2 >= bpm) j2 -= bpm;                    // (16 + lane) mod bpm
+    bits += code_blocks(W, T, 16, nblk, j2, jb, bpm, (unsigned)kEntRegionWords / 2u, bits, fits);
     return bits;
 }
 
@@ -312,7 +332,7 @@ JG_DEV_NOINLINE bool ent_tile_slow(const LaunchParams& P, EntWarp& W, const EntT
     for (int lo = 0; lo < nblk; lo += kSlowBlocks) {
         warp_sync();
         clear_region(W.region, kEntRegionWords + 8);
-        const unsigned tg = code_blocks(W, T, lo, lo + kSlowBlocks < nblk ? lo + kSlowBlocks : nblk, (lo + lane) % bpm, jb, bpm, fits);
+        const unsigned tg = code_blocks(W, T, lo, lo + kSlowBlocks < nblk ? lo + kSlowBlocks : nblk, (lo + lane) % bpm, jb, bpm, 0u, 0u, fits);
         bits += tg;
         // running last-7-bits of the tile (a group may hold fewer than 7)
         tail = tg >= 7u ? tail_bits(W.region, tg) : (((tail << tg) | peek_bits(W.region, 0u, tg)) & 0x7fu);
@@ -331,7 +351,7 @@ JG_DEV_NOINLINE bool ent_tile_slow(const LaunchParams& P, EntWarp& W, const EntT
         const int hi = lo + kSlowBlocks < nblk ? lo + kSlowBlocks : nblk;
         warp_sync();
         clear_region(W.region, kEntRegionWords + 8);
-        unsigned tg = code_blocks(W, T, lo, hi, (lo + lane) % bpm, jb, bpm, fits);
+        unsigned tg = code_blocks(W, T, lo, hi, (lo + lane) % bpm, jb, bpm, 0u, 0u, fits);
         if (pad && hi == nblk) {
             if (lane == 0) set_ones(W.region, tg, pad);
             warp_sync();
@@ -432,7 +452,8 @@ void entropy_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTAN
             if (lane < nblk) P.dbg_bits[P.images[img_idx].first_block + (unsigned long long)(b0 + lane)] = nb;
         }
         bool fits;
-        unsigned bits = code_blocks(W, T, 0, nblk, lane_j, jb, bpm, fits);
+        unsigned bits = code_tile(W, T, nblk, lane_j, jb, bpm, fits);
+        if (P.win_words < kWinWordsMax && bits > 32u * (unsigned)P.win_words) fits = false;   // parity tests: force the slow path
         if (fits) {
             // Publish the tile's bit count and last bits NOW: they are consumed (by us and by every successor)
             // one iteration later.

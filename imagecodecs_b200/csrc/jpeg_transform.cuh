@@ -49,7 +49,7 @@ struct TSmem { TWarp<LAYOUT> wm[kWarps]; };
 
 struct TLane {
     float pq_l[8], pq_c[8];      // reciprocal quantisers of column u = lane & 7: [v] = pqt[8v+u]
-    int zz[8];                   // zigzag position of (v, u)
+    unsigned zz2[8];             // byte offset of (v, u) inside a zigzag-ordered block
 };
 
 // (v*pq + 1024) + 0.5, floor, - 1024 (jpeg_enc.h:808-816) for a pair; the results are the LOW 16 BITS of kx / ky.
@@ -100,125 +100,151 @@ JG_DEV void rgb_pair(const uint32_t* wa, const uint32_t* wb, int ia, int ib, f32
 #endif
 }
 
+// Shared-memory addresses (32-bit, see jpeg_device.h) a lane works with: fixed for the whole kernel
+struct TAddr {
+    unsigned xch;        // the lane group's exchange space
+    unsigned stage;      // the warp's staging area
+};
+
 // copy `nblk` staged blocks (kCoefStride apart) to global memory, 16 bytes per lane and step
 template <int MAXBLK>
-JG_DEV void stage_to_global(const int16_t* stage, int16_t* gout, int nblk)
+JG_DEV void stage_to_global(unsigned stage, int16_t* gout, int nblk)
 {
     const int t = JG_TID & 31;
 #pragma unroll
     for (int q = 0; q < (MAXBLK * 8 + 31) / 32; ++q) {
         const int c = q * 32 + t, blk = c >> 3, part = c & 7;
-        if (blk < nblk) {
-            const uint4 v = *reinterpret_cast<const uint4*>(stage + blk * kCoefStride + part * 8);
-            *reinterpret_cast<uint4*>(gout + blk * 64 + part * 8) = v;
+        if (blk < nblk) *reinterpret_cast<uint4*>(gout + blk * 64 + part * 8) = lds_v4(stage + (unsigned)(blk * kCoefStride + part * 8) * 2u);
+    }
+}
+
+// The pixels one lane needs for one iteration, as loaded words.  They are fetched ONE ITERATION AHEAD (right after the
+// previous iteration has turned its own pixels into floats), so the global-memory latency runs under the row and column
+// passes instead of in front of them.
+template <int LAYOUT, int NC>
+struct TPixels {
+    static constexpr int WORDS = LAYOUT == LAYOUT_420 ? 16 * NC / 4 : (LAYOUT == LAYOUT_444 ? 8 * NC / 4 : 2);
+    uint32_t a[WORDS];          // 4:2:0: the lane's 16-pixel row; 4:4:4 / gray: its row of MCU (block) A
+    uint32_t b[LAYOUT == LAYOUT_420 ? 1 : WORDS];   // 4:4:4 / gray: its row of MCU (block) B
+};
+
+template <int LAYOUT, int NC>
+JG_DEV void fetch_pixels(const ImageDesc& im, int my0, int mx0, int nM, TPixels<LAYOUT, NC>& px)
+{
+    const int t = JG_TID & 31, u = t & 7;
+#pragma unroll
+    for (int i = 0; i < TPixels<LAYOUT, NC>::WORDS; ++i) px.a[i] = 0u;
+    if (LAYOUT == LAYOUT_420) {
+        const int grp = t >> 4, r16 = t & 15;
+        if (grp < nM) {
+            int my, mx;
+            mcu_pos(im, my0, mx0, grp, my, mx);
+            int y = my * 16 + r16; if (y >= im.h) y = im.h - 1;            // replicate the last row (jpeg_enc.h:1106-1111)
+            load_segment<NC, 16>(im, mx * 16, y, reinterpret_cast<uint32_t (&)[16 * NC / 4]>(px.a));
+        }
+    } else {
+        constexpr int C = LAYOUT == LAYOUT_444 ? NC : 1;
+        const int g = t >> 3;
+        const int sa = LAYOUT == LAYOUT_444 ? g : 2 * g, sb = LAYOUT == LAYOUT_444 ? g + 4 : 2 * g + 1;   // the lane group's two MCUs / blocks
+#pragma unroll
+        for (int i = 0; i < TPixels<LAYOUT, NC>::WORDS; ++i) px.b[i] = 0u;
+        if (sa < nM) {
+            int my, mx;
+            mcu_pos(im, my0, mx0, sa, my, mx);
+            int y = my * 8 + u; if (y >= im.h) y = im.h - 1;
+            load_segment<C, 8>(im, mx * 8, y, reinterpret_cast<uint32_t (&)[8 * C / 4]>(px.a));
+        }
+        if (sb < nM) {
+            int my, mx;
+            mcu_pos(im, my0, mx0, sb, my, mx);
+            int y = my * 8 + u; if (y >= im.h) y = im.h - 1;
+            load_segment<C, 8>(im, mx * 8, y, reinterpret_cast<uint32_t (&)[8 * C / 4]>(px.b));
         }
     }
 }
 
 // ---- 4:4:4: eight MCUs per iteration, lane group g owns MCUs g and g + 4 -----------------------------------------
-template <int NC>
-JG_DEV void transform_iter_444(TWarp<LAYOUT_444>& W, const ImageDesc& im, int my0, int mx0, int nM, int16_t* gout, const TLane& LC)
+template <int NC, class Prefetch>
+JG_DEV void transform_iter_444(const TAddr& A, const TPixels<LAYOUT_444, NC>& px, int nM, int16_t* gout, const TLane& LC, Prefetch&& prefetch)
 {
     const int t = JG_TID & 31, u = t & 7, g = t >> 3;
-    f32x2* xt = reinterpret_cast<f32x2*>(W.xch) + g * (3 * kTileFloats);
-    const bool vA = g < nM, vB = g + 4 < nM;
-    uint32_t wA[8 * NC / 4], wB[8 * NC / 4];
-#pragma unroll
-    for (int i = 0; i < 8 * NC / 4; ++i) { wA[i] = 0u; wB[i] = 0u; }
-    if (vA) {
-        int my, mx;
-        mcu_pos(im, my0, mx0, g, my, mx);
-        int y = my * 8 + u; if (y >= im.h) y = im.h - 1;               // replicate the last row (jpeg_enc.h:1106-1111)
-        load_segment<NC, 8>(im, mx * 8, y, wA);
-    }
-    if (vB) {
-        int my, mx;
-        mcu_pos(im, my0, mx0, g + 4, my, mx);
-        int y = my * 8 + u; if (y >= im.h) y = im.h - 1;
-        load_segment<NC, 8>(im, mx * 8, y, wB);
-    }
     f32x2 sy[8], sb[8], sr[8];       // .x = MCU A, .y = MCU B
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         f32x2 R, Gc, B;
-        rgb_pair<NC>(wA, wB, i, i, R, Gc, B);
+        rgb_pair<NC>(px.a, px.b, i, i, R, Gc, B);
         // jpeg_enc.h:1118-1120, additions packed over the two MCUs
         sy[i] = f2_sub(f2_add(f2_add(f2_mul(f2(0.299f, 0.299f), R), f2_mul(f2(0.587f, 0.587f), Gc)), f2_mul(f2(0.114f, 0.114f), B)),
                        f2(128.0f, 128.0f));
         sb[i] = f2_add(f2_sub(f2_mul(f2(-0.1687f, -0.1687f), R), f2_mul(f2(0.3313f, 0.3313f), Gc)), f2_mul(f2(0.5f, 0.5f), B));
         sr[i] = f2_sub(f2_sub(f2_mul(f2(0.5f, 0.5f), R), f2_mul(f2(0.4187f, 0.4187f), Gc)), f2_mul(f2(0.0813f, 0.0813f), B));
     }
+    prefetch();                       // the pixel registers are free: the next iteration's loads go out now
+    const unsigned row = A.xch + (unsigned)(u * 9) * 8u;
     aan8x2(sy);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) xt[u * 9 + i] = sy[i];
+    for (int i = 0; i < 8; ++i) sts_v2f(row + 8u * i, sy[i]);
     aan8x2(sb);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) xt[kTileFloats + u * 9 + i] = sb[i];
+    for (int i = 0; i < 8; ++i) sts_v2f(row + 8u * (kTileFloats + i), sb[i]);
     aan8x2(sr);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) xt[2 * kTileFloats + u * 9 + i] = sr[i];
+    for (int i = 0; i < 8; ++i) sts_v2f(row + 8u * (2 * kTileFloats + i), sr[i]);
     warp_sync();
+    const unsigned colA = A.xch + 8u * (unsigned)u;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         f32x2 col[8];
 #pragma unroll
-        for (int v = 0; v < 8; ++v) col[v] = xt[c * kTileFloats + v * 9 + u];
+        for (int v = 0; v < 8; ++v) col[v] = lds_v2f(colA + 8u * (unsigned)(c * kTileFloats + v * 9));
         aan8x2(col);
-        int16_t* dA = W.stage + (g * 3 + c) * kCoefStride;
-        int16_t* dB = W.stage + ((g + 4) * 3 + c) * kCoefStride;
+        const unsigned dA = A.stage + 2u * (unsigned)((g * 3 + c) * kCoefStride), dB = A.stage + 2u * (unsigned)(((g + 4) * 3 + c) * kCoefStride);
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
             unsigned ka, kb;
             quantise2(col[v], c ? LC.pq_c[v] : LC.pq_l[v], ka, kb);
-            dA[LC.zz[v]] = (int16_t)ka;
-            dB[LC.zz[v]] = (int16_t)kb;     // (an absent MCU B computes on zeros into its own staging slot, never copied out)
+            sts_u16(dA + LC.zz2[v], ka);
+            sts_u16(dB + LC.zz2[v], kb);   // (an absent MCU B computes on zeros into its own staging slot, never copied out)
         }
     }
     warp_sync();
-    stage_to_global<24>(W.stage, gout, nM * 3);
+    stage_to_global<24>(A.stage, gout, nM * 3);
 }
 
 // ---- 4:2:0: two MCUs per iteration, 16 lanes per MCU, lane r16 owns pixel row r16 ---------------------------------
-template <int NC>
-JG_DEV void transform_iter_420(TWarp<LAYOUT_420>& W, const ImageDesc& im, int my0, int mx0, int nM, int16_t* gout, const TLane& LC)
+template <int NC, class Prefetch>
+JG_DEV void transform_iter_420(const TAddr& A, const TPixels<LAYOUT_420, NC>& px, int nM, int16_t* gout, const TLane& LC, Prefetch&& prefetch)
 {
     const int t = JG_TID & 31, u = t & 7, grp = t >> 4, r16 = t & 15, h = r16 >> 3;
-    float* base = W.xch + grp * (6 * kTileFloats);
-    f32x2* ypair = reinterpret_cast<f32x2*>(base);           // pair tile 0: (Y00, Y01), pair tile 1: (Y10, Y11)
-    float* ctile = base + 4 * kTileFloats;                   // Cb tile, Cr tile
+    const unsigned ypair = A.xch;                                    // pair tile 0: (Y00, Y01), pair tile 1: (Y10, Y11)
+    const unsigned ctile = A.xch + 4u * (4 * kTileFloats);           // Cb tile, Cr tile
     const bool valid = grp < nM;
     f32x2 cbs[4], crs[4];            // horizontal pair sums (a+b) of this row: .x samples 0-3, .y samples 4-7
+    f32x2 sy[8];                     // .x = pixel i (left luma block), .y = pixel i + 8 (right luma block)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { cbs[i] = f2(0.0f, 0.0f); crs[i] = f2(0.0f, 0.0f); }
-    if (valid) {
-        int my, mx;
-        mcu_pos(im, my0, mx0, grp, my, mx);
-        int y = my * 16 + r16; if (y >= im.h) y = im.h - 1;
-        uint32_t w[16 * NC / 4];
-        load_segment<NC, 16>(im, mx * 16, y, w);
-        f32x2 sy[8];                 // .x = pixel i (left luma block), .y = pixel i + 8 (right luma block)
+    for (int j = 0; j < 4; ++j) {
+        f32x2 cb[2], cr[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            f32x2 cb[2], cr[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int i = 2 * j + e;
-                f32x2 R, Gc, B;
-                rgb_pair<NC>(w, w, i, i + 8, R, Gc, B);
-                sy[i] = f2_sub(f2_add(f2_add(f2_mul(f2(0.299f, 0.299f), R), f2_mul(f2(0.587f, 0.587f), Gc)),
-                                      f2_mul(f2(0.114f, 0.114f), B)), f2(128.0f, 128.0f));
-                cb[e] = f2_add(f2_sub(f2_mul(f2(-0.1687f, -0.1687f), R), f2_mul(f2(0.3313f, 0.3313f), Gc)),
-                               f2_mul(f2(0.5f, 0.5f), B));
-                cr[e] = f2_sub(f2_sub(f2_mul(f2(0.5f, 0.5f), R), f2_mul(f2(0.4187f, 0.4187f), Gc)),
-                               f2_mul(f2(0.0813f, 0.0813f), B));
-            }
-            cbs[j] = f2_add(cb[0], cb[1]);
-            crs[j] = f2_add(cr[0], cr[1]);
+        for (int e = 0; e < 2; ++e) {
+            const int i = 2 * j + e;
+            f32x2 R, Gc, B;
+            rgb_pair<NC>(px.a, px.a, i, i + 8, R, Gc, B);
+            sy[i] = f2_sub(f2_add(f2_add(f2_mul(f2(0.299f, 0.299f), R), f2_mul(f2(0.587f, 0.587f), Gc)),
+                                  f2_mul(f2(0.114f, 0.114f), B)), f2(128.0f, 128.0f));
+            cb[e] = f2_add(f2_sub(f2_mul(f2(-0.1687f, -0.1687f), R), f2_mul(f2(0.3313f, 0.3313f), Gc)),
+                           f2_mul(f2(0.5f, 0.5f), B));
+            cr[e] = f2_sub(f2_sub(f2_mul(f2(0.5f, 0.5f), R), f2_mul(f2(0.4187f, 0.4187f), Gc)),
+                           f2_mul(f2(0.0813f, 0.0813f), B));
         }
-        aan8x2(sy);
-        f32x2* ty = ypair + h * kTileFloats + (r16 & 7) * 9;
+        cbs[j] = f2_add(cb[0], cb[1]);
+        crs[j] = f2_add(cr[0], cr[1]);
+    }
+    prefetch();                       // the pixel registers are free: the next iteration's loads go out now
+    aan8x2(sy);
+    if (valid) {
+        const unsigned ty = ypair + 8u * (unsigned)(h * kTileFloats + (r16 & 7) * 9);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ty[i] = sy[i];
+        for (int i = 0; i < 8; ++i) sts_v2f(ty + 8u * i, sy[i]);
     }
     // vertical pairs live in neighbouring lanes: the even lane finishes Cb, the odd lane Cr;
     // sample = ((a+b) + (c+d)) * 0.25f with (a+b) from the even row (extended mode); the addition commutes
@@ -231,88 +257,79 @@ JG_DEV void transform_iter_420(TWarp<LAYOUT_420>& W, const ImageDesc& im, int my
         const f32x2 q = f2_mul(f2_add(mine, other), f2(0.25f, 0.25f));
         samp[i] = q.x; samp[4 + i] = q.y;
     }
-    if (valid) row_pass_store(samp, ctile + (r16 & 1) * kTileFloats, r16 >> 1);
+    aan8(samp);
+    if (valid) {
+        const unsigned tc = ctile + 4u * (unsigned)((r16 & 1) * kTileFloats + (r16 >> 1) * 9);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sts_f32(tc + 4u * i, samp[i]);
+    }
     warp_sync();
     if (valid) {
         // lanes 0-7 finish (Y00, Y01) and Cb, lanes 8-15 (Y10, Y11) and Cr
         f32x2 col[8];
 #pragma unroll
-        for (int v = 0; v < 8; ++v) col[v] = ypair[h * kTileFloats + v * 9 + u];
+        for (int v = 0; v < 8; ++v) col[v] = lds_v2f(ypair + 8u * (unsigned)(h * kTileFloats + v * 9 + u));
         aan8x2(col);
-        int16_t* dL = W.stage + (grp * 6 + 2 * h) * kCoefStride;
-        int16_t* dR = dL + kCoefStride;
+        const unsigned dL = A.stage + 2u * (unsigned)((grp * 6 + 2 * h) * kCoefStride), dR = dL + 2u * kCoefStride;
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
             unsigned kl, kr;
             quantise2(col[v], LC.pq_l[v], kl, kr);
-            dL[LC.zz[v]] = (int16_t)kl;
-            dR[LC.zz[v]] = (int16_t)kr;
+            sts_u16(dL + LC.zz2[v], kl);
+            sts_u16(dR + LC.zz2[v], kr);
         }
         float c[8];
 #pragma unroll
-        for (int v = 0; v < 8; ++v) c[v] = ctile[h * kTileFloats + v * 9 + u];
+        for (int v = 0; v < 8; ++v) c[v] = lds_f32(ctile + 4u * (unsigned)(h * kTileFloats + v * 9 + u));
         aan8(c);
-        int16_t* dC = W.stage + (grp * 6 + 4 + h) * kCoefStride;
+        const unsigned dC = A.stage + 2u * (unsigned)((grp * 6 + 4 + h) * kCoefStride);
 #pragma unroll
-        for (int v = 0; v < 8; ++v) dC[LC.zz[v]] = (int16_t)quantise1(c[v], LC.pq_c[v]);
+        for (int v = 0; v < 8; ++v) sts_u16(dC + LC.zz2[v], quantise1(c[v], LC.pq_c[v]));
     }
     warp_sync();
-    stage_to_global<12>(W.stage, gout, nM * 6);
+    stage_to_global<12>(A.stage, gout, nM * 6);
 }
 
 // ---- gray: eight blocks per iteration, lane group g owns blocks 2g and 2g + 1 ------------------------------------
-JG_DEV void transform_iter_gray(TWarp<LAYOUT_GRAY>& W, const ImageDesc& im, int my0, int mx0, int nM, int16_t* gout, const TLane& LC)
+template <class Prefetch>
+JG_DEV void transform_iter_gray(const TAddr& A, const TPixels<LAYOUT_GRAY, 1>& px, int nM, int16_t* gout, const TLane& LC, Prefetch&& prefetch)
 {
     const int t = JG_TID & 31, u = t & 7, g = t >> 3;
-    f32x2* xt = reinterpret_cast<f32x2*>(W.xch) + g * kTileFloats;
-    const bool vA = 2 * g < nM, vB = 2 * g + 1 < nM;
-    uint32_t wA[2] = {0u, 0u}, wB[2] = {0u, 0u};
-    if (vA) {
-        int my, mx;
-        mcu_pos(im, my0, mx0, 2 * g, my, mx);
-        int y = my * 8 + u; if (y >= im.h) y = im.h - 1;
-        load_segment<1, 8>(im, mx * 8, y, wA);
-    }
-    if (vB) {
-        int my, mx;
-        mcu_pos(im, my0, mx0, 2 * g + 1, my, mx);
-        int y = my * 8 + u; if (y >= im.h) y = im.h - 1;
-        load_segment<1, 8>(im, mx * 8, y, wB);
-    }
     f32x2 s[8];
-#pragma unroll
 #if JG_U8_VIA_PRMT
+#pragma unroll
     for (int i = 0; i < 8; ++i)
-        s[i] = f2_sub(f2_sub(f2(u8_biased(wA[i >> 2], i & 3), u8_biased(wB[i >> 2], i & 3)), f2(kU8Bias, kU8Bias)), f2(128.0f, 128.0f));
+        s[i] = f2_sub(f2_sub(f2(u8_biased(px.a[i >> 2], i & 3), u8_biased(px.b[i >> 2], i & 3)), f2(kU8Bias, kU8Bias)), f2(128.0f, 128.0f));
 #else
-    for (int i = 0; i < 8; ++i) s[i] = f2_sub(f2(u8_to_f(byte_of(wA, i)), u8_to_f(byte_of(wB, i))), f2(128.0f, 128.0f));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = f2_sub(f2(u8_to_f(byte_of(px.a, i)), u8_to_f(byte_of(px.b, i))), f2(128.0f, 128.0f));
 #endif
+    prefetch();
     aan8x2(s);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) xt[u * 9 + i] = s[i];
+    for (int i = 0; i < 8; ++i) sts_v2f(A.xch + 8u * (unsigned)(u * 9 + i), s[i]);
     warp_sync();
     f32x2 col[8];
 #pragma unroll
-    for (int v = 0; v < 8; ++v) col[v] = xt[v * 9 + u];
+    for (int v = 0; v < 8; ++v) col[v] = lds_v2f(A.xch + 8u * (unsigned)(v * 9 + u));
     aan8x2(col);
-    int16_t* dA = W.stage + (2 * g) * kCoefStride;
-    int16_t* dB = dA + kCoefStride;
+    const unsigned dA = A.stage + 2u * (unsigned)((2 * g) * kCoefStride), dB = dA + 2u * kCoefStride;
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
         unsigned ka, kb;
         quantise2(col[v], LC.pq_l[v], ka, kb);
-        dA[LC.zz[v]] = (int16_t)ka;
-        dB[LC.zz[v]] = (int16_t)kb;
+        sts_u16(dA + LC.zz2[v], ka);
+        sts_u16(dB + LC.zz2[v], kb);
     }
     warp_sync();
-    stage_to_global<8>(W.stage, gout, nM);
+    stage_to_global<8>(A.stage, gout, nM);
 }
 
 // ------------------------------------------------------------------------------------------
 // kernel A: one warp per item (ITEM_MCUS consecutive MCUs of one image)
 // ------------------------------------------------------------------------------------------
 #ifndef JG_TR_MINB
-#define JG_TR_MINB 5          // resident CTAs per SM the register allocation aims at (variant builds: tools/build_variants.py)
+#define JG_TR_MINB 4          // resident CTAs per SM the register allocation aims at (variant builds: tools/build_variants.py)
 #endif
 template <int LAYOUT, int NC>
 JG_KERNEL(kThreads, JG_TR_MINB)
@@ -331,7 +348,7 @@ void transform_kernel(const JG_GRID_CONSTANT TransformParams P, const JG_GRID_CO
         for (int v = 0; v < 8; ++v) {
             LC.pq_l[v] = Q.luma[8 * v + u];
             LC.pq_c[v] = Q.chroma[8 * v + u];
-            LC.zz[v] = zz_of(8 * v + u);
+            LC.zz2[v] = 2u * (unsigned)zz_of(8 * v + u);
         }
     }
     unsigned img, local;
@@ -349,19 +366,31 @@ void transform_kernel(const JG_GRID_CONSTANT TransformParams P, const JG_GRID_CO
     }
     const ImageDesc im = P.images[img];
     TWarp<LAYOUT>& W = S.wm[t >> 5];
+    TAddr A;
+    A.xch = smem_addr(W.xch) + 4u * (unsigned)(((t & 31) / (32 / G::GROUPS)) * G::GROUP_FLOATS);
+    A.stage = smem_addr(W.stage);
     const int m_begin = (int)local * G::ITEM_MCUS;
     const int m_end = (im.n_mcus - m_begin < G::ITEM_MCUS) ? im.n_mcus : m_begin + G::ITEM_MCUS;
     int16_t* gout = P.coefs + (im.first_block + (unsigned long long)m_begin * G::BPM) * 64ull;
     int my0 = m_begin / im.mcus_x, mx0 = m_begin - my0 * im.mcus_x;
+    TPixels<LAYOUT, NC> px;
+    fetch_pixels<LAYOUT, NC>(im, my0, mx0, m_end - m_begin < G::ITER_MCUS ? m_end - m_begin : G::ITER_MCUS, px);
 #pragma unroll 1
     for (int m0 = m_begin; m0 < m_end; m0 += G::ITER_MCUS) {
         const int nM = m_end - m0 < G::ITER_MCUS ? m_end - m0 : G::ITER_MCUS;
-        if (LAYOUT == LAYOUT_444) transform_iter_444<NC>(reinterpret_cast<TWarp<LAYOUT_444>&>(W), im, my0, mx0, nM, gout, LC);
-        else if (LAYOUT == LAYOUT_420) transform_iter_420<NC>(reinterpret_cast<TWarp<LAYOUT_420>&>(W), im, my0, mx0, nM, gout, LC);
-        else transform_iter_gray(reinterpret_cast<TWarp<LAYOUT_GRAY>&>(W), im, my0, mx0, nM, gout, LC);
+        // position and size of the NEXT iteration, whose pixels are requested in the middle of this one
+        int mx1 = mx0 + G::ITER_MCUS, my1 = my0;
+        while (mx1 >= im.mcus_x) { mx1 -= im.mcus_x; ++my1; }
+        const int left = m_end - m0 - G::ITER_MCUS;
+        const int nM1 = left < 0 ? 0 : (left < G::ITER_MCUS ? left : G::ITER_MCUS);
+        TPixels<LAYOUT, NC> nx;
+        auto prefetch = [&]() { fetch_pixels<LAYOUT, NC>(im, my1, mx1, nM1, nx); };
+        if constexpr (LAYOUT == LAYOUT_444) transform_iter_444<NC>(A, px, nM, gout, LC, prefetch);
+        else if constexpr (LAYOUT == LAYOUT_420) transform_iter_420<NC>(A, px, nM, gout, LC, prefetch);
+        else transform_iter_gray(A, px, nM, gout, LC, prefetch);
+        px = nx;
         gout += G::ITER_BLOCKS * 64;
-        mx0 += G::ITER_MCUS;
-        while (mx0 >= im.mcus_x) { mx0 -= im.mcus_x; ++my0; }
+        mx0 = mx1; my0 = my1;
     }
 }
 

@@ -171,7 +171,6 @@ int emu_encode_split(const uint8_t* pixels, int n_images, int w, int h, int ncom
                      uint8_t* scan_out, size_t scan_cap, unsigned long long* scan_bytes, unsigned* img_status,
                      int16_t* dbg_coefs, uint32_t* dbg_bits)
 {
-    (void)win_words;
     const int layout = ncomp == 1 ? LAYOUT_GRAY : (subsampling ? LAYOUT_420 : LAYOUT_444);
     uint8_t ql[64], qc[64];
     if (!build_qt(quality_mode, quality, ql, qc)) return -1;
@@ -248,7 +247,7 @@ int emu_encode_split(const uint8_t* pixels, int n_images, int w, int h, int ncom
     std::vector<uint32_t> sched(schedule_words(n_images));
     build_schedule(counts.data(), n_images, sched.data());
     P.sched = sched.data();
-    P.win_words = kWinWordsMax;
+    P.win_words = win_words ? win_words : kWinWordsMax;      // a small value sends every tile with more bits the slow way
     P.ticket = &ticket; P.ticket2 = &ticket2; P.error = &error;
     P.desc_bits = desc_bits.data(); P.desc_ff = desc_ff.data(); P.desc_dc = nullptr;
     P.raw_bytes = raw_bytes.data(); P.first_chunk = first_chunk.data();

@@ -16,6 +16,8 @@ CASES = [
     ("unaligned pitch (byte loader)", (1, 131, 67, 3, "photo"), 0, 3, 0, 0, 2),
     ("noise: dense symbols, many 0xFF", (1, 96, 96, 3, "noise"), 0, 3, 0, 0, 2),
     ("forced tiny window: multi-group tiles", (1, 96, 64, 3, "noise"), 0, 3, 0, 64, 2),
+    ("forced tiny window, sparse 4:2:0 (short last groups)", (2, 104, 56, 3, "photo"), 1, 50, 1, 8, 2),
+    ("forced tiny window, gray", (1, 72, 40, 1, "photo"), 1, 85, 0, 4, 1),
     ("4:2:0 q75", (2, 120, 72, 3, "photo"), 1, 75, 1, 0, 2),
     ("4:2:0 edge + rgba", (1, 33, 47, 4, "photo"), 1, 90, 1, 0, 2),
     ("gray q85", (2, 200, 130, 1, "photo"), 1, 85, 0, 0, 2),
