@@ -143,6 +143,8 @@ JG_DEV uint4 lds_v4(unsigned a)
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
+// a value the compiler must keep in a register instead of recomputing it where it is used (shared-memory addresses in hot loops)
+JG_DEV unsigned pinned(unsigned v) { unsigned r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
 JG_DEV void mbar_init(unsigned long long* bar, unsigned arrivals)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals) : "memory");

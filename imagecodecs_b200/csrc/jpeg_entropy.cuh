@@ -42,26 +42,31 @@ namespace jg {
 constexpr int kEntBlocks = 32;                              // blocks per tile at most: one per lane in the map phase
 constexpr int kEntCoefStride = 72;                          // int16 per staged block: 144-byte rows (the TMA box is 72 wide over a 64-wide tensor,
                                                             // the out-of-bounds columns arrive as zeros) keep 32 lanes off each other's banks
-constexpr int kSubWords = 20;                               // words of a lane's private stream (640 bits)
-constexpr int kEntRegionWords = 1024;                       // a tile's merged bits on the fast path: 32768 at most
-constexpr int kSlowBlocks = 4;                              // slow path: 4 blocks at a time (<= 256 symbols, <= 8 x 59 bits per lane)
-constexpr int kEntModePlain = 0, kEntModeRestart = 2;
+constexpr int kSubWords = 16;                               // words of a lane's private stream (512 bits)
+constexpr int kEntRegionWords = 768;                        // a tile's merged bits on the fast path: 24576 at most
+constexpr int kListMax = 1024;                              // symbols coded in one go (a tile with more is coded in two halves)
+constexpr int kSlowBlocks = 4;                              // slow path: 4 blocks at a time (<= 256 symbols, <= 8 x 59 bits per lane: always fit)
+constexpr int kEntModePlain = 0, kEntModeRestart = 2;      // + 1: deferred write-out (launches with few images)
 constexpr unsigned kEntStageBytes = kEntBlocks * kEntCoefStride * 2;   // what one TMA box delivers (out-of-bounds rows count)
 // list entry: bits 0-5 zigzag position, 6-10 block of the tile, 11-15 the symbol's Huffman table as a multiple of 128 bytes
 constexpr unsigned kEntryBlockPos = 0x7ffu;
-constexpr unsigned kTabDc = 0u, kTabAc = 2u, kTabChroma = 1u, kTabAcChroma = 16u;   // luma DC 0, chroma DC 1, luma AC 2, chroma AC 18
+constexpr unsigned kTabRunBytes = 136u, kTabAcBytes = 16u * kTabRunBytes;    // see EntTables
+constexpr unsigned kTabDc = 0u, kTabAc = 2u, kTabChroma = 1u, kTabAcChroma = kTabAcBytes / 128u;   // luma DC 0, chroma DC 1, luma AC 2, chroma AC 19
+static_assert(kTabAcBytes % 128u == 0u, "table offsets are multiples of 128 bytes");
 
 struct EntWarp {
     alignas(128) int16_t coef[kEntBlocks * kEntCoefStride];  // TMA destination
     alignas(16) uint32_t sub[kEntBlocks * kSubWords];        // word k of lane l at [k * 32 + l] (conflict-free)
     alignas(16) uint32_t region[kEntRegionWords + 8];        // the tile's merged bits (MSB-first words); survives into the next iteration
-    uint2 mask[kEntBlocks];                                  // symbol maps of the staged blocks
+    alignas(16) uint16_t list[kListMax];                     // the symbols being coded, in scan order
     alignas(8) unsigned long long mbar;                      // completion of the staged coefficients
     Pending pend[2];
 };
-// Huffman tables as the symbol loop wants them: entry [(run << 4) | category] = {code, length + category}; the two DC
-// tables (16 entries, run 0) at byte 0 and 128, the two AC tables (256 entries) at byte 256 and 2304
-struct EntTables { uint2 e[32 + 512]; };
+// Huffman tables as the symbol loop wants them: entry (run, category) = {code, length + category} at byte 136 * run +
+// 8 * category of its table -- 17 entries per run, so that symbols of one category and different runs do not share a bank
+// (with 16 the bank depended on the category alone: 9.5 wavefronts per lookup, measured).  The two DC tables (run 0) at
+// byte 0 and 128, the two AC tables (16 runs x 136 bytes) at byte 256 and 2432.
+struct EntTables { uint2 e[(256 + 2 * kTabAcBytes) / 8]; };
 struct EntSmem {
     EntWarp wm[kEntWarps];
     EntTables tab;
@@ -84,9 +89,9 @@ JG_DEV unsigned nonzero8(uint4 v)
     return (a | (a >> 15)) & 0xffu;
 }
 
-// Map phase, lane = block `slot` of the staged tile (active: slot < nblk): the block's symbol map goes to W.mask[slot], its
+// Map phase, lane = block `slot` of the staged tile (active: slot < nblk): returns the block's symbol map (zero if inactive); its
 // DC difference REPLACES the DC in the staged block (after every lane has read its predictor: the warp barrier inside).
-JG_DEV void map_block(EntWarp& W, int slot, int slot_j, int nblk, int jb, int bpm, int b0, int pred_outside, bool restart)
+JG_DEV uint2 map_block(EntWarp& W, int slot, int slot_j, int nblk, int jb, int bpm, int b0, int pred_outside, bool restart)
 {
     const bool active = slot < nblk;
     int16_t* cz = W.coef + slot * kEntCoefStride;
@@ -114,27 +119,36 @@ JG_DEV void map_block(EntWarp& W, int slot, int slot_j, int nblk, int jb, int bp
     if (active) cz[0] = (int16_t)diff;
     fence_proxy_async();               // ... a generic store into the TMA's destination: ordered before the next tile's copy
     uint2 m; m.x = mlo; m.y = mhi;
-    W.mask[slot] = m;
     warp_sync();
+    return m;
 }
 
-// List phase: the lane appends the symbols of block `slot` (map m, class cls) at list[at...], in scan order.
-JG_DEV void list_block(uint16_t* list, unsigned at, int slot, uint2 m, unsigned cls)
+// List phase: the lane appends the symbols of one half (word = 0: positions 0..31, 1: positions 32..63) or of both halves
+// (word = 2) of block `slot` (map m, class cls) at shared address `la`, in scan order.
+JG_DEV void list_block(unsigned la, int slot, uint2 m, unsigned cls, int word)
 {
-    uint16_t* lp = list + at;
     const unsigned blk = (unsigned)slot << 6;
-    const unsigned dc = blk | ((kTabDc + (cls ? kTabChroma : 0u)) << 11), ac = blk | ((kTabAc + (cls ? kTabAcChroma : 0u)) << 11);
+    const unsigned ac = blk | ((kTabAc + (cls ? kTabAcChroma : 0u)) << 11);
+    // bit-reversed maps: the next position is 31 - (index of the highest set bit)
+    if (word != 1) {
+        sts_u16(la, blk | ((kTabDc + (cls ? kTabChroma : 0u)) << 11));      // position 0: the DC difference, always there
+        la += 2u;
 #pragma unroll 1
-    for (unsigned w = bit_reverse(m.x); w;) {                        // bit-reversed map: the next position is a clz
-        const unsigned p = (unsigned)i_clz(w);
-        w &= ~(0x80000000u >> p);
-        *lp++ = (uint16_t)((p ? ac : dc) | p);
+        for (unsigned w = bit_reverse(m.x & ~1u); w;) {
+            const unsigned f = 31u - (unsigned)i_clz(w);
+            sts_u16(la, ac + 31u - f);
+            la += 2u;
+            w &= ~(1u << f);
+        }
     }
+    if (word != 0) {
 #pragma unroll 1
-    for (unsigned w = bit_reverse(m.y); w;) {
-        const unsigned p = (unsigned)i_clz(w);
-        w &= ~(0x80000000u >> p);
-        *lp++ = (uint16_t)(ac | 32u | p);
+        for (unsigned w = bit_reverse(m.y); w;) {
+            const unsigned f = 31u - (unsigned)i_clz(w);
+            sts_u16(la, ac + 63u - f);
+            la += 2u;
+            w &= ~(1u << f);
+        }
     }
 }
 
@@ -157,29 +171,52 @@ JG_DEV unsigned code_symbols(const EntTables& T, const int16_t* coef, const uint
         }
         t = t2;
     };
-    const unsigned tabs = smem_addr(&T.e[0]), cz = smem_addr(coef);
+    const unsigned tabs = pinned(smem_addr(&T.e[0])), cz = pinned(smem_addr(coef));
     unsigned la = smem_addr(list) + 2u * s0;
     unsigned tp = s0 ? (lds_u16(la - 2u) & kEntryBlockPos) : 0xffffu;   // block | position of the symbol before mine
-#pragma unroll 1
-    for (unsigned i = 0; i < n; ++i, la += 2u) {
-        const unsigned e = lds_u16(la);
+    auto coef_of = [&](unsigned e) { return lds_s16(cz + 2u * (e & kEntryBlockPos) + (((e & kEntryBlockPos) >> 6) << 4)); };   // block * 144 + position * 2
+    // one symbol: its Huffman code + amplitude bits, the ZRL codes in front of it, its table
+    struct Sym { unsigned val, len, tb, nz; };
+    auto lookup = [&](unsigned e, int v, unsigned before, Sym& y) {
         const unsigned bp = e & kEntryBlockPos;
-        const int v = lds_s16(cz + 2u * bp + ((bp >> 6) << 4));    // block * 144 + position * 2
         // zeros since the previous symbol of the block (jpeg_enc.h:856-862); the first symbol of a block is its DC (position 0)
-        unsigned run = ((bp ^ tp) < 64u) ? bp - tp - 1u : (bp & 63u);
-        tp = bp;
+        unsigned run = ((bp ^ before) < 64u) ? bp - before - 1u : (bp & 63u);
         if (v == 0) run = 0u;                                  // the end-of-block code (and a zero DC difference): entry 0 of its table
-        const unsigned tb = tabs + ((e >> 11) << 7);           // table of the symbol
-        if (run >= 16u) {                                      // one ZRL per 16 zeros (:863-867)
-            const uint2 z = lds_u64(tb + 8u * 0xF0u);
+        y.tb = tabs + ((e >> 11) << 7);                        // table of the symbol
+        y.nz = run >> 4;                                       // one ZRL per 16 zeros (:863-867)
+        const unsigned lz = (unsigned)i_clz((unsigned)(v < 0 ? -v : v));          // category = 32 - lz (jpeg_enc.h:598-608)
+        const uint2 h = lds_u64(y.tb + 256u + (run & 15u) * kTabRunBytes - 8u * lz);   // entry (run, category): {code, length + category}
+        const unsigned x = funnel_lc(0u, (unsigned)(v + (v >> 31)), lz);           // amplitude bits (:601-609), left-aligned; none for category 0
+        y.val = funnel_rc(x, h.x, lz);                                             // (code << category) | amplitude
+        y.len = h.y;
+        return bp;
+    };
+    auto emit = [&](const Sym& y) {
+        if (y.nz) {
+            const uint2 z = lds_u64(y.tb + 15u * kTabRunBytes);
 #pragma unroll 1
-            for (unsigned k = run >> 4; k; --k) put(z.x, z.y);
-            run &= 15u;
+            for (unsigned k = y.nz; k; --k) put(z.x, z.y);
         }
-        const unsigned lz = (unsigned)i_clz((unsigned)(v < 0 ? -v : v));   // category = 32 - lz (jpeg_enc.h:598-608)
-        const uint2 h = lds_u64(tb + 256u + (run << 7) - 8u * lz);          // entry (run << 4) | category: {code, length + category}
-        const unsigned x = funnel_lc(0u, (unsigned)(v + (v >> 31)), lz);    // amplitude bits (:601-609), left-aligned; none for category 0
-        put(funnel_rc(x, h.x, lz), h.y);                                    // (code << category) | amplitude
+        put(y.val, y.len);
+    };
+    // TWO symbols per iteration: their loads, category and table lookups are independent and overlap (the loop is bound by
+    // the latency of that chain, not by issue slots); list entries and coefficients are requested one iteration ahead.
+    // (Entries after the lane's last one are read -- they lie inside the list area -- and never used.)
+    unsigned e0 = lds_u16(la), e1 = lds_u16(la + 2u);
+    int v0 = coef_of(e0), v1 = coef_of(e1);
+#pragma unroll 1
+    for (unsigned i = 0; i < n; i += 2u) {
+        la += 4u;
+        const unsigned e2 = lds_u16(la), e3 = lds_u16(la + 2u);
+        const int v2 = coef_of(e2), v3 = coef_of(e3);
+        const bool two = i + 1u < n;
+        Sym a, b;
+        const unsigned bp0 = lookup(e0, v0, tp, a);
+        tp = lookup(two ? e1 : 0u, two ? v1 : 0, bp0, b);
+        if (!two) { b.val = 0u; b.len = 0u; b.nz = 0u; }      // an odd count: nothing is appended for the missing symbol
+        emit(a);
+        emit(b);
+        e0 = e2; e1 = e3; v0 = v2; v1 = v3;
     }
     if (t & 31u) sts_u32(wa, alo << (32u - (t & 31u)));                     // the rest, left-aligned
     return t;
@@ -216,68 +253,99 @@ JG_DEV void merge_streams(const uint32_t* sub, unsigned nbits, unsigned incl, ui
     warp_sync();
 }
 
+// The tile this warp coded one iteration ago: its bits still sit in the region and leave right before the region is needed
+// again -- for the first merge of the next tile.  By then a whole map + list + code phase has passed since its size was
+// published, and the sizes of its predecessors are almost always there: the look-back does not wait.
+struct PendingOut {
+    int g = -1;          // tile (launch-wide index), -1: none
+    int slot = 0;        // its Pending record
+    bool failed = false; // the look-back timed out: the kernel gives up
+};
+JG_DEV_NOINLINE bool ent_tile_back(const LaunchParams& P, EntWarp& W, int g, int slot);
+JG_DEV void flush_pending(const LaunchParams& P, EntWarp& W, PendingOut& po)
+{
+    if (po.g < 0) return;
+    if (!ent_tile_back(P, W, po.g, po.slot)) po.failed = true;
+    po.g = -1;
+}
+
 // Blocks [lo, hi) of the staged + mapped tile -> their bits appended at bit `bit_base` of the region (zero from there on).
-// The symbol list of the blocks lives at word `list_off` of the region while they are coded (zeroed again before the
-// merge).  Lane = block lo + lane in the list phase.  Returns the bits of the blocks; `fits` = streams and total fit.
-JG_DEV unsigned code_blocks(EntWarp& W, const EntTables& T, int lo, int hi, int slot_j, int jb, int bpm, unsigned list_off,
+// List phase: with up to 16 blocks two lanes share a block (its two map words), else lane = block lo + lane.
+// Returns the bits of the blocks; `fits` = symbols, streams and total fit.
+template <bool DEFER>
+JG_DEV unsigned code_blocks(const LaunchParams& P, EntWarp& W, const EntTables& T, PendingOut& po, uint2 own, int lo, int hi, int lo_j, int jb, int bpm,
                             unsigned bit_base, bool& fits)
 {
     const int lane = JG_TID & 31;
-    const int slot = lo + lane;
+    const bool pairs = hi - lo <= 16;
+    const int slot = lo + (pairs ? lane >> 1 : lane);
     const bool mine = slot < hi;
-    uint2 m; m.x = 0; m.y = 0;
+    uint2 m;                         // the map of block `slot`: lane `slot` built it (own)
+    m.x = warp_shfl_u32(own.x, slot & 31);
+    m.y = warp_shfl_u32(own.y, slot & 31);
     unsigned cls = 0;
+    if (!mine) { m.x = 0; m.y = 0; }
     if (mine) {
-        m = W.mask[slot];
-        int j = jb + slot_j; if (j >= bpm) j -= bpm;     // slot_j = slot mod bpm
+        int j = jb + lo_j + (slot - lo); while (j >= bpm) j -= bpm;      // lo_j = lo mod bpm; (jb + slot) mod bpm
         int delta;
         block_role(bpm, j, cls, delta);
     }
-    const unsigned cnt = (unsigned)(i_popc(m.x) + i_popc(m.y));
+    const int word = pairs ? lane & 1 : 2;
+    const unsigned cnt = (unsigned)((word != 1 ? i_popc(m.x) : 0) + (word != 0 ? i_popc(m.y) : 0));
     const unsigned incl = warp_scan_incl_u32(cnt);
     const unsigned S = warp_shfl_u32(incl, 31);
-    uint16_t* list = reinterpret_cast<uint16_t*>(W.region + list_off);
-    if (mine) list_block(list, incl - cnt, slot, m, cls);
+    // The list: with the deferred write-out the region still holds the previous tile, so it has the list area to itself
+    // (1024 symbols); otherwise it starts in the free space of the region above the bits merged so far and runs on
+    // into the list area behind it (the two are contiguous)
+    static_assert(offsetof(EntWarp, list) == offsetof(EntWarp, region) + sizeof(uint32_t) * (kEntRegionWords + 8), "the list area follows the region");
+    const unsigned list_word = DEFER ? (unsigned)(kEntRegionWords + 8) : ((bit_base + 31u) >> 5) + 2u;       // first word (of the region) the list may use
+    fits = S <= 2u * ((unsigned)(kEntRegionWords + 8) - list_word) + (unsigned)kListMax;
+    if (!fits) return 0u;
+    const uint16_t* list = reinterpret_cast<const uint16_t*>(W.region + list_word);
+    if (mine) list_block(smem_addr(list) + 2u * (incl - cnt), slot, m, cls, word);
     warp_sync();
     const unsigned q = (S + 31u) >> 5;                   // symbols per lane
     const unsigned s0 = (unsigned)lane * q < S ? (unsigned)lane * q : S;
     const unsigned n = S - s0 < q ? S - s0 : q;
     const unsigned nbits = code_symbols(T, W.coef, list, s0, n, W.sub + lane);
-    warp_sync();                                         // every lane is done with the list
-    clear_words16(W.region + list_off, (S + 1u) >> 1);   // (ends with a warp barrier)
+    warp_sync();                                         // the streams are complete, every lane is done with the list
     const unsigned incl_bits = warp_scan_incl_u32(nbits);
     const unsigned bits = warp_shfl_u32(incl_bits, 31);
     fits = warp_ballot(nbits > (unsigned)kSubWords * 32u) == 0u && bit_base + bits <= (unsigned)kEntRegionWords * 32u;
+    if (DEFER) {
+        flush_pending(P, W, po);                         // the region is needed now: the previous tile leaves
+        if (po.failed) fits = false;
+    } else if (list_word < (unsigned)(kEntRegionWords + 8)) {
+        // the part of the list that lay in the region: zero again before bits are OR-ed in
+        const unsigned nw = (S + 1u) >> 1, room = (unsigned)(kEntRegionWords + 8) - list_word;
+        clear_region(W.region + list_word, nw < room ? nw : room);
+    }
     if (fits) merge_streams(W.sub, nbits, bit_base + incl_bits, W.region);
     return bits;
 }
 
-// The whole staged + mapped tile on the fast path.  A tile with many symbols is coded in two halves (16 blocks each):
-// every lane then holds half as many bits (its stream takes 640), and the second half's list sits in the upper half of
-// the region, above the first half's merged bits.
-JG_DEV unsigned code_tile(EntWarp& W, const EntTables& T, int nblk, int lane_j, int jb, int bpm, bool& fits)
+// The whole staged + mapped tile on the fast path.  A tile with more than 1024 symbols (or with a lane stream beyond 512
+// bits) is coded in two halves of 16 blocks: half the symbols and half the bits per lane.
+template <bool DEFER>
+JG_DEV unsigned code_tile(const LaunchParams& P, EntWarp& W, const EntTables& T, PendingOut& po, uint2 own, int nblk, int jb, int bpm, bool& fits)
 {
-    const int lane = JG_TID & 31;
-    unsigned cnt = 0;
-    if (lane < nblk) { const uint2 m = W.mask[lane]; cnt = (unsigned)(i_popc(m.x) + i_popc(m.y)); }
+    const unsigned cnt = (unsigned)(i_popc(own.x) + i_popc(own.y));
     const unsigned S = warp_shfl_u32(warp_scan_incl_u32(cnt), 31);
-    if (S <= 3u * (unsigned)kEntRegionWords / 2u || nblk <= 16) {      // up to 48 symbols per lane in one go
-        const unsigned bits = code_blocks(W, T, 0, nblk, lane_j, jb, bpm, 0u, 0u, fits);
-        if (fits || nblk <= 16 || bits > (unsigned)kEntRegionWords * 32u) return bits;
+    if (S <= (DEFER ? (unsigned)kListMax : 3u * (unsigned)kListMax / 2u) || nblk <= 16) {      // (beyond 48 symbols per lane the streams tend to overflow)
+        const unsigned bits = code_blocks<DEFER>(P, W, T, po, own, 0, nblk, 0, jb, bpm, 0u, fits);
+        if (fits || po.failed || nblk <= 16 || bits > (unsigned)kEntRegionWords * 32u) return bits;
         // a lane's stream overflowed: once more, in halves
     }
-    unsigned bits = code_blocks(W, T, 0, 16, lane_j, jb, bpm, 0u, 0u, fits);
-    if (!fits || bits > (unsigned)kEntRegionWords * 16u) { fits = false; return bits; }
-    int j2 = lane_j + 16 % bpm; if (j2 >= bpm) j2 -= bpm;                    // (16 + lane) mod bpm
-    bits += code_blocks(W, T, 16, nblk, j2, jb, bpm, (unsigned)kEntRegionWords / 2u, bits, fits);
+    unsigned bits = code_blocks<DEFER>(P, W, T, po, own, 0, 16, 0, jb, bpm, 0u, fits);
+    if (!fits) return bits;
+    bits += code_blocks<DEFER>(P, W, T, po, own, 16, nblk, 16 % bpm, jb, bpm, bits, fits);
     return bits;
 }
 
 // Bits of every block of the mapped tile, for the stage dumps of the parity tests (lane = block; not on the product's path).
-JG_DEV_NOINLINE unsigned count_block_bits(const EntWarp& W, const EntTables& T, int slot, int nblk, int jb, int bpm)
+JG_DEV_NOINLINE unsigned count_block_bits(const EntWarp& W, const EntTables& T, uint2 m, int slot, int nblk, int jb, int bpm)
 {
     if (slot >= nblk) return 0u;
-    const uint2 m = W.mask[slot];
     unsigned cls; int delta;
     block_role(bpm, (jb + slot) % bpm, cls, delta);
     const int16_t* cz = W.coef + slot * kEntCoefStride;
@@ -290,14 +358,14 @@ JG_DEV_NOINLINE unsigned count_block_bits(const EntWarp& W, const EntTables& T, 
         prev = pos;
         if (v == 0) run = 0;
         const uint2* tb = T.e + 16u * ((pos ? kTabAc + (cls ? kTabAcChroma : 0u) : (cls ? kTabChroma : 0u)));
-        bits += (run >> 4) * tb[0xF0].y;
+        bits += (run >> 4) * tb[15 * 17].y;
         const unsigned cat = v ? 32u - (unsigned)i_clz((unsigned)(v < 0 ? -v : v)) : 0u;
-        bits += tb[((run & 15u) << 4) | cat].y;
+        bits += tb[(run & 15u) * 17u + cat].y;
     }
     return bits;
 }
 
-JG_DEV bool ent_tile_back(const LaunchParams& P, EntWarp& W, int g, int slot)
+JG_DEV_NOINLINE bool ent_tile_back(const LaunchParams& P, EntWarp& W, int g, int slot)
 {
     const Pending pd = W.pend[slot];
     const bool first = g == pd.first_tile_of_img;
@@ -322,9 +390,10 @@ JG_DEV bool ent_tile_back(const LaunchParams& P, EntWarp& W, int g, int slot)
 // learn the tile's size and last bits (successors must not wait for the whole slow pass), then again to be written.
 // Returns false on a look-back timeout.
 template <bool restart>
-JG_DEV_NOINLINE bool ent_tile_slow(const LaunchParams& P, EntWarp& W, const EntTables& T, int g, int nblk, int jb, int bpm, int slot)
+JG_DEV_NOINLINE bool ent_tile_slow(const LaunchParams& P, EntWarp& W, const EntTables& T, uint2 own, int g, int nblk, int jb, int bpm, int slot)
 {
     const int lane = JG_TID & 31;
+    PendingOut po;                    // (nothing pending: the caller has written the previous tile out)
     const Pending pd = W.pend[slot];
     const bool first = g == pd.first_tile_of_img;
     bool fits;
@@ -332,7 +401,7 @@ JG_DEV_NOINLINE bool ent_tile_slow(const LaunchParams& P, EntWarp& W, const EntT
     for (int lo = 0; lo < nblk; lo += kSlowBlocks) {
         warp_sync();
         clear_region(W.region, kEntRegionWords + 8);
-        const unsigned tg = code_blocks(W, T, lo, lo + kSlowBlocks < nblk ? lo + kSlowBlocks : nblk, (lo + lane) % bpm, jb, bpm, 0u, 0u, fits);
+        const unsigned tg = code_blocks<false>(P, W, T, po, own, lo, lo + kSlowBlocks < nblk ? lo + kSlowBlocks : nblk, lo % bpm, jb, bpm, 0u, fits);
         bits += tg;
         // running last-7-bits of the tile (a group may hold fewer than 7)
         tail = tg >= 7u ? tail_bits(W.region, tg) : (((tail << tg) | peek_bits(W.region, 0u, tg)) & 0x7fu);
@@ -351,7 +420,7 @@ JG_DEV_NOINLINE bool ent_tile_slow(const LaunchParams& P, EntWarp& W, const EntT
         const int hi = lo + kSlowBlocks < nblk ? lo + kSlowBlocks : nblk;
         warp_sync();
         clear_region(W.region, kEntRegionWords + 8);
-        unsigned tg = code_blocks(W, T, lo, hi, (lo + lane) % bpm, jb, bpm, 0u, 0u, fits);
+        unsigned tg = code_blocks<false>(P, W, T, po, own, lo, hi, lo % bpm, jb, bpm, 0u, fits);
         if (pad && hi == nblk) {
             if (lane == 0) set_ones(W.region, tg, pad);
             warp_sync();
@@ -371,7 +440,14 @@ JG_DEV_NOINLINE bool ent_tile_slow(const LaunchParams& P, EntWarp& W, const EntT
 // ------------------------------------------------------------------------------------------
 // kernel B: coefficients -> unstuffed entropy-coded bits (raw), bits chained over the tiles of an image
 // ------------------------------------------------------------------------------------------
-template <int MODE>
+// DEFER (chosen by the host for launches with few images): the previous tile is written out in the MIDDLE of the
+// iteration -- after the current tile's symbols are coded, right before its merge needs the region -- instead of at the
+// top.  With one image all ~2600 tiles in flight are consecutive tiles of that image; a write-out at the top of the
+// iteration asks for the sizes of tiles that were drawn nanoseconds before ours and are published at the same moment as
+// ours: every warp waits for the slowest of its 32 predecessors (16384^2 gray: 1.03 ms, ~100 polling rounds per tile);
+// with most of an iteration in between the sizes are there (0.60 ms).  With many images in flight the round-robin tickets
+// provide that slack, and the write-out at the top hides the TMA latency of the new tile (~7 % faster there).
+template <int MODE, bool DEFER>
 JG_KERNEL(kEntThreads, 3)
 void entropy_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTANT CoefMap cmap)
 {
@@ -385,7 +461,7 @@ void entropy_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTAN
         uint2 e;
         e.x = h >> 8;
         e.y = (h & 0xffu) + (unsigned)(k & 15);
-        S.tab.e[i] = e;
+        S.tab.e[i < 32 ? i : (256u + (unsigned)cls * kTabAcBytes) / 8u + (unsigned)(k >> 4) * 17u + (unsigned)(k & 15)] = e;
     }
     EntWarp& W = S.wm[t >> 5];
     const EntTables& T = S.tab;
@@ -397,7 +473,7 @@ void entropy_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTAN
     const int bpm = P.bpm, bpt = P.blocks_per_tile;
     const int lane_j = lane % bpm;
     unsigned phase = 0;
-    int p1_g = -1;                    // the tile coded one iteration ago, still to be written
+    PendingOut po;                    // the tile coded one iteration ago, still to be written
     for (int slot = 0;; slot ^= 1) {
         int img_idx;
         const int g = draw_tile(P, img_idx);
@@ -436,27 +512,31 @@ void entropy_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTAN
                 pd.base = 0;
             }
         }
-        // ---- the previous tile goes out while the copy is in flight ----
-        if (p1_g >= 0) {
-            if (!ent_tile_back(P, W, p1_g, slot ^ 1)) break;
-            p1_g = -1;
+        // ---- the previous tile goes out while the copy is in flight (DEFER: later, inside code_tile) ----
+        if (!DEFER || !have) {
+            flush_pending(P, W, po);
+            if (po.failed) break;
         }
         if (!have) break;
         mbar_wait(&W.mbar, phase);
         phase ^= 1u;
 
         // ---- map (lane = block), then list + code (lane = an equal share of the tile's symbols) ----
-        map_block(W, lane, lane_j, nblk, jb, bpm, b0, pred_outside, restart);
+        const uint2 own = map_block(W, lane, lane_j, nblk, jb, bpm, b0, pred_outside, restart);
         if (P.dbg_bits) {
-            const unsigned nb = count_block_bits(W, T, lane, nblk, jb, bpm);
+            const unsigned nb = count_block_bits(W, T, own, lane, nblk, jb, bpm);
             if (lane < nblk) P.dbg_bits[P.images[img_idx].first_block + (unsigned long long)(b0 + lane)] = nb;
         }
         bool fits;
-        unsigned bits = code_tile(W, T, nblk, lane_j, jb, bpm, fits);
-        if (P.win_words < kWinWordsMax && bits > 32u * (unsigned)P.win_words) fits = false;   // parity tests: force the slow path
+        unsigned bits = code_tile<DEFER>(P, W, T, po, own, nblk, jb, bpm, fits);
+        if (po.failed) break;
+        if (P.win_words < kWinWordsMax && bits > 32u * (unsigned)P.win_words) {                // parity tests: force the slow path
+            fits = false;
+            warp_sync();
+            clear_region(W.region, kEntRegionWords + 8);
+        }
         if (fits) {
-            // Publish the tile's bit count and last bits NOW: they are consumed (by us and by every successor)
-            // one iteration later.
+            // Publish the tile's bit count and last bits NOW: they are consumed (by us and by every successor) later.
             unsigned tail = tail_bits(W.region, bits);
             if (restart && (bits & 7u) != 0u) {      // restart interval: 1-bits up to the byte boundary (T.81 F.1.2.3)
                 const unsigned pad = 8u - (bits & 7u);
@@ -469,9 +549,11 @@ void entropy_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTAN
                 W.pend[slot].T = bits; W.pend[slot].tail = tail;
             }
             warp_sync();
-            p1_g = g;
+            po.g = g; po.slot = slot;
         } else {
-            if (!ent_tile_slow<restart>(P, W, T, g, nblk, jb, bpm, slot)) break;
+            flush_pending(P, W, po);
+            if (po.failed) break;
+            if (!ent_tile_slow<restart>(P, W, T, own, g, nblk, jb, bpm, slot)) break;
         }
     }
 }

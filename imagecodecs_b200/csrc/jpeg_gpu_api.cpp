@@ -584,7 +584,7 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
             P.blocks_per_tile = g.restart ? kEntTileBlocksRestart : kEntTileBlocks;
             P.dbg_coefs = nullptr;
             const int grid = std::min((g.n_tiles + kEntWarps - 1) / kEntWarps, dev.sm_count * dev.entropy_ctas_per_sm);
-            JG_CUDA(entropy_launch(grid, s, P, p->cmap, g.restart ? 2 : 0));
+            JG_CUDA(entropy_launch(grid, s, P, p->cmap, (g.restart ? 2 : 0) | (P.n_images < kDeepMaxImages ? 1 : 0)));
         }
         if (p->timing) JG_CUDA(cudaEventRecord(p->events[4 * gi + 2], s));
         JG_CUDA(stuff_launch(dev.sm_count * dev.stuff_ctas_per_sm, s, P));

@@ -94,6 +94,7 @@ JG_DEV unsigned lds_u16(unsigned a) { unsigned short v; memcpy(&v, emu::tls.cta-
 JG_DEV int lds_s16(unsigned a) { short v; memcpy(&v, emu::tls.cta->smem + a, 2); return (int)v; }
 JG_DEV uint2 lds_u64(unsigned a) { uint2 v; memcpy(&v, emu::tls.cta->smem + a, 8); return v; }
 JG_DEV void sts_u32(unsigned a, unsigned v) { memcpy(emu::tls.cta->smem + a, &v, 4); }
+JG_DEV unsigned pinned(unsigned v) { return v; }
 JG_DEV void sts_u16(unsigned a, unsigned v) { const unsigned short h = (unsigned short)v; memcpy(emu::tls.cta->smem + a, &h, 2); }
 JG_DEV void sts_f32(unsigned a, float v) { memcpy(emu::tls.cta->smem + a, &v, 4); }
 JG_DEV float lds_f32(unsigned a) { float v; memcpy(&v, emu::tls.cta->smem + a, 4); return v; }

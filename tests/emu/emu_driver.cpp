@@ -260,8 +260,12 @@ int emu_encode_split(const uint8_t* pixels, int n_images, int w, int h, int ncom
     cmap.q[1] = (unsigned long long)n_images * n_blocks;
     const int gridB = n_ctas > (n_tiles + kEntWarps - 1) / kEntWarps ? (n_tiles + kEntWarps - 1) / kEntWarps : n_ctas;
     launch(gridB, sizeof(EntSmem), [&] {
-        if (restart) entropy_kernel<kEntModeRestart>(P, cmap);
-        else entropy_kernel<kEntModePlain>(P, cmap);
+        // the host's rule: few images -> deferred write-out; here both get exercised
+        const bool defer = n_images < 2;
+        if (restart && defer) entropy_kernel<kEntModeRestart, true>(P, cmap);
+        else if (restart) entropy_kernel<kEntModeRestart, false>(P, cmap);
+        else if (defer) entropy_kernel<kEntModePlain, true>(P, cmap);
+        else entropy_kernel<kEntModePlain, false>(P, cmap);
     }, kEntThreads);
     if (!error) launch(1, sizeof(StuffSmem), [&] { plan_chunks_kernel(P); });
     if (!error) launch(n_ctas, sizeof(StuffSmem), [&] { stuff_kernel(P); });
