@@ -202,8 +202,9 @@ def decode(jpeg, timed=False):
     return (img, ms.value) if timed else img
 
 
-def decode_batch(files, timed=False):
-    """Decode a list of JPEG files (bytes) in one call; returns list of uint8 arrays (None where a file failed)."""
+def decode_batch(files, timed=False, alloc=None):
+    """Decode a list of JPEG files (bytes) in one call; returns list of uint8 arrays (None where a file failed).
+    alloc(nbytes) -> 1-D uint8 array supplies the pixel buffers (e.g. views of pinned memory); default: np.empty."""
     L = lib()
     n = len(files)
     bufs = [np.frombuffer(f, dtype=np.uint8) for f in files]
@@ -213,7 +214,8 @@ def decode_batch(files, timed=False):
     w, h, nc = C.c_int(0), C.c_int(0), C.c_int(0)
     for i, b in enumerate(bufs):
         ok = L.jpeg_gpu_decode_info(b.ctypes.data, b.size, C.byref(w), C.byref(h), C.byref(nc))
-        a = np.empty(w.value * h.value * nc.value if ok else 1, np.uint8)
+        size = w.value * h.value * nc.value if ok else 1
+        a = alloc(size) if alloc is not None else np.empty(size, np.uint8)
         pix.append(a)
         outs[i] = Decoded(a.ctypes.data, a.size if ok else 0, 0, 0, 0, 0)
     ms = C.c_float(0)

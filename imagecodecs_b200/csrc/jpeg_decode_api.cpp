@@ -5,6 +5,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <utility>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "jpeg_decode.cuh"
@@ -31,14 +35,41 @@ const char* result_text(int rc)
     }
 }
 
+// The decoder's own stream-ordered memory pool (one per device, created on first use): it keeps its memory between calls
+// -- the default pool hands everything back at every synchronisation -- without touching the release threshold of the
+// device's DEFAULT pool, which other users of cudaMallocAsync in the process (torch) share.
+cudaMemPool_t decoder_pool(int dev_id)
+{
+    static std::mutex m;
+    static std::vector<std::pair<int, cudaMemPool_t>> pools;
+    std::lock_guard<std::mutex> lk(m);
+    for (auto& kv : pools) if (kv.first == dev_id) return kv.second;
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev_id;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { (void)cudaGetLastError(); pool = nullptr; }
+    if (pool) {
+        unsigned long long keep_all = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all);
+    }
+    pools.push_back({dev_id, pool});
+    return pool;
+}
+
 struct DeviceBuffers {     // freed in order on every exit path
     cudaStream_t s = nullptr;
+    cudaMemPool_t pool = nullptr;       // nullptr: the device's default pool
     std::vector<void*> ptrs;
     template <typename T>
     T* alloc(size_t n)
     {
         void* p = nullptr;
-        if (cudaMallocAsync(&p, std::max<size_t>(n * sizeof(T), 16), s) != cudaSuccess) return nullptr;
+        const size_t bytes = std::max<size_t>(n * sizeof(T), 16);
+        if ((pool ? cudaMallocFromPoolAsync(&p, bytes, pool, s) : cudaMallocAsync(&p, bytes, s)) != cudaSuccess) return nullptr;
         ptrs.push_back(p);
         return (T*)p;
     }
@@ -81,10 +112,29 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
     size_t data_bytes = 0, iv_words = 0, coef_words = 0, plane_bytes = 0, out_total = 0;
     int n_ok = 0, max_iv = 0;
     unsigned long long max_blocks[3] = {0, 0, 0};
+    // the marker loops of the files are independent of one another: a small pool of host threads walks them (a file of
+    // the bench batch takes ~0.1 ms; 256 of them one after the other were a quarter of the whole call)
+    std::vector<int> parse_rc((size_t)n, (int)kNoJpeg);
+    {
+        const int workers = std::max(1, std::min({n / 8, 16, (int)std::thread::hardware_concurrency()}));
+        std::atomic<int> next{0};
+        auto work = [&] {
+            for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1))
+                parse_rc[i] = in[i].data ? parse(in[i].data, in[i].size, &jobs[i].I, false) : (int)kNoJpeg;
+        };
+        std::vector<std::thread> pool;
+        for (int k = 1; k < workers; ++k) pool.emplace_back(work);
+        work();
+        for (std::thread& th : pool) th.join();
+    }
     for (int i = 0; i < n; ++i) {
         Job& j = jobs[i];
         outs[i].width = outs[i].height = outs[i].ncomp = 0;
-        int rc = in[i].data ? parse(in[i].data, in[i].size, &j.I, false) : (int)kNoJpeg;
+        int rc = parse_rc[i];
+        // A header may announce far more blocks than the scan can hold (a 200-byte file with a 65535 x 65535 frame).  NanoJPEG
+        // would try to allocate the planes and, at this size, report NJ_OUT_OF_MEM; so does this, BEFORE anything is
+        // allocated: every block takes at least 4 bits of scan.
+        if (rc == kOk && j.I.plane_bytes > ((size_t)1 << 31) && j.I.n_blocks > 2 * (j.I.scan_end - j.I.scan_off) + 1024) rc = kOutOfMem;
         size_t slot = 0;
         if (rc == kOk) {                                      // the 65536-entry tables are built once per distinct DHT content
             while (slot < dht_sets.size() && dht_sets[slot] != j.I.dht) ++slot;
@@ -128,19 +178,8 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
     if (jpeg_gpu_device_count() == 0 && jpeg_gpu_init(nullptr, 0) <= 0) return 0;
     JD_CUDA(cudaSetDevice(jg::cuda_device_of(0)));
 
-    {   // keep the stream-ordered pool's memory between calls (the default hands it back at every synchronisation)
-        static int pool_ready_for = -1;
-        const int dev_id = jg::cuda_device_of(0);
-        if (pool_ready_for != dev_id) {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, dev_id) == cudaSuccess) {
-                unsigned long long keep_all = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all);
-            }
-            pool_ready_for = dev_id;
-        }
-    }
     DeviceBuffers B;
+    B.pool = decoder_pool(jg::cuda_device_of(0));
     JD_CUDA(cudaStreamCreateWithFlags(&B.s, cudaStreamNonBlocking));
     uint8_t* d_data = B.alloc<uint8_t>(data_bytes);
     uint32_t* d_iv = B.alloc<uint32_t>(iv_words);
@@ -343,7 +382,20 @@ int jpeg_gpu_decode_info(const uint8_t* jpeg, size_t size, int* width, int* heig
     if (!jpeg) return 0;
     jd::Info I;
     int rc = jd::parse(jpeg, size, &I, false);
-    if (rc == jd::kOk) { std::vector<uint16_t> tables; rc = jd::build_vlc_tables(I.dht, &tables); }   // a file njDecode would reject is rejected here too
+    if (rc == jd::kOk) {
+        // a file njDecode would reject (bad Huffman tables) is rejected here too; files of one encoder carry the same DHT
+        // bytes, so the last verdict is remembered instead of building the 4 x 65536-entry tables for every file of a batch
+        static std::mutex m;
+        static std::vector<uint8_t> last_dht;
+        static int last_rc = jd::kOk;
+        std::lock_guard<std::mutex> lk(m);
+        if (last_dht != I.dht) {
+            std::vector<uint16_t> tables;
+            last_rc = jd::build_vlc_tables(I.dht, &tables);
+            last_dht = I.dht;
+        }
+        rc = last_rc;
+    }
     if (rc != jd::kOk) { jg::set_error_text(result_text(rc)); return 0; }
     if (width) *width = I.width;
     if (height) *height = I.height;
