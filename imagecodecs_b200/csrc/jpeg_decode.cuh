@@ -685,9 +685,11 @@ __device__ __forceinline__ int v_taps(int h, int oy, int (&row)[4], int (&k)[4])
 __global__ void upsample_v_kernel(const PlaneOp* __restrict__ ops)
 {
     const PlaneOp o = ops[blockIdx.z];
-    const int x = 4 * (int)(blockIdx.x * blockDim.x + threadIdx.x), oy = (int)blockIdx.y;
-    if (x >= o.w || oy >= 2 * o.h) return;
+    const int x = 4 * (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (x >= o.w) return;
     const int n = o.w - x < 4 ? o.w - x : 4;
+    // (2 h output rows: one more than gridDim.y can hold for the tallest planes, so the rows are strided over the grid)
+    for (int oy = (int)blockIdx.y; oy < 2 * o.h; oy += (int)gridDim.y) {
     unsigned char v[4] = {0, 0, 0, 0};
     if (n == 4 && ((((size_t)o.in) | (size_t)o.s) & 3u) == 0) {
         // four columns at once: one word per input row instead of four bytes (same integer sums as upsample_v)
@@ -705,6 +707,7 @@ __global__ void upsample_v_kernel(const PlaneOp* __restrict__ ops)
         for (int i = 0; i < n; ++i) v[i] = upsample_v(o.in, o.h, o.s, oy, x + i);
     }
     store4(o.out + (size_t)oy * o.w + x, v, n);
+    }
 }
 __global__ void color_kernel(const ColorOp* __restrict__ ops)
 {

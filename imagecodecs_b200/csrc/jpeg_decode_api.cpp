@@ -295,7 +295,7 @@ int decode_batch(const jpeg_gpu_stream* in, int n, jpeg_gpu_decoded* outs, int p
             keep.push_back(std::move(ops));
             const std::vector<PlaneOp>& kept = keep.back();
             JD_CUDA(cudaMemcpyAsync(d_ops, kept.data(), kept.size() * sizeof(PlaneOp), cudaMemcpyHostToDevice, B.s));
-            rounds.push_back({dir, d_ops, dim3((unsigned)((gw + 511) / 512), (unsigned)gh, (unsigned)kept.size())});   // four pixels per thread
+            rounds.push_back({dir, d_ops, dim3((unsigned)((gw + 511) / 512), (unsigned)std::min(gh, 65535), (unsigned)kept.size())});   // four pixels per thread; rows beyond the grid limit: strided (vertical pass)
             any = true;
         }
         if (!any) break;

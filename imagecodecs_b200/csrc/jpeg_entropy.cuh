@@ -331,10 +331,17 @@ JG_DEV unsigned code_tile(const LaunchParams& P, EntWarp& W, const EntTables& T,
 {
     const unsigned cnt = (unsigned)(i_popc(own.x) + i_popc(own.y));
     const unsigned S = warp_shfl_u32(warp_scan_incl_u32(cnt), 31);
-    if (S <= (DEFER ? (unsigned)kListMax : 3u * (unsigned)kListMax / 2u) || nblk <= 16) {      // (beyond 48 symbols per lane the streams tend to overflow)
+    if (S <= (unsigned)kListMax || nblk <= 16) {
         const unsigned bits = code_blocks<DEFER>(P, W, T, po, own, 0, nblk, 0, jb, bpm, 0u, fits);
         if (fits || po.failed || nblk <= 16 || bits > (unsigned)kEntRegionWords * 32u) return bits;
         // a lane's stream overflowed: once more, in halves
+    } else if (S <= 3u * (unsigned)kListMax / 2u) {
+        // up to 48 symbols per lane still go in one piece (two halves cost ~25 % more), but their list needs the region:
+        // the previous tile leaves now, before the list phase (a dense tile takes long enough for its predecessors' sizes to be there)
+        flush_pending(P, W, po);
+        if (po.failed) { fits = false; return 0u; }
+        const unsigned bits = code_blocks<false>(P, W, T, po, own, 0, nblk, 0, jb, bpm, 0u, fits);
+        if (fits || bits > (unsigned)kEntRegionWords * 32u) return bits;
     }
     unsigned bits = code_blocks<DEFER>(P, W, T, po, own, 0, 16, 0, jb, bpm, 0u, fits);
     if (!fits) return bits;

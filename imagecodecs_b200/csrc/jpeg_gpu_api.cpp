@@ -103,7 +103,7 @@ struct Device {
     std::mutex* pool_mutex = nullptr;
     std::multimap<size_t, void*>* pool_dev = nullptr;    // free device blocks by size
     std::multimap<size_t, void*>* pool_host = nullptr;   // free pinned host blocks by size
-    size_t pooled_bytes = 0;
+    size_t pooled_bytes = 0, pooled_host_bytes = 0;
 };
 
 std::mutex g_mutex;
@@ -156,7 +156,15 @@ size_t pool_class(size_t bytes)
     return c;
 }
 
-constexpr size_t kPoolLimit = 24ull << 30;   // keep at most this much idle device memory cached per GPU
+// Idle memory the caching allocator keeps per GPU: device blocks up to JPEG_GPU_POOL_LIMIT_MB (default 24 GB: a config-5 sized
+// plan comes back without a cudaMalloc), pinned host blocks up to JPEG_GPU_PINNED_POOL_LIMIT_MB (default 1 GB); beyond that
+// blocks go back to the driver.  (Blocks are recycled only after the freeing plan's stream has drained: plan_free.)
+size_t pool_limit(bool host)
+{
+    static const size_t dev_limit = [] { const char* e = getenv("JPEG_GPU_POOL_LIMIT_MB"); return (e ? (size_t)strtoull(e, nullptr, 10) : (size_t)24576) << 20; }();
+    static const size_t host_limit = [] { const char* e = getenv("JPEG_GPU_PINNED_POOL_LIMIT_MB"); return (e ? (size_t)strtoull(e, nullptr, 10) : (size_t)1024) << 20; }();
+    return host ? host_limit : dev_limit;
+}
 
 bool pool_alloc(Device& d, size_t bytes, bool host, void** out)
 {
@@ -168,7 +176,7 @@ bool pool_alloc(Device& d, size_t bytes, bool host, void** out)
         if (f != m.end()) {
             *out = f->second;
             m.erase(f);
-            if (!host) d.pooled_bytes -= c;
+            (host ? d.pooled_host_bytes : d.pooled_bytes) -= c;
             return true;
         }
     }
@@ -195,9 +203,10 @@ void pool_free(Device& d, void* p, size_t bytes, bool host)
     if (!p) return;
     const size_t c = pool_class(bytes);
     std::lock_guard<std::mutex> lk(*d.pool_mutex);
-    if (!host && d.pooled_bytes + c > kPoolLimit) { cudaFree(p); return; }
+    size_t& pooled = host ? d.pooled_host_bytes : d.pooled_bytes;
+    if (pooled + c > pool_limit(host)) { if (host) cudaFreeHost(p); else cudaFree(p); return; }
     (host ? *d.pool_host : *d.pool_dev).emplace(c, p);
-    if (!host) d.pooled_bytes += c;
+    pooled += c;
 }
 
 bool ensure_init()
@@ -584,7 +593,7 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
             P.blocks_per_tile = g.restart ? kEntTileBlocksRestart : kEntTileBlocks;
             P.dbg_coefs = nullptr;
             const int grid = std::min((g.n_tiles + kEntWarps - 1) / kEntWarps, dev.sm_count * dev.entropy_ctas_per_sm);
-            JG_CUDA(entropy_launch(grid, s, P, p->cmap, (g.restart ? 2 : 0) | (P.n_images < kDeepMaxImages ? 1 : 0)));
+            JG_CUDA(entropy_launch(grid, s, P, p->cmap, (g.restart ? 2 : 0) | 1));     // deferred write-out: never slower
         }
         if (p->timing) JG_CUDA(cudaEventRecord(p->events[4 * gi + 2], s));
         JG_CUDA(stuff_launch(dev.sm_count * dev.stuff_ctas_per_sm, s, P));

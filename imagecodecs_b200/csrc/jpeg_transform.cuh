@@ -328,8 +328,11 @@ JG_DEV void transform_iter_gray(const TAddr& A, const TPixels<LAYOUT_GRAY, 1>& p
 // ------------------------------------------------------------------------------------------
 // kernel A: one warp per item (ITEM_MCUS consecutive MCUs of one image)
 // ------------------------------------------------------------------------------------------
+// Resident CTAs per SM the register allocation aims at: 4 (128 registers) for 4:2:0 and gray, 3 (168) for 4:4:4, whose lanes
+// hold two MCUs of three components.  Measured (tools/build_variants.py): 6 -> 5 -> 4 CTAs 1.31 / 1.27 / 1.06 ms for the
+// 4:2:0 batch, 4 -> 3 CTAs 0.886 -> 0.840 ms for the 4:4:4 one (and 1.06 -> 1.10 for 4:2:0): registers beat occupancy here.
 #ifndef JG_TR_MINB
-#define JG_TR_MINB 4          // resident CTAs per SM the register allocation aims at (variant builds: tools/build_variants.py)
+#define JG_TR_MINB (LAYOUT == LAYOUT_444 ? 3 : 4)
 #endif
 template <int LAYOUT, int NC>
 JG_KERNEL(kThreads, JG_TR_MINB)
