@@ -79,6 +79,7 @@ struct LaunchParams {
     const int16_t* coefs;            // [blocks of the plan][64] int16, zigzag order; an image starts at ImageDesc.first_block
     int bpm;                         // blocks per MCU of the launch: 1 gray, 3 4:4:4, 6 4:2:0
     int blocks_per_tile;             // pass B tile: 32 blocks (24 = whole MCUs with restart intervals)
+    int few_images;                  // single-image launch: consecutive tickets are consecutive tiles of one image
 };
 
 // pass B (jpeg_entropy.cuh): tiles, CTA shape, and the TMA descriptor of the coefficient plane

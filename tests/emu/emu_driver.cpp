@@ -14,6 +14,7 @@
 #include <functional>
 #include <thread>
 #include <vector>
+#include <cstdlib>
 
 namespace jg {
 namespace emu {
@@ -253,7 +254,8 @@ int emu_encode_split(const uint8_t* pixels, int n_images, int w, int h, int ncom
     P.raw_bytes = raw_bytes.data(); P.first_chunk = first_chunk.data();
     P.scan_bytes = scan_bytes; P.img_status = img_status; P.huff = &lut;
     P.dbg_coefs = nullptr; P.dbg_bits = dbg_bits;
-    P.coefs = coefs.data(); P.bpm = bpm; P.blocks_per_tile = bpt;
+    P.coefs = coefs.data(); P.bpm = bpm; P.blocks_per_tile = bpt; P.few_images = n_images < 2;
+    if (const char* e = getenv("EMU_FEW_IMAGES")) P.few_images = atoi(e);   // both mid-density routes of code_tile
     CoefMap cmap;
     memset(&cmap, 0, sizeof cmap);
     cmap.q[0] = (unsigned long long)(size_t)coefs.data();
