@@ -17,6 +17,7 @@
 #define JG_DEV_NOINLINE __device__ __noinline__
 #define JG_TID ((int)threadIdx.x)
 #define JG_CTA_ID ((int)blockIdx.x)
+#define JG_GRID_DIM ((int)gridDim.x)
 #define JG_KERNEL(threads, min_ctas) __global__ __launch_bounds__(threads, min_ctas)
 #define JG_GRID_CONSTANT __grid_constant__
 #define JG_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
@@ -90,6 +91,7 @@ JG_DEV unsigned warp_scan_incl_u32(unsigned v)
     return v;
 }
 JG_DEV unsigned warp_max_u32(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }   // one REDUX
+JG_DEV unsigned warp_sum_u32(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
 JG_DEV float warp_shfl_xor_f32(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 JG_DEV unsigned long long warp_shfl_u64(unsigned long long v, int lane) { return __shfl_sync(0xffffffffu, v, lane); }
 JG_DEV unsigned long long warp_shfl_xor_u64(unsigned long long v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }

@@ -56,6 +56,9 @@ void set_error(const char* fmt, ...)
     } while (0)
 
 // ---- kernel specialisations -------------------------------------------------------------
+// the group totals of the stuffing pass's two-level scan (jpeg_stuff.cuh), padded to keep what follows 16-byte aligned
+size_t ff_groups_bytes(size_t chunks) { return ((chunks / 32 + 2) * 4 + 15) / 16 * 16; }
+
 struct Spec {
     int layout, nc;
     cudaError_t (*prepare)(int*);
@@ -309,7 +312,7 @@ struct jpeg_gpu_plan {
         QuantSet quant;
         std::vector<int> items;
         int n_tiles = 0, tiles_per_image = 0;
-        size_t state_off = 0;     // offset of {ticket, ticket2, error, pad, desc_bits[], desc_ff[], desc_dc[]} in d_state
+        size_t state_off = 0;     // offset of {ticket, error, pad, desc_bits[], desc_ff[], ff_groups[], desc_dc[]} in d_state
         size_t max_chunks = 0;    // upper bound of stuffing chunks (from the capacities)
         unsigned long long* d_raw_bytes = nullptr;    // into d_aux
         unsigned* d_first_chunk = nullptr;
@@ -413,7 +416,7 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
     p->arena_bytes = arena;
     p->pixels_bytes = pixels;
 
-    // device state: per group {ticket u32, error u32, ticket2 u32, pad} + desc_bits + desc_ff + desc_dc
+    // device state: per group {ticket u32, error u32, pad} + desc_bits + desc_ff + ff_groups + desc_dc
     size_t state = 0, res_index = 0;
     for (auto& g : p->groups) {
         int tiles = 0;
@@ -458,7 +461,7 @@ bool plan_build(jpeg_gpu_plan* p, const jpeg_gpu_image* images, int n, bool wors
         size_t chunks = 1;
         for (int idx : g.items) chunks += (p->items[idx].scan_cap + kChunkBytes - 1) / kChunkBytes;
         g.max_chunks = chunks;
-        state += 16 + (size_t)tiles * 8 + chunks * 8 + (((size_t)tiles * 12 + 15) / 16) * 16;
+        state += 16 + (size_t)tiles * 8 + chunks * 8 + ff_groups_bytes(chunks) + (((size_t)tiles * 12 + 15) / 16) * 16;
         g.result_off = res_index;
         res_index += g.items.size();
     }
@@ -562,10 +565,10 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
         uint8_t* st = p->d_state + g.state_off;
         P.ticket = reinterpret_cast<unsigned*>(st);
         P.error = reinterpret_cast<unsigned*>(st + 4);
-        P.ticket2 = reinterpret_cast<unsigned*>(st + 8);
         P.desc_bits = reinterpret_cast<unsigned long long*>(st + 16);
         P.desc_ff = P.desc_bits + g.n_tiles;
-        P.desc_dc = reinterpret_cast<unsigned*>(P.desc_ff + g.max_chunks);
+        P.ff_groups = reinterpret_cast<unsigned*>(P.desc_ff + g.max_chunks);
+        P.desc_dc = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(P.ff_groups) + ff_groups_bytes(g.max_chunks));
         P.raw_bytes = g.d_raw_bytes;
         P.first_chunk = g.d_first_chunk;
         P.scan_bytes = g.d_scan_bytes;

@@ -63,11 +63,11 @@ struct LaunchParams {
     const uint32_t* sched;           // otherwise: the ticket schedule (build_schedule, jpeg_tables.h)
     int win_words;                   // region words actually used (kWinWordsMin..kWinWordsMax)
     unsigned* ticket;                // zeroed before the launch (encode)
-    unsigned* ticket2;               // zeroed before the launch (stuff)
     unsigned* error;                 // OUT: non-zero if a look-back timed out
     unsigned long long* desc_bits;   // [n_tiles], zeroed: status | the tile's last 7 bits | bits of the tile -> inclusive bit prefix
     unsigned* desc_dc;               // [3 * n_tiles], zeroed: valid<<31 | quantised DC of the tile's last block per component
-    unsigned long long* desc_ff;     // [max_chunks], zeroed: 0xFF bytes of the chunk -> inclusive count
+    unsigned long long* desc_ff;     // [max_chunks] chunk -> image << 32 | extra bytes (stuffed zeros, markers) of the chunks before it in its group of 32
+    unsigned* ff_groups;             // [max_chunks / 32 + 1] extra bytes of a group of chunks -> exclusive prefix over the launch
     unsigned long long* raw_bytes;   // [n_images] bytes of unstuffed scan (encode -> plan/stuff)
     unsigned* first_chunk;           // [n_images + 1] chunk table (plan -> stuff)
     unsigned long long* scan_bytes;  // [n_images] OUT: bytes of scan + EOI

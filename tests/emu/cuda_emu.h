@@ -16,6 +16,7 @@
 #define JG_GRID_CONSTANT
 #define JG_TID (::jg::emu::tls.tid)
 #define JG_CTA_ID (::jg::emu::tls.cta->id)
+#define JG_GRID_DIM (::jg::emu::tls.cta->grid)
 #define JG_DYNAMIC_SMEM(name) unsigned char* name = ::jg::emu::tls.cta->smem
 #define JG_CONST_TABLE static const
 #define JG_WARP_ANY(x) (x)
@@ -35,6 +36,7 @@ struct Cta {
     unsigned char* smem;
     int nthreads;
     int id;                           // blockIdx.x
+    int grid;                         // gridDim.x
 };
 struct Tls { int tid; Cta* cta; };
 extern thread_local Tls tls;
@@ -165,6 +167,11 @@ JG_DEV unsigned warp_max_u32(unsigned v)
         const unsigned o = (unsigned)warp_exchange(v, (emu::tls.tid & 31) ^ m);
         if (o > v) v = o;
     }
+    return v;
+}
+JG_DEV unsigned warp_sum_u32(unsigned v)
+{
+    for (int m = 16; m > 0; m >>= 1) v += (unsigned)warp_exchange(v, (emu::tls.tid & 31) ^ m);
     return v;
 }
 JG_DEV float warp_shfl_xor_f32(float v, int m)

@@ -42,7 +42,7 @@ void* thread_main(void* p)
 }
 
 // "launch" n_ctas CTAs of kThreads threads that all run concurrently
-void launch(int n_ctas, size_t smem_bytes, const std::function<void()>& body, int kThreads = jg::kThreads, int first_cta = 0)
+void launch(int n_ctas, size_t smem_bytes, const std::function<void()>& body, int kThreads = jg::kThreads, int first_cta = 0, int grid = 0)
 {
     std::vector<emu::Cta> ctas(n_ctas);
     std::vector<ThreadArg> args((size_t)n_ctas * kThreads);
@@ -54,6 +54,7 @@ void launch(int n_ctas, size_t smem_bytes, const std::function<void()>& body, in
         emu::Cta& cta = ctas[c];
         cta.nthreads = kThreads;
         cta.id = first_cta + c;
+        cta.grid = grid > 0 ? grid : first_cta + n_ctas;
         cta.smem = (unsigned char*)aligned_alloc(64, (smem_bytes + 63) / 64 * 64);
         pthread_barrier_init(&cta.bar, nullptr, kThreads);
         for (int wv = 0; wv < kThreads / 32; ++wv) pthread_barrier_init(&cta.wbar[wv], nullptr, 32);
@@ -124,7 +125,8 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
     const size_t max_chunks = (size_t)n_images * ((scan_cap + kChunkBytes - 1) / kChunkBytes) + 1;
     std::vector<unsigned long long> desc_bits(n_tiles, 0), desc_ff(max_chunks, 0), raw_bytes(n_images, 0);
     std::vector<unsigned> first_chunk(n_images + 1, 0), desc_dc(3 * (size_t)n_tiles, 0);
-    unsigned ticket = 0, ticket2 = 0, error = 0;
+    unsigned ticket = 0, error = 0;
+    std::vector<unsigned> ff_groups(max_chunks / 32 + 2, 0);
     for (int i = 0; i < n_images; ++i) { scan_bytes[i] = 0; img_status[i] = 0; }
 
     LaunchParams P;
@@ -135,7 +137,7 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
     build_schedule(counts.data(), n_images, sched.data());
     P.sched = sched.data();
     P.win_words = win_words ? (win_words < kWinWordsMin ? kWinWordsMin : (win_words > kWinWordsMax ? kWinWordsMax : win_words)) : kWinWordsMax;
-    P.ticket = &ticket; P.ticket2 = &ticket2; P.error = &error;
+    P.ticket = &ticket; P.error = &error; P.ff_groups = ff_groups.data();
     P.desc_bits = desc_bits.data(); P.desc_ff = desc_ff.data(); P.desc_dc = desc_dc.data();
     P.raw_bytes = raw_bytes.data(); P.first_chunk = first_chunk.data();
     P.scan_bytes = scan_bytes; P.img_status = img_status; P.huff = &lut;
@@ -158,8 +160,12 @@ int emu_encode(const uint8_t* pixels, int n_images, int w, int h, int ncomp, int
         else JG_RUN(LAYOUT_GRAY, 1);
 #undef JG_RUN
     });
-    if (!error) launch(1, sizeof(StuffSmem), [&] { plan_chunks_kernel(P); });
-    if (!error) launch(n_ctas, sizeof(StuffSmem), [&] { stuff_kernel(P); });
+    if (!error) {
+        launch(1, sizeof(StuffSmem), [&] { plan_chunks_kernel(P); });
+        launch(n_ctas, sizeof(StuffSmem), [&] { count_ff_kernel(P); }, kCountThreads);
+        launch(1, sizeof(StuffSmem), [&] { scan_groups_kernel(P); });
+        launch(n_ctas, sizeof(StuffSmem), [&] { stuff_kernel(P); });
+    }
     free(raw);
     return (int)error;
 }
@@ -215,7 +221,8 @@ int emu_encode_split(const uint8_t* pixels, int n_images, int w, int h, int ncom
     const size_t max_chunks = (size_t)n_images * ((scan_cap + kChunkBytes - 1) / kChunkBytes) + 1;
     std::vector<unsigned long long> desc_bits(n_tiles, 0), desc_ff(max_chunks, 0), raw_bytes(n_images, 0);
     std::vector<unsigned> first_chunk(n_images + 1, 0);
-    unsigned ticket = 0, ticket2 = 0, error = 0;
+    unsigned ticket = 0, error = 0;
+    std::vector<unsigned> ff_groups(max_chunks / 32 + 2, 0);
     for (int i = 0; i < n_images; ++i) { scan_bytes[i] = 0; img_status[i] = 0; }
 
     // ---- pass A ----
@@ -249,7 +256,7 @@ int emu_encode_split(const uint8_t* pixels, int n_images, int w, int h, int ncom
     build_schedule(counts.data(), n_images, sched.data());
     P.sched = sched.data();
     P.win_words = win_words ? win_words : kWinWordsMax;      // a small value sends every tile with more bits the slow way
-    P.ticket = &ticket; P.ticket2 = &ticket2; P.error = &error;
+    P.ticket = &ticket; P.error = &error; P.ff_groups = ff_groups.data();
     P.desc_bits = desc_bits.data(); P.desc_ff = desc_ff.data(); P.desc_dc = nullptr;
     P.raw_bytes = raw_bytes.data(); P.first_chunk = first_chunk.data();
     P.scan_bytes = scan_bytes; P.img_status = img_status; P.huff = &lut;
@@ -269,8 +276,12 @@ int emu_encode_split(const uint8_t* pixels, int n_images, int w, int h, int ncom
         else if (defer) entropy_kernel<kEntModePlain, true>(P, cmap);
         else entropy_kernel<kEntModePlain, false>(P, cmap);
     }, kEntThreads);
-    if (!error) launch(1, sizeof(StuffSmem), [&] { plan_chunks_kernel(P); });
-    if (!error) launch(n_ctas, sizeof(StuffSmem), [&] { stuff_kernel(P); });
+    if (!error) {
+        launch(1, sizeof(StuffSmem), [&] { plan_chunks_kernel(P); });
+        launch(n_ctas, sizeof(StuffSmem), [&] { count_ff_kernel(P); }, kCountThreads);
+        launch(1, sizeof(StuffSmem), [&] { scan_groups_kernel(P); });
+        launch(n_ctas, sizeof(StuffSmem), [&] { stuff_kernel(P); });
+    }
     free(raw);
     return (int)error;
 }

@@ -134,3 +134,20 @@ def test_emulated_kernel_restart_intervals(shape, qm, q, sub, ctas):
         assert hdr + scans[i] == want and status[i] == 0
         plain = oracle.oracle_encode(batch[i], qm, q, sub)
         assert np.array_equal(oracle.ref_decode(want), oracle.ref_decode(plain))
+
+
+def test_emulated_stuffing_pass_over_many_chunks():
+    """The stuffing pass's two-level scan (jpeg_stuff.cuh: 32 chunks of 8 KB per group, group totals scanned by one CTA):
+    images of 62 and 38 chunks in one launch -- groups that straddle the image boundary, more than one group per image,
+    ~2000 stuffed zeros per image -- and the same with restart markers."""
+    imgs = np.stack([oracle.synth_batch(1, 384, 320, 3, "noise")[0], oracle.synth_batch(1, 384, 320, 3, "photo")[0]])
+    hdr = oracle.oracle_headers(384, 320, 3, 0, 0, 3)
+    scans, _, status = emu_encode(imgs, 0, 3, 0, n_ctas=3)
+    for i in range(2):
+        assert status[i] == 0 and hdr + scans[i] == oracle.oracle_encode(imgs[i], 0, 3, 0), i
+    assert len(scans[0]) > 32 * 8192 and len(scans[1]) > 32 * 8192
+    ri = oracle.restart_interval(3, 0)
+    rhdr = oracle.oracle_headers(384, 320, 3, 0, 0, 3, restart=ri)
+    rscans, _, status = emu_encode(imgs, 0, 3, 0, n_ctas=2, flags=2)
+    for i in range(2):
+        assert status[i] == 0 and rhdr + rscans[i] == oracle.oracle_encode(imgs[i], 0, 3, 0, restart=ri), i
