@@ -855,8 +855,8 @@ int jpeg_gpu_plan_kernel_times(jpeg_gpu_plan* p, float* encode_ms, float* stuff_
 
 int jpeg_gpu_plan_is_fused(const jpeg_gpu_plan* p) { return p && p->fused ? 1 : 0; }
 
-// fused: encode + plan_chunks + stuff; split: transform + entropy + plan_chunks + stuff
-int jpeg_gpu_plan_launches(const jpeg_gpu_plan* p) { return p ? (p->fused ? 3 : 4) * (int)p->groups.size() : 0; }
+// pass 1 (split: transform + entropy; fused: one encode kernel) + pass 2 (plan_chunks + count_ff + scan_groups + stuff)
+int jpeg_gpu_plan_launches(const jpeg_gpu_plan* p) { return p ? (p->fused ? 5 : 6) * (int)p->groups.size() : 0; }
 
 size_t jpeg_gpu_plan_num_blocks(const jpeg_gpu_plan* p) { return p ? p->n_blocks : 0; }
 

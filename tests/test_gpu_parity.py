@@ -284,7 +284,7 @@ def test_device_resident_pixels_and_plan_reuse(gpu):
     plan = gpu.Plan.for_arrays([dev[i] for i in range(6)], 1, 75, 1, device=0)
     plan.run(); a = plan.fetch()
     plan.run(); b = plan.fetch()            # same plan, second launch: state is reset correctly
-    assert a == b and plan.launches == (3 if plan.fused else 4)      # (transform + entropy | fused encode) + plan + stuff
+    assert a == b and plan.launches == (5 if plan.fused else 6)      # (transform + entropy | fused encode) + plan + count + scan + stuff
     host = dev.cpu().numpy()
     for i in (0, 5):
         assert a[i] == oracle.oracle_encode(host[i], 1, 75, 1)
