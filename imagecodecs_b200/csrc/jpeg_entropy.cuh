@@ -20,14 +20,18 @@
 //            2. map     lane l reads block l once (8 x LDS.128) and builds the 64-bit map of what the block
 //                       codes: bit 0 the DC difference, bits 1..62 the non-zero coefficients, bit 63 either the
 //                       last coefficient or -- where that is zero -- the end-of-block code.  A symbol is a set bit.
-//            3. list    a warp scan of the 32 symbol counts; every lane writes its block's symbols
-//                       (block, position, table) into ONE list for the tile, in scan order.
-//            4. code    the list is cut into 32 EQUAL pieces: lane l codes symbols [l*q, (l+1)*q) -- whatever
-//                       blocks they belong to -- serially into its own word stream: coefficient, run from the
-//                       previous list entry, category (clz), {code, length} from ONE 8-byte table load, append to
-//                       a 64-bit register accumulator, full words to shared memory.  Every lane does the same
-//                       amount of work however the symbols are spread over luma / chroma, busy / flat blocks; no
-//                       scan, no atomics, no vote inside the loop.
+//            3. share   a warp scan of the 32 symbol counts cuts the tile's symbols into 32 EQUAL pieces: lane l codes
+//                       symbols [l*q, (l+1)*q) -- whatever blocks they belong to.  It finds its first block with five
+//                       shuffles over the scanned counts and drops the symbols of that block that belong to the lanes
+//                       before it with a popcount search in the block's map.  (Until late in round 2 a list phase
+//                       wrote every symbol as a 16-bit entry first -- a lane per block, so the busiest block of the
+//                       tile set the pace: 22 % of the kernel's instructions.)
+//            4. code    the lane walks the maps (count-leading-zeros over the bit-reversed map gives the next
+//                       position, position 63 ends a block and loads the next block's map) and codes its symbols
+//                       serially into its own word stream: coefficient, run from the previous position, category (clz),
+//                       {code, length} from ONE 8-byte table load, append to a 64-bit register accumulator, full words
+//                       to shared memory.  Every lane does the same amount of work however the symbols are spread over
+//                       luma / chroma, busy / flat blocks; no scan, no atomics, no vote inside the loop.
 //            5. merge   a warp scan of the 32 stream lengths places them; every lane shifts its words to their
 //                       final bit position in the tile's region (plain stores for words it owns alone, atomicOr
 //                       for the two it shares with its neighbours).
@@ -42,14 +46,18 @@ namespace jg {
 constexpr int kEntBlocks = 32;                              // blocks per tile at most: one per lane in the map phase
 constexpr int kEntCoefStride = 72;                          // int16 per staged block: 144-byte rows (the TMA box is 72 wide over a 64-wide tensor,
                                                             // the out-of-bounds columns arrive as zeros) keep 32 lanes off each other's banks
-constexpr int kSubWords = 16;                               // words of a lane's private stream (512 bits)
+#ifndef JG_ENT_SUBWORDS
+#define JG_ENT_SUBWORDS 24
+#endif
+constexpr int kSubWords = JG_ENT_SUBWORDS;                  // words of a lane's private stream (768 bits)
 constexpr int kEntRegionWords = 768;                        // a tile's merged bits on the fast path: 24576 at most
-constexpr int kListMax = 1024;                              // symbols coded in one go (a tile with more is coded in two halves)
+#ifndef JG_ENT_PIECE
+#define JG_ENT_PIECE 96
+#endif
+constexpr int kOnePieceSymbols = JG_ENT_PIECE * kSubWords;     // a tile with more symbols is coded in two halves right away (3 symbols per stream word: ~10.7 bits each)
 constexpr int kSlowBlocks = 4;                              // slow path: 4 blocks at a time (<= 256 symbols, <= 8 x 59 bits per lane: always fit)
 constexpr int kEntModePlain = 0, kEntModeRestart = 2;      // + 1: deferred write-out (launches with few images)
 constexpr unsigned kEntStageBytes = kEntBlocks * kEntCoefStride * 2;   // what one TMA box delivers (out-of-bounds rows count)
-// list entry: bits 0-5 zigzag position, 6-10 block of the tile, 11-15 the symbol's Huffman table as a multiple of 128 bytes
-constexpr unsigned kEntryBlockPos = 0x7ffu;
 constexpr unsigned kTabRunBytes = 136u, kTabAcBytes = 16u * kTabRunBytes;    // see EntTables
 constexpr unsigned kTabDc = 0u, kTabAc = 2u, kTabChroma = 1u, kTabAcChroma = kTabAcBytes / 128u;   // luma DC 0, chroma DC 1, luma AC 2, chroma AC 19
 static_assert(kTabAcBytes % 128u == 0u, "table offsets are multiples of 128 bytes");
@@ -58,7 +66,8 @@ struct EntWarp {
     alignas(128) int16_t coef[kEntBlocks * kEntCoefStride];  // TMA destination
     alignas(16) uint32_t sub[kEntBlocks * kSubWords];        // word k of lane l at [k * 32 + l] (conflict-free)
     alignas(16) uint32_t region[kEntRegionWords + 8];        // the tile's merged bits (MSB-first words); survives into the next iteration
-    alignas(16) uint16_t list[kListMax];                     // the symbols being coded, in scan order
+    alignas(8) uint2 rec[kEntBlocks + 4];                    // per block: {map of positions 0..31, map of 32..63} bit-reversed (position p at bit 31 - p mod 32);
+                                                             // bit 0 of .y (position 63, always coded) carries the block's class instead.  The last 4 stay zero
     alignas(8) unsigned long long mbar;                      // completion of the staged coefficients
     Pending pend[2];
 };
@@ -95,7 +104,7 @@ JG_DEV uint2 map_block(EntWarp& W, int slot, int slot_j, int nblk, int jb, int b
 {
     const bool active = slot < nblk;
     int16_t* cz = W.coef + slot * kEntCoefStride;
-    unsigned mlo = 0, mhi = 0;
+    unsigned mlo = 0, mhi = 0, cls_of = 0;
     int diff = 0;
     if (active) {
         const uint4* row = reinterpret_cast<const uint4*>(cz);
@@ -109,6 +118,7 @@ JG_DEV uint2 map_block(EntWarp& W, int slot, int slot_j, int nblk, int jb, int b
         int j = jb + slot_j; if (j >= bpm) j -= bpm;                 // slot_j = slot mod bpm
         unsigned cls; int delta;
         block_role(bpm, j, cls, delta);
+        cls_of = cls;
         const int ps = slot - delta;                                 // predecessor of the same component, tile-relative
         int pred = 0;
         if (ps >= 0) pred = W.coef[ps * kEntCoefStride];
@@ -119,43 +129,16 @@ JG_DEV uint2 map_block(EntWarp& W, int slot, int slot_j, int nblk, int jb, int b
     if (active) cz[0] = (int16_t)diff;
     fence_proxy_async();               // ... a generic store into the TMA's destination: ordered before the next tile's copy
     uint2 m; m.x = mlo; m.y = mhi;
+    uint2 r; r.x = bit_reverse(mlo); r.y = (bit_reverse(mhi) & ~1u) | cls_of;
+    W.rec[slot] = r;                   // (an inactive lane: zeros)
     warp_sync();
     return m;
 }
 
-// List phase: the lane appends the symbols of one half (word = 0: positions 0..31, 1: positions 32..63) or of both halves
-// (word = 2) of block `slot` (map m, class cls) at shared address `la`, in scan order.
-JG_DEV void list_block(unsigned la, int slot, uint2 m, unsigned cls, int word)
-{
-    const unsigned blk = (unsigned)slot << 6;
-    const unsigned ac = blk | ((kTabAc + (cls ? kTabAcChroma : 0u)) << 11);
-    // bit-reversed maps: the next position is 31 - (index of the highest set bit)
-    if (word != 1) {
-        sts_u16(la, blk | ((kTabDc + (cls ? kTabChroma : 0u)) << 11));      // position 0: the DC difference, always there
-        la += 2u;
-#pragma unroll 1
-        for (unsigned w = bit_reverse(m.x & ~1u); w;) {
-            const unsigned f = 31u - (unsigned)i_clz(w);
-            sts_u16(la, ac + 31u - f);
-            la += 2u;
-            w &= ~(1u << f);
-        }
-    }
-    if (word != 0) {
-#pragma unroll 1
-        for (unsigned w = bit_reverse(m.y); w;) {
-            const unsigned f = 31u - (unsigned)i_clz(w);
-            sts_u16(la, ac + 63u - f);
-            la += 2u;
-            w &= ~(1u << f);
-        }
-    }
-}
-
-// Code phase: the lane codes symbols [s0, s0 + n) of the list into its private word stream (word k at shared address
-// sub + 128 * k); returns the bits.  Words beyond kSubWords pile up on the last slot (the count tells: slow path).
-// Everything inside the loop works on 32-bit shared-memory addresses.
-JG_DEV unsigned code_symbols(const EntTables& T, const int16_t* coef, const uint16_t* list, unsigned s0, unsigned n, const uint32_t* sub)
+// Code phase: the lane codes n symbols, starting with symbol r of block `blk` of the mapped tile, into its private word
+// stream (word k at shared address sub + 128 * k); returns the bits.  Words beyond kSubWords pile up on the last slot (the
+// count tells: the caller takes another route).  Everything inside the loop works on 32-bit shared-memory addresses.
+JG_DEV unsigned code_symbols(const EntTables& T, const int16_t* coef, const uint2* rec, unsigned blk, unsigned r, unsigned n, const uint32_t* sub)
 {
     unsigned alo = 0, ahi = 0;       // the last 64 bits appended
     unsigned t = 0;                  // bits so far
@@ -171,25 +154,74 @@ JG_DEV unsigned code_symbols(const EntTables& T, const int16_t* coef, const uint
         }
         t = t2;
     };
-    const unsigned tabs = pinned(smem_addr(&T.e[0])), cz = pinned(smem_addr(coef));
-    unsigned la = smem_addr(list) + 2u * s0;
-    unsigned tp = s0 ? (lds_u16(la - 2u) & kEntryBlockPos) : 0xffffu;   // block | position of the symbol before mine
-    auto coef_of = [&](unsigned e) { return lds_s16(cz + 2u * (e & kEntryBlockPos) + (((e & kEntryBlockPos) >> 6) << 4)); };   // block * 144 + position * 2
+    const unsigned tabs = pinned(smem_addr(&T.e[0]));
+    // the walk: what is left of the current block's map (wh: positions 0..31, wl: 32..63, most significant bit first), its
+    // record and coefficients, the position of the symbol before, the block's two tables
+    unsigned ra = smem_addr(rec) + 8u * blk;
+    unsigned cb = smem_addr(coef) + 2u * (unsigned)kEntCoefStride * blk;
+    unsigned wh, wl, prevp = 0xffffffffu, dc_tb, ac_tb;
+    auto open_block = [&]() {
+        const uint2 q = lds_u64(ra);
+        wh = q.x; wl = q.y | 1u;
+        const unsigned cls = q.y & 1u;
+        dc_tb = tabs + cls * 128u;
+        ac_tb = tabs + 256u + cls * kTabAcBytes;
+    };
+    open_block();
+    if (r) {
+        // the first r symbols of the block belong to the lanes before me
+        const unsigned ch = (unsigned)i_popc(wh);
+        unsigned w = wh, base = 0u;
+        if (r >= ch) {                                     // all of the first word (never empty: the DC is there)
+            r -= ch;
+            prevp = 32u - (unsigned)i_ffs(wh);
+            w = wl; base = 32u; wh = 0u;
+        }
+        if (r) {
+            unsigned pos = 0u;                             // the longest run of leading bits of w that holds r set bits
+#pragma unroll
+            for (unsigned sh = 16u; sh; sh >>= 1) {
+                if ((unsigned)i_popc(w >> (32u - pos - sh)) <= r) pos += sh;
+            }
+            const unsigned keep = 0xffffffffu >> pos;
+            prevp = base + 32u - (unsigned)i_ffs(w & ~keep);
+            w &= keep;
+        }
+        if (base) wl = w; else wh = w;
+    }
+    // next symbol of the walk: address of its coefficient, zeros since the symbol before it in the block
+    // (jpeg_enc.h:856-862; the DC at position 0 opens the block), its table
+    struct Pos { unsigned ca, run, tb; };
+    auto step = [&](Pos& o) {
+        const bool inhi = wh != 0u;
+        const unsigned w = inhi ? wh : wl;
+        const unsigned f = (unsigned)i_clz(w);             // (w == 0 only behind the lane's last symbol: those are never used)
+        const unsigned p = inhi ? f : f + 32u;
+        const unsigned w2 = w & ~(0x80000000u >> (f & 31u));
+        wh = inhi ? w2 : 0u;
+        wl = inhi ? wl : w2;
+        o.ca = cb + 2u * p;
+        o.run = p - prevp - 1u;
+        o.tb = p ? ac_tb : dc_tb;
+        prevp = p;
+        if (p == 63u) {                                    // the block's last symbol: its last coefficient or the end-of-block code (:884-887)
+            ra += 8u;
+            cb += 2u * (unsigned)kEntCoefStride;
+            prevp = 0xffffffffu;
+            open_block();
+        }
+    };
     // one symbol: its Huffman code + amplitude bits, the ZRL codes in front of it, its table
     struct Sym { unsigned val, len, tb, nz; };
-    auto lookup = [&](unsigned e, int v, unsigned before, Sym& y) {
-        const unsigned bp = e & kEntryBlockPos;
-        // zeros since the previous symbol of the block (jpeg_enc.h:856-862); the first symbol of a block is its DC (position 0)
-        unsigned run = ((bp ^ before) < 64u) ? bp - before - 1u : (bp & 63u);
-        if (v == 0) run = 0u;                                  // the end-of-block code (and a zero DC difference): entry 0 of its table
-        y.tb = tabs + ((e >> 11) << 7);                        // table of the symbol
+    auto lookup = [&](const Pos& q, int v, Sym& y) {
+        const unsigned run = v == 0 ? 0u : q.run;              // the end-of-block code (and a zero DC difference): entry 0 of its table
+        y.tb = q.tb;
         y.nz = run >> 4;                                       // one ZRL per 16 zeros (:863-867)
         const unsigned lz = (unsigned)i_clz((unsigned)(v < 0 ? -v : v));          // category = 32 - lz (jpeg_enc.h:598-608)
-        const uint2 h = lds_u64(y.tb + 256u + (run & 15u) * kTabRunBytes - 8u * lz);   // entry (run, category): {code, length + category}
+        const uint2 h = lds_u64(q.tb + 256u + (run & 15u) * kTabRunBytes - 8u * lz);   // entry (run, category): {code, length + category}
         const unsigned x = funnel_lc(0u, (unsigned)(v + (v >> 31)), lz);           // amplitude bits (:601-609), left-aligned; none for category 0
         y.val = funnel_rc(x, h.x, lz);                                             // (code << category) | amplitude
         y.len = h.y;
-        return bp;
     };
     auto emit = [&](const Sym& y) {
         if (y.nz) {
@@ -200,23 +232,24 @@ JG_DEV unsigned code_symbols(const EntTables& T, const int16_t* coef, const uint
         put(y.val, y.len);
     };
     // TWO symbols per iteration: their loads, category and table lookups are independent and overlap (the loop is bound by
-    // the latency of that chain, not by issue slots); list entries and coefficients are requested one iteration ahead.
-    // (Entries after the lane's last one are read -- they lie inside the list area -- and never used.)
-    unsigned e0 = lds_u16(la), e1 = lds_u16(la + 2u);
-    int v0 = coef_of(e0), v1 = coef_of(e1);
+    // the latency of that chain, not by issue slots); positions and coefficients are requested one iteration ahead.
+    // (The walk runs up to four symbols past the lane's last one -- into the next blocks' records, or the zero records
+    // behind the tile -- and those are never used.)
+    Pos q0, q1;
+    step(q0); step(q1);
+    int v0 = lds_s16(q0.ca), v1 = lds_s16(q1.ca);
 #pragma unroll 1
     for (unsigned i = 0; i < n; i += 2u) {
-        la += 4u;
-        const unsigned e2 = lds_u16(la), e3 = lds_u16(la + 2u);
-        const int v2 = coef_of(e2), v3 = coef_of(e3);
-        const bool two = i + 1u < n;
+        Pos q2, q3;
+        step(q2); step(q3);
+        const int v2 = lds_s16(q2.ca), v3 = lds_s16(q3.ca);
         Sym a, b;
-        const unsigned bp0 = lookup(e0, v0, tp, a);
-        tp = lookup(two ? e1 : 0u, two ? v1 : 0, bp0, b);
-        if (!two) { b.val = 0u; b.len = 0u; b.nz = 0u; }      // an odd count: nothing is appended for the missing symbol
+        lookup(q0, v0, a);
+        lookup(q1, v1, b);
+        if (i + 1u >= n) { b.val = 0u; b.len = 0u; b.nz = 0u; }     // an odd count: nothing is appended for the missing symbol
         emit(a);
         emit(b);
-        e0 = e2; e1 = e3; v0 = v2; v1 = v3;
+        q0 = q2; q1 = q3; v0 = v2; v1 = v3;
     }
     if (t & 31u) sts_u32(wa, alo << (32u - (t & 31u)));                     // the rest, left-aligned
     return t;
@@ -254,7 +287,7 @@ JG_DEV void merge_streams(const uint32_t* sub, unsigned nbits, unsigned incl, ui
 }
 
 // The tile this warp coded one iteration ago: its bits still sit in the region and leave right before the region is needed
-// again -- for the first merge of the next tile.  By then a whole map + list + code phase has passed since its size was
+// again -- for the first merge of the next tile.  By then a whole map + code phase has passed since its size was
 // published, and the sizes of its predecessors are almost always there: the look-back does not wait.
 struct PendingOut {
     int g = -1;          // tile (launch-wide index), -1: none
@@ -270,83 +303,50 @@ JG_DEV void flush_pending(const LaunchParams& P, EntWarp& W, PendingOut& po)
 }
 
 // Blocks [lo, hi) of the staged + mapped tile -> their bits appended at bit `bit_base` of the region (zero from there on).
-// List phase: with up to 16 blocks two lanes share a block (its two map words), else lane = block lo + lane.
-// Returns the bits of the blocks; `fits` = symbols, streams and total fit.
-template <bool DEFER>
-JG_DEV unsigned code_blocks(const LaunchParams& P, EntWarp& W, const EntTables& T, PendingOut& po, uint2 own, int lo, int hi, int lo_j, int jb, int bpm,
-                            unsigned bit_base, bool& fits)
+// The previous tile, whose bits still sit in the region, leaves after the symbols are coded, right before the merge.
+// Returns the bits of the blocks; `fits` = every lane's stream and the total fit.
+JG_DEV unsigned code_blocks(const LaunchParams& P, EntWarp& W, const EntTables& T, PendingOut& po, uint2 own, int lo, int hi, unsigned bit_base, bool& fits)
 {
     const int lane = JG_TID & 31;
-    const bool pairs = hi - lo <= 16;
-    const int slot = lo + (pairs ? lane >> 1 : lane);
-    const bool mine = slot < hi;
-    uint2 m;                         // the map of block `slot`: lane `slot` built it (own)
-    m.x = warp_shfl_u32(own.x, slot & 31);
-    m.y = warp_shfl_u32(own.y, slot & 31);
-    unsigned cls = 0;
-    if (!mine) { m.x = 0; m.y = 0; }
-    if (mine) {
-        int j = jb + lo_j + (slot - lo); while (j >= bpm) j -= bpm;      // lo_j = lo mod bpm; (jb + slot) mod bpm
-        int delta;
-        block_role(bpm, j, cls, delta);
-    }
-    const int word = pairs ? lane & 1 : 2;
-    const unsigned cnt = (unsigned)((word != 1 ? i_popc(m.x) : 0) + (word != 0 ? i_popc(m.y) : 0));
+    const unsigned cnt = (lane >= lo && lane < hi) ? (unsigned)(i_popc(own.x) + i_popc(own.y)) : 0u;      // lane = block
     const unsigned incl = warp_scan_incl_u32(cnt);
     const unsigned S = warp_shfl_u32(incl, 31);
-    // The list: with the deferred write-out the region still holds the previous tile, so it has the list area to itself
-    // (1024 symbols); otherwise it starts in the free space of the region above the bits merged so far and runs on
-    // into the list area behind it (the two are contiguous)
-    static_assert(offsetof(EntWarp, list) == offsetof(EntWarp, region) + sizeof(uint32_t) * (kEntRegionWords + 8), "the list area follows the region");
-    const unsigned list_word = DEFER ? (unsigned)(kEntRegionWords + 8) : ((bit_base + 31u) >> 5) + 2u;       // first word (of the region) the list may use
-    fits = S <= 2u * ((unsigned)(kEntRegionWords + 8) - list_word) + (unsigned)kListMax;
-    if (!fits) return 0u;
-    const uint16_t* list = reinterpret_cast<const uint16_t*>(W.region + list_word);
-    if (mine) list_block(smem_addr(list) + 2u * (incl - cnt), slot, m, cls, word);
-    warp_sync();
     const unsigned q = (S + 31u) >> 5;                   // symbols per lane
     const unsigned s0 = (unsigned)lane * q < S ? (unsigned)lane * q : S;
     const unsigned n = S - s0 < q ? S - s0 : q;
-    const unsigned nbits = code_symbols(T, W.coef, list, s0, n, W.sub + lane);
-    warp_sync();                                         // the streams are complete, every lane is done with the list
+    // the block that holds symbol s0: the number of blocks whose inclusive count is <= s0 (31 for a lane without symbols)
+    unsigned b = 0;
+#pragma unroll
+    for (unsigned st = 16u; st; st >>= 1) {
+        const unsigned v = warp_shfl_u32(incl, (int)(b + st - 1u));
+        if (v <= s0) b += st;
+    }
+    const unsigned before = warp_shfl_u32(incl - cnt, (int)b);
+    const unsigned nbits = code_symbols(T, W.coef, W.rec, b, n ? s0 - before : 0u, n, W.sub + lane);
+    warp_sync();                                         // the streams are complete
     const unsigned incl_bits = warp_scan_incl_u32(nbits);
     const unsigned bits = warp_shfl_u32(incl_bits, 31);
     fits = warp_ballot(nbits > (unsigned)kSubWords * 32u) == 0u && bit_base + bits <= (unsigned)kEntRegionWords * 32u;
-    if (DEFER) {
-        flush_pending(P, W, po);                         // the region is needed now: the previous tile leaves
-        if (po.failed) fits = false;
-    } else if (list_word < (unsigned)(kEntRegionWords + 8)) {
-        // the part of the list that lay in the region: zero again before bits are OR-ed in
-        const unsigned nw = (S + 1u) >> 1, room = (unsigned)(kEntRegionWords + 8) - list_word;
-        clear_region(W.region + list_word, nw < room ? nw : room);
-    }
+    flush_pending(P, W, po);                             // the region is needed now: the previous tile leaves
+    if (po.failed) fits = false;
     if (fits) merge_streams(W.sub, nbits, bit_base + incl_bits, W.region);
     return bits;
 }
 
-// The whole staged + mapped tile on the fast path.  A tile with more than 1024 symbols (or with a lane stream beyond 512
-// bits) is coded in two halves of 16 blocks: half the symbols and half the bits per lane.
-template <bool DEFER>
-JG_DEV unsigned code_tile(const LaunchParams& P, EntWarp& W, const EntTables& T, PendingOut& po, uint2 own, int nblk, int jb, int bpm, bool& fits)
+// The whole staged + mapped tile on the fast path.  A tile with more than 48 symbols per lane (or one where a lane's
+// stream went beyond its 512 bits) is coded in two halves of 16 blocks: half the symbols and half the bits per lane.
+JG_DEV unsigned code_tile(const LaunchParams& P, EntWarp& W, const EntTables& T, PendingOut& po, uint2 own, int nblk, bool& fits)
 {
     const unsigned cnt = (unsigned)(i_popc(own.x) + i_popc(own.y));
     const unsigned S = warp_shfl_u32(warp_scan_incl_u32(cnt), 31);
-    if (S <= (unsigned)kListMax || nblk <= 16) {
-        const unsigned bits = code_blocks<DEFER>(P, W, T, po, own, 0, nblk, 0, jb, bpm, 0u, fits);
+    if (S <= (unsigned)kOnePieceSymbols || nblk <= 16) {
+        const unsigned bits = code_blocks(P, W, T, po, own, 0, nblk, 0u, fits);
         if (fits || po.failed || nblk <= 16 || bits > (unsigned)kEntRegionWords * 32u) return bits;
         // a lane's stream overflowed: once more, in halves
-    } else if (S <= 3u * (unsigned)kListMax / 2u && !P.few_images) {
-        // up to 48 symbols per lane still go in one piece (two halves cost ~25 % more), but their list needs the region:
-        // the previous tile leaves now, before the list phase.  Not in a single-image launch, where the previous ticket is
-        // the previous tile of the same image and the early look-back would wait for it (16384^2 RGB tje-2: 6.8 ms this way, 4.0 ms in deferred halves)
-        flush_pending(P, W, po);
-        if (po.failed) { fits = false; return 0u; }
-        const unsigned bits = code_blocks<false>(P, W, T, po, own, 0, nblk, 0, jb, bpm, 0u, fits);
-        if (fits || bits > (unsigned)kEntRegionWords * 32u) return bits;
     }
-    unsigned bits = code_blocks<DEFER>(P, W, T, po, own, 0, 16, 0, jb, bpm, 0u, fits);
+    unsigned bits = code_blocks(P, W, T, po, own, 0, 16, 0u, fits);
     if (!fits) return bits;
-    bits += code_blocks<DEFER>(P, W, T, po, own, 16, nblk, 16 % bpm, jb, bpm, bits, fits);
+    bits += code_blocks(P, W, T, po, own, 16, nblk, bits, fits);
     return bits;
 }
 
@@ -398,7 +398,7 @@ JG_DEV_NOINLINE bool ent_tile_back(const LaunchParams& P, EntWarp& W, int g, int
 // learn the tile's size and last bits (successors must not wait for the whole slow pass), then again to be written.
 // Returns false on a look-back timeout.
 template <bool restart>
-JG_DEV_NOINLINE bool ent_tile_slow(const LaunchParams& P, EntWarp& W, const EntTables& T, uint2 own, int g, int nblk, int jb, int bpm, int slot)
+JG_DEV_NOINLINE bool ent_tile_slow(const LaunchParams& P, EntWarp& W, const EntTables& T, uint2 own, int g, int nblk, int slot)
 {
     const int lane = JG_TID & 31;
     PendingOut po;                    // (nothing pending: the caller has written the previous tile out)
@@ -409,7 +409,7 @@ JG_DEV_NOINLINE bool ent_tile_slow(const LaunchParams& P, EntWarp& W, const EntT
     for (int lo = 0; lo < nblk; lo += kSlowBlocks) {
         warp_sync();
         clear_region(W.region, kEntRegionWords + 8);
-        const unsigned tg = code_blocks<false>(P, W, T, po, own, lo, lo + kSlowBlocks < nblk ? lo + kSlowBlocks : nblk, lo % bpm, jb, bpm, 0u, fits);
+        const unsigned tg = code_blocks(P, W, T, po, own, lo, lo + kSlowBlocks < nblk ? lo + kSlowBlocks : nblk, 0u, fits);
         bits += tg;
         // running last-7-bits of the tile (a group may hold fewer than 7)
         tail = tg >= 7u ? tail_bits(W.region, tg) : (((tail << tg) | peek_bits(W.region, 0u, tg)) & 0x7fu);
@@ -428,7 +428,7 @@ JG_DEV_NOINLINE bool ent_tile_slow(const LaunchParams& P, EntWarp& W, const EntT
         const int hi = lo + kSlowBlocks < nblk ? lo + kSlowBlocks : nblk;
         warp_sync();
         clear_region(W.region, kEntRegionWords + 8);
-        unsigned tg = code_blocks<false>(P, W, T, po, own, lo, hi, lo % bpm, jb, bpm, 0u, fits);
+        unsigned tg = code_blocks(P, W, T, po, own, lo, hi, 0u, fits);
         if (pad && hi == nblk) {
             if (lane == 0) set_ones(W.region, tg, pad);
             warp_sync();
@@ -448,15 +448,13 @@ JG_DEV_NOINLINE bool ent_tile_slow(const LaunchParams& P, EntWarp& W, const EntT
 // ------------------------------------------------------------------------------------------
 // kernel B: coefficients -> unstuffed entropy-coded bits (raw), bits chained over the tiles of an image
 // ------------------------------------------------------------------------------------------
-// DEFER (chosen by the host for launches with few images): the previous tile is written out in the MIDDLE of the
-// iteration -- after the current tile's symbols are coded, right before its merge needs the region -- instead of at the
-// top.  With one image all ~2600 tiles in flight are consecutive tiles of that image; a write-out at the top of the
-// iteration asks for the sizes of tiles that were drawn nanoseconds before ours and are published at the same moment as
-// ours: every warp waits for the slowest of its 32 predecessors (16384^2 gray: 1.03 ms, ~100 polling rounds per tile);
-// with most of an iteration in between the sizes are there (0.60 ms).  With many images in flight the round-robin tickets
-// provide that slack, and the write-out at the top hides the TMA latency of the new tile (~7 % faster there).
-template <int MODE, bool DEFER>
-JG_KERNEL(kEntThreads, 3)
+// The previous tile is written out in the MIDDLE of the iteration -- after the current tile's symbols are coded, right
+// before its merge needs the region -- instead of at the top.  With one image all ~2600 tiles in flight are consecutive
+// tiles of that image; a write-out at the top of the iteration asks for the sizes of tiles that were drawn nanoseconds
+// before ours and are published at the same moment as ours: every warp waits for the slowest of its 32 predecessors
+// (16384^2 gray: 1.03 ms, ~100 polling rounds per tile); with most of an iteration in between the sizes are there (0.60 ms).
+template <int MODE>
+JG_KERNEL(kEntThreads, JG_ENT_MINB)
 void entropy_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTANT CoefMap cmap)
 {
     constexpr bool restart = MODE == kEntModeRestart;
@@ -475,6 +473,7 @@ void entropy_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTAN
     const EntTables& T = S.tab;
     if (lane == 0) mbar_init(&W.mbar, 1u);
     clear_region(W.region, kEntRegionWords + 8);
+    if (lane < 4) { uint2 z; z.x = 0u; z.y = 0u; W.rec[kEntBlocks + lane] = z; }
     mbar_fence_init();
     cta_sync();       // tables + barriers are set up: the only CTA barrier; from here every warp is on its own
 
@@ -520,23 +519,21 @@ void entropy_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTAN
                 pd.base = 0;
             }
         }
-        // ---- the previous tile goes out while the copy is in flight (DEFER: later, inside code_tile) ----
-        if (!DEFER || !have) {
-            flush_pending(P, W, po);
-            if (po.failed) break;
+        if (!have) {
+            flush_pending(P, W, po);                     // the last tile of this warp
+            break;
         }
-        if (!have) break;
         mbar_wait(&W.mbar, phase);
         phase ^= 1u;
 
-        // ---- map (lane = block), then list + code (lane = an equal share of the tile's symbols) ----
+        // ---- map (lane = block), then code (lane = an equal share of the tile's symbols) ----
         const uint2 own = map_block(W, lane, lane_j, nblk, jb, bpm, b0, pred_outside, restart);
         if (P.dbg_bits) {
             const unsigned nb = count_block_bits(W, T, own, lane, nblk, jb, bpm);
             if (lane < nblk) P.dbg_bits[P.images[img_idx].first_block + (unsigned long long)(b0 + lane)] = nb;
         }
         bool fits;
-        unsigned bits = code_tile<DEFER>(P, W, T, po, own, nblk, jb, bpm, fits);
+        unsigned bits = code_tile(P, W, T, po, own, nblk, fits);
         if (po.failed) break;
         if (P.win_words < kWinWordsMax && bits > 32u * (unsigned)P.win_words) {                // parity tests: force the slow path
             fits = false;
@@ -561,7 +558,7 @@ void entropy_kernel(const JG_GRID_CONSTANT LaunchParams P, const JG_GRID_CONSTAN
         } else {
             flush_pending(P, W, po);
             if (po.failed) break;
-            if (!ent_tile_slow<restart>(P, W, T, own, g, nblk, jb, bpm, slot)) break;
+            if (!ent_tile_slow<restart>(P, W, T, own, g, nblk, slot)) break;
         }
     }
 }

@@ -25,9 +25,6 @@
 #include <vector>
 
 #include "jpeg_launch.h"
-#ifndef JG_FEW_IMAGES
-#define JG_FEW_IMAGES 2   // a single-image launch: tiles of 1025..1536 symbols go in deferred halves (measured: 1 image 3.92 vs 6.60 ms, >= 2 images the early flush wins)
-#endif
 #include "jpeg_tables.h"
 
 namespace {
@@ -597,10 +594,9 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
             P.coefs = p->d_coefs;
             P.bpm = kSpecs[g.spec].layout == LAYOUT_444 ? 3 : (kSpecs[g.spec].layout == LAYOUT_420 ? 6 : 1);
             P.blocks_per_tile = g.restart ? kEntTileBlocksRestart : kEntTileBlocks;
-            P.few_images = P.n_images < JG_FEW_IMAGES ? 1 : 0;
             P.dbg_coefs = nullptr;
             const int grid = std::min((g.n_tiles + kEntWarps - 1) / kEntWarps, dev.sm_count * dev.entropy_ctas_per_sm);
-            JG_CUDA(entropy_launch(grid, s, P, p->cmap, (g.restart ? 2 : 0) | 1));     // deferred write-out: never slower
+            JG_CUDA(entropy_launch(grid, s, P, p->cmap, g.restart));
         }
         if (p->timing) JG_CUDA(cudaEventRecord(p->events[4 * gi + 2], s));
         JG_CUDA(stuff_launch(dev.sm_count * dev.stuff_ctas_per_sm, s, P));

@@ -79,12 +79,17 @@ struct LaunchParams {
     const int16_t* coefs;            // [blocks of the plan][64] int16, zigzag order; an image starts at ImageDesc.first_block
     int bpm;                         // blocks per MCU of the launch: 1 gray, 3 4:4:4, 6 4:2:0
     int blocks_per_tile;             // pass B tile: 32 blocks (24 = whole MCUs with restart intervals)
-    int few_images;                  // single-image launch: consecutive tickets are consecutive tiles of one image
 };
 
 // pass B (jpeg_entropy.cuh): tiles, CTA shape, and the TMA descriptor of the coefficient plane
 constexpr int kEntTileBlocks = 32, kEntTileBlocksRestart = 24;
-constexpr int kEntThreads = 192, kEntWarps = kEntThreads / 32;      // 6 warps: three CTAs of ~75 KB per SM
+#ifndef JG_ENT_WARPS
+#define JG_ENT_WARPS 20
+#endif
+#ifndef JG_ENT_MINB
+#define JG_ENT_MINB 1
+#endif
+constexpr int kEntWarps = JG_ENT_WARPS, kEntThreads = 32 * kEntWarps;      // ONE CTA of 20 warps per SM: 20 x 10.9 KB + the tables once (three CTAs of 6 warps: 18 warps; measured 7 % slower)
 // A CUtensorMap (cuTensorMapEncodeTiled, filled in by the host: 2-D, int16, {64, blocks} with a {72, 32} box), passed
 // by value as a __grid_constant__ kernel parameter.  Under the CPU emulation: q[0] = base pointer, q[1] = rows.
 struct alignas(64) CoefMap { unsigned long long q[16]; };
@@ -116,7 +121,7 @@ JG_DECLARE_SPEC(2, 1)
 #undef JG_DECLARE_SPEC
 // layout-independent pass B of the split pipeline (jpeg_entropy.cu); mode 0 plain, 2 restart intervals
 cudaError_t entropy_prepare(int* ctas_per_sm);
-cudaError_t entropy_launch(int grid, cudaStream_t stream, const LaunchParams& P, const CoefMap& cmap, int mode);
+cudaError_t entropy_launch(int grid, cudaStream_t stream, const LaunchParams& P, const CoefMap& cmap, bool restart);
 // layout-independent second pass (jpeg_stuff.cu)
 size_t stuff_smem_bytes();
 cudaError_t stuff_prepare(int* ctas_per_sm);

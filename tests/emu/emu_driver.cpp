@@ -261,20 +261,15 @@ int emu_encode_split(const uint8_t* pixels, int n_images, int w, int h, int ncom
     P.raw_bytes = raw_bytes.data(); P.first_chunk = first_chunk.data();
     P.scan_bytes = scan_bytes; P.img_status = img_status; P.huff = &lut;
     P.dbg_coefs = nullptr; P.dbg_bits = dbg_bits;
-    P.coefs = coefs.data(); P.bpm = bpm; P.blocks_per_tile = bpt; P.few_images = n_images < 2;
-    if (const char* e = getenv("EMU_FEW_IMAGES")) P.few_images = atoi(e);   // both mid-density routes of code_tile
+    P.coefs = coefs.data(); P.bpm = bpm; P.blocks_per_tile = bpt;
     CoefMap cmap;
     memset(&cmap, 0, sizeof cmap);
     cmap.q[0] = (unsigned long long)(size_t)coefs.data();
     cmap.q[1] = (unsigned long long)n_images * n_blocks;
     const int gridB = n_ctas > (n_tiles + kEntWarps - 1) / kEntWarps ? (n_tiles + kEntWarps - 1) / kEntWarps : n_ctas;
     launch(gridB, sizeof(EntSmem), [&] {
-        // the host's rule: few images -> deferred write-out; here both get exercised
-        const bool defer = n_images < 2;
-        if (restart && defer) entropy_kernel<kEntModeRestart, true>(P, cmap);
-        else if (restart) entropy_kernel<kEntModeRestart, false>(P, cmap);
-        else if (defer) entropy_kernel<kEntModePlain, true>(P, cmap);
-        else entropy_kernel<kEntModePlain, false>(P, cmap);
+        if (restart) entropy_kernel<kEntModeRestart>(P, cmap);
+        else entropy_kernel<kEntModePlain>(P, cmap);
     }, kEntThreads);
     if (!error) {
         launch(1, sizeof(StuffSmem), [&] { plan_chunks_kernel(P); });

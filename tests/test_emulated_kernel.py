@@ -75,7 +75,7 @@ def test_ticket_schedule_is_a_round_robin_bijection(tiles, force):
 
 
 @pytest.mark.parametrize("qm,q,sub,ctas", [(1, 90, 1, 1), (1, 97, 0, 2), (0, 3, 0, 1), (1, 98, 0, 1), (1, 85, 0, 3)])
-def test_emulated_kernel_sparse_dense_transitions(qm, q, sub, ctas, monkeypatch):
+def test_emulated_kernel_sparse_dense_transitions(qm, q, sub, ctas):
     """Smooth / noise / smooth bands: the warps switch between half-region tiles (written two
     iterations later), whole-region tiles and the slow path, every combination of pending tiles."""
     w, h = 176, 240
@@ -94,11 +94,8 @@ def test_emulated_kernel_sparse_dense_transitions(qm, q, sub, ctas, monkeypatch)
     if ctas == 1:
         scans, sizes, status = emu_encode(np.stack([img, img]), qm, q, sub, n_ctas=2)   # two images: the plain kernel
         assert hdr + scans[0] == want and hdr + scans[1] == want
-    # tiles of 1025..1536 symbols: one early-flushed piece in big launches, two deferred halves in small ones -- both routes
-    for few in ("0", "1"):
-        monkeypatch.setenv("EMU_FEW_IMAGES", few)
-        scans, sizes, status = emu_encode(np.stack([img, img[::-1].copy()]), qm, q, sub, n_ctas=2)
-        assert hdr + scans[0] == want and hdr + scans[1] == oracle.oracle_encode(img[::-1].copy(), qm, q, sub)
+    scans, sizes, status = emu_encode(np.stack([img, img[::-1].copy()]), qm, q, sub, n_ctas=2)
+    assert hdr + scans[0] == want and hdr + scans[1] == oracle.oracle_encode(img[::-1].copy(), qm, q, sub)
 
 
 @pytest.mark.parametrize("w,h,nc,qm,q,sub", [(45, 37, 3, 0, 3, 0), (64, 32, 3, 1, 75, 1), (33, 20, 4, 0, 2, 0), (40, 24, 4, 1, 90, 1)])
