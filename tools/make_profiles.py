@@ -43,8 +43,8 @@ def hot(rep, kernel, tiles):
 rows = [r for r in csv.reader(open(os.path.join(out_dir, "%s_launches.csv" % tag))) if len(r) > 10]
 hdr = rows[0]
 out = ["# ncu launch list, %s final kernel set.  Command (ran plain first, exit 0):" % tag,
-       "#   ncu --metrics gpu__time_duration.sum --clock-control none -k regex:\"transform_kernel|entropy_kernel|plan_chunks|stuff_kernel\" -c 120 --csv python bench.py --steps 2 --warmup 3 --no-cpu --no-twin --no-configs",
-       "# (-k filters out torch's synthetic-data kernels; a step = transform + entropy + plan_chunks + stuff; the short launches are the e2e leg's chunks;",
+       "#   ncu --metrics gpu__time_duration.sum --clock-control none -k regex:\"transform_kernel|entropy_kernel|plan_chunks|count_ff|scan_groups|stuff_kernel\" -c 180 --csv python bench.py --steps 2 --warmup 3 --no-cpu --no-twin --no-configs",
+       "# (-k filters out torch's synthetic-data kernels; a step = transform + entropy + plan_chunks + count_ff + scan_groups + stuff; the short launches are the e2e leg's chunks;",
        "#  per-launch times are cold-cache and serialised: compare SHARES)",
        "kernel,grid,block,duration_ns"]
 tot = {}
@@ -70,7 +70,7 @@ json.dump({"pass1_dram_bytes_per_launch_config2": int(p1),
            "config2_kernels": {k: int(v) for k, v in tr.items()}, "native_twin_64x1080p_tje2_kernels": {k: int(v) for k, v in tr2.items()}},
           open(os.path.join(prof, "traffic.json"), "w"), indent=1)
 hs = "# where the instructions, the stall samples and the shared-memory wavefronts go (tools/ncu_blocks.py, tools/ncu_sass.py on the .ncu-rep files)\n"
-hs += "\n## 4:2:0 q75, entropy_kernel (97920 x 4 tiles)\n" + hot(os.path.join(out_dir, "%s_final.ncu-rep" % tag), "entropy", 391680)
+hs += "\n## 4:2:0 q75, entropy_kernel (391680 tiles)\n" + hot(os.path.join(out_dir, "%s_final.ncu-rep" % tag), "entropy", 391680)
 hs += "\n## 4:2:0 q75, transform_kernel (per 2-MCU warp iteration: 1044480 of them)\n" + hot(os.path.join(out_dir, "%s_final.ncu-rep" % tag), "transform", 1044480)
 hs += "\n## tje-2 4:4:4, entropy_kernel (194400 tiles)\n" + hot(os.path.join(out_dir, "%s_twin444.ncu-rep" % tag), "entropy", 194400)
 hs += "\n## tje-2 4:4:4, transform_kernel (per 8-MCU warp iteration: 259200 of them)\n" + hot(os.path.join(out_dir, "%s_twin444.ncu-rep" % tag), "transform", 259200)
@@ -93,7 +93,7 @@ def sass_of(obj, start, stop):
         if on and not l.strip().startswith("/* 0x"): keep_l.append(l)
     return keep_l
 for obj, start, name in (("kernel_1_3.o", "transform_kernel", "transform_420_3"), ("kernel_0_3.o", "transform_kernel", "transform_444_3"),
-                         ("jpeg_entropy.o", "entropy_kernelILi0ELb1E", "entropy"), ("jpeg_stuff.o", "stuff_kernel", "stuff")):
+                         ("jpeg_entropy.o", "entropy_kernelILi0E", "entropy"), ("jpeg_stuff.o", "stuff_kernel", "stuff"), ("jpeg_stuff.o", "count_ff_kernel", "count_ff")):
     lines = sass_of(obj, start, None)
     open(os.path.join(prof, "%s_sass_%s.txt" % (tag, name)), "w").write("\n".join(lines))
     print(name, "SASS lines", len(lines), "FFMA", sum("FFMA" in l for l in lines), "FADD2", sum("FADD2" in l for l in lines),
