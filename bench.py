@@ -339,10 +339,11 @@ def run_ours(args):
                     parity = "check failed: %r" % (e,)
         t = max_over_ranks(ms)
         tot_mp, tot_px, tot_scan = sum_over_ranks(mp), sum_over_ranks(px_bytes), sum_over_ranks(scan)
+        used = max(1, int(sum_over_ranks(1 if active else 0)))
         res.update({"value": round(tot_mp / (t * 1e-3), 1) if t > 0 else None, "unit": UNIT, "ms_per_step": round(t, 4),
-                    "roofline_frac": round((tot_px + tot_scan) / (t * 1e-3) / 1e9 / peak, 4) if t > 0 else None,
+                    "roofline_frac": round((tot_px + tot_scan) / (t * 1e-3) / 1e9 / (peak * used), 4) if t > 0 else None,   # per GPU that took part
                     "out_bytes_per_px": round(tot_scan / (tot_mp * 1e6), 4) if tot_mp else None,
-                    "images": int(sum_over_ranks(pixels.shape[0] if pixels is not None else 0)), "gpus_used": int(sum_over_ranks(1 if active else 0)),
+                    "images": int(sum_over_ranks(pixels.shape[0] if pixels is not None else 0)), "gpus_used": used if tot_mp else 0,
                     "parity_vs_cpu_checker": parity})
         if keep:
             return res, plan, pixels
