@@ -509,13 +509,17 @@ def run_ours(args):
                     return a
 
                 t0 = time.perf_counter()
+                dec_px, dec_ms = jg.decode_batch(rfiles, timed=True, alloc=alloc)       # first full-size call: grows the decoder's memory pool
+                dec_first = (time.perf_counter() - t0) * 1e3
+                used[0] = 0
+                t0 = time.perf_counter()
                 dec_px, dec_ms = jg.decode_batch(rfiles, timed=True, alloc=alloc)
                 dec_call = (time.perf_counter() - t0) * 1e3
                 ok = all(np.array_equal(dec_px[i], oracle.ref_decode(rfiles[i])) for i in (0, n_img - 1))
                 decode[key] = {"workload": "the same %d images, IJG q75 4:2:0, %s" % (n_img, "one restart interval per 24 blocks" if flags else
                                                                                      "ordinary files (no restart markers): self-synchronising subsequences"),
                                "value": round(n_img * W * H / 1e6 / (dec_ms * 1e-3), 1), "unit": UNIT, "kernels_ms": round(dec_ms, 3),
-                               "call_ms_host_files_to_host_pixels": round(dec_call, 1), "host_buffers": "files pageable, pixels pinned", "pixels_identical_to_reference_decoder": bool(ok)}
+                               "call_ms_host_files_to_host_pixels": round(dec_call, 1), "first_call_ms": round(dec_first, 1), "host_buffers": "files pageable, pixels pinned", "pixels_identical_to_reference_decoder": bool(ok)}
                 del dec_px, pinned
             except Exception as e:
                 decode[key] = {"error": repr(e)}

@@ -146,6 +146,26 @@ def test_two_host_threads_inside_the_library_at_once(gpu):
             assert out[t][k] == oracle.oracle_encode(batches[t][k], *modes[t]), (t, k)
 
 
+def test_contiguous_host_batches_upload_as_one_copy_with_the_same_files(gpu):
+    """jpeg_gpu_encode_batch uploads images that follow one another in host memory (and in the plan's pixel arena) with ONE
+    copy per run: slices of one array, the same images as separate arrays, a run broken by an image of another size, by a
+    bottom-up image and by an image whose size is not a multiple of the arena's alignment all give the oracle's bytes."""
+    rng = np.random.default_rng(11)
+    big = np.stack([oracle.synth_image(256, 128, 3, n=i) for i in range(6)])           # 98304 bytes each: a multiple of 256
+    odd = np.stack([oracle.synth_image(250, 125, 3, n=20 + i) for i in range(4)])       # 93750 bytes: runs break at every image
+    other = oracle.synth_image(96, 64, 3, n=40)
+    batch = [big[0], big[1], big[2], other, big[3], big[4], big[5], odd[0], odd[1], odd[2], odd[3]]
+    want = [oracle.oracle_encode(im, 1, 85, 1) for im in batch]
+    files, st = gpu.encode_batch(batch, 1, 85, 1, device=0)                              # slices: pointers are contiguous
+    assert st == [0] * len(batch) and files == want
+    files, st = gpu.encode_batch([im.copy() for im in batch], 1, 85, 1, device=0)        # separate allocations
+    assert st == [0] * len(batch) and files == want
+    # bottom-up rows: the same memory read from the last row upwards == the flipped image
+    files, st = gpu.encode_batch([big[i] for i in range(6)], 0, 2, 0, device=0, bottom_up=True)
+    assert st == [0] * 6 and files == [oracle.oracle_encode(np.ascontiguousarray(big[i][::-1]), 0, 2, 0) for i in range(6)]
+    del rng
+
+
 MULTI_GPU_SCRIPT = r"""
 import sys, numpy as np
 sys.path.insert(0, %r)
