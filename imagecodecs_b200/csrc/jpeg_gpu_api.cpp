@@ -595,7 +595,9 @@ bool plan_run(jpeg_gpu_plan* p, cudaStream_t s)
             P.bpm = kSpecs[g.spec].layout == LAYOUT_444 ? 3 : (kSpecs[g.spec].layout == LAYOUT_420 ? 6 : 1);
             P.blocks_per_tile = g.restart ? kEntTileBlocksRestart : kEntTileBlocks;
             P.dbg_coefs = nullptr;
-            const int grid = std::min((g.n_tiles + kEntWarps - 1) / kEntWarps, dev.sm_count * dev.entropy_ctas_per_sm);
+            // persistent CTAs of kEntWarps warps that draw tiles from a ticket; with few tiles still one CTA per SM, so that the
+            // tiles spread over the SMs instead of filling a handful of them (warps that draw no ticket leave at once)
+            const int grid = std::min(g.n_tiles, dev.sm_count * dev.entropy_ctas_per_sm);
             JG_CUDA(entropy_launch(grid, s, P, p->cmap, g.restart));
         }
         if (p->timing) JG_CUDA(cudaEventRecord(p->events[4 * gi + 2], s));
