@@ -34,6 +34,15 @@ struct TGeo {
     // exchange space of one lane group, in floats: 4:4:4 three pair tiles, 4:2:0 two pair tiles + two single tiles, gray one pair tile
     static constexpr int GROUP_FLOATS = LAYOUT == LAYOUT_444 ? 3 * 2 * kTileFloats : (LAYOUT == LAYOUT_420 ? 6 * kTileFloats : 2 * kTileFloats);
     static constexpr int GROUPS = LAYOUT == LAYOUT_420 ? 2 : 4;
+    // Staging area: block b of the iteration at int16 offset b * kCoefStride + (b / BPM) * MCU_PAD.  A 16-bit scatter store
+    // covers FOUR blocks (8 lanes each) whose 8 zigzag positions fall on pseudo-random banks; the four patterns interfere
+    // least when the blocks sit 8 banks apart (2.5 wavefronts per store; any placement: >= 2.5, brute force).  With 144-byte
+    // blocks alone the four blocks of a 4:2:0 store are 0, 8, 24 and 0 banks apart (3.75 per store, measured 4), those of a
+    // 4:4:4 store 0, 12, 24, 4 (2.75): a pad of 96 / 48 bytes per MCU puts them at 0, 8, 16, 24.
+    static constexpr int MCU_PAD = LAYOUT == LAYOUT_420 ? 48 : (LAYOUT == LAYOUT_444 ? 24 : 0);
+    static constexpr int STAGE_INT16 = ITER_BLOCKS * kCoefStride + ITER_MCUS * MCU_PAD;
+    static JG_DEV int stage_off(int b) { return b * kCoefStride + (b / BPM) * MCU_PAD; }
+    static JG_DEV int stage_off(int mcu, int j) { return (mcu * BPM + j) * kCoefStride + mcu * MCU_PAD; }   // block j of MCU mcu
 };
 static_assert(TGeo<LAYOUT_444>::ITEM_MCUS == transform_item_mcus(LAYOUT_444) && TGeo<LAYOUT_420>::ITEM_MCUS == transform_item_mcus(LAYOUT_420) &&
               TGeo<LAYOUT_GRAY>::ITEM_MCUS == transform_item_mcus(LAYOUT_GRAY), "host and kernel agree on the item size");
@@ -42,7 +51,7 @@ template <int LAYOUT>
 struct TWarp {
     using G = TGeo<LAYOUT>;
     alignas(16) float xch[G::GROUPS * G::GROUP_FLOATS];                 // row pass -> column pass
-    alignas(16) int16_t stage[G::ITER_BLOCKS * kCoefStride];             // zigzag scatter -> 16-byte vectors
+    alignas(16) int16_t stage[G::STAGE_INT16];                           // zigzag scatter -> 16-byte vectors
 };
 template <int LAYOUT>
 struct TSmem { TWarp<LAYOUT> wm[kWarps]; };
@@ -106,15 +115,16 @@ struct TAddr {
     unsigned stage;      // the warp's staging area
 };
 
-// copy `nblk` staged blocks (kCoefStride apart) to global memory, 16 bytes per lane and step
-template <int MAXBLK>
+// copy `nblk` staged blocks (at TGeo::stage_off) to global memory, 16 bytes per lane and step
+template <int LAYOUT>
 JG_DEV void stage_to_global(unsigned stage, int16_t* gout, int nblk)
 {
+    using G = TGeo<LAYOUT>;
     const int t = JG_TID & 31;
 #pragma unroll
-    for (int q = 0; q < (MAXBLK * 8 + 31) / 32; ++q) {
+    for (int q = 0; q < (G::ITER_BLOCKS * 8 + 31) / 32; ++q) {
         const int c = q * 32 + t, blk = c >> 3, part = c & 7;
-        if (blk < nblk) *reinterpret_cast<uint4*>(gout + blk * 64 + part * 8) = lds_v4(stage + (unsigned)(blk * kCoefStride + part * 8) * 2u);
+        if (blk < nblk) *reinterpret_cast<uint4*>(gout + blk * 64 + part * 8) = lds_v4(stage + (unsigned)(G::stage_off(blk) + part * 8) * 2u);
     }
 }
 
@@ -198,7 +208,7 @@ JG_DEV void transform_iter_444(const TAddr& A, const TPixels<LAYOUT_444, NC>& px
 #pragma unroll
         for (int v = 0; v < 8; ++v) col[v] = lds_v2f(colA + 8u * (unsigned)(c * kTileFloats + v * 9));
         aan8x2(col);
-        const unsigned dA = A.stage + 2u * (unsigned)((g * 3 + c) * kCoefStride), dB = A.stage + 2u * (unsigned)(((g + 4) * 3 + c) * kCoefStride);
+        const unsigned dA = A.stage + 2u * (unsigned)TGeo<LAYOUT_444>::stage_off(g, c), dB = A.stage + 2u * (unsigned)TGeo<LAYOUT_444>::stage_off(g + 4, c);
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
             unsigned ka, kb;
@@ -208,7 +218,7 @@ JG_DEV void transform_iter_444(const TAddr& A, const TPixels<LAYOUT_444, NC>& px
         }
     }
     warp_sync();
-    stage_to_global<24>(A.stage, gout, nM * 3);
+    stage_to_global<LAYOUT_444>(A.stage, gout, nM * 3);
 }
 
 // ---- 4:2:0: two MCUs per iteration, 16 lanes per MCU, lane r16 owns pixel row r16 ---------------------------------
@@ -270,7 +280,7 @@ JG_DEV void transform_iter_420(const TAddr& A, const TPixels<LAYOUT_420, NC>& px
 #pragma unroll
         for (int v = 0; v < 8; ++v) col[v] = lds_v2f(ypair + 8u * (unsigned)(h * kTileFloats + v * 9 + u));
         aan8x2(col);
-        const unsigned dL = A.stage + 2u * (unsigned)((grp * 6 + 2 * h) * kCoefStride), dR = dL + 2u * kCoefStride;
+        const unsigned dL = A.stage + 2u * (unsigned)TGeo<LAYOUT_420>::stage_off(grp, 2 * h), dR = dL + 2u * kCoefStride;
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
             unsigned kl, kr;
@@ -282,12 +292,12 @@ JG_DEV void transform_iter_420(const TAddr& A, const TPixels<LAYOUT_420, NC>& px
 #pragma unroll
         for (int v = 0; v < 8; ++v) c[v] = lds_f32(ctile + 4u * (unsigned)(h * kTileFloats + v * 9 + u));
         aan8(c);
-        const unsigned dC = A.stage + 2u * (unsigned)((grp * 6 + 4 + h) * kCoefStride);
+        const unsigned dC = A.stage + 2u * (unsigned)TGeo<LAYOUT_420>::stage_off(grp, 4 + h);
 #pragma unroll
         for (int v = 0; v < 8; ++v) sts_u16(dC + LC.zz2[v], quantise1(c[v], LC.pq_c[v]));
     }
     warp_sync();
-    stage_to_global<12>(A.stage, gout, nM * 6);
+    stage_to_global<LAYOUT_420>(A.stage, gout, nM * 6);
 }
 
 // ---- gray: eight blocks per iteration, lane group g owns blocks 2g and 2g + 1 ------------------------------------
@@ -322,7 +332,7 @@ JG_DEV void transform_iter_gray(const TAddr& A, const TPixels<LAYOUT_GRAY, 1>& p
         sts_u16(dB + LC.zz2[v], kb);
     }
     warp_sync();
-    stage_to_global<8>(A.stage, gout, nM);
+    stage_to_global<LAYOUT_GRAY>(A.stage, gout, nM);
 }
 
 // ------------------------------------------------------------------------------------------
