@@ -36,7 +36,7 @@
 //                       final bit position in the tile's region (plain stores for words it owns alone, atomicOr
 //                       for the two it shares with its neighbours).
 //            6. publish + (one iteration later) chain + write, exactly as in jpeg_kernel.cuh.
-// A tile with more than 32768 bits or a lane stream beyond 640 bits (noise at all-ones quantisers) goes the slow way:
+// A tile with more than 24576 bits, or one whose halves still overflow a lane's 768-bit stream, goes the slow way:
 // four blocks at a time (always fit), written piecewise; same bytes.
 #pragma once
 #include "jpeg_kernel.cuh"
@@ -56,7 +56,7 @@ constexpr int kEntRegionWords = 768;                        // a tile's merged b
 #endif
 constexpr int kOnePieceSymbols = JG_ENT_PIECE * kSubWords;     // a tile with more symbols is coded in two halves right away (3 symbols per stream word: ~10.7 bits each)
 constexpr int kSlowBlocks = 4;                              // slow path: 4 blocks at a time (<= 256 symbols, <= 8 x 59 bits per lane: always fit)
-constexpr int kEntModePlain = 0, kEntModeRestart = 2;      // + 1: deferred write-out (launches with few images)
+constexpr int kEntModePlain = 0, kEntModeRestart = 2;
 constexpr unsigned kEntStageBytes = kEntBlocks * kEntCoefStride * 2;   // what one TMA box delivers (out-of-bounds rows count)
 constexpr unsigned kTabRunBytes = 136u, kTabAcBytes = 16u * kTabRunBytes;    // see EntTables
 constexpr unsigned kTabDc = 0u, kTabAc = 2u, kTabChroma = 1u, kTabAcChroma = kTabAcBytes / 128u;   // luma DC 0, chroma DC 1, luma AC 2, chroma AC 19
@@ -342,7 +342,7 @@ JG_DEV unsigned code_blocks(const LaunchParams& P, EntWarp& W, const EntTables& 
 }
 
 // The whole staged + mapped tile on the fast path.  A tile with more than 48 symbols per lane (or one where a lane's
-// stream went beyond its 512 bits) is coded in two halves of 16 blocks: half the symbols and half the bits per lane.
+// stream went beyond its 768 bits) is coded in two halves of 16 blocks: half the symbols and half the bits per lane.
 JG_DEV unsigned code_tile(const LaunchParams& P, EntWarp& W, const EntTables& T, PendingOut& po, uint2 own, int nblk, bool& fits)
 {
     const unsigned cnt = (unsigned)(i_popc(own.x) + i_popc(own.y));
