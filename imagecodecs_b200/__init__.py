@@ -219,7 +219,7 @@ def decode_batch(files, timed=False, alloc=None):
         pix.append(a)
         outs[i] = Decoded(a.ctypes.data, a.size if ok else 0, 0, 0, 0, 0)
     ms = C.c_float(0)
-    L.jpeg_gpu_decode_batch(ins, n, outs, 0, C.byref(ms))
+    L.jpeg_gpu_decode_batch(ins, n, outs, 0, C.byref(ms) if timed else None)    # timed: one piece, kernels back to back; else pipelined chunks
     res = []
     for i in range(n):
         o = outs[i]

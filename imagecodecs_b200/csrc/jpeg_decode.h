@@ -63,7 +63,7 @@ int subsequence_log2(const Info& info, size_t batch_scan_bytes);
 
 // The marker loop of njDecode up to and including the SOS header, plus the split of the scan
 // into restart intervals.  Returns an nj_result_t.
-int parse(const uint8_t* jpeg, size_t size, Info* info, bool build_vlc = true);
+int parse(const uint8_t* jpeg, size_t size, Info* info, bool build_vlc = true, bool header_only = false);   // header_only: stops at the scan (frame size, tables)
 // njDecodeDHT (:573-614) over the collected DHT payloads; a batch builds each distinct table set once
 int build_vlc_tables(const std::vector<uint8_t>& dht, std::vector<uint16_t>* vlc);
 

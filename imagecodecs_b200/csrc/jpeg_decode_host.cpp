@@ -194,7 +194,7 @@ int subsequence_log2(const Info& I, size_t batch_scan_bytes)
     return batch_scan_bytes >= ((size_t)8 << 20) ? 7 : batch_scan_bytes >= ((size_t)2 << 20) ? 6 : 5;
 }
 
-int parse(const uint8_t* jpeg, size_t size, Info* I, bool build_vlc)
+int parse(const uint8_t* jpeg, size_t size, Info* I, bool build_vlc, bool header_only)
 {
     size &= 0x7FFFFFFF;
     if (size < 2 || jpeg[0] != 0xFF || jpeg[1] != 0xD8) return kNoJpeg;
@@ -237,6 +237,7 @@ scan:
     // The entropy-coded data: split at the RSTm markers (njDecodeScan :707-715 expects RST(k mod 8) after
     // every rstinterval MCUs), ends at EOI or at the end of the file.
     I->scan_off = (size_t)(c.p - jpeg);
+    if (header_only) return kOk;
     I->interval_off.clear();
     I->interval_off.push_back((uint32_t)I->scan_off);
     size_t pos = I->scan_off;

@@ -518,6 +518,25 @@ def test_decoder_subsequences_for_restart_free_scans(gpu):
         assert (got[i] is None) == (want is None) and (want is None or np.array_equal(got[i], want)), i
 
 
+def test_large_decode_batches_are_pipelined_in_chunks_with_the_same_pixels(gpu):
+    """jpeg_gpu_decode_batch with host buffers and 64 or more files cuts the batch into chunks of 32 that three host threads
+    decode on their own streams (download of one chunk beside the kernels of the next); with kernel_ms it stays in one piece.
+    Same pixels either way, == the reference decoder; a broken file in the middle fails alone."""
+    imgs = [oracle.synth_image(160 + 8 * (i % 5), 96 + 8 * (i % 3), 3 if i % 7 else 1, n=i) for i in range(75)]
+    sub = [1 if im.shape[2] == 3 and i % 2 else 0 for i, im in enumerate(imgs)]
+    flags = [gpu.FLAG_RESTART if i % 3 == 0 else 0 for i in range(75)]
+    files, st = gpu.encode_batch(imgs, 1, 80, sub, device=0, flags=flags)
+    assert st == [0] * 75
+    files[40] = files[40][:300]                              # cut inside the scan
+    piped = gpu.decode_batch(files)
+    whole, ms = gpu.decode_batch(files, timed=True)
+    assert ms > 0
+    for i, f in enumerate(files):
+        want = oracle.ref_decode(f)
+        assert (piped[i] is None) == (want is None) == (whole[i] is None), i
+        assert want is None or (np.array_equal(piped[i], want) and np.array_equal(whole[i], want)), i
+
+
 def test_encode_decode_round_trip_on_the_gpu(gpu):
     """Both directions on the device: pixels -> restart-interval JPEG -> pixels.  The decoded images equal what the
     reference decoder makes of the same files, and they are close to the originals (PSNR), for a batch of mixed shapes."""
